@@ -1,0 +1,396 @@
+// mniw_draw.cu — posterior draw (A, Sigma) ~ MNIW(eta) (second half of PGAS.sample_params,
+// reference src/PGAS.py:306-343 with prior_mniw_2naturalPara_inv, src/BayesianInferrence.py:35-45).
+//
+// The reference forms V = eta1^-1 explicitly (Cholesky + cho_solve against the identity, 2 M^3
+// flops), factors it again (V_chol = chol(V), M^3/3) and multiplies Nrm V_chol.  Here ONE
+// factorisation is done: the reverse ("UL") Cholesky eta1 = U U^T, U upper triangular, obtained
+// as the ordinary lower Cholesky L' of the index-reversed matrix J eta1 J (U = J L' J).  Then
+//   mean^T       = eta1^-1 eta0 = U^-T U^-1 eta0           (two triangular solves, n_x columns)
+//   V_chol       = U^-T  exactly (the lower Cholesky factor of V is unique and U^-T is lower
+//                  triangular with positive diagonal and U^-T U^-1 = V)
+//   Nrm V_chol   = X with U X^T = Nrm^T                    (one triangular solve, n_x columns)
+//   Nrm V_chol^T = X with U^T X^T = Nrm^T                  (PGAS_FLAG_VCHOL_TRANSPOSE)
+// so the draw costs M^3/3 + O(n_x M^2) flops instead of 2.67 M^3 and needs no inverse.
+// The inverse-Wishart part (p = n_x <= 4) follows src/PGAS.py:312-335 literally in one thread.
+// One CTA per chain; the factor lives in the caller's workspace (L2-resident for M <= ~2000).
+#include "common.cuh"
+#include "sweep_args.cuh"
+
+constexpr int DT = 256;      // threads
+constexpr int NB = 32;       // panel width
+constexpr int TS = 64;       // trailing-update tile
+
+struct DrawArgs {
+    int M, nx, n_chains, flags;
+    double eta3;
+    const double* eta0;      // (n_chains, M, nx)
+    const double* eta1;      // (n_chains, M, M)
+    const double* eta2;      // (n_chains, nx, nx)
+    long long eta_stride0, eta_stride1, eta_stride2;    // 0 when a single eta is shared by all chains
+    int rng_mode;
+    unsigned long long seed;
+    unsigned chain_base, iteration;
+    const double* chi2;      // (n_chains, nx)
+    const double* G;         // (n_chains, nx, nx)
+    const double* Nrm;       // (n_chains, nx, M)
+    double* A;               // (n_chains, nx, M)
+    double* S;               // (n_chains, nx, nx)
+    int* status;             // (n_chains)
+    double* wsB;             // (n_chains, M, M)      reversed eta1 -> L'
+    double* wsF;             // (n_chains, M, 2 nx)   forward right-hand sides / solutions
+    double* wsK;             // (n_chains, M, 2 nx)   backward right-hand sides / solutions
+};
+
+// chi-square(nu) = 2 Gamma(nu/2, 1) by Marsaglia-Tsang; attempts indexed by the Philox counter
+__device__ double philox_chisquare(unsigned long long seed, unsigned chain, unsigned iter, unsigned idx, double nu) {
+    double a = 0.5 * nu, boost = 1.0;
+    unsigned attempt = 0;
+    if (a < 1.0) {
+        double u, ub;
+        philox_uniform2(seed, PURPOSE_DRAW_CHI, chain, iter, 0x40000000u, idx, u, ub);
+        boost = pow(u + (1.0 / 9007199254740992.0), 1.0 / a);
+        a += 1.0;
+    }
+    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (;; ++attempt) {
+        double x, xb, u, ub;
+        philox_normal2(seed, PURPOSE_DRAW_CHI, chain, iter, 2 * attempt, idx, x, xb);
+        philox_uniform2(seed, PURPOSE_DRAW_CHI, chain, iter, 2 * attempt + 1, idx, u, ub);
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        if (log(u + (1.0 / 9007199254740992.0)) < 0.5 * x * x + d - d * v + d * log(v) || attempt > 1000) return 2.0 * d * v * boost;
+    }
+}
+
+__global__ void __launch_bounds__(DT) mniw_draw_kernel(const __grid_constant__ DrawArgs a) {
+    const int chain = blockIdx.x, tid = threadIdx.x;
+    const int M = a.M, nx = a.nx, R2 = 2 * nx;
+    const bool vt = (a.flags & PGAS_FLAG_VCHOL_TRANSPOSE) != 0;
+    const double* eta0 = a.eta0 + (size_t)chain * a.eta_stride0;
+    const double* eta1 = a.eta1 + (size_t)chain * a.eta_stride1;
+    const double* eta2 = a.eta2 + (size_t)chain * a.eta_stride2;
+    double* B = a.wsB + (size_t)chain * M * M;
+    double* F = a.wsF + (size_t)chain * M * R2;
+    double* K = a.wsK + (size_t)chain * M * R2;
+    double* Aout = a.A + (size_t)chain * nx * M;
+
+    __shared__ double Dg[NB][NB + 1];                 // diagonal block
+    __shared__ __align__(16) double PiT[NB][TS];      // panel rows of tile i, transposed [p][row]
+    __shared__ __align__(16) double PjT[NB][TS];
+    __shared__ double xs[NB][2 * PGAS_MAX_NX];
+    __shared__ double red[DT / 32][PGAS_MAX_NX * PGAS_MAX_NX];
+    __shared__ double Sc[PGAS_MAX_NX][PGAS_MAX_NX];   // S_chol
+    __shared__ int s_status;
+    if (tid == 0) s_status = 0;
+
+    // ---- 0. B = J eta1 J (lower part), right-hand sides
+    for (size_t e = tid; e < (size_t)M * M; e += DT) {
+        const int i = (int)(e / M), j = (int)(e % M);
+        if (j <= i) B[e] = eta1[(size_t)(M - 1 - i) * M + (M - 1 - j)];
+    }
+    for (int e = tid; e < M * nx; e += DT) {
+        const int i = e / nx, k = e % nx;
+        F[(size_t)i * R2 + k] = eta0[(size_t)(M - 1 - i) * nx + k];
+        double z;
+        if (a.rng_mode == 1) {
+            z = a.Nrm[((size_t)chain * nx + k) * M + (M - 1 - i)];
+        } else {
+            // Nrm[k, m] = normal #(k*M + m): pairs share a Philox block
+            const unsigned flat = (unsigned)(k * M + (M - 1 - i));
+            double za, zb;
+            philox_normal2(a.seed, PURPOSE_DRAW_N, a.chain_base + chain, a.iteration, 0u, flat >> 1, za, zb);
+            z = (flat & 1) ? zb : za;
+        }
+        if (vt) K[(size_t)i * R2 + nx + k] = z; else F[(size_t)i * R2 + nx + k] = z;
+    }
+    __syncthreads();
+
+    // ---- 1. blocked right-looking Cholesky B = L' L'^T (in place, lower)
+    for (int kb = 0; kb < M; kb += NB) {
+        const int nb = min(NB, M - kb);
+        for (int e = tid; e < NB * NB; e += DT) {
+            const int r = e / NB, c = e % NB;
+            Dg[r][c] = (r < nb && c <= r) ? B[(size_t)(kb + r) * M + kb + c] : (r == c ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        for (int j = 0; j < nb; ++j) {
+            if (tid == 0) {
+                const double d = Dg[j][j];
+                if (!(d > 0.0) && s_status == 0) s_status = kb + j + 1;
+                Dg[j][j] = sqrt(d);
+            }
+            __syncthreads();
+            if (tid > j && tid < nb) Dg[tid][j] /= Dg[j][j];
+            __syncthreads();
+            for (int e = tid; e < nb * nb; e += DT) {
+                const int r = e / nb, c = e % nb;
+                if (c > j && r >= c) Dg[r][c] -= Dg[r][j] * Dg[c][j];
+            }
+            __syncthreads();
+        }
+        for (int e = tid; e < nb * nb; e += DT) {
+            const int r = e / nb, c = e % nb;
+            if (c <= r) B[(size_t)(kb + r) * M + kb + c] = Dg[r][c];
+        }
+        // panel: rows below the diagonal block, X Dg^T = B[i, kb:kb+nb]
+        for (int i = kb + nb + tid; i < M; i += DT) {
+            double x[NB];
+            double* row = B + (size_t)i * M + kb;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) x[c] = (c < nb) ? row[c] : 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                double v = x[c];
+#pragma unroll
+                for (int p = 0; p < c; ++p) v = fma(-x[p], Dg[c][p], v);
+                x[c] = v / Dg[c][c];
+            }
+#pragma unroll
+            for (int c = 0; c < NB; ++c) if (c < nb) row[c] = x[c];
+        }
+        __syncthreads();
+        // trailing update: B[i,j] -= sum_p P[i,p] P[j,p] on the lower-triangular 64x64 tiles
+        const int r0 = kb + nb;
+        const int nt = (M - r0 + TS - 1) / TS;
+        const int ty = tid / 16, tx = tid % 16;
+        for (int bi = 0; bi < nt; ++bi)
+            for (int bj = 0; bj <= bi; ++bj) {
+                for (int e = tid; e < TS * NB; e += DT) {
+                    const int rr = e / NB, p = e % NB;
+                    const int gi = r0 + bi * TS + rr, gj = r0 + bj * TS + rr;
+                    PiT[p][rr] = (gi < M && p < nb) ? B[(size_t)gi * M + kb + p] : 0.0;
+                    PjT[p][rr] = (gj < M && p < nb) ? B[(size_t)gj * M + kb + p] : 0.0;
+                }
+                __syncthreads();
+                double acc[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+#pragma unroll 4
+                for (int p = 0; p < NB; ++p) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(&PiT[p][ty * 4]);
+                    const double2 a1 = *reinterpret_cast<const double2*>(&PiT[p][ty * 4 + 2]);
+                    const double2 b0 = *reinterpret_cast<const double2*>(&PjT[p][tx * 4]);
+                    const double2 b1 = *reinterpret_cast<const double2*>(&PjT[p][tx * 4 + 2]);
+                    const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int gi = r0 + bi * TS + ty * 4 + r, gj = r0 + bj * TS + tx * 4 + c;
+                        if (gi < M && gj <= gi) B[(size_t)gi * M + gj] -= acc[r][c];
+                    }
+                __syncthreads();
+            }
+    }
+
+    // ---- 2. forward solve L' F = rhs (all 2 nx columns; the unused ones are skipped by width)
+    const int wf = vt ? nx : R2;               // active forward columns
+    for (int kb = 0; kb < M; kb += NB) {
+        const int nb = min(NB, M - kb);
+        if (tid < wf) {
+            for (int r = 0; r < nb; ++r) {
+                double v = F[(size_t)(kb + r) * R2 + tid];
+                for (int p = 0; p < r; ++p) v = fma(-B[(size_t)(kb + r) * M + kb + p], xs[p][tid], v);
+                v /= B[(size_t)(kb + r) * M + kb + r];
+                xs[r][tid] = v;
+                F[(size_t)(kb + r) * R2 + tid] = v;
+            }
+        }
+        __syncthreads();
+        for (int i = kb + nb + tid; i < M; i += DT) {
+            double acc[2 * PGAS_MAX_NX];
+#pragma unroll
+            for (int c = 0; c < 2 * PGAS_MAX_NX; ++c) acc[c] = 0.0;
+            const double* row = B + (size_t)i * M + kb;
+            for (int p = 0; p < nb; ++p) {
+                const double l = row[p];
+#pragma unroll
+                for (int c = 0; c < 2 * PGAS_MAX_NX; ++c) if (c < wf) acc[c] = fma(l, xs[p][c], acc[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 2 * PGAS_MAX_NX; ++c) if (c < wf) F[(size_t)i * R2 + c] -= acc[c];
+        }
+        __syncthreads();
+    }
+    // ---- 3. backward solve L'^T K = [y | (Nrm part when transposed)]
+    const int wk = vt ? R2 : nx;
+    for (int e = tid; e < M * nx; e += DT) K[(size_t)(e / nx) * R2 + e % nx] = F[(size_t)(e / nx) * R2 + e % nx];
+    __syncthreads();
+    for (int kb = ((M - 1) / NB) * NB; kb >= 0; kb -= NB) {
+        const int nb = min(NB, M - kb);
+        if (tid < wk) {
+            for (int r = nb - 1; r >= 0; --r) {
+                double v = K[(size_t)(kb + r) * R2 + tid];
+                for (int p = r + 1; p < nb; ++p) v = fma(-B[(size_t)(kb + p) * M + kb + r], xs[p][tid], v);
+                v /= B[(size_t)(kb + r) * M + kb + r];
+                xs[r][tid] = v;
+                K[(size_t)(kb + r) * R2 + tid] = v;
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < kb; j += DT) {
+            double acc[2 * PGAS_MAX_NX];
+#pragma unroll
+            for (int c = 0; c < 2 * PGAS_MAX_NX; ++c) acc[c] = 0.0;
+            for (int p = 0; p < nb; ++p) {
+                const double l = B[(size_t)(kb + p) * M + j];
+#pragma unroll
+                for (int c = 0; c < 2 * PGAS_MAX_NX; ++c) if (c < wk) acc[c] = fma(l, xs[p][c], acc[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 2 * PGAS_MAX_NX; ++c) if (c < wk) K[(size_t)j * R2 + c] -= acc[c];
+        }
+        __syncthreads();
+    }
+    // now: mean[k][m] = K[M-1-m][k];  X[k][m] = (vt ? K : F)[M-1-m][nx + k]
+
+    // ---- 4. Psi = eta2 - mean eta0   (src/BayesianInferrence.py:42)
+    {
+        double part[PGAS_MAX_NX * PGAS_MAX_NX];
+#pragma unroll
+        for (int e = 0; e < PGAS_MAX_NX * PGAS_MAX_NX; ++e) part[e] = 0.0;
+        for (int mm = tid; mm < M; mm += DT)
+            for (int r = 0; r < nx; ++r)
+                for (int c = 0; c < nx; ++c)
+                    part[r * PGAS_MAX_NX + c] = fma(K[(size_t)(M - 1 - mm) * R2 + r], eta0[(size_t)mm * nx + c], part[r * PGAS_MAX_NX + c]);
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int e = 0; e < PGAS_MAX_NX * PGAS_MAX_NX; ++e) {
+            const double v = warp_sum(part[e]);
+            if (lane == 0) red[warp][e] = v;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // inverse-Wishart draw, src/PGAS.py:312-335
+        double Psi[PGAS_MAX_NX][PGAS_MAX_NX], Cr[PGAS_MAX_NX][PGAS_MAX_NX], Li[PGAS_MAX_NX][PGAS_MAX_NX];
+        double Tm[PGAS_MAX_NX][PGAS_MAX_NX], Cm[PGAS_MAX_NX][PGAS_MAX_NX], Ci[PGAS_MAX_NX][PGAS_MAX_NX];
+        for (int r = 0; r < nx; ++r)
+            for (int c = 0; c < nx; ++c) {
+                double s = 0.0;
+                for (int w = 0; w < DT / 32; ++w) s += red[w][r * PGAS_MAX_NX + c];
+                Psi[r][c] = eta2[r * nx + c] - s;
+            }
+        // chol_row = chol(Psi)  (:317)
+        for (int i = 0; i < nx; ++i) for (int j = 0; j < nx; ++j) { Cr[i][j] = 0.0; Li[i][j] = 0.0; Tm[i][j] = 0.0; Ci[i][j] = 0.0; }
+        for (int j = 0; j < nx; ++j) {
+            double d = Psi[j][j];
+            for (int k = 0; k < j; ++k) d -= Cr[j][k] * Cr[j][k];
+            if (!(d > 0.0) && s_status == 0) s_status = -(j + 1);
+            d = sqrt(d);
+            Cr[j][j] = d;
+            for (int i = j + 1; i < nx; ++i) {
+                double v = Psi[i][j];
+                for (int k = 0; k < j; ++k) v -= Cr[i][k] * Cr[j][k];
+                Cr[i][j] = v / d;
+            }
+        }
+        // L = chol_row^-1  (:319)
+        for (int j = 0; j < nx; ++j) {
+            Li[j][j] = 1.0 / Cr[j][j];
+            for (int i = j + 1; i < nx; ++i) {
+                double v = 0.0;
+                for (int k = j; k < i; ++k) v -= Cr[i][k] * Li[k][j];
+                Li[i][j] = v / Cr[i][i];
+            }
+        }
+        // T = tril(normals,-1) + diag(sqrt(chi2(nu - i)))  (:323-329)
+        for (int i = 0; i < nx; ++i) {
+            double c2;
+            if (a.rng_mode == 1) c2 = a.chi2[(size_t)chain * nx + i];
+            else c2 = philox_chisquare(a.seed, a.chain_base + chain, a.iteration, (unsigned)i, a.eta3 - (double)i);
+            Tm[i][i] = sqrt(c2);
+            for (int j = 0; j < i; ++j) {
+                if (a.rng_mode == 1) Tm[i][j] = a.G[((size_t)chain * nx + i) * nx + j];
+                else {
+                    const unsigned flat = (unsigned)(i * nx + j);
+                    double za, zb;
+                    philox_normal2(a.seed, PURPOSE_DRAW_G, a.chain_base + chain, a.iteration, 0u, flat >> 1, za, zb);
+                    Tm[i][j] = (flat & 1) ? zb : za;
+                }
+            }
+        }
+        // C = L T (:332);  S_chol = C^-T (:334);  S = S_chol S_chol^T (:335)
+        for (int i = 0; i < nx; ++i)
+            for (int j = 0; j < nx; ++j) {
+                double s = 0.0;
+                for (int k = 0; k < nx; ++k) s += Li[i][k] * Tm[k][j];
+                Cm[i][j] = s;
+            }
+        for (int j = 0; j < nx; ++j) {                 // Ci = C^-1 (C lower triangular)
+            Ci[j][j] = 1.0 / Cm[j][j];
+            for (int i = j + 1; i < nx; ++i) {
+                double v = 0.0;
+                for (int k = j; k < i; ++k) v -= Cm[i][k] * Ci[k][j];
+                Ci[i][j] = v / Cm[i][i];
+            }
+        }
+        for (int i = 0; i < nx; ++i)
+            for (int j = 0; j < nx; ++j) Sc[i][j] = Ci[j][i];        // S_chol = C^-T (upper triangular)
+        for (int i = 0; i < nx; ++i)
+            for (int j = 0; j < nx; ++j) {
+                double s = 0.0;
+                for (int k = 0; k < nx; ++k) s += Sc[i][k] * Sc[j][k];
+                a.S[((size_t)chain * nx + i) * nx + j] = s;
+            }
+        if (a.status) a.status[chain] = s_status;
+    }
+    __syncthreads();
+    // ---- 5. A = mean + S_chol (Nrm V_chol)   (:338-341)
+    const double* Xs = vt ? K : F;
+    for (int e = tid; e < nx * M; e += DT) {
+        const int k = e / M, mm = e % M;
+        double v = K[(size_t)(M - 1 - mm) * R2 + k];
+        for (int j = 0; j < nx; ++j) v = fma(Sc[k][j], Xs[(size_t)(M - 1 - mm) * R2 + nx + j], v);
+        Aout[(size_t)k * M + mm] = v;
+    }
+}
+
+static size_t draw_ws_per_chain(int M, int nx) {
+    return sizeof(double) * ((size_t)M * M + 2 * (size_t)M * 2 * nx);
+}
+
+extern "C" size_t pgas_mniw_draw_workspace_bytes(int32_t M, int32_t n_x, int32_t n_chains) {
+    return draw_ws_per_chain(M, n_x) * (size_t)n_chains + 256;
+}
+
+int pgas_launch_mniw_draw(const double* eta0, const double* eta1, const double* eta2, double eta3, bool shared_eta, int M, int nx,
+                          int n_chains, const pgas_rng* rng, int flags, double* A, double* S, int* status, void* ws, size_t ws_bytes,
+                          cudaStream_t st) {
+    if (!eta0 || !eta1 || !eta2 || !A || !S || !rng || !ws) PGAS_FAIL(-1, "pgas_mniw_draw_f64: null argument");
+    if (M < 1 || nx < 1 || nx > PGAS_MAX_NX || n_chains < 1) PGAS_FAIL(-2, "bad shape (M=%d n_x=%d n_chains=%d)", M, nx, n_chains);
+    if (ws_bytes < pgas_mniw_draw_workspace_bytes(M, nx, n_chains)) PGAS_FAIL(-5, "workspace too small for the MNIW draw");
+    if (rng->mode == 1 && (!rng->chi2 || !rng->G || !rng->Nrm)) PGAS_FAIL(-1, "injected rng mode needs chi2, G and Nrm");
+    DrawArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = M; a.nx = nx; a.n_chains = n_chains; a.flags = flags; a.eta3 = eta3;
+    a.eta0 = eta0; a.eta1 = eta1; a.eta2 = eta2;
+    a.eta_stride0 = shared_eta ? 0 : (long long)M * nx;
+    a.eta_stride1 = shared_eta ? 0 : (long long)M * M;
+    a.eta_stride2 = shared_eta ? 0 : (long long)nx * nx;
+    a.rng_mode = rng->mode; a.seed = rng->seed; a.chain_base = rng->chain_base; a.iteration = rng->iteration;
+    a.chi2 = rng->chi2; a.G = rng->G; a.Nrm = rng->Nrm;
+    a.A = A; a.S = S; a.status = status;
+    char* w = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    a.wsB = (double*)w;
+    a.wsF = a.wsB + (size_t)n_chains * M * M;
+    a.wsK = a.wsF + (size_t)n_chains * M * 2 * nx;
+    mniw_draw_kernel<<<n_chains, DT, 0, st>>>(a);
+    PGAS_KERNEL_CHECK();
+    return 0;
+}
+
+extern "C" int pgas_mniw_draw_f64(const double* eta0, const double* eta1, const double* eta2, double eta3, int32_t M, int32_t n_x,
+                                  int32_t n_chains, const pgas_rng* rng, int32_t flags, double* A_out, double* S_out,
+                                  int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream) {
+    return pgas_launch_mniw_draw(eta0, eta1, eta2, eta3, false, M, n_x, n_chains, rng, flags, A_out, S_out, status_out, workspace,
+                                 workspace_bytes, (cudaStream_t)stream);
+}

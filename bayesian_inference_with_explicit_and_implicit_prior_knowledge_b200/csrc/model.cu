@@ -1,0 +1,210 @@
+// model.cu — model descriptor (host -> device), error plumbing, version.
+//
+// pgas_model_create stands in for condSequentialMonteCarlo.__init__ (reference src/PGAS.py:24-43)
+// plus the closure built by generate_Hilbert_BasisFunction (src/BasisFunctions.py:59-66): it
+// uploads the data, the Gaussian likelihood and GP-input map parameters, and converts the
+// (M, D) integer frequency table into the packed tensor-product ROW layout the kernels use
+// (common.cuh: DevModel / ROW_*).
+#include <stdarg.h>
+#include <algorithm>
+#include <map>
+#include <vector>
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void pgas_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* pgas_last_error(void) { return g_err; }
+extern "C" int pgas_version(void) { return 100; }
+extern "C" int pgas_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// lower Cholesky of a small SPD matrix (n <= 4); returns false if not positive definite
+static bool small_chol(const double* A, int n, int lda, double* L /* n x n, row-major, lda n */) {
+    for (int i = 0; i < n * n; ++i) L[i] = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double d = A[j * lda + j];
+        for (int k = 0; k < j; ++k) d -= L[j * n + k] * L[j * n + k];
+        if (!(d > 0.0)) return false;
+        d = sqrt(d);
+        L[j * n + j] = d;
+        for (int i = j + 1; i < n; ++i) {
+            double v = A[i * lda + j];
+            for (int k = 0; k < j; ++k) v -= L[i * n + k] * L[j * n + k];
+            L[i * n + j] = v / d;
+        }
+    }
+    return true;
+}
+
+extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
+    if (!p || !out) PGAS_FAIL(-1, "pgas_model_create: null argument");
+    if (p->n_x < 1 || p->n_x > PGAS_MAX_NX) PGAS_FAIL(-2, "n_x=%d outside [1,%d]", p->n_x, PGAS_MAX_NX);
+    if (p->n_y < 1 || p->n_y > PGAS_MAX_NY) PGAS_FAIL(-2, "n_y=%d outside [1,%d]", p->n_y, PGAS_MAX_NY);
+    if (p->n_u < 0 || p->n_u > PGAS_MAX_NU) PGAS_FAIL(-2, "n_u=%d outside [0,%d]", p->n_u, PGAS_MAX_NU);
+    if (p->D < 1 || p->D > PGAS_MAX_D) PGAS_FAIL(-2, "D=%d outside [1,%d]", p->D, PGAS_MAX_D);
+    if (p->M < 1 || p->T < 2) PGAS_FAIL(-2, "need M >= 1 and T >= 2 (M=%d, T=%d)", p->M, p->T);
+    if (!p->freq || !p->observations) PGAS_FAIL(-1, "freq / observations must not be null");
+    if (p->n_u > 0 && !p->inputs) PGAS_FAIL(-1, "inputs must not be null when n_u > 0");
+    if (p->idx_step < 1 || p->idx_start < 1) PGAS_FAIL(-2, "idx_start and idx_step must be >= 1");
+    if (p->map_kind == PGAS_MAP_VEHICLE_SLIP && (p->n_x < 2 || p->n_u < 2))
+        PGAS_FAIL(-2, "vehicle slip map needs n_x >= 2 and n_u >= 2");
+    if (p->map_kind != PGAS_MAP_AFFINE && p->map_kind != PGAS_MAP_VEHICLE_SLIP) PGAS_FAIL(-2, "unknown map_kind %d", p->map_kind);
+
+    const int D = p->D, M = p->M;
+    DevModel dm;
+    memset(&dm, 0, sizeof(dm));
+    dm.n_x = p->n_x; dm.n_y = p->n_y; dm.n_u = p->n_u; dm.D = D; dm.M = M; dm.T = p->T;
+    dm.f_start = p->idx_start; dm.f_step = p->idx_step;
+    dm.map_kind = p->map_kind; dm.flags = p->flags;
+    dm.norm = 1.0;
+    for (int d = 0; d < D; ++d) {
+        if (!(p->half_width[d] > 0.0)) PGAS_FAIL(-2, "half_width[%d] must be positive", d);
+        dm.center[d] = p->center[d];
+        dm.L[d] = p->half_width[d];
+        dm.inv2L[d] = 1.0 / (2.0 * p->half_width[d]);
+        dm.norm *= sqrt(1.0 / p->half_width[d]);          // src/BasisFunctions.py:78-79
+        dm.bz[d] = p->bz[d];
+        for (int k = 0; k < PGAS_MAX_NX + PGAS_MAX_NU; ++k) dm.Az[d][k] = 0.0;
+        // Az is given over [state (n_x); input (n_u)]; the kernels index inputs at column n_x + k
+        for (int k = 0; k < p->n_x + p->n_u; ++k) dm.Az[d][k] = p->Az[d][k];
+    }
+    dm.slip_lf = p->slip_lf; dm.slip_lr = p->slip_lr;
+    for (int r = 0; r < p->n_y; ++r) {
+        dm.h0[r] = p->h0[r];
+        for (int k = 0; k < p->n_x; ++k) dm.H[r][k] = p->H[r][k];
+    }
+    {   // R = Lr Lr^T; Rw = Lr^-1; constant of the log-density
+        double Lr[PGAS_MAX_NY * PGAS_MAX_NY], Rm[PGAS_MAX_NY * PGAS_MAX_NY];
+        const int n = p->n_y;
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Rm[i * n + j] = p->R[i][j];
+        if (!small_chol(Rm, n, n, Lr)) PGAS_FAIL(-3, "observation covariance R is not positive definite");
+        double logdet = 0.0;
+        for (int j = 0; j < n; ++j) {
+            logdet += log(Lr[j * n + j]);
+            dm.Rw[j][j] = 1.0 / Lr[j * n + j];
+            for (int i = j + 1; i < n; ++i) {
+                double v = 0.0;
+                for (int k = j; k < i; ++k) v -= Lr[i * n + k] * dm.Rw[k][j];
+                dm.Rw[i][j] = v / Lr[i * n + i];
+            }
+        }
+        dm.R_logc = -0.5 * n * log(2.0 * M_PI) - logdet;
+    }
+    {
+        double Lp[PGAS_MAX_NX * PGAS_MAX_NX], Pm[PGAS_MAX_NX * PGAS_MAX_NX];
+        const int n = p->n_x;
+        for (int i = 0; i < n; ++i) { dm.m0[i] = p->m0[i]; for (int j = 0; j < n; ++j) Pm[i * n + j] = p->P0[i][j]; }
+        if (!small_chol(Pm, n, n, Lp)) PGAS_FAIL(-3, "initial covariance P0 is not positive definite");
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) dm.P0c[i][j] = Lp[i * n + j];
+    }
+
+    // ---- packed row layout --------------------------------------------------------------
+    // lattice positions pos = (freq - idx_start) / idx_step; leading dims 0..D-2, last dim D-1
+    std::vector<int> pos((size_t)M * D);
+    for (int mI = 0; mI < M; ++mI)
+        for (int d = 0; d < D; ++d) {
+            const int f = p->freq[(size_t)mI * D + d] - p->idx_start;
+            if (f < 0 || f % p->idx_step) PGAS_FAIL(-4, "frequency %d of basis %d is not on the lattice %d + k*%d",
+                                                    p->freq[(size_t)mI * D + d], mI, p->idx_start, p->idx_step);
+            pos[(size_t)mI * D + d] = f / p->idx_step;
+            dm.npos = std::max(dm.npos, f / p->idx_step + 1);
+        }
+    // key of a row = (slow position, fast position); D==1 -> (0,0), D==2 -> (0,p0), D==3 -> (p0,p1)
+    std::map<std::pair<int, int>, std::vector<std::pair<int, int>>> rows;   // -> list of (last pos, m)
+    int max_slow = 0;
+    for (int mI = 0; mI < M; ++mI) {
+        int slow = 0, fast = 0;
+        if (D == 2) fast = pos[(size_t)mI * D];
+        if (D == 3) { slow = pos[(size_t)mI * D]; fast = pos[(size_t)mI * D + 1]; }
+        rows[{slow, fast}].push_back({pos[(size_t)mI * D + D - 1], mI});
+        max_slow = std::max(max_slow, slow);
+    }
+    // enumerate rows in recurrence order; each row is followed by the advance code of the NEXT row
+    struct Row { int len; std::vector<std::pair<int, int>> items; };
+    std::vector<Row> row_list;
+    std::vector<int> row_adv;                 // how row i is reached from row i-1
+    for (int slow = 0; slow <= max_slow; ++slow) {
+        int max_fast = 0;
+        for (auto& kv : rows) if (kv.first.first == slow) max_fast = std::max(max_fast, kv.first.second);
+        for (int fast = 0; fast <= max_fast; ++fast) {
+            Row r; r.len = 0;
+            auto it = rows.find({slow, fast});
+            if (it != rows.end()) { r.items = it->second; for (auto& e : r.items) r.len = std::max(r.len, e.first + 1); }
+            row_list.push_back(r);
+            row_adv.push_back(fast == 0 ? (slow == 0 ? ROW_ADV_NONE : ROW_ADV_SLOW) : ROW_ADV_FAST);
+        }
+    }
+    std::vector<int> chunk_meta, perm;
+    dm.jmax = 0;
+    for (size_t ri = 0; ri < row_list.size(); ++ri) {
+        const Row& r = row_list[ri];
+        const int nch = std::max(1, (r.len + CHUNK - 1) / CHUNK);      // an empty row still carries its flags
+        dm.jmax = std::max(dm.jmax, nch * CHUNK);
+        const size_t o = perm.size();
+        perm.resize(o + (size_t)nch * CHUNK, -1);
+        for (auto& e : r.items) {
+            if (perm[o + e.first] != -1) PGAS_FAIL(-4, "duplicate basis function index tuple (basis %d)", e.second);
+            perm[o + e.first] = e.second;
+        }
+        for (int c = 0; c < nch; ++c) {
+            int meta = c;
+            if (c == nch - 1) {
+                meta |= META_ROW_END;
+                const int next_adv = (ri + 1 < row_list.size()) ? row_adv[ri + 1] : ROW_ADV_NONE;
+                meta |= next_adv << META_ADV_SHIFT;
+            }
+            chunk_meta.push_back(meta);
+        }
+    }
+    dm.n_chunks = (int)chunk_meta.size();
+    dm.n_packed = (int)perm.size();
+
+    // ---- one device arena ---------------------------------------------------------------
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_rows = al(sizeof(int) * dm.n_chunks), b_perm = al(sizeof(int) * dm.n_packed), b_freq = al(sizeof(int) * M * D);
+    const size_t b_obs = al(sizeof(double) * (size_t)p->T * p->n_y), b_in = al(sizeof(double) * (size_t)p->T * std::max(p->n_u, 1));
+    const size_t total = b_rows + b_perm + b_freq + b_obs + b_in;
+    char* arena = nullptr;
+    PGAS_CUDA(cudaMalloc((void**)&arena, total));
+    size_t o = 0;
+    auto up = [&](const void* src, size_t bytes, size_t slot) -> const void* {
+        const void* d = arena + o;
+        if (bytes) cudaMemcpy(arena + o, src, bytes, cudaMemcpyHostToDevice);
+        o += slot;
+        return d;
+    };
+    dm.chunk_meta = (const int*)up(chunk_meta.data(), sizeof(int) * dm.n_chunks, b_rows);
+    dm.perm = (const int*)up(perm.data(), sizeof(int) * dm.n_packed, b_perm);
+    dm.freq = (const int*)up(p->freq, sizeof(int) * M * D, b_freq);
+    dm.obs = (const double*)up(p->observations, sizeof(double) * (size_t)p->T * p->n_y, b_obs);
+    dm.inputs = (const double*)up(p->inputs, p->n_u ? sizeof(double) * (size_t)p->T * p->n_u : 0, b_in);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(arena); PGAS_FAIL((int)e, "model upload failed: %s", cudaGetErrorString(e)); }
+
+    pgas_model* mdl = new pgas_model;
+    mdl->dev = dm;
+    mdl->arena = arena;
+    mdl->arena_bytes = total;
+    *out = mdl;
+    return 0;
+}
+
+extern "C" int pgas_model_destroy(pgas_model* model) {
+    if (!model) return 0;
+    cudaFree(model->arena);
+    delete model;
+    return 0;
+}
+
+extern "C" int pgas_model_jmax(const pgas_model* model) { return model ? model->dev.jmax : -1; }
+int pgas_model_npos(const pgas_model* model) { return model->dev.npos; }

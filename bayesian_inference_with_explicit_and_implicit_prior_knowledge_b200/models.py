@@ -1,0 +1,285 @@
+"""Model descriptors: how the reference's user callables reach the CUDA kernels.
+
+The reference passes arbitrary Python callables `basis_fcn(state, input)` and
+`likelihood_fcn(obs, state, input)` (src/PGAS.py:24-43) and lets JAX trace them.  A persistent
+CUDA kernel cannot call Python, so the callables are TRACED ONCE on the host with symbolic
+affine values and reduced to a parameter block of a compiled-in family:
+
+  basis_fcn      -> Hilbert-space GP basis of an affine map of (state, input)
+                    (every shipped Theta-conditioned model: src/EMPS.py:110-113,
+                    src/Toy_Example.py:146) or of the vehicle slip angles (src/Vehicle.py:50-57);
+  likelihood_fcn -> Gaussian log-density of obs around an affine map of the state
+                    (src/EMPS.py:250-252, src/Toy_Example.py:142-144).
+
+A callable outside these families raises at construction time; nothing falls back to the host.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+# ----------------------------------------------------------------------------- affine tracer
+class Affine:
+    """Symbolic vector  A @ v + b  over the variables v = [state; input]."""
+    __array_priority__ = 1000
+
+    def __init__(self, A, b, scalar=False):
+        self.A = np.atleast_2d(np.asarray(A, dtype=np.float64))
+        self.b = np.atleast_1d(np.asarray(b, dtype=np.float64))
+        self.scalar = scalar
+
+    @property
+    def shape(self):
+        return () if self.scalar else (self.A.shape[0],)
+
+    def __len__(self):
+        return self.A.shape[0]
+
+    def __getitem__(self, idx):
+        if isinstance(idx, (int, np.integer)):
+            return Affine(self.A[idx:idx + 1] if idx != -1 else self.A[-1:], self.b[[idx]], scalar=True)
+        return Affine(self.A[idx], self.b[idx])
+
+    @staticmethod
+    def _const(x, n):
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 0:
+            return np.full(n, float(x))
+        return x.ravel()
+
+    def __add__(self, o):
+        if isinstance(o, Affine):
+            return Affine(self.A + o.A, self.b + o.b, self.scalar and o.scalar)
+        return Affine(self.A, self.b + self._const(o, len(self)), self.scalar and np.ndim(o) == 0)
+
+    __radd__ = __add__
+
+    def __neg__(self):
+        return Affine(-self.A, -self.b, self.scalar)
+
+    def __sub__(self, o):
+        return self + (-o if isinstance(o, Affine) else -np.asarray(o, dtype=np.float64))
+
+    def __rsub__(self, o):
+        return (-self) + o
+
+    def __mul__(self, o):
+        if isinstance(o, Affine):
+            raise TypeError("product of two state-dependent values is not affine")
+        c = self._const(o, len(self))
+        return Affine(self.A * c[:, None], self.b * c, self.scalar and np.ndim(o) == 0)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        if isinstance(o, Affine):
+            raise TypeError("division by a state-dependent value is not affine")
+        c = self._const(o, len(self))
+        return Affine(self.A / c[:, None], self.b / c, self.scalar and np.ndim(o) == 0)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kw):
+        if method != "__call__":
+            return NotImplemented
+        a, b = (inputs + (None,))[:2]
+        if ufunc is np.add:
+            return a + b if isinstance(a, Affine) else b + a
+        if ufunc is np.subtract:
+            return a - b if isinstance(a, Affine) else (-b) + a
+        if ufunc is np.multiply:
+            return a * b if isinstance(a, Affine) else b * a
+        if ufunc in (np.divide, np.true_divide) and isinstance(a, Affine):
+            return a / b
+        if ufunc is np.negative:
+            return -a
+        raise TypeError(f"{ufunc.__name__} of a state-dependent value is outside the compiled-in (affine) model families")
+
+    def __array_function__(self, func, types, args, kwargs):
+        if func in (np.hstack, np.concatenate):
+            parts = [p if isinstance(p, Affine) else Affine(np.zeros((np.size(p), self.A.shape[1])), np.ravel(p))
+                     for p in args[0]]
+            return Affine(np.vstack([p.A for p in parts]), np.concatenate([p.b for p in parts]))
+        if func in (np.atleast_1d, np.ravel, np.asarray, np.squeeze):
+            return Affine(self.A, self.b, scalar=(func is np.squeeze and len(self) == 1))
+        raise TypeError(f"numpy.{func.__name__} of a state-dependent value is not supported by the model tracer")
+
+
+def hstack(parts):
+    """stand-in for jnp.hstack usable on traced values"""
+    if any(isinstance(p, Affine) for p in parts):
+        ref = next(p for p in parts if isinstance(p, Affine))
+        return ref.__array_function__(np.hstack, (), (parts,), {})
+    return np.hstack(parts)
+
+
+def _tracers(n_x, n_u):
+    eye = np.eye(n_x + n_u)
+    return Affine(eye[:n_x], np.zeros(n_x)), Affine(eye[n_x:], np.zeros(n_u))
+
+
+# ----------------------------------------------------------------------------- basis
+class BasisExpr:
+    """Result of applying a HilbertBasis to a traced value: hgp(Az v + bz)."""
+
+    def __init__(self, hgp, Az, bz):
+        self.hgp, self.Az, self.bz = hgp, np.atleast_2d(Az), np.atleast_1d(bz)
+        self.map_kind = _lib.MAP_AFFINE
+        self.slip = (0.0, 0.0)
+
+    def __len__(self):
+        return self.hgp.M
+
+
+class VehicleSlipBasis:
+    """basis over the slip angles (alpha_f, alpha_r) of src/Vehicle.py:50-57 (D = 2)."""
+
+    def __init__(self, hgp, l_f, l_r):
+        assert hgp.D == 2, "slip-angle basis is two-dimensional (front, rear)"
+        self.hgp, self.slip = hgp, (float(l_f), float(l_r))
+        self.map_kind = _lib.MAP_VEHICLE_SLIP
+        self.Az, self.bz = np.zeros((2, 4)), np.zeros(2)
+
+    def __len__(self):
+        return self.hgp.M
+
+
+def trace_basis(basis_fcn, n_x, n_u):
+    """Reduce `basis_fcn(state, input)` to a descriptor (BasisExpr / VehicleSlipBasis)."""
+    if isinstance(basis_fcn, (BasisExpr, VehicleSlipBasis)):
+        return basis_fcn
+    from .BasisFunctions import HilbertBasis
+    if isinstance(basis_fcn, HilbertBasis):
+        if basis_fcn.D != n_x:
+            raise ValueError("a bare HilbertBasis as basis_fcn must have D == n_x")
+        return BasisExpr(basis_fcn, np.hstack([np.eye(n_x), np.zeros((n_x, n_u))]), np.zeros(n_x))
+    s, u = _tracers(n_x, n_u)
+    try:
+        out = basis_fcn(s, u if n_u > 0 else np.zeros(0))
+    except TypeError as e:
+        raise TypeError("basis_fcn is outside the compiled-in model families (Hilbert-space GP basis of an "
+                        f"affine map of state/input, or models.VehicleSlipBasis): {e}") from e
+    if not isinstance(out, (BasisExpr, VehicleSlipBasis)):
+        raise TypeError("basis_fcn must return the value of a generate_Hilbert_BasisFunction basis")
+    return out
+
+
+# ----------------------------------------------------------------------------- likelihood
+class GaussianLikelihood:
+    """likelihood_fcn(obs, state, input) = log N(obs; H state + h0, R)."""
+
+    def __init__(self, H, h0, R):
+        self.H = np.atleast_2d(np.asarray(H, dtype=np.float64))
+        self.h0 = np.atleast_1d(np.asarray(h0, dtype=np.float64))
+        self.R = np.atleast_2d(np.asarray(R, dtype=np.float64))
+        assert self.R.shape == (self.H.shape[0],) * 2
+
+    def logpdf_torch(self, obs, states):
+        """obs (..., n_y), states (..., n_x) CUDA tensors -> log-density (...); library ops, used only for
+        the final log-likelihood table of PGAS.__call__ (src/PGAS.py:383-392), not in the sweep."""
+        import torch
+        H = torch.as_tensor(self.H, device=states.device)
+        h0 = torch.as_tensor(self.h0, device=states.device)
+        Lr = torch.linalg.cholesky(torch.as_tensor(self.R, device=states.device))
+        d = obs - (states @ H.T + h0)
+        e = torch.linalg.solve_triangular(Lr, d.unsqueeze(-1), upper=False).squeeze(-1)
+        n = self.R.shape[0]
+        return -0.5 * (e * e).sum(-1) - 0.5 * n * np.log(2 * np.pi) - torch.log(torch.diagonal(Lr)).sum()
+
+
+def gaussian_likelihood(f_y, R, n_x=None):
+    """Build the likelihood descriptor from an (affine) output map f_y(state) and covariance R —
+    the shape every shipped `likelihood_fcn` lambda has (src/EMPS.py:250-252)."""
+    R = np.atleast_2d(np.asarray(R, dtype=np.float64))
+
+    def build(nx):
+        s, _ = _tracers(nx, 0)
+        out = f_y(s)
+        if not isinstance(out, Affine):
+            raise TypeError("output map must be affine in the state")
+        return GaussianLikelihood(out.A[:, :nx], out.b, R)
+    if n_x is not None:
+        return build(n_x)
+    lazy = _LazyLikelihood(build)
+    return lazy
+
+
+class _LazyLikelihood:
+    def __init__(self, build):
+        self._build = build
+
+    def resolve(self, n_x):
+        return self._build(n_x)
+
+
+def resolve_likelihood(lik, n_x):
+    if isinstance(lik, GaussianLikelihood):
+        return lik
+    if isinstance(lik, _LazyLikelihood):
+        return lik.resolve(n_x)
+    raise TypeError("likelihood_fcn must be built with models.gaussian_likelihood(f_y, R) "
+                    "(Gaussian observation of an affine output map); arbitrary Python callables "
+                    "cannot run inside the persistent CUDA sweep")
+
+
+# ----------------------------------------------------------------------------- device model
+class DeviceModel:
+    """Owns a pgas_model handle (include/pgas_b200.h: pgas_model_create)."""
+
+    def __init__(self, observations, inputs, m0, P0, likelihood, basis, flags=0):
+        _lib.require_cuda()
+        obs = np.ascontiguousarray(np.asarray(observations, dtype=np.float64))
+        self.T = obs.shape[0]
+        obs = obs.reshape(self.T, -1)
+        inp = np.asarray(inputs, dtype=np.float64)
+        inp = inp.reshape(self.T, -1) if inp.size else np.zeros((self.T, 0))
+        inp = np.ascontiguousarray(inp)
+        m0 = np.atleast_1d(np.asarray(m0, dtype=np.float64))
+        P0 = np.atleast_2d(np.asarray(P0, dtype=np.float64))
+        self.n_x, self.n_y, self.n_u = m0.shape[0], obs.shape[1], inp.shape[1]
+        self.basis = trace_basis(basis, self.n_x, self.n_u)
+        self.likelihood = resolve_likelihood(likelihood, self.n_x)
+        hgp = self.basis.hgp
+        self.M, self.D = hgp.M, hgp.D
+        self.flags = int(flags)
+        if self.likelihood.H.shape != (self.n_y, self.n_x):
+            raise ValueError(f"likelihood maps to {self.likelihood.H.shape[0]} outputs, observations have {self.n_y}")
+        p = _lib.ModelParams()
+        p.n_x, p.n_y, p.n_u, p.D, p.M, p.T = self.n_x, self.n_y, self.n_u, self.D, self.M, self.T
+        self._freq = np.ascontiguousarray(hgp.freq, dtype=np.int32)
+        p.freq = self._freq.ctypes.data_as(C.POINTER(C.c_int32))
+        p.idx_start, p.idx_step = hgp.idx_start, hgp.idx_step
+        for d in range(self.D):
+            p.center[d] = hgp.center[d]
+            p.half_width[d] = hgp.half_width[d]
+            p.bz[d] = self.basis.bz[d]
+            for k in range(self.n_x + self.n_u):
+                p.Az[d][k] = self.basis.Az[d, k] if k < self.basis.Az.shape[1] else 0.0
+        p.map_kind = self.basis.map_kind
+        p.slip_lf, p.slip_lr = self.basis.slip
+        for r in range(self.n_y):
+            p.h0[r] = self.likelihood.h0[r]
+            for k in range(self.n_x):
+                p.H[r][k] = self.likelihood.H[r, k]
+            for c in range(self.n_y):
+                p.R[r][c] = self.likelihood.R[r, c]
+        self._obs, self._inp = obs, inp
+        p.observations = obs.ctypes.data_as(C.POINTER(C.c_double))
+        p.inputs = inp.ctypes.data_as(C.POINTER(C.c_double)) if self.n_u else None
+        for i in range(self.n_x):
+            p.m0[i] = m0[i]
+            for j in range(self.n_x):
+                p.P0[i][j] = P0[i, j]
+        p.flags = self.flags
+        h = C.c_void_p()
+        _lib.check(_lib.lib().pgas_model_create(C.byref(p), C.byref(h)))
+        self.handle = h
+        self.jmax = _lib.lib().pgas_model_jmax(h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().pgas_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

@@ -1,0 +1,193 @@
+/*
+ * pgas_b200.h — C ABI of libpgas_b200.so: the B200-native (sm_100a) implementation of the
+ * particle-Gibbs-with-ancestor-sampling hot path of
+ * VolkmannB/bayesian-inference-with-explicit-and-implicit-prior-knowledge.
+ *
+ * The reference has no FFI: its seam is the Python API of src/*.py.  Each entry point below
+ * names the reference function (file:line) it replaces; INTEGRATION.md shows the ctypes stub a
+ * maintainer would put behind that function.  Conventions:
+ *   - plain pointers and sizes only; every array pointer is a DEVICE pointer to float64 /
+ *     int32 data in C (row-major) order unless the comment says "host";
+ *   - the library never allocates result memory and never frees caller memory; scratch comes
+ *     from a caller workspace sized by the matching *_workspace_bytes query;
+ *   - all work is enqueued on the cudaStream_t passed as `void* stream` (0 = legacy default);
+ *   - every function returns 0 on success, <0 for an argument/shape error, >0 for a CUDA error
+ *     code; pgas_last_error() returns a thread-local message.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef PGAS_B200_H
+#define PGAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGAS_MAX_NX 4      /* state dimension n_x                      */
+#define PGAS_MAX_NY 2      /* observation dimension n_y                */
+#define PGAS_MAX_NU 4      /* input dimension n_u                      */
+#define PGAS_MAX_D 3       /* GP input dimension D                     */
+#define PGAS_MAX_GP 2      /* GPs of the marginalised path (group B)   */
+
+/* GP-input map g: (state, input) -> z in R^D fed to the Hilbert basis. */
+enum { PGAS_MAP_AFFINE = 0,      /* z = Az [state; input] + bz  (src/EMPS.py:110-113, src/Toy_Example.py:146) */
+       PGAS_MAP_VEHICLE_SLIP = 1 /* z = (alpha_f, alpha_r) of src/Vehicle.py:50-57, input = [delta, v_x]     */ };
+
+/* reference quirks; the default 0 reproduces the reference bit for bit */
+enum { PGAS_FLAG_ANCESTOR_GATHER = 1, /* propagate x_t^i from x_{t-1}^{a_i} instead of x_{t-1}^i (src/PGAS.py:131-133) */
+       PGAS_FLAG_INPUT_PREV      = 2, /* sweep pairs x_{t-1} with inputs[t-1] instead of inputs[t] (src/PGAS.py:52-54)  */
+       PGAS_FLAG_VCHOL_TRANSPOSE = 4  /* A = mean + S_chol Nrm V_chol^T instead of V_chol (src/PGAS.py:341)             */ };
+
+/* Host-side description of one Theta-conditioned model: the data and the two user callables of
+ * condSequentialMonteCarlo.__init__ (src/PGAS.py:24-43) restricted to the shipped families:
+ * basis_fcn = Hilbert-space GP basis of a map of (state,input); likelihood_fcn = Gaussian
+ * log-density of the observation around H state + h0.  All pointers are HOST pointers, copied. */
+typedef struct pgas_model_params {
+    int32_t n_x, n_y, n_u, D, M, T;
+    /* Hilbert basis (src/BasisFunctions.py:8-80): integer frequencies S (M x D), phi_m(z) =
+     * prod_d L_d^-1/2 sin(pi S[m,d] (z_d - center_d + L_d) / (2 L_d)); frequencies lie on the
+     * lattice idx_start + k*idx_step (src/BasisFunctions.py:24-25). */
+    const int32_t* freq;          /* (M, D) host */
+    int32_t idx_start, idx_step;
+    double center[PGAS_MAX_D];
+    double half_width[PGAS_MAX_D]; /* L_d = domain_size_d / 2 */
+    /* GP-input map */
+    int32_t map_kind;
+    double Az[PGAS_MAX_D][PGAS_MAX_NX + PGAS_MAX_NU];
+    double bz[PGAS_MAX_D];
+    double slip_lf, slip_lr;
+    /* Gaussian likelihood N(y; H x + h0, R) */
+    double H[PGAS_MAX_NY][PGAS_MAX_NX];
+    double h0[PGAS_MAX_NY];
+    double R[PGAS_MAX_NY][PGAS_MAX_NY];
+    /* data and initial distribution */
+    const double* observations;   /* (T, n_y) host */
+    const double* inputs;         /* (T, n_u) host; may be NULL when n_u == 0 */
+    double m0[PGAS_MAX_NX];
+    double P0[PGAS_MAX_NX][PGAS_MAX_NX];
+    int32_t flags;                /* PGAS_FLAG_* */
+} pgas_model_params;
+
+typedef struct pgas_model pgas_model;   /* opaque; owns device copies of the tables/data */
+
+/* Random-number source of a sweep / draw.  Injected mode (testing): device
+ * arrays of variates.  Philox mode (production): Philox-4x32-10, key = seed, counter =
+ * (particle, time, iteration, purpose<<24 | chain). */
+typedef struct pgas_rng {
+    int32_t mode;                 /* 0 = Philox, 1 = injected */
+    uint64_t seed;
+    uint32_t chain_base;          /* chain c of this call uses chain id chain_base + c */
+    uint32_t iteration;
+    /* injected sweep variates (device): Z (n_chains,T,N,n_x) normals, U (n_chains,T,2) uniforms:
+     * U[t,0]=u_res(t), U[t,1]=u_anc(t) for t>=1; U[0,0]=u_idx */
+    const double* Z;
+    const double* U;
+    /* injected draw variates (device): chi2 (n_chains,n_x), G (n_chains,n_x,n_x), Nrm (n_chains,n_x,M) */
+    const double* chi2;
+    const double* G;
+    const double* Nrm;
+} pgas_rng;
+
+const char* pgas_last_error(void);
+int pgas_version(void);
+int pgas_device_count(void);
+
+/* condSequentialMonteCarlo.__init__ (src/PGAS.py:24-43) + generate_Hilbert_BasisFunction's closure
+ * (src/BasisFunctions.py:63-66): uploads tables/data, builds the packed tensor-product row layout. */
+int pgas_model_create(const pgas_model_params* params, pgas_model** out);
+int pgas_model_destroy(pgas_model* model);
+/* largest last-dimension lattice position + 1 (register-table length the sweep needs) */
+int pgas_model_jmax(const pgas_model* model);
+
+/* systematic_SISR (src/Filtering.py:6-37).  w (n_sets,N) unnormalised weights, u (n_sets) uniforms
+ * -> idx_out (n_sets,N) int32.  One CTA per set. */
+int pgas_resample_f64(const double* w, int32_t N, int32_t n_sets, const double* u,
+                      int32_t* idx_out, void* stream);
+
+/* vmap(basis_fcn) (src/BasisFunctions.py:77-80 via src/PGAS.py:52,67,294): states (n,n_x), inputs
+ * (n,n_u) [input_stride 0 = one shared input row] -> phi_out (n,M) in the reference's basis order. */
+int pgas_hgp_eval_f64(const pgas_model* model, const double* states, const double* inputs,
+                      int32_t input_stride, int32_t n, double* phi_out, void* stream);
+
+/* condSequentialMonteCarlo.step (src/PGAS.py:79-153), one step for testing/teacher forcing:
+ * logw (N), state (N,n_x), Theta (n_x,M), Sigma (n_x,n_x), ref_t (n_x), u2 = {u_res,u_anc} (2),
+ * z (N,n_x) -> logw_out (N), state_out (N,n_x), anc_out (N) int32.  Runs the sweep kernel for a
+ * single time step `t` (same code path as pgas_csmc_sweep_f64). */
+int pgas_csmc_step_f64(const pgas_model* model, int32_t N, int32_t t, const double* logw,
+                       const double* state, const double* Theta, const double* Sigma,
+                       const double* ref_t, const double* u2, const double* z,
+                       double* logw_out, double* state_out, int32_t* anc_out,
+                       int32_t cluster_size, void* stream);
+
+/* condSequentialMonteCarlo.__call__ (src/PGAS.py:176-228) for n_chains independent chains: the
+ * persistent sweep kernel (one CTA or one thread-block cluster per chain, particles resident in
+ * shared memory for all T steps), the final categorical pick (:224-225) and
+ * reconstruct_trajectory (src/Filtering.py:40-55).
+ *   ref_traj (n_chains,T,n_x), Theta (n_chains,n_x,M), Sigma (n_chains,n_x,n_x)
+ *   -> traj_out (n_chains,T,n_x); optional (may be NULL... see below) traces:
+ *      state_trace (n_chains,T,N,n_x), anc_trace (n_chains,T-1,N) int32, logw_last (n_chains,N),
+ *      final_idx (n_chains) int32.
+ * state_trace and anc_trace are required (the backward pass reads them); logw_last/final_idx may
+ * be NULL.  cluster_size: 0 = choose automatically, else 1,2,4,8,16. */
+size_t pgas_csmc_sweep_workspace_bytes(const pgas_model* model, int32_t N, int32_t n_chains);
+int pgas_csmc_sweep_f64(const pgas_model* model, int32_t N, int32_t n_chains,
+                        const double* ref_traj, const double* Theta, const double* Sigma,
+                        const pgas_rng* rng, double* state_trace, int32_t* anc_trace,
+                        double* logw_last, int32_t* final_idx, double* traj_out,
+                        int32_t cluster_size, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* reconstruct_trajectory (src/Filtering.py:40-55): particles (n_sets,T,N,n), ancestry
+ * (n_sets,T-1,N) int32, idx (n_sets) int32 -> traj (n_sets,T,n). */
+int pgas_reconstruct_trajectory_f64(const double* particles, const int32_t* ancestry,
+                                    const int32_t* idx, int32_t n_sets, int32_t T, int32_t N,
+                                    int32_t n, double* traj_out, void* stream);
+
+/* First half of PGAS.sample_params (src/PGAS.py:294-303; prior_mniw_calcStatistics,
+ * src/BayesianInferrence.py:53-61): traj (n_chains,T,n_x) -> T0 (n_chains,M,n_x) = Phi^T Y,
+ * T1 (n_chains,M,M) = Phi^T Phi, T2 (n_chains,n_x,n_x) = Y^T Y; T3 = T-1 is implicit.
+ * Phi is recomputed on the fly from the trajectory and never stored. */
+int pgas_suffstats_f64(const pgas_model* model, const double* traj, int32_t n_chains,
+                       double* T0_out, double* T1_out, double* T2_out, void* stream);
+
+/* Second half of PGAS.sample_params (src/PGAS.py:306-343; prior_mniw_2naturalPara_inv,
+ * src/BayesianInferrence.py:35-45): eta0 (n_chains,M,n_x), eta1 (n_chains,M,M), eta2
+ * (n_chains,n_x,n_x), eta3 (scalar, host) -> A_out (n_chains,n_x,M), S_out (n_chains,n_x,n_x).
+ * eta1 is not modified.  status_out (n_chains) int32 device: 0 ok, k>0 = eta1 lost positive
+ * definiteness at pivot k (the reference would return NaN). */
+size_t pgas_mniw_draw_workspace_bytes(int32_t M, int32_t n_x, int32_t n_chains);
+int pgas_mniw_draw_f64(const double* eta0, const double* eta1, const double* eta2, double eta3,
+                       int32_t M, int32_t n_x, int32_t n_chains, const pgas_rng* rng,
+                       int32_t flags, double* A_out, double* S_out, int32_t* status_out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* PGAS.__call__ (src/PGAS.py:345-397) for n_chains independent chains, entirely on the device:
+ * K iterations of (sweep -> pick -> backward trace -> sufficient statistics -> MNIW draw).
+ *   prior eta0 (M,n_x), eta1 (M,M), eta2 (n_x,n_x) device, eta3 host scalar (shared by chains);
+ *   init_ref (n_chains,T,n_x)
+ *   -> state_trace_out (n_chains,K,T,n_x)  [row k = trajectory of iteration k; row 0 = init_ref],
+ *      optional A_trace_out (n_chains,K,n_x,M), S_trace_out (n_chains,K,n_x,n_x) (may be NULL).
+ * In injected mode rng->Z/U hold (K,n_chains,...) blocks (block k used by sweep k; block 0 unused)
+ * and rng->chi2/G/Nrm hold (K,n_chains,...) blocks (block k = draw after trajectory k). */
+size_t pgas_run_chains_workspace_bytes(const pgas_model* model, int32_t N, int32_t n_chains);
+int pgas_run_chains_f64(const pgas_model* model, int32_t N, int32_t K, int32_t n_chains,
+                        const double* eta0, const double* eta1, const double* eta2, double eta3,
+                        const double* init_ref, const pgas_rng* rng, double* state_trace_out,
+                        double* A_trace_out, double* S_trace_out, int32_t cluster_size,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* The variates the Philox mode would use, written out so a CPU checker can be fed the same
+ * numbers: Z (n_chains,T,N,n_x), U (n_chains,T,2) for sweep `rng->iteration`. */
+int pgas_philox_sweep_variates_f64(const pgas_rng* rng, int32_t n_chains, int32_t T, int32_t N,
+                                   int32_t n_x, double* Z_out, double* U_out, void* stream);
+
+/* Machine denominators for the FP64 rooflines: a register-resident DFMA loop and
+ * a register-resident DMMA (mma.sync m8n8k4 f64) loop on all SMs.  Results in TFLOP/s (host). */
+int pgas_measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGAS_B200_H */

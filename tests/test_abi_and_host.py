@@ -1,0 +1,121 @@
+"""CPU tests: the C-ABI library builds for sm_100a, loads and exports every symbol the header
+declares (no compute calls without a GPU); host-side logic (lattice search, model tracer, keys)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "pgas_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(pgas_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 18
+    L = helpers.pkg("_lib")
+    for n in sorted(names):
+        assert hasattr(built_lib, n), f"{n} declared in include/pgas_b200.h but not exported"
+        assert n in L.EXPORTS, f"{n} has no ctypes prototype in _lib.EXPORTS"
+    assert built_lib.pgas_version() >= 100
+
+
+def test_struct_layout_matches_header():
+    import ctypes as C
+    L = helpers.pkg("_lib")
+    # pgas_model_params: 6 int32, ptr, 2 int32, doubles..., checked through field offsets that the C compiler would produce
+    assert L.ModelParams.freq.offset == 24
+    assert L.ModelParams.center.offset == 40
+    assert C.sizeof(L.Rng) == 64
+
+
+def test_no_cpu_fallback_without_device(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    F = helpers.pkg("Filtering")
+    with pytest.raises(helpers.pkg("_lib").PgasError):
+        F.systematic_SISR(0.5, np.ones(4))
+    p = helpers.make_problem("smo", T=5, N=8)
+    cs = helpers.product_csmc(p)
+    with pytest.raises(helpers.pkg("_lib").PgasError):
+        cs(helpers.pkg("random").key(1), p["ref"], p["Theta"], p["Sigma"])
+
+
+def test_product_does_not_import_the_oracle():
+    pkg_dir = os.path.join(ROOT, helpers.PKG)
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+    for f in os.listdir(os.path.join(ROOT, "src")):
+        if f.endswith(".py"):
+            assert "oracle" not in open(os.path.join(ROOT, "src", f)).read(), f
+
+
+@pytest.mark.parametrize("kind", ["smo", "emps", "toy", "vehicle"])
+def test_lattice_search_matches_oracle(kind):
+    p = helpers.make_problem(kind)
+    hgp, sd = helpers.pkg("BasisFunctions").generate_Hilbert_BasisFunction(*p["hgp_args"])
+    assert np.array_equal(hgp.freq, p["ohgp"].indices)
+    assert np.allclose(sd, p["sd"], rtol=1e-14, atol=0)
+    assert np.allclose(hgp.eigen_val, p["ohgp"].eig_val, rtol=1e-15)
+
+
+def test_model_tracer_affine_families():
+    MD, BF = helpers.pkg("models"), helpers.pkg("BasisFunctions")
+    hgp3, _ = BF.generate_Hilbert_BasisFunction(27, np.array([[-1.0, 1.0]] * 3), 0.1, 20)
+    e = MD.trace_basis(lambda s, u: hgp3(np.hstack([s, u]) / np.array([0.4, 0.4, 160.0])), 2, 1)   # src/EMPS.py:110-113
+    assert np.allclose(e.Az, np.diag([2.5, 2.5, 1 / 160.0])) and np.allclose(e.bz, 0)
+    hgp1, _ = BF.generate_Hilbert_BasisFunction(9, np.array([-0.2, 0.2]), 0.4 / 9, 20)
+    e = MD.trace_basis(lambda s, u: hgp1(s[1]), 2, 1)                                               # src/EMPS.py:90-91
+    assert np.allclose(e.Az, [[0, 1, 0]])
+    e = MD.trace_basis(lambda s, u: hgp1(2.0 * s[0] - 0.5 + u[0] * 0.1), 2, 1)
+    assert np.allclose(e.Az, [[2, 0, 0.1]]) and np.allclose(e.bz, [-0.5])
+    with pytest.raises(TypeError):
+        MD.trace_basis(lambda s, u: hgp1(np.sin(s[0])), 2, 1)
+    with pytest.raises(TypeError):
+        MD.trace_basis(lambda s, u: s[0], 2, 1)
+    lik = MD.resolve_likelihood(MD.gaussian_likelihood(lambda x: x[0], np.eye(1) * 1e-4), 2)       # src/EMPS.py:250-252
+    assert np.allclose(lik.H, [[1, 0]]) and np.allclose(lik.h0, 0) and np.allclose(lik.R, 1e-4)
+    with pytest.raises(TypeError):
+        MD.resolve_likelihood(lambda o, s, i: 0.0, 2)
+
+
+def test_keys_split_and_uniform():
+    R = helpers.pkg("random")
+    k = R.key(12345678)
+    a, b = R.split(k)
+    assert a.seed != b.seed and a.seed != k.seed
+    assert [x.seed for x in R.split(k)] == [a.seed, b.seed]          # deterministic
+    assert len({x.seed for x in R.split(k, 50)}) == 50
+    u = R.uniform(a)
+    assert 0.0 <= u < 1.0 and R.uniform(a) == u
+    us = R.uniform(b, (1000,))
+    assert abs(us.mean() - 0.5) < 0.05
+    from oracle import philox as OPH
+    assert [int(v) for v in R.philox4x32(0, 0, 0, 0, 0, 0)] == [int(v) for v in OPH.philox(0, 0, 0, 0, 0)]
+
+
+def test_natural_parameter_host_conversions_match_oracle():
+    from oracle import mniw as OM
+    BI = helpers.pkg("BayesianInferrence")
+    rng = np.random.default_rng(0)
+    M, n = 9, 2
+    mean = rng.normal(size=(n, M)); B = rng.normal(size=(M, M)); V = B @ B.T + M * np.eye(M)
+    Psi = np.array([[2.0, 0.1], [0.1, 1.0]])
+    for a, b in zip(BI.prior_mniw_2naturalPara(mean, V, Psi, 5), OM.prior_mniw_2naturalPara(mean, V, Psi, 5)):
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-13)
+    eta = OM.prior_mniw_2naturalPara(mean, V, Psi, 5)
+    for a, b in zip(BI.prior_mniw_2naturalPara_inv(*eta), OM.prior_mniw_2naturalPara_inv(*eta)):
+        assert np.allclose(a, b, rtol=1e-11, atol=1e-12)
+    assert np.allclose(BI.prior_mniw_mean(eta[0], eta[1]), OM.prior_mniw_mean(eta[0], eta[1]), rtol=1e-11)
+    phi = rng.normal(size=M)
+    for a, b in zip(BI.prior_mniw_Predictive(mean, V, Psi, 5, phi), OM.prior_mniw_Predictive(mean, V, Psi, 5, phi)):
+        assert np.allclose(a, b, rtol=1e-12)
+    T = (eta[0], eta[1], eta[2] + np.eye(n), 7.0)
+    assert abs(BI.prior_mniw_log_base_measure(*T) - OM.prior_mniw_log_base_measure(*T)) < 1e-9
