@@ -4,14 +4,13 @@
 // (src/BasisFunctions.py:77-80, src/PGAS.py:52-55 and :67-70) WITHOUT forming phi:
 //   phi_m(z) = norm * prod_d sin(pi f_{m,d} t_d),  t_d = (z_d - c_d + L_d) / (2 L_d)
 // and the frequencies f sit on a lattice f_start + p*f_step, so
-//   mu_k = norm * sum_rows lead(row) * sum_{p < len(row)} Theta'[row,p,k] * s_last[p]
-// with s_last[p] = sin(pi (f_start + p f_step) t_last) kept in REGISTERS (statically indexed,
-// built by the 3-term recurrence s[p+1] = 2cos(pi f_step t) s[p] - s[p-1]) and the leading
-// dimensions' sines carried as running recurrences across rows (common.cuh).  Rows are walked
-// as a flat list of 4-position chunks whose Theta' values are prefetched one chunk ahead, so
-// the shared-memory latency is off the DFMA dependency chain.
-// Cost per particle: n_packed*NX DFMA + JMAX + ~6 per row, versus M*(D + 2 NX) flops for the
-// phi-then-einsum formulation and M*D libm sines in the reference.
+//   mu_k(p) = sum_rows lead[p,row] * sum_j Theta'[row,j,k] * s_last[p,j]
+// i.e. a dense (particles x positions) x (positions x rows*n_x) product followed by a row
+// scaling — run on the FP64 tensor pipe (DMMA m8n8k4) with the sines built by the 3-term
+// recurrence s[j+1] = 2cos(pi f_step t) s[j] - s[j-1] (one sincospi per dimension per particle
+// instead of the reference's M*D libm sines).  An earlier sparse DFMA walk over the selected
+// lattice points executed ~40 % fewer flops but spent 80 % of its issue slots on control flow
+// (profiles/r01_sweep_dfma_walk.md); the dense tile form is branch-free.
 #pragma once
 #include "common.cuh"
 
@@ -19,134 +18,147 @@
 // twoc = 2 cos(pi f_step t)
 __device__ __forceinline__ void sine_seed(double t, int f_start, int f_step, double& cur, double& prev, double& twoc) {
     double ss, cs;
-    sincospi((double)f_step * t, &ss, &cs);
+    sincospi_bf((double)f_step * t, ss, cs);
     twoc = 2.0 * cs;
     if (f_start == f_step) {
         cur = ss;
         prev = 0.0;
     } else {
         double sa, ca;
-        sincospi((double)f_start * t, &sa, &ca);
+        sincospi_bf((double)f_start * t, sa, ca);
         cur = sa;
         prev = sa * cs - ca * ss;
     }
 }
 
-// Theta' of one chunk: CHUNK positions x NX outputs, contiguous in shared memory, all lanes read
-// the same address (broadcast).
-template <int NX>
-struct ThetaChunk {
-    double v[CHUNK][NX];
-    __device__ __forceinline__ void load(const double* __restrict__ th, int c) {
-        constexpr int ND = CHUNK * NX;
-        const double* p = th + (size_t)c * ND;
-        if constexpr (ND % 2 == 0) {
-            const double2* p2 = reinterpret_cast<const double2*>(p);
-#pragma unroll
-            for (int i = 0; i < ND / 2; ++i) {
-                const double2 t = p2[i];
-                v[(2 * i) / NX][(2 * i) % NX] = t.x;
-                v[(2 * i + 1) / NX][(2 * i + 1) % NX] = t.y;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < ND; ++i) v[i / NX][i % NX] = p[i];
-        }
-    }
-};
+constexpr int HALF = 16;        // particles per shared sine tile (half a warp)
+constexpr int TILE_PS = 24;     // tile row pitch in doubles: 24 = 8 mod 16 keeps the 4x8 fragment reads conflict-free
+constexpr int NTB = 5;          // column tiles accumulated per pass (accumulators: 2 groups x NTB x 2 doubles)
 
-// 2*CHUNK*NX... the chunk's FMAs against the statically indexed sine block B (positions 4B..4B+3);
-// positions alternate between two accumulator sets -> 2*NX independent DFMA chains.
-#define PGAS_CHUNK_CASE(B)                                                                   \
-    case (B):                                                                                \
-        if constexpr ((B) * CHUNK < JMAX) {                                                  \
-            _Pragma("unroll") for (int i = 0; i < CHUNK; ++i) {                              \
-                _Pragma("unroll") for (int k = 0; k < NX; ++k) {                             \
-                    if (i & 1) acc1[k] = fma(tc.v[i][k], s[(B) * CHUNK + i], acc1[k]);       \
-                    else       acc0[k] = fma(tc.v[i][k], s[(B) * CHUNK + i], acc0[k]);       \
-                }                                                                            \
-            }                                                                                \
-        }                                                                                    \
-        break;
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
-// th: shared-memory Theta' in chunk order [chunk][CHUNK][NX] (already scaled by norm);
-// meta: shared-memory chunk metadata (common.cuh).
-template <int NX, int D, int JMAX>
-__device__ __forceinline__ void eval_mu(const double* __restrict__ th, const int* __restrict__ meta, int n_chunks, int f_start,
-                                        int f_step, const double tz[D], double mu[NX]) {
-    static_assert(JMAX % CHUNK == 0 && JMAX <= 40, "JMAX must be a multiple of CHUNK and <= 40");
-    double s[JMAX];
+// doubles of shared memory one warp needs for its sine tile
+__host__ __device__ __forceinline__ int sine_tile_doubles(const DevModel& m) {
+    int rows = m.jmax;
+    for (int d = 0; d + 1 < m.D; ++d) rows += m.npos_d[d];
+    return rows * TILE_PS;
+}
+
+// Warp-cooperative auxiliary mean for the warp's 32 particles (lane i owns particle il0 + i):
+//   mu_k(p) = sum_r lead[p,r] (S B)[p, r n_x + k]      (see common.cuh)
+// Each lane builds its particle's sine tables with the 3-term recurrence and parks them in the
+// warp's shared tile (two passes of 16 particles); the contraction over the last dimension runs
+// on the FP64 tensor pipe (mma.sync m8n8k4: A = sines, B = Theta' fragments from shared memory),
+// the per-row scaling and the 4-lane reduction finish it.  Row leaders (lane%4 == 0) write
+// mu to mus[k*P + particle]; after the closing __syncwarp every owner can read its own entry.
+template <int NX, int D>
+__device__ __forceinline__ void eval_mu_warp(const DevModel& m, const double* __restrict__ bfrag, const int* __restrict__ rowpos, double* __restrict__ tile, const double tz[D],
+                                             int lane, double* __restrict__ mus, int P, int il0) {
+    const int q = lane & 3, r = lane >> 2;
+    const int KS = m.KS, NTNP = m.NTNP;
+    // tile layout: last dimension first (jmax rows), then the leading dimensions
+    int dim_off[D];
+    dim_off[D - 1] = 0;
     {
-        double cur, prev, twoc;
-        sine_seed(tz[D - 1], f_start, f_step, cur, prev, twoc);
-        s[0] = cur;
-        s[1] = fma(twoc, cur, -prev);
+        int o = m.jmax;
 #pragma unroll
-        for (int p = 2; p < JMAX; ++p) s[p] = fma(twoc, s[p - 1], -s[p - 2]);
+        for (int d = 0; d + 1 < D; ++d) { dim_off[d] = o; o += m.npos_d[d]; }
     }
-    // leading dimensions: fast = D-2, slow = D-3
-    double fcur = 1.0, fprev = 0.0, ftwoc = 0.0, fcur0 = 1.0, fprev0 = 0.0;
-    double scur = 1.0, sprev = 0.0, stwoc = 0.0;
-    if constexpr (D >= 2) {
-        sine_seed(tz[D - 2], f_start, f_step, fcur, fprev, ftwoc);
-        fcur0 = fcur; fprev0 = fprev;
-    }
-    if constexpr (D >= 3) sine_seed(tz[D - 3], f_start, f_step, scur, sprev, stwoc);
-    double acc0[NX], acc1[NX];
+    double cur0[D], prev0[D], twoc[D];
 #pragma unroll
-    for (int k = 0; k < NX; ++k) { mu[k] = 0.0; acc0[k] = 0.0; acc1[k] = 0.0; }
+    for (int d = 0; d < D; ++d) sine_seed(tz[d], m.f_start, m.f_step, cur0[d], prev0[d], twoc[d]);
 
-    // one chunk: FMAs against its sine block, then (row end) fold into mu and step the leading sines
-    auto body = [&](const ThetaChunk<NX>& tc, int mt) {
-        switch (mt & 0xff) {
-            PGAS_CHUNK_CASE(0) PGAS_CHUNK_CASE(1) PGAS_CHUNK_CASE(2) PGAS_CHUNK_CASE(3) PGAS_CHUNK_CASE(4)
-            PGAS_CHUNK_CASE(5) PGAS_CHUNK_CASE(6) PGAS_CHUNK_CASE(7) PGAS_CHUNK_CASE(8) PGAS_CHUNK_CASE(9)
-            default: break;
-        }
-        if (mt & META_ROW_END) {
-            double lead = 1.0;
-            if constexpr (D == 2) lead = fcur;
-            if constexpr (D >= 3) lead = fcur * scur;
+    for (int h = 0; h < 2; ++h) {
+        // ---- sines of this half's 16 particles -> tile[dim][pos][16]
+        if ((lane >> 4) == h) {
 #pragma unroll
-            for (int k = 0; k < NX; ++k) {
-                mu[k] = fma(lead, acc0[k] + acc1[k], mu[k]);
-                acc0[k] = 0.0;
-                acc1[k] = 0.0;
-            }
-            if constexpr (D >= 2) {
-                const int adv = (mt >> META_ADV_SHIFT) & 3;
-                if (adv == ROW_ADV_FAST) {
-                    const double n = fma(ftwoc, fcur, -fprev);
-                    fprev = fcur; fcur = n;
-                } else if (adv == ROW_ADV_SLOW) {
-                    if constexpr (D >= 3) {
-                        const double n = fma(stwoc, scur, -sprev);
-                        sprev = scur; scur = n;
-                    }
-                    fcur = fcur0; fprev = fprev0;
+            for (int d = 0; d < D; ++d) {
+                const int np = (d == D - 1) ? m.jmax : m.npos_d[d];
+                double* col = tile + (size_t)dim_off[d] * TILE_PS + (lane & 15);
+                double cur = cur0[d], prev = prev0[d];
+                for (int p = 0; p < np; ++p) {
+                    col[(size_t)p * TILE_PS] = cur;
+                    const double n = fma(twoc[d], cur, -prev);
+                    prev = cur; cur = n;
                 }
             }
         }
-    };
+        __syncwarp();
+        double mup[2][NX];
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int k = 0; k < NX; ++k) mup[g][k] = 0.0;
 
-    // software-pipelined walk over the chunk list: chunk c+1's Theta' is loaded while chunk c is
-    // multiplied (two register buffers, loop unrolled by two so no register copies are needed)
-    ThetaChunk<NX> ta, tb;
-    int ma, mb = 0;
-    ta.load(th, 0);
-    ma = meta[0];
-    int c = 0;
-    for (; c + 1 < n_chunks; c += 2) {
-        tb.load(th, c + 1);
-        mb = meta[c + 1];
-        body(ta, ma);
-        if (c + 2 < n_chunks) {
-            ta.load(th, c + 2);
-            ma = meta[c + 2];
+        for (int nb = 0; nb < NTNP; nb += NTB) {
+            double acc[2][NTB][2];
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+#pragma unroll
+                for (int j = 0; j < NTB; ++j) { acc[g][j][0] = 0.0; acc[g][j][1] = 0.0; }
+            for (int ks = 0; ks < KS; ++ks) {
+                const int ntc = m.ntcount[ks] - nb;           // kernel-parameter data: warp-uniform
+                if (ntc <= 0) continue;
+                const double* arow = tile + (size_t)(4 * ks + q) * TILE_PS + r;
+                const double a0 = arow[0], a1 = arow[8];
+                const double* bp = bfrag + ((size_t)ks * NTNP + nb) * 32 + lane;
+                double bv[NTB];
+#pragma unroll
+                for (int j = 0; j < NTB; ++j) bv[j] = bp[j * 32];   // tiles past ntcount hold zeros: always loadable
+#pragma unroll
+                for (int j = 0; j < NTB; ++j) {
+                    if (j < ntc) {
+                        dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, bv[j]);
+                        dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, bv[j]);
+                    }
+                }
+            }
+            // ---- per-row scaling by the leading-dimension sines (padding rows have zero accumulators)
+#pragma unroll
+            for (int j = 0; j < NTB; ++j) {
+                const int c0 = 8 * (nb + j) + 2 * q;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (NX == 2 && e == 1) break;               // both columns of the pair belong to one row
+                    const int row = (c0 + e) / NX;
+                    double lead0 = 1.0, lead1 = 1.0;
+#pragma unroll
+                    for (int d = 0; d + 1 < D; ++d) {
+                        const double* lp = tile + (size_t)(dim_off[d] + rowpos[row * MAX_LEAD + d]) * TILE_PS + r;
+                        lead0 *= lp[0];
+                        lead1 *= lp[8];
+                    }
+                    if constexpr (NX == 2) {
+                        mup[0][0] = fma(lead0, acc[0][j][0], mup[0][0]);
+                        mup[0][1] = fma(lead0, acc[0][j][1], mup[0][1]);
+                        mup[1][0] = fma(lead1, acc[1][j][0], mup[1][0]);
+                        mup[1][1] = fma(lead1, acc[1][j][1], mup[1][1]);
+                    } else {
+                        const int k = (c0 + e) - row * NX;
+#pragma unroll
+                        for (int kk = 0; kk < NX; ++kk) {
+                            mup[0][kk] = fma((kk == k) ? lead0 : 0.0, acc[0][j][e], mup[0][kk]);
+                            mup[1][kk] = fma((kk == k) ? lead1 : 0.0, acc[1][j][e], mup[1][kk]);
+                        }
+                    }
+                }
+            }
         }
-        body(tb, mb);
+        // ---- reduce over the 4 lanes of a fragment row, row leaders publish
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int k = 0; k < NX; ++k) {
+                double v = mup[g][k];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                const int il = il0 + HALF * h + 8 * g + r;
+                if (q == 0 && il < P) mus[(size_t)k * P + il] = v;
+            }
+        __syncwarp();
     }
-    if (c < n_chunks) body(ta, ma);
 }
 
 // GP-input map (state, input) -> normalised lattice coordinate t_d = (z_d - c_d + L_d)/(2 L_d)

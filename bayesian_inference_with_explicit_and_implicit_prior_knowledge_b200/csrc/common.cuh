@@ -6,6 +6,7 @@
 #include <string.h>
 #include <math.h>
 #include "../../include/pgas_b200.h"
+#include "fastmath.cuh"
 
 // ---------------------------------------------------------------------------------- errors
 void pgas_set_error(const char* fmt, ...);
@@ -16,25 +17,27 @@ void pgas_set_error(const char* fmt, ...);
 #define PGAS_KERNEL_CHECK() PGAS_CUDA(cudaGetLastError())
 
 // ---------------------------------------------------------------------------------- model
-// Packed tensor-product layout of the Hilbert basis (see DESIGN.md "Basis layout"):
-// basis functions are grouped into ROWS sharing the lattice positions of the leading D-1
-// dimensions; inside a row the last dimension runs over positions 0..len-1 (holes and the tail
-// up to a multiple of CHUNK are padded, their Theta entry is 0).
-//   mu_k = norm * sum_rows lead(row) * sum_p Theta'[row,p,k] s_last[p]
-// A row is cut into CHUNKs of 4 consecutive last-dimension positions; the kernel walks the flat
-// chunk list.  Per chunk one int of metadata: bits 0-7 = position block (positions 4b..4b+3),
-// bit 8 = last chunk of its row, bits 9-10 = how the NEXT row's leading sines follow from this
-// row's: consecutive rows differ by ONE unit advance of the faster leading dimension or by
-// "advance the slower dimension and reset the faster to 0", so the leading sines are carried as
-// 3-term recurrences instead of tables.
-constexpr int CHUNK = 4;
-enum { ROW_ADV_NONE = 0, ROW_ADV_FAST = 1, ROW_ADV_SLOW = 2 };
-constexpr int META_ROW_END = 0x100;
-constexpr int META_ADV_SHIFT = 9;
+// Tensor-product layout of the Hilbert basis for the FP64 tensor-core contraction (DESIGN.md
+// "Basis layout").  Basis functions sharing the lattice positions of the leading D-1 dimensions
+// form a ROW r (R rows); inside a row the last dimension runs over positions j.  With
+//   S[p, j]        = sin(pi f_j t_last(p))                       (particles x KP, KP = 4 KS)
+//   B[j, r*n_x+k]  = norm * Theta[k, m(r, j)]   (0 where absent)  (KP x NCOL, NCOL = 8 NTN)
+//   lead[p, r]     = prod_{d < D-1} sin(pi f_{pos_d(r)} t_d(p))
+// the auxiliary mean is  mu_k(p) = sum_r lead[p, r] * (S B)[p, r*n_x+k]:  a dense (8 particles x
+// 4 positions) x (4 positions x 8 columns) DMMA tile product per (ks, nt), followed by a per-row
+// scaling and a 4-lane reduction.  B is stored in mma.sync m8n8k4 fragment order:
+//   Bfrag[(ks*NTNP + nt)*32 + lane] = B[4 ks + lane%4][8 nt + lane/4]
+// Rows are sorted by decreasing length, so the all-zero tiles outside the quarter-disc the
+// lattice search selects are the trailing column tiles of each position step: ntcount[ks].
+constexpr int MAX_LEAD = PGAS_MAX_D - 1;
 
 struct DevModel {
     int n_x, n_y, n_u, D, M, T;
-    int n_chunks, jmax, n_packed; // jmax = max padded row length (multiple of CHUNK), n_packed = n_chunks*CHUNK
+    int R, NTN, KS, n_packed;     // rows, column tiles (8 wide), position steps (4 deep), KS*NTNP*32 fragment slots
+    int jmax;                     // positions of the last dimension incl. padding (= 4 KS)
+    int npos_d[PGAS_MAX_D];       // lattice positions used per dimension (max position + 1)
+    int NTNP;                     // NTN rounded up to a multiple of the accumulator block (zero tiles)
+    int ntcount[16];              // per position step: column tiles up to the last non-zero one
     int f_start, f_step;
     int npos;                     // max lattice position over all dimensions + 1
     int map_kind, flags;
@@ -46,8 +49,8 @@ struct DevModel {
     double Rw[PGAS_MAX_NY][PGAS_MAX_NY];            // inverse of chol(R) (lower): e = Rw (y - mean)
     double R_logc;                                  // -n_y/2 log(2 pi) - sum log diag chol(R)
     double m0[PGAS_MAX_NX], P0c[PGAS_MAX_NX][PGAS_MAX_NX];   // chol(P0) lower
-    const int* chunk_meta;  // [n_chunks]
-    const int* perm;        // [n_packed] packed slot -> basis index m, or -1 (padding)
+    const int* perm;        // [n_packed] fragment slot -> m * 4 + k of the Theta entry it holds, or -1 (zero)
+    const int* row_pos;     // [8*NTN / n_x rounded up][MAX_LEAD] leading-dimension positions of each row (0 for padding rows)
     const int* freq;        // [M*D] integer frequencies, reference order
     const double* obs;      // (T,n_y)
     const double* inputs;   // (T,n_u)
@@ -99,9 +102,9 @@ __device__ __forceinline__ void philox_normal2(uint64_t seed, uint32_t purpose, 
                                                uint32_t t, uint32_t i, double& za, double& zb) {
     double ua, ub;
     philox_uniform2(seed, purpose, chain, iter, t, i, ua, ub);
-    double r = sqrt(-2.0 * log(ua + (1.0 / 9007199254740992.0)));
+    const double r = sqrt_bf(fmax(-2.0 * log_unit_bf(ua + (1.0 / 9007199254740992.0)), 1e-300));
     double s, c;
-    sincospi(2.0 * ub, &s, &c);
+    sincospi_bf(2.0 * ub, s, c);
     za = r * c;
     zb = r * s;
 }

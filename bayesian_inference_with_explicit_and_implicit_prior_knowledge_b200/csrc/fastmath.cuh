@@ -1,0 +1,121 @@
+// fastmath.cuh — branch-free float64 elementary functions for the sweep kernel.
+//
+// The sweep runs at 2 warps per SM sub-partition (one particle per thread, ~220 particles per
+// SM at the BASELINE shapes), so its step time is set by DEPENDENT-instruction latency (DFMA:
+// 8 cycles measured on B200), not by issue rate.  libdevice's sincospi/exp/log/sqrt/div carry
+// slow-path branches and calls that stop ptxas from interleaving independent evaluations; these
+// versions are straight-line (Horner chains the scheduler can interleave across the D basis
+// dimensions, the two softmax numerators, and the Box-Muller pieces).  Accuracy ~1 ulp
+// (checked against long double in tests/test_abi_and_host.py's NumPy mirror and on the GPU).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// sin(pi x), cos(pi x): reduce to r = x - n/2, |r| <= 1/4 (exact), Taylor in t = r^2
+__device__ __forceinline__ void sincospi_bf(double x, double& s_out, double& c_out) {
+    const double n = rint(x + x);
+    const double r = fma(-0.5, n, x);
+    const double t = r * r;
+    double ps = -2.2948428997269873e-08;
+    ps = fma(ps, t, 7.952054001475513e-07);
+    ps = fma(ps, t, -2.1915353447830217e-05);
+    ps = fma(ps, t, 0.00046630280576761255);
+    ps = fma(ps, t, -0.0073704309457143504);
+    ps = fma(ps, t, 0.08214588661112823);
+    ps = fma(ps, t, -0.5992645293207921);
+    ps = fma(ps, t, 2.5501640398773455);
+    ps = fma(ps, t, -5.16771278004997);
+    ps = fma(ps, t, 3.141592653589793);
+    double pc = 3.604730797462501e-09;
+    pc = fma(pc, t, -1.3878952462213771e-07);
+    pc = fma(pc, t, 4.303069587032947e-06);
+    pc = fma(pc, t, -0.0001046381049248457);
+    pc = fma(pc, t, 0.0019295743094039231);
+    pc = fma(pc, t, -0.02580689139001406);
+    pc = fma(pc, t, 0.2353306303588932);
+    pc = fma(pc, t, -1.3352627688545895);
+    pc = fma(pc, t, 4.0587121264167685);
+    pc = fma(pc, t, -4.934802200544679);
+    const double s = r * ps, c = fma(pc, t, 1.0);
+    const int q = (int)__double2ll_rn(n) & 3;
+    const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;
+    s_out = (q & 2) ? -a : a;                    // q: 0 -> s, 1 -> c, 2 -> -s, 3 -> -c
+    c_out = ((q + 1) & 2) ? -b : b;              // q: 0 -> c, 1 -> -s, 2 -> -c, 3 -> s
+}
+
+// exp(x) for x <= 0 (softmax numerators); 0 below the normal range, NaN propagates
+__device__ __forceinline__ double exp_neg_bf(double x) {
+    const double n = rint(x * 1.4426950408889634);
+    double r = fma(-n, 6.93147180369123816490e-01, x);
+    r = fma(-n, 1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;
+    p = fma(p, r, 2.08767569878681e-09);
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 0.0001984126984126984);
+    p = fma(p, r, 0.001388888888888889);
+    p = fma(p, r, 0.008333333333333333);
+    p = fma(p, r, 0.041666666666666664);
+    p = fma(p, r, 0.16666666666666666);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int e = (int)n;
+    const double scale = __longlong_as_double((long long)(e + 1023) << 52);
+    const double v = p * scale;
+    return (x < -708.0) ? 0.0 : ((x > 0.0) ? exp(x) : v);     // x > 0 never happens after max subtraction
+}
+
+// 1/d for normal positive d: float seed + two Newton steps (~1 ulp)
+__device__ __forceinline__ double rcp_bf(double d) {
+    double y = (double)__frcp_rn((float)d);
+    y = y * fma(-d, y, 2.0);
+    y = y * fma(-d, y, 2.0);
+    return fma(y, fma(-d, y, 1.0), y);
+}
+
+// log(u), u in (0, 1]
+__device__ __forceinline__ double log_unit_bf(double u) {
+    const long long bits = __double_as_longlong(u);
+    int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);   // [1,2)
+    const bool big = m > 1.4142135623730951;
+    m = big ? 0.5 * m : m;
+    e += big ? 1 : 0;
+    const double num = m - 1.0, den = m + 1.0;
+    const double y = rcp_bf(den);
+    double f = num * y;
+    f = fma(fma(-den, f, num), y, f);
+    const double t = f * f;
+    double p = 1.0 / 23.0;
+    p = fma(p, t, 1.0 / 21.0);
+    p = fma(p, t, 1.0 / 19.0);
+    p = fma(p, t, 1.0 / 17.0);
+    p = fma(p, t, 1.0 / 15.0);
+    p = fma(p, t, 1.0 / 13.0);
+    p = fma(p, t, 1.0 / 11.0);
+    p = fma(p, t, 1.0 / 9.0);
+    p = fma(p, t, 1.0 / 7.0);
+    p = fma(p, t, 1.0 / 5.0);
+    p = fma(p, t, 1.0 / 3.0);
+    const double lm = fma(2.0 * f * t, p, 2.0 * f);
+    const double de = (double)e;
+    return fma(de, 6.93147180369123816490e-01, fma(de, 1.90821492927058770002e-10, lm));
+}
+
+// sqrt(a), a > 0 normal: float rsqrt seed + Newton (~1 ulp)
+__device__ __forceinline__ double sqrt_bf(double a) {
+    double y = (double)rsqrtf((float)a);
+    y = y * fma(-0.5 * a, y * y, 1.5);
+    y = y * fma(-0.5 * a, y * y, 1.5);
+    double s = a * y;
+    return fma(fma(-s, s, a), 0.5 * y, s);
+}
+
+// correctly rounded a / N given rN = RN(1/N) (Markstein): equals IEEE division for integer N < 2^24
+__device__ __forceinline__ double div_by_count(double a, double dN, double rN) {
+    const double q = a * rN;
+    return fma(fma(-q, dN, a), rN, q);
+}

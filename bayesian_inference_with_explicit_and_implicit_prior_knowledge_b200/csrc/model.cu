@@ -119,59 +119,60 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
             pos[(size_t)mI * D + d] = f / p->idx_step;
             dm.npos = std::max(dm.npos, f / p->idx_step + 1);
         }
-    // key of a row = (slow position, fast position); D==1 -> (0,0), D==2 -> (0,p0), D==3 -> (p0,p1)
-    std::map<std::pair<int, int>, std::vector<std::pair<int, int>>> rows;   // -> list of (last pos, m)
-    int max_slow = 0;
+    // rows = distinct leading-position tuples, sorted by decreasing last-dimension extent so that
+    // the non-zero tiles of every position step are a prefix of the column tiles
+    std::map<std::vector<int>, int> row_of;
+    std::vector<std::vector<int>> row_lead;
+    std::vector<int> row_len, m_row(M);
+    int kp = 0;
+    for (int d = 0; d < PGAS_MAX_D; ++d) dm.npos_d[d] = 0;
     for (int mI = 0; mI < M; ++mI) {
-        int slow = 0, fast = 0;
-        if (D == 2) fast = pos[(size_t)mI * D];
-        if (D == 3) { slow = pos[(size_t)mI * D]; fast = pos[(size_t)mI * D + 1]; }
-        rows[{slow, fast}].push_back({pos[(size_t)mI * D + D - 1], mI});
-        max_slow = std::max(max_slow, slow);
+        std::vector<int> lead(pos.begin() + (size_t)mI * D, pos.begin() + (size_t)mI * D + (D - 1));
+        auto it = row_of.find(lead);
+        if (it == row_of.end()) {
+            it = row_of.insert({lead, (int)row_lead.size()}).first;
+            row_lead.push_back(lead);
+            row_len.push_back(0);
+        }
+        m_row[mI] = it->second;
+        row_len[it->second] = std::max(row_len[it->second], pos[(size_t)mI * D + D - 1] + 1);
+        kp = std::max(kp, pos[(size_t)mI * D + D - 1] + 1);
+        for (int d = 0; d < D; ++d) dm.npos_d[d] = std::max(dm.npos_d[d], pos[(size_t)mI * D + d] + 1);
     }
-    // enumerate rows in recurrence order; each row is followed by the advance code of the NEXT row
-    struct Row { int len; std::vector<std::pair<int, int>> items; };
-    std::vector<Row> row_list;
-    std::vector<int> row_adv;                 // how row i is reached from row i-1
-    for (int slow = 0; slow <= max_slow; ++slow) {
-        int max_fast = 0;
-        for (auto& kv : rows) if (kv.first.first == slow) max_fast = std::max(max_fast, kv.first.second);
-        for (int fast = 0; fast <= max_fast; ++fast) {
-            Row r; r.len = 0;
-            auto it = rows.find({slow, fast});
-            if (it != rows.end()) { r.items = it->second; for (auto& e : r.items) r.len = std::max(r.len, e.first + 1); }
-            row_list.push_back(r);
-            row_adv.push_back(fast == 0 ? (slow == 0 ? ROW_ADV_NONE : ROW_ADV_SLOW) : ROW_ADV_FAST);
+    const int nx = p->n_x;
+    dm.R = (int)row_lead.size();
+    std::vector<int> order(dm.R), rank(dm.R);
+    for (int r = 0; r < dm.R; ++r) order[r] = r;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return row_len[a] > row_len[b]; });
+    for (int r = 0; r < dm.R; ++r) rank[order[r]] = r;
+    dm.KS = (kp + 3) / 4;
+    if (dm.KS > 16) PGAS_FAIL(-20, "basis needs %d lattice positions in its last dimension; this build supports <= 64", kp);
+    dm.jmax = dm.KS * 4;
+    dm.NTN = (dm.R * nx + 7) / 8;
+    constexpr int NTB_HOST = 5;              // keep equal to NTB in basis_eval.cuh
+    dm.NTNP = (dm.NTN + NTB_HOST - 1) / NTB_HOST * NTB_HOST;
+    dm.n_packed = dm.KS * dm.NTNP * 32;
+    std::vector<int> perm((size_t)dm.n_packed, -1);
+    for (int ks = 0; ks < 16; ++ks) dm.ntcount[ks] = 0;
+    for (int mI = 0; mI < M; ++mI) {
+        const int j = pos[(size_t)mI * D + D - 1], r = rank[m_row[mI]];
+        for (int k = 0; k < nx; ++k) {
+            const int col = r * nx + k, ks = j / 4, nt = col / 8;
+            const int lane = (col % 8) * 4 + (j % 4);             // lane%4 = j%4, lane/4 = col%8
+            int& slot = perm[((size_t)ks * dm.NTNP + nt) * 32 + lane];
+            if (slot != -1) PGAS_FAIL(-4, "duplicate basis function index tuple (basis %d)", mI);
+            slot = mI * 4 + k;
+            dm.ntcount[ks] = std::max(dm.ntcount[ks], nt + 1);
         }
     }
-    std::vector<int> chunk_meta, perm;
-    dm.jmax = 0;
-    for (size_t ri = 0; ri < row_list.size(); ++ri) {
-        const Row& r = row_list[ri];
-        const int nch = std::max(1, (r.len + CHUNK - 1) / CHUNK);      // an empty row still carries its flags
-        dm.jmax = std::max(dm.jmax, nch * CHUNK);
-        const size_t o = perm.size();
-        perm.resize(o + (size_t)nch * CHUNK, -1);
-        for (auto& e : r.items) {
-            if (perm[o + e.first] != -1) PGAS_FAIL(-4, "duplicate basis function index tuple (basis %d)", e.second);
-            perm[o + e.first] = e.second;
-        }
-        for (int c = 0; c < nch; ++c) {
-            int meta = c;
-            if (c == nch - 1) {
-                meta |= META_ROW_END;
-                const int next_adv = (ri + 1 < row_list.size()) ? row_adv[ri + 1] : ROW_ADV_NONE;
-                meta |= next_adv << META_ADV_SHIFT;
-            }
-            chunk_meta.push_back(meta);
-        }
-    }
-    dm.n_chunks = (int)chunk_meta.size();
-    dm.n_packed = (int)perm.size();
+    const int n_rows_padded = (8 * dm.NTNP + nx - 1) / nx + 1;
+    std::vector<int> row_pos((size_t)n_rows_padded * MAX_LEAD, 0);
+    for (int r = 0; r < dm.R; ++r)
+        for (int d = 0; d < D - 1; ++d) row_pos[(size_t)rank[r] * MAX_LEAD + d] = row_lead[r][d];
 
     // ---- one device arena ---------------------------------------------------------------
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t b_rows = al(sizeof(int) * dm.n_chunks), b_perm = al(sizeof(int) * dm.n_packed), b_freq = al(sizeof(int) * M * D);
+    const size_t b_rows = al(sizeof(int) * row_pos.size()), b_perm = al(sizeof(int) * dm.n_packed), b_freq = al(sizeof(int) * M * D);
     const size_t b_obs = al(sizeof(double) * (size_t)p->T * p->n_y), b_in = al(sizeof(double) * (size_t)p->T * std::max(p->n_u, 1));
     const size_t total = b_rows + b_perm + b_freq + b_obs + b_in;
     char* arena = nullptr;
@@ -183,7 +184,7 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
         o += slot;
         return d;
     };
-    dm.chunk_meta = (const int*)up(chunk_meta.data(), sizeof(int) * dm.n_chunks, b_rows);
+    dm.row_pos = (const int*)up(row_pos.data(), sizeof(int) * row_pos.size(), al(sizeof(int) * row_pos.size()));
     dm.perm = (const int*)up(perm.data(), sizeof(int) * dm.n_packed, b_perm);
     dm.freq = (const int*)up(p->freq, sizeof(int) * M * D, b_freq);
     dm.obs = (const double*)up(p->observations, sizeof(double) * (size_t)p->T * p->n_y, b_obs);

@@ -17,8 +17,6 @@
 
 namespace cg = cooperative_groups;
 
-constexpr int NT = 256;          // threads per CTA
-constexpr int NW = NT / 32;
 constexpr int MAXC = 16;         // largest (non-portable) cluster
 
 
@@ -72,16 +70,48 @@ __device__ __forceinline__ double cdf_value(double p, double f, double g, double
 }
 __device__ __forceinline__ double clip01(double v) { return fmin(fmax(v, 0.0), 1.0); }
 
-// U_j = (u + j) / N exactly as src/Filtering.py:28 evaluates it
-__device__ __forceinline__ double strat_point(double u, int j, double dN) { return __ddiv_rn(__dadd_rn(u, (double)j), dN); }
+// U_j = (u + j) / N exactly as src/Filtering.py:28 evaluates it (correctly rounded quotient)
+__device__ __forceinline__ double strat_point(double u, int j, double dN, double rN) {
+    return div_by_count(__dadd_rn(u, (double)j), dN, rN);
+}
 
-// smallest j in [0,N] with U_j > b  (U_j is non-decreasing in j)
-__device__ __forceinline__ int first_point_above(double b, double u, int N, double dN) {
-    double g = floor(b * dN - u);
-    int j = (g < 0.0) ? 0 : (g > (double)N ? N : (int)g);
-    while (j > 0 && strat_point(u, j - 1, dN) > b) --j;
-    while (j < N && !(strat_point(u, j, dN) > b)) ++j;
+// smallest j in [0,N] with U_j > b  (U_j is non-decreasing in j): four candidates around the
+// arithmetic guess are tested in parallel; the loops only run if the guess was off by more
+__device__ __forceinline__ int first_point_above(double b, double u, int N, double dN, double rN) {
+    const double g = floor(fma(b, dN, -u));
+    int j = (g < 1.0) ? 0 : (g > (double)N ? N : (int)g - 1);
+    const bool c0 = strat_point(u, j, dN, rN) > b, c1 = strat_point(u, j + 1, dN, rN) > b;
+    const bool c2 = strat_point(u, j + 2, dN, rN) > b, c3 = strat_point(u, j + 3, dN, rN) > b;
+    j = c0 ? j : (c1 ? j + 1 : (c2 ? j + 2 : (c3 ? j + 3 : j + 4)));
+    j = min(j, N);
+    while (j > 0 && strat_point(u, j - 1, dN, rN) > b) --j;
+    while (j < N && !(strat_point(u, j, dN, rN) > b)) ++j;
     return j;
+}
+
+// number of elements of the non-decreasing array w that are < x.  w is padded with +inf to a
+// multiple of 256 entries (nblk blocks), so the search is three fixed-radix levels whose loads and
+// compares are all independent: block (<= 16 probes), 16 probes of stride 16, 16 neighbours.
+__device__ __forceinline__ int count_below_padded(const double* __restrict__ w, int nblk, double x) {
+    int base = 0;
+    if (nblk > 1) {
+        int c = 0;
+        for (int b = 0; b < nblk; ++b) c += (w[b * 256 + 255] < x) ? 1 : 0;
+        base = min(c, nblk - 1) * 256;
+    }
+    const double* w1 = w + base;
+    int c1 = 0;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) c1 += (w1[16 * g + 15] < x) ? 1 : 0;
+    c1 = min(c1, 15);
+    const double2* w2 = reinterpret_cast<const double2*>(w1 + 16 * c1);
+    int c2 = 0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const double2 v = w2[g];
+        c2 += ((v.x < x) ? 1 : 0) + ((v.y < x) ? 1 : 0);
+    }
+    return base + 16 * c1 + c2;
 }
 
 // per-step constants staged in shared memory (double-buffered by step parity)
@@ -125,8 +155,9 @@ __device__ __forceinline__ void load_step_const(const SweepArgs& a, int chain, i
     }
 }
 
-template <int NX, int NY, int D, int JMAX>
+template <int NX, int NY, int D, int NT>
 __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant__ SweepArgs a) {
+    constexpr int NW = NT / 32;
     const DevModel& m = a.m;
     cg::cluster_group cluster = cg::this_cluster();
     const int C = a.C;
@@ -138,41 +169,43 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
     const int Pc = max(0, min(P, N - base));          // valid particles of this CTA
     const int PPT = (P + NT - 1) / NT;
     const bool gather = (m.flags & PGAS_FLAG_ANCESTOR_GATHER) != 0;
-    const double dN = (double)N;
+    const double dN = (double)N, rN = 1.0 / (double)N;
 
     // ------------------------------------------------------------------ shared memory carve
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sp = reinterpret_cast<double*>(smem_raw);
-    double* th = sp;            sp += ((size_t)m.n_packed * NX + 1) & ~(size_t)1;
+    double* bfrag = sp;         sp += m.n_packed;                          // Theta' in DMMA B-fragment order
+    double* tiles = sp;         sp += (size_t)NW * sine_tile_doubles(m);   // per-warp sine tiles
     double* xs = sp;            sp += (size_t)NX * P;          // [k][i]
     double* mus = sp;           sp += (size_t)NX * P;          // [k][i] auxiliary mean
     double* logw = sp;          sp += P;
     double* laux = sp;          sp += P;
-    double* b1 = sp;            sp += P;                       // lw_aux -> prefix -> CDF
+    const int nblk = (P + 255) / 256;
+    double* b1 = sp;            sp += nblk * 256;              // lw_aux -> prefix -> CDF (padded with +inf for the search)
     double* b2 = sp;            sp += P;                       // lw_anc -> prefix
     double* lauxg = sp;         sp += P;                       // l_aux[a_i], pushed by the CDF owner
     double* mug = sp;           sp += gather ? (size_t)NX * P : 0;
     double* exch = sp;          sp += MAXC * 4;                // per-CTA (m1,s1,m2,s2), all-gathered
     double* gsum = sp;          sp += 2 * (MAXC + 1);          // exclusive CDF offsets G1[c], G2[c], c = 0..C
     double* fx = sp;            sp += 2 * MAXC + 2;            // rescale factors exp(m_c - M); then 1/S1, 1/S2
-    double* wtmax = sp;         sp += NW * 2;
-    double* wtscan = sp;        sp += 2 * NW * 2;
+    double* unit = sp;          sp += (size_t)PPT * NW * 4;    // per (round, warp): (max1, sum1, max2, sum2)
+    double* ufac = sp;          sp += (size_t)PPT * NW * 4;    // per (round, warp): (f1, G1, f2, G2)
     double* chol = sp;          sp += NX * NX;                 // chol(Sigma) lower
     double* sw = sp;            sp += NX * NX;                 // chol(Sigma)^-1
     double* slogc = sp;         sp += 2;
     StepConst* sc = reinterpret_cast<StepConst*>(sp);  sp += 2 * ((sizeof(StepConst) + 7) / 8);
     int* ip = reinterpret_cast<int*>(sp);
-    int* meta = ip;             ip += m.n_chunks;
+    int* rowpos = ip;           ip += ((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD;
     int* cnt = ip;              ip += 2;
 
     // ------------------------------------------------------------------ prologue
-    for (int r = tid; r < m.n_chunks; r += NT) meta[r] = m.chunk_meta[r];
-    {   // Theta' = norm * Theta in packed order
+    for (int r = tid; r < ((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD; r += NT) rowpos[r] = m.row_pos[r];
+    for (int r = Pc + tid; r < nblk * 256; r += NT) b1[r] = INFINITY;
+    {   // Theta' = norm * Theta scattered into B-fragment order
         const double* Th = a.Theta + (size_t)chain * NX * m.M;
         for (int s = tid; s < m.n_packed; s += NT) {
-            const int mm = m.perm[s];
-#pragma unroll
-            for (int k = 0; k < NX; ++k) th[(size_t)s * NX + k] = (mm >= 0) ? m.norm * Th[(size_t)k * m.M + mm] : 0.0;
+            const int e = m.perm[s];
+            bfrag[s] = (e >= 0) ? m.norm * Th[(size_t)(e & 3) * m.M + (e >> 2)] : 0.0;
         }
     }
     if (tid == 0) {
@@ -250,101 +283,116 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
         StepConst nxt;                                       // prefetch of step t+1 (thread 0)
         if (tid == 0 && t + 1 < a.t_end) load_step_const(a, chain, t + 1, &nxt);
 
-        // ---- A1: auxiliary mean, first-stage log-weights (src/PGAS.py:89-101, :109-117)
-        double tmax1 = -INFINITY, tmax2 = -INFINITY;
+        // ---- A: auxiliary mean (DMMA), first-stage log-weights (src/PGAS.py:89-101, :109-117), and the
+        //      softmax numerators (:102,:118) with a WARP-local shift: exp(lw - max_warp) and its in-warp
+        //      inclusive scan need no block-wide reduction; the (max, sum) pair of every warp is combined
+        //      once per step by warp 0 (online-softmax rescaling), first across the CTA, then across the cluster.
         for (int q = 0; q < PPT; ++q) {
-            const int il = q * NT + tid;
-            if (il < Pc) {
-                double x[NX], tz[D], mu[NX];
+            const int il = q * NT + tid, il0 = q * NT + warp * 32;
+            double lwa = -INFINITY, lwr = -INFINITY;
+            if (il0 < Pc) {                                   // warp-uniform: the whole warp takes part in the DMMA
+                double tz[D];
 #pragma unroll
-                for (int k = 0; k < NX; ++k) x[k] = xs[(size_t)k * P + il];
-                gp_input<NX, D>(m, x, k_t.u, tz);
-                eval_mu<NX, D, JMAX>(th, meta, m.n_chunks, m.f_start, m.f_step, tz, mu);
-                const double la = gauss_loglik<NX, NY>(m, k_t.y, mu);
-                const double lwa = la + logw[il];
-                const double h = gauss_logpdf_state<NX>(sw, slogc[0], k_t.ref, mu);
-                const double lwr = lwa + h;
+                for (int d = 0; d < D; ++d) tz[d] = 0.0;
+                if (il < Pc) {
+                    double x[NX];
 #pragma unroll
-                for (int k = 0; k < NX; ++k) mus[(size_t)k * P + il] = mu[k];
-                laux[il] = la;
-                b1[il] = lwa;
-                b2[il] = lwr;
-                tmax1 = fmax(tmax1, lwa);
-                tmax2 = fmax(tmax2, lwr);
+                    for (int k = 0; k < NX; ++k) x[k] = xs[(size_t)k * P + il];
+                    gp_input<NX, D>(m, x, k_t.u, tz);
+                }
+                eval_mu_warp<NX, D>(m, bfrag, rowpos, tiles + (size_t)warp * sine_tile_doubles(m), tz, lane, mus, P, il0);
+                if (il < Pc) {
+                    double mu[NX];
+#pragma unroll
+                    for (int k = 0; k < NX; ++k) mu[k] = mus[(size_t)k * P + il];
+                    const double la = gauss_loglik<NX, NY>(m, k_t.y, mu);
+                    lwa = la + logw[il];
+                    lwr = lwa + gauss_logpdf_state<NX>(sw, slogc[0], k_t.ref, mu);
+                    laux[il] = la;
+                }
+                const double m1w = warp_max(lwa), m2w = warp_max(lwr);
+                const double e1 = (il < Pc) ? exp_neg_bf(lwa - m1w) : 0.0;
+                const double e2 = (il < Pc) ? exp_neg_bf(lwr - m2w) : 0.0;
+                const double s1 = warp_scan_incl(e1, lane), s2 = warp_scan_incl(e2, lane);
+                if (il < Pc) { b1[il] = s1; b2[il] = s2; }
+                if (lane == 31) {
+                    double* up = unit + (size_t)(q * NW + warp) * 4;
+                    up[0] = m1w; up[1] = s1; up[2] = m2w; up[3] = s2;
+                }
+            } else if (lane == 31) {
+                double* up = unit + (size_t)(q * NW + warp) * 4;
+                up[0] = -INFINITY; up[1] = 0.0; up[2] = -INFINITY; up[3] = 0.0;
             }
         }
-        tmax1 = warp_max(tmax1);
-        tmax2 = warp_max(tmax2);
-        if (lane == 0) { wtmax[warp * 2] = tmax1; wtmax[warp * 2 + 1] = tmax2; }
         __syncthreads();
-        double m1c = wtmax[0], m2c = wtmax[1];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) { m1c = fmax(m1c, wtmax[w * 2]); m2c = fmax(m2c, wtmax[w * 2 + 1]); }
 
-        // ---- A2: exp and CTA-wide inclusive scan in particle order (softmax numerators, src/PGAS.py:102,118)
-        double carry1 = 0.0, carry2 = 0.0;
-        for (int q = 0; q < PPT; ++q) {
-            const int il = q * NT + tid;
-            const bool v = il < Pc;
-            const double e1 = v ? exp(b1[il] - m1c) : 0.0;
-            const double e2 = v ? exp(b2[il] - m2c) : 0.0;
-            const double s1 = warp_scan_incl(e1, lane), s2 = warp_scan_incl(e2, lane);
-            double* wt = wtscan + (q & 1) * NW * 2;
-            if (lane == 31) { wt[warp * 2] = s1; wt[warp * 2 + 1] = s2; }
-            __syncthreads();
-            double run1 = carry1, run2 = carry2, my1 = 0.0, my2 = 0.0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                if (w == warp) { my1 = run1; my2 = run2; }
-                run1 += wt[w * 2];
-                run2 += wt[w * 2 + 1];
+        // ---- X1: warp 0 folds the warp pairs into the CTA pair; all-gather across the cluster; fold again
+        const int c_last = (N - 1) / P;                       // CTA owning particle N-1 (later CTAs are empty)
+        const int U = PPT * NW;
+        double m1c = 0.0, m2c = 0.0, s1c = 0.0, s2c = 0.0;
+        if (warp == 0) {
+            m1c = -INFINITY; m2c = -INFINITY;
+            for (int u = lane; u < U; u += 32) { m1c = fmax(m1c, unit[u * 4]); m2c = fmax(m2c, unit[u * 4 + 2]); }
+            m1c = warp_max(m1c);
+            m2c = warp_max(m2c);
+            for (int u0 = 0; u0 < U; u0 += 32) {
+                const int u = u0 + lane;
+                const bool vu = u < U;
+                const double mu1 = vu ? unit[u * 4] : -INFINITY, mu2 = vu ? unit[u * 4 + 2] : -INFINITY;
+                const double f1 = (mu1 == -INFINITY) ? 0.0 : exp_neg_bf(mu1 - m1c);
+                const double f2 = (mu2 == -INFINITY) ? 0.0 : exp_neg_bf(mu2 - m2c);
+                const double v1 = vu ? __dmul_rn(unit[u * 4 + 1], f1) : 0.0, v2 = vu ? __dmul_rn(unit[u * 4 + 3], f2) : 0.0;
+                // exclusive prefix in unit order with the same association the particles use (G + s f)
+                double i1 = warp_scan_incl(v1, lane), i2 = warp_scan_incl(v2, lane);
+                double x1 = __shfl_up_sync(0xffffffffu, i1, 1), x2 = __shfl_up_sync(0xffffffffu, i2, 1);
+                x1 = (lane == 0) ? s1c : __dadd_rn(s1c, x1);
+                x2 = (lane == 0) ? s2c : __dadd_rn(s2c, x2);
+                if (vu) {
+                    double* fp = ufac + (size_t)u * 4;
+                    fp[0] = f1; fp[1] = x1; fp[2] = f2; fp[3] = x2;
+                }
+                // carry = exclusive prefix of the last lane + its value (what its last particle computes)
+                s1c = __shfl_sync(0xffffffffu, __dadd_rn(x1, v1), 31);
+                s2c = __shfl_sync(0xffffffffu, __dadd_rn(x2, v2), 31);
             }
-            carry1 = run1;
-            carry2 = run2;
-            if (v) { b1[il] = my1 + s1; b2[il] = my2 + s2; }
+            if (C > 1) {
+                if (lane < C) {
+                    double* dst = cluster.map_shared_rank(exch, lane) + rank * 4;
+                    dst[0] = m1c; dst[1] = s1c; dst[2] = m2c; dst[3] = s2c;
+                }
+            } else if (lane == 0) {
+                exch[0] = m1c; exch[1] = s1c; exch[2] = m2c; exch[3] = s2c;
+            }
+            __syncwarp();
         }
-
-        // ---- X1: all-gather (m1c, s1c, m2c, s2c) across the cluster
         if (C > 1) {
-            if (tid < C) {
-                double* dst = cluster.map_shared_rank(exch, tid) + rank * 4;
-                dst[0] = m1c; dst[1] = carry1; dst[2] = m2c; dst[3] = carry2;
-            }
             cluster_arrive();
             cluster_wait();
-        } else {
-            if (tid == 0) { exch[0] = m1c; exch[1] = carry1; exch[2] = m2c; exch[3] = carry2; }
-            __syncthreads();
         }
-
-        // ---- B1: global normalisers and this CTA's CDF segment (warp 0 reduces the C pairs once)
-        const int c_last = (N - 1) / P;                       // CTA owning particle N-1 (later CTAs are empty)
         if (warp == 0) {
             const bool vc = lane < C;
             const double mc1 = vc ? exch[lane * 4] : -INFINITY, mc2 = vc ? exch[lane * 4 + 2] : -INFINITY;
             const double M1 = warp_max(mc1), M2 = warp_max(mc2);
+            const double f1 = (mc1 == -INFINITY) ? 0.0 : exp_neg_bf(mc1 - M1);
+            const double f2 = (mc2 == -INFINITY) ? 0.0 : exp_neg_bf(mc2 - M2);
+            const double v1 = vc ? exch[lane * 4 + 1] * f1 : 0.0, v2 = vc ? exch[lane * 4 + 3] * f2 : 0.0;
+            // every CTA of the cluster runs the same shuffle tree on the same data -> identical bits
+            const double i1 = warp_scan_incl(v1, lane), i2 = warp_scan_incl(v2, lane);
+            const double r1 = rcp_bf(__shfl_sync(0xffffffffu, i1, 31)), r2 = rcp_bf(__shfl_sync(0xffffffffu, i2, 31));
+            // CTA holding the reference ancestor: number of leading CTAs whose whole CDF segment lies below u_anc
+            const unsigned below = __ballot_sync(0xffffffffu, lane <= c_last && __dmul_rn(i2, r2) < k_t.uanc);
             if (vc) {
-                fx[lane * 2] = (mc1 == -INFINITY) ? 0.0 : exp(mc1 - M1);
-                fx[lane * 2 + 1] = (mc2 == -INFINITY) ? 0.0 : exp(mc2 - M2);
+                fx[lane * 2] = f1;
+                fx[lane * 2 + 1] = f2;
+                gsum[(lane + 1) * 2] = i1;
+                gsum[(lane + 1) * 2 + 1] = i2;
             }
-            __syncwarp();
             if (lane == 0) {
-                double g1 = 0.0, g2 = 0.0;
-                for (int c = 0; c < C; ++c) {                 // fixed order: every CTA of the cluster gets identical bits
-                    gsum[c * 2] = g1;
-                    gsum[c * 2 + 1] = g2;
-                    g1 = __fma_rn(exch[c * 4 + 1], fx[c * 2], g1);
-                    g2 = __fma_rn(exch[c * 4 + 3], fx[c * 2 + 1], g2);
-                }
-                gsum[C * 2] = g1;
-                gsum[C * 2 + 1] = g2;
-                const double r1 = 1.0 / g1, r2 = 1.0 / g2;
+                gsum[0] = 0.0;
+                gsum[1] = 0.0;
                 fx[2 * MAXC] = r1;
                 fx[2 * MAXC + 1] = r2;
-                // CTA holding the reference ancestor: number of leading CTAs whose whole CDF segment lies below u_anc
-                int cs = 0;
-                while (cs <= c_last && __dmul_rn(gsum[(cs + 1) * 2 + 1], r2) < k_t.uanc) ++cs;
-                cnt[1] = cs;
+                cnt[1] = __popc(below);
             }
         }
         if (tid == 0 && t + 1 < a.t_end) sc[(t + 1) & 1] = nxt;
@@ -357,10 +405,14 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
         for (int q = 0; q < PPT; ++q) {
             const int il = q * NT + tid;
             if (il < Pc) {
+                const double* fp = ufac + (size_t)(q * NW + warp) * 4;
+                // CTA-level inclusive prefix of this particle: G_unit + s_i f_unit
+                const double p1 = __dadd_rn(fp[1], __dmul_rn(b1[il], fp[0]));
+                const double p2 = __dadd_rn(fp[3], __dmul_rn(b2[il], fp[2]));
                 // W = clip(cumsum(w / sum w), 0, 1)  (src/Filtering.py:23-32)
-                b1[il] = clip01(cdf_value(b1[il], myf1, myg1, S1));
+                b1[il] = clip01(cdf_value(p1, myf1, myg1, S1));
                 // cumsum(softmax(lw_anc)) < u_anc  (src/PGAS.py:118-124), not clipped
-                if (rank == cstar) mycnt += (cdf_value(b2[il], myf2, myg2, S2) < k_t.uanc) ? 1 : 0;
+                if (rank == cstar) mycnt += (cdf_value(p2, myf2, myg2, S2) < k_t.uanc) ? 1 : 0;
             }
         }
         if (rank == cstar) {
@@ -372,19 +424,14 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
         // ---- B2: systematic resampling (src/Filtering.py:28-35) by the owner of the CDF segment
         {
             const double blo = clip01(__dmul_rn(myg1, S1)), bhi = clip01(__dmul_rn(g1hi, S1));
-            const int jlo = (rank == 0) ? 0 : first_point_above(blo, k_t.ures, N, dN);
-            int jhi = (rank == c_last) ? N : first_point_above(bhi, k_t.ures, N, dN);
+            const int jlo = (rank == 0) ? 0 : first_point_above(blo, k_t.ures, N, dN, rN);
+            int jhi = (rank == c_last) ? N : first_point_above(bhi, k_t.ures, N, dN, rN);
             if (rank > c_last) jhi = jlo;                     // empty CTA
             int* anc_row = a.anc_trace + ((size_t)chain * a.anc_rows + (t - 1 - a.row_off + a.anc_shift)) * N;
             for (int j = jlo + tid; j < jhi; j += NT) {
                 if (j == N - 1) continue;                     // overwritten by the reference ancestor (:127)
-                const double uj = strat_point(k_t.ures, j, dN);
-                int lo = 0, hi = Pc;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (b1[mid] < uj) lo = mid + 1; else hi = mid;
-                }
-                const int k = min(lo, Pc - 1);
+                const double uj = strat_point(k_t.ures, j, dN, rN);
+                const int k = min(count_below_padded(b1, nblk, uj), Pc - 1);
                 anc_row[j] = base + k;
                 const int cj = j / P, jl = j - cj * P;
                 double* dl = (C > 1 && cj != rank) ? cluster.map_shared_rank(lauxg, cj) : lauxg;
@@ -467,15 +514,26 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------ launch
-static size_t sweep_smem_bytes(const DevModel& m, int NX, int P, bool gather) {
-    size_t d = (((size_t)m.n_packed * NX + 1) & ~(size_t)1) + (size_t)NX * P * 2 + (size_t)P * 5 + (gather ? (size_t)NX * P : 0) +
-               MAXC * 4 + 2 * (MAXC + 1) + 2 * MAXC + 2 + NW * 2 + 2 * NW * 2 + 2 * NX * NX + 2 + 2 * ((sizeof(StepConst) + 7) / 8);
-    return d * 8 + (size_t)(m.n_chunks + 2) * 4 + 16;
+static size_t sweep_smem_bytes(const DevModel& m, int NX, int P, bool gather, int NT) {
+    const int NW = NT / 32;
+    size_t d = (size_t)m.n_packed + (size_t)NW * sine_tile_doubles(m) + (size_t)NX * P * 2 + (size_t)P * 4 + (size_t)((P + 255) / 256) * 256 +
+               (gather ? (size_t)NX * P : 0) + MAXC * 4 + 2 * (MAXC + 1) + 2 * MAXC + 2 + (size_t)((P + NT - 1) / NT) * NW * 8 + 2 * NX * NX + 2 +
+               2 * ((sizeof(StepConst) + 7) / 8);
+    return d * 8 + (size_t)(((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD + 2) * 4 + 32;
 }
 
-template <int NX, int NY, int D, int JMAX>
+// threads per CTA: 512 (16 warps hide the dependent-FP64 latency best) when the per-warp sine tiles
+// still fit shared memory, else 256
+static int sweep_threads(const DevModel& m, int P) {
+    const bool gather = (m.flags & PGAS_FLAG_ANCESTOR_GATHER) != 0;
+    return (sweep_smem_bytes(m, m.n_x, P, gather, 512) <= 227 * 1024 && P > 128) ? 512 : 256;
+}
+
+static int* g_query_clusters = nullptr;      // debug: when set, launch_variant reports occupancy instead of launching
+
+template <int NX, int NY, int D, int NT>
 static int launch_variant(const SweepArgs& a, size_t smem, cudaStream_t stream) {
-    auto kern = csmc_sweep_kernel<NX, NY, D, JMAX>;
+    auto kern = csmc_sweep_kernel<NX, NY, D, NT>;
     PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (a.C > 8) PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
@@ -490,27 +548,24 @@ static int launch_variant(const SweepArgs& a, size_t smem, cudaStream_t stream) 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (g_query_clusters) {
+        PGAS_CUDA(cudaOccupancyMaxActiveClusters(g_query_clusters, kern, &cfg));
+        return 0;
+    }
     PGAS_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     return 0;
-}
-
-template <int NX, int NY, int D>
-static int launch_jmax(const SweepArgs& a, size_t smem, cudaStream_t stream) {
-    const int j = a.m.jmax;
-    if (j <= 12) return launch_variant<NX, NY, D, 12>(a, smem, stream);
-    if (j <= 20) return launch_variant<NX, NY, D, 20>(a, smem, stream);
-    if (j <= 40) return launch_variant<NX, NY, D, 40>(a, smem, stream);
-    PGAS_FAIL(-20, "basis needs %d lattice positions in its last dimension; this build supports <= 40", j);
 }
 
 int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
     const DevModel& m = a.m;
     const bool gather = (m.flags & PGAS_FLAG_ANCESTOR_GATHER) != 0;
-    const size_t smem = sweep_smem_bytes(m, m.n_x, a.P, gather);
+    const int nt = sweep_threads(m, a.P);
+    const size_t smem = sweep_smem_bytes(m, m.n_x, a.P, gather, nt);
     if (smem > 227 * 1024)
         PGAS_FAIL(-21, "sweep needs %zu bytes of shared memory per CTA (N=%d over a cluster of %d); use a larger cluster", smem, a.N, a.C);
 #define PGAS_DISPATCH(NXv, NYv, Dv) \
-    if (m.n_x == NXv && m.n_y == NYv && m.D == Dv) return launch_jmax<NXv, NYv, Dv>(a, smem, stream);
+    if (m.n_x == NXv && m.n_y == NYv && m.D == Dv)            \
+        return nt == 512 ? launch_variant<NXv, NYv, Dv, 512>(a, smem, stream) : launch_variant<NXv, NYv, Dv, 256>(a, smem, stream);
     PGAS_DISPATCH(1, 1, 1)
     PGAS_DISPATCH(2, 1, 1)
     PGAS_DISPATCH(2, 1, 2)
@@ -522,19 +577,35 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
 }
 
 size_t pgas_sweep_smem_for(const DevModel& m, int P) {
-    return sweep_smem_bytes(m, m.n_x, P, (m.flags & PGAS_FLAG_ANCESTOR_GATHER) != 0);
+    return sweep_smem_bytes(m, m.n_x, P, (m.flags & PGAS_FLAG_ANCESTOR_GATHER) != 0, sweep_threads(m, P));
 }
 
-// choose the cluster size: the smallest power of two whose per-CTA particle slice fits shared
-// memory, then grown while the whole launch still fits the GPU (chains * C <= #SM) so that few
-// chains still spread over many SMs.
+// choose the cluster size: the largest power of two such that (i) every chain's cluster is resident
+// at once — the number of co-resident clusters measured on B200 with cudaOccupancyMaxActiveClusters is
+// 148 / 74 / 33 / 15 / 7 for sizes 1 / 2 / 4 / 8 / 16 (GPC granularity; profiles/r01_microbench.md) —
+// (ii) a CTA keeps at least 128 particles, and (iii) the per-CTA slice fits shared memory.
 int pgas_choose_cluster(const DevModel& m, int N, int n_chains, int requested) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (requested > 0) return requested;
-    int C = 1;
-    while (C < MAXC && pgas_sweep_smem_for(m, (N + C - 1) / C) > 200 * 1024) C *= 2;
-    while (C < MAXC && n_chains * C * 2 <= sms && (N + 2 * C - 1) / (2 * C) >= 64) C *= 2;
-    return C;
+    static const int sizes[5] = {16, 8, 4, 2, 1}, resident[5] = {7, 15, 33, 74, 148};
+    int fallback = MAXC;
+    for (int i = 0; i < 5; ++i) {
+        const int C = sizes[i], P = (N + C - 1) / C;
+        if (pgas_sweep_smem_for(m, P) > 227 * 1024) break;           // smaller clusters only need more
+        fallback = C;
+        if (n_chains <= resident[i] && (P >= 128 || C == 1)) return C;
+    }
+    return fallback;                                                 // more chains than SMs: smallest cluster that fits
+}
+
+// how many clusters of `cluster_size` CTAs of the sweep kernel the device can hold at once
+extern "C" int pgas_debug_max_active_clusters(const pgas_model* model, int32_t N, int32_t cluster_size) {
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = model->dev;
+    a.N = N; a.n_chains = 1; a.C = cluster_size; a.P = (N + cluster_size - 1) / cluster_size;
+    int n = -1;
+    g_query_clusters = &n;
+    const int rc = pgas_launch_sweep(a, 0);
+    g_query_clusters = nullptr;
+    return rc ? -rc : n;
 }

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(BT) resample_kernel(const double* __restrict__
     const double* w = w_in + (size_t)set * N;
     const double u = u_in[set];
     double sm = 0.0;
-    for (int i = tid; i < N; i += BT) sm += fmin(fmax(w[i], 0.0), INFINITY);
+    for (int i = tid; i < N; i += BT) sm += (w[i] != w[i]) ? w[i] : fmax(w[i], 0.0);      // clip keeps NaN (jnp.clip)
     sm = warp_sum(sm);
     if (lane == 0) red[warp] = sm;
     __syncthreads();
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(BT) resample_kernel(const double* __restrict__
     for (int i0 = 0; i0 < N; i0 += BT, ++q) {
         const int i = i0 + tid;
         double e = 0.0;
-        if (i < N) e = ok ? __ddiv_rn(fmin(fmax(w[i], 0.0), INFINITY), sm) : __ddiv_rn(1.0, dN);
+        if (i < N) e = ok ? __ddiv_rn(fmax(w[i], 0.0), sm) : __ddiv_rn(1.0, dN);
         const double s = warp_scan_incl(e, lane);
         if (lane == 31) wt[q & 1][warp] = s;
         __syncthreads();
@@ -229,7 +229,7 @@ static int fill_rng(SweepArgs& a, const pgas_rng* rng) {
 }
 
 static int check_cluster(int C, int N) {
-    if (C != 1 && C != 2 && C != 4 && C != 8 && C != 16) PGAS_FAIL(-2, "cluster_size must be 0 (auto), 1, 2, 4, 8 or 16 (got %d)", C);
+    if (C < 1 || C > 16) PGAS_FAIL(-2, "cluster_size must be 0 (auto) or 1..16 (got %d)", C);
     if (N < 2) PGAS_FAIL(-2, "need at least 2 particles (N=%d)", N);
     return 0;
 }

@@ -99,7 +99,7 @@ def test_basis_large_lattices(built_lib):
 def test_step_parity_teacher_forced(built_lib, kind, N, cluster):
     p = helpers.make_problem(kind, T=12, N=N, seed=N + cluster)
     r = helpers.run_step_parity(p, n_steps=8, cluster_size=cluster)
-    assert r["ok"], r
+    assert r["ok"], str(r)
 
 
 @pytest.mark.parametrize("flags", [1, 2, 3])
@@ -118,7 +118,7 @@ def test_step_parity_quirk_flags(built_lib, flags):
 def test_sweep_parity_injected(built_lib, kind, N, T, cluster):
     p = helpers.make_problem(kind, T=T, N=N, seed=T)
     r = helpers.run_sweep_parity(p, cluster_size=cluster)
-    assert r["ok"], r
+    assert r["ok"], str(r)
     assert r["rows_compared"] >= 1
 
 
@@ -126,7 +126,7 @@ def test_sweep_gather_mode(built_lib):
     p = helpers.make_problem("smo", T=30, N=384, seed=4, flags=1)
     for cluster in (1, 2):
         r = helpers.run_sweep_parity(p, cluster_size=cluster)
-        assert r["ok"], r
+        assert r["ok"], str(r)
 
 
 def test_sweep_philox_stream_matches_restatement(built_lib):
@@ -146,7 +146,7 @@ def test_sweep_philox_stream_matches_restatement(built_lib):
     assert np.max(np.abs(Z[0].cpu().numpy() - Zo)) < 1e-13              # log/sincos differ in the last ulps
     p = helpers.make_problem("smo", T=T, N=N, seed=2)
     r = helpers.run_sweep_parity(p, cluster_size=1, philox_seed=seed)
-    assert r["ok"], r
+    assert r["ok"], str(r)
 
 
 def test_chain_ids_give_identical_results_regardless_of_batching(built_lib):
@@ -171,13 +171,13 @@ def test_chain_ids_give_identical_results_regardless_of_batching(built_lib):
 def test_suffstats_and_draw_parity(built_lib, kind, M, T):
     p = helpers.make_problem(kind, T=T, N=32, M=M, seed=M)
     r = helpers.run_draw_parity(p)
-    assert r["ok"], r
+    assert r["ok"], str(r)
 
 
 def test_draw_transpose_flag(built_lib):
     p = helpers.make_problem("smo", T=50, N=32, M=41, seed=1, flags=4)
     r = helpers.run_draw_parity(p)
-    assert r["ok"], r
+    assert r["ok"], str(r)
 
 
 def test_draw_philox_stream(built_lib):
@@ -224,14 +224,31 @@ def test_run_chains_matches_oracle(built_lib, kind, cluster):
     st_o, ll_o, A_o, S_o = OP.pgas_run(p["omodel"], N, K, p["prior"], p["ref"],
                                        lambda k: {n: V[n][k, 0] for n in V})
     st_g = out["state_trace"][0].cpu().numpy()            # (K,T,n_x)
-    # iteration 0 (initial reference + first draw) must match to tolerance; later iterations match
-    # as long as no CDF tie flipped an index (checked by the sweep tests), so compare with a looser
-    # bound that still catches any structural error
-    assert helpers.rel_err(out["A_trace"][0, 0].cpu().numpy(), A_o[0]) < helpers.REL_TOL
-    assert helpers.rel_err(out["S_trace"][0, 0].cpu().numpy(), S_o[0]) < helpers.REL_TOL
     assert np.array_equal(st_g[0], p["ref"])
-    assert helpers.rel_err(st_g, np.swapaxes(st_o, 0, 1)) < 1e-7
-    assert helpers.rel_err(out["A_trace"][0].cpu().numpy(), A_o) < 1e-6
+    # Iteration k is compared as long as iteration k-1 agreed: the Gibbs chain feeds each sweep the previous
+    # draw, and the sampled dynamics Theta^(k) are not contractive in general, so rounding-level differences
+    # (or one flipped CDF tie) legitimately grow from one iteration to the next.  Every sweep / draw is
+    # additionally replayed from the ORACLE's previous iterate, which isolates each call of the loop.
+    cs = pg.cSMC
+    agreed = 0
+    for k in range(K):
+        if k >= 1:
+            sw = cs.sweep(_dev(st_o[:, k - 1]), _dev(A_o[k - 1]), _dev(S_o[k - 1]),
+                          variates=dict(Z=_dev(V["Z"][k]), U=_dev(V["U"][k])))
+            o = OP.csmc_sweep(p["omodel"], N, st_o[:, k - 1], A_o[k - 1], S_o[k - 1], V["Z"][k, 0], V["U"][k, 0])
+            assert np.array_equal(sw["anc_trace"][0].cpu().numpy(), o["anc_trace"]), k
+            assert int(sw["idx"][0]) == o["idx"], k
+            assert helpers.rel_err(sw["state_trace"][0, 1].cpu().numpy(), o["state_trace"][1]) < helpers.REL_TOL, k
+        A_g, S_g = pg.sample_params(None, _dev(st_o[:, k][None]),
+                                    variates=dict(chi2=_dev(V["chi2"][k]), G=_dev(V["G"][k]), Nrm=_dev(V["Nrm"][k])))
+        assert helpers.rel_err(A_g[0].cpu().numpy(), A_o[k]) < helpers.REL_TOL, k
+        assert helpers.rel_err(S_g[0].cpu().numpy(), S_o[k]) < helpers.REL_TOL, k
+        if agreed == k and helpers.rel_err(st_g[k], st_o[:, k]) < 1e-7 and \
+                helpers.rel_err(out["A_trace"][0, k].cpu().numpy(), A_o[k]) < 1e-7:
+            agreed = k + 1
+    assert agreed >= 2, agreed                 # initial draw and the first full Gibbs iteration
+    if kind == "smo":
+        assert agreed == K, agreed             # contractive synthetic dynamics: the whole run agrees
 
 
 def test_pgas_reference_call_signature(built_lib):

@@ -58,7 +58,13 @@ def time_sweep(kind, N, T, M, n_chains, cluster, reps=3):
                 particle_steps_per_s=ps, alg_tflops=ps * (2 * p["M"] * 2 + p["M"] * 2) / 1e12, finite=bool(torch.isfinite(st).all()))
 
 
-for cfg in [("smo", 4096, 201, 256, 8, 16), ("smo", 4096, 201, 256, 8, 8), ("smo", 4096, 201, 256, 16, 8), ("smo", 4096, 201, 256, 37, 4),
+pp = helpers.make_problem("smo", T=5, N=4096, M=256, seed=1)
+csq = helpers.product_csmc(pp, 16)
+lib.pgas_debug_max_active_clusters.restype = C.c_int
+lib.pgas_debug_max_active_clusters.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+print(json.dumps({"max_active_clusters": {c: lib.pgas_debug_max_active_clusters(csq.model.handle, 4096, c) for c in range(2, 17)}}), flush=True)
+
+for cfg in [("smo", 4096, 201, 256, 1, 16), ("smo", 4096, 201, 256, 4, 16), ("smo", 4096, 201, 256, 8, 16), ("smo", 4096, 201, 256, 8, 8), ("smo", 4096, 201, 256, 16, 8), ("smo", 4096, 201, 256, 37, 4),
             ("smo", 4096, 201, 256, 74, 2), ("smo", 2048, 201, 256, 148, 1), ("smo", 200, 751, 41, 1, 1), ("smo", 200, 751, 41, 148, 1),
             ("vehicle", 16384, 101, 1024, 8, 16), ("vehicle", 16384, 101, 1024, 9, 16)]:
     print(json.dumps(time_sweep(*cfg)), flush=True)
