@@ -109,6 +109,7 @@ EXPORTS = {
     "pgas_last_error": (C.c_char_p, []),
     "pgas_version": (C.c_int, []),
     "pgas_device_count": (C.c_int, []),
+    "pgas_launch_count": (C.c_longlong, []),
     "pgas_model_create": (C.c_int, [C.POINTER(ModelParams), C.POINTER(C.c_void_p)]),
     "pgas_model_destroy": (C.c_int, [C.c_void_p]),
     "pgas_model_jmax": (C.c_int, [C.c_void_p]),

@@ -14,7 +14,9 @@ void pgas_set_error(const char* fmt, ...);
 #define PGAS_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
     pgas_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
     return (int)e__; } } while (0)
-#define PGAS_KERNEL_CHECK() PGAS_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this (bench.py reports the count: pgas_launch_count)
+extern long long g_pgas_launches;
+#define PGAS_KERNEL_CHECK() do { __atomic_add_fetch(&g_pgas_launches, 1, __ATOMIC_RELAXED); PGAS_CUDA(cudaGetLastError()); } while (0)
 
 // ---------------------------------------------------------------------------------- model
 // Tensor-product layout of the Hilbert basis for the FP64 tensor-core contraction (DESIGN.md

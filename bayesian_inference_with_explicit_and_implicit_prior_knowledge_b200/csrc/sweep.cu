@@ -553,6 +553,7 @@ static int launch_variant(const SweepArgs& a, size_t smem, cudaStream_t stream) 
         return 0;
     }
     PGAS_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    __atomic_add_fetch(&g_pgas_launches, 1, __ATOMIC_RELAXED);
     return 0;
 }
 

@@ -93,6 +93,8 @@ typedef struct pgas_rng {
 const char* pgas_last_error(void);
 int pgas_version(void);
 int pgas_device_count(void);
+/* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */
+long long pgas_launch_count(void);
 
 /* condSequentialMonteCarlo.__init__ (src/PGAS.py:24-43) + generate_Hilbert_BasisFunction's closure
  * (src/BasisFunctions.py:63-66): uploads tables/data, builds the packed tensor-product row layout. */
