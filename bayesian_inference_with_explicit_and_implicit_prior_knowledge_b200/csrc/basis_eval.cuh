@@ -31,9 +31,9 @@ __device__ __forceinline__ void sine_seed(double t, int f_start, int f_step, dou
     }
 }
 
-constexpr int HALF = 16;        // particles per shared sine tile (half a warp)
-constexpr int TILE_PS = 24;     // tile row pitch in doubles: 24 = 8 mod 16 keeps the 4x8 fragment reads conflict-free
-constexpr int NTB = 5;          // column tiles accumulated per pass (accumulators: 2 groups x NTB x 2 doubles)
+constexpr int QUART = 8;        // particles per shared sine tile (one DMMA fragment row group)
+constexpr int TILE_PS = 8;      // tile row pitch in doubles: a 4x8 fragment read covers 256 contiguous bytes
+constexpr int NTB = 5;          // column tiles accumulated per pass (accumulators: NTB x 2 doubles)
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -48,13 +48,17 @@ __host__ __device__ __forceinline__ int sine_tile_doubles(const DevModel& m) {
 
 // Warp-cooperative auxiliary mean for the warp's 32 particles (lane i owns particle il0 + i):
 //   mu_k(p) = sum_r lead[p,r] (S B)[p, r n_x + k]      (see common.cuh)
-// Each lane builds its particle's sine tables with the 3-term recurrence and parks them in the
-// warp's shared tile (two passes of 16 particles); the contraction over the last dimension runs
-// on the FP64 tensor pipe (mma.sync m8n8k4: A = sines, B = Theta' fragments from shared memory),
-// the per-row scaling and the 4-lane reduction finish it.  Row leaders (lane%4 == 0) write
-// mu to mus[k*P + particle]; after the closing __syncwarp every owner can read its own entry.
+// Four passes of 8 particles.  In a pass all 32 lanes build the sine tables of those 8 particles in
+// the warp's shared tile: lane L serves particle 8h + (L & 7), dimension group (L >> 3) & 1 (last /
+// leading), position parity L >> 4, each running the 3-term recurrence with stride 2,
+//   s[j+2] = (2cos(2 theta)) s[j] - s[j-2],   2cos(2 theta) = (2cos theta)^2 - 2,
+// from seeds fetched by shuffle from the owner lane.  The contraction over the last dimension runs
+// on the FP64 tensor pipe (mma.sync m8n8k4: A = sines, B = Theta' fragments from shared memory);
+// the per-row scaling and a 4-lane reduction finish it.  Row leaders (lane%4 == 0) write mu to
+// mus[k*P + particle]; after the closing __syncwarp every owner can read its own entry.
 template <int NX, int D>
-__device__ __forceinline__ void eval_mu_warp(const DevModel& m, const double* __restrict__ bfrag, const int* __restrict__ rowpos, double* __restrict__ tile, const double tz[D],
+__device__ __forceinline__ void eval_mu_warp(const DevModel& m, const double* __restrict__ bfrag, const int* __restrict__ rowpos,
+                                             double* __restrict__ tile, const double tz[D],
                                              int lane, double* __restrict__ mus, int P, int il0) {
     const int q = lane & 3, r = lane >> 2;
     const int KS = m.KS, NTNP = m.NTNP;
@@ -69,50 +73,54 @@ __device__ __forceinline__ void eval_mu_warp(const DevModel& m, const double* __
     double cur0[D], prev0[D], twoc[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) sine_seed(tz[d], m.f_start, m.f_step, cur0[d], prev0[d], twoc[d]);
+    const int dsel = (lane >> 3) & 1, par = lane >> 4;
 
-    for (int h = 0; h < 2; ++h) {
-        // ---- sines of this half's 16 particles -> tile[dim][pos][16]
-        if ((lane >> 4) == h) {
+    for (int h = 0; h < 4; ++h) {
+        // ---- sines of this pass's 8 particles -> tile[dim][pos][8]
+        {
+            const int src = QUART * h + (lane & 7);
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                const int np = (d == D - 1) ? m.jmax : m.npos_d[d];
-                double* col = tile + (size_t)dim_off[d] * TILE_PS + (lane & 15);
-                double cur = cur0[d], prev = prev0[d];
-                for (int p = 0; p < np; ++p) {
-                    col[(size_t)p * TILE_PS] = cur;
-                    const double n = fma(twoc[d], cur, -prev);
-                    prev = cur; cur = n;
+                const double c = __shfl_sync(0xffffffffu, cur0[d], src), pv = __shfl_sync(0xffffffffu, prev0[d], src);
+                const double tc = __shfl_sync(0xffffffffu, twoc[d], src);
+                const bool mine = (D == 1) ? (dsel == 0) : ((d == D - 1) == (dsel == 0));
+                if (mine) {
+                    const int np = (d == D - 1) ? m.jmax : m.npos_d[d];
+                    double* col = tile + (size_t)dim_off[d] * TILE_PS + (lane & 7);
+                    const double tc2 = fma(tc, tc, -2.0);
+                    double cur = par ? fma(tc, c, -pv) : c;            // s[1] : s[0]
+                    double prev = par ? pv : fma(tc, pv, -c);          // s[-1] : s[-2]
+                    for (int p = par; p < np; p += 2) {
+                        col[(size_t)p * TILE_PS] = cur;
+                        const double n = fma(tc2, cur, -prev);
+                        prev = cur; cur = n;
+                    }
                 }
             }
         }
         __syncwarp();
-        double mup[2][NX];
+        double mup[NX];
 #pragma unroll
-        for (int g = 0; g < 2; ++g)
-#pragma unroll
-            for (int k = 0; k < NX; ++k) mup[g][k] = 0.0;
+        for (int k = 0; k < NX; ++k) mup[k] = 0.0;
 
         for (int nb = 0; nb < NTNP; nb += NTB) {
-            double acc[2][NTB][2];
+            double acc[NTB][2];
 #pragma unroll
-            for (int g = 0; g < 2; ++g)
-#pragma unroll
-                for (int j = 0; j < NTB; ++j) { acc[g][j][0] = 0.0; acc[g][j][1] = 0.0; }
+            for (int j = 0; j < NTB; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
             for (int ks = 0; ks < KS; ++ks) {
                 const int ntc = m.ntcount[ks] - nb;           // kernel-parameter data: warp-uniform
                 if (ntc <= 0) continue;
-                const double* arow = tile + (size_t)(4 * ks + q) * TILE_PS + r;
-                const double a0 = arow[0], a1 = arow[8];
+                const double a0 = tile[(size_t)(4 * ks + q) * TILE_PS + r];
                 const double* bp = bfrag + ((size_t)ks * NTNP + nb) * 32 + lane;
                 double bv[NTB];
 #pragma unroll
                 for (int j = 0; j < NTB; ++j) bv[j] = bp[j * 32];   // tiles past ntcount hold zeros: always loadable
-#pragma unroll
-                for (int j = 0; j < NTB; ++j) {
-                    if (j < ntc) {
-                        dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, bv[j]);
-                        dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, bv[j]);
-                    }
+                switch (ntc) {                                   // warp-uniform: straight-line DMMAs, no predication
+                    default: dmma_m8n8k4(acc[4][0], acc[4][1], a0, bv[4]);
+                    case 4: dmma_m8n8k4(acc[3][0], acc[3][1], a0, bv[3]);
+                    case 3: dmma_m8n8k4(acc[2][0], acc[2][1], a0, bv[2]);
+                    case 2: dmma_m8n8k4(acc[1][0], acc[1][1], a0, bv[1]);
+                    case 1: dmma_m8n8k4(acc[0][0], acc[0][1], a0, bv[0]);
                 }
             }
             // ---- per-row scaling by the leading-dimension sines (padding rows have zero accumulators)
@@ -123,40 +131,29 @@ __device__ __forceinline__ void eval_mu_warp(const DevModel& m, const double* __
                 for (int e = 0; e < 2; ++e) {
                     if (NX == 2 && e == 1) break;               // both columns of the pair belong to one row
                     const int row = (c0 + e) / NX;
-                    double lead0 = 1.0, lead1 = 1.0;
+                    double lead = 1.0;
 #pragma unroll
-                    for (int d = 0; d + 1 < D; ++d) {
-                        const double* lp = tile + (size_t)(dim_off[d] + rowpos[row * MAX_LEAD + d]) * TILE_PS + r;
-                        lead0 *= lp[0];
-                        lead1 *= lp[8];
-                    }
+                    for (int d = 0; d + 1 < D; ++d) lead *= tile[(size_t)(dim_off[d] + rowpos[row * MAX_LEAD + d]) * TILE_PS + r];
                     if constexpr (NX == 2) {
-                        mup[0][0] = fma(lead0, acc[0][j][0], mup[0][0]);
-                        mup[0][1] = fma(lead0, acc[0][j][1], mup[0][1]);
-                        mup[1][0] = fma(lead1, acc[1][j][0], mup[1][0]);
-                        mup[1][1] = fma(lead1, acc[1][j][1], mup[1][1]);
+                        mup[0] = fma(lead, acc[j][0], mup[0]);
+                        mup[1] = fma(lead, acc[j][1], mup[1]);
                     } else {
                         const int k = (c0 + e) - row * NX;
 #pragma unroll
-                        for (int kk = 0; kk < NX; ++kk) {
-                            mup[0][kk] = fma((kk == k) ? lead0 : 0.0, acc[0][j][e], mup[0][kk]);
-                            mup[1][kk] = fma((kk == k) ? lead1 : 0.0, acc[1][j][e], mup[1][kk]);
-                        }
+                        for (int kk = 0; kk < NX; ++kk) mup[kk] = fma((kk == k) ? lead : 0.0, acc[j][e], mup[kk]);
                     }
                 }
             }
         }
         // ---- reduce over the 4 lanes of a fragment row, row leaders publish
 #pragma unroll
-        for (int g = 0; g < 2; ++g)
-#pragma unroll
-            for (int k = 0; k < NX; ++k) {
-                double v = mup[g][k];
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                const int il = il0 + HALF * h + 8 * g + r;
-                if (q == 0 && il < P) mus[(size_t)k * P + il] = v;
-            }
+        for (int k = 0; k < NX; ++k) {
+            double v = mup[k];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            const int il = il0 + QUART * h + r;
+            if (q == 0 && il < P) mus[(size_t)k * P + il] = v;
+        }
         __syncwarp();
     }
 }

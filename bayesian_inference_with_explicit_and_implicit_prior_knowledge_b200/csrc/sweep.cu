@@ -465,10 +465,11 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
         const bool last_step = (t + 1 == a.t_end);
         constexpr int ZQ = 4;                                 // particles per thread whose noise is drawn under the barrier
         double zreg[ZQ][NX];
+        // the draws of a thread's particles are independent chains (Philox -> log/sqrt/sincospi): issued
+        // back to back without per-lane branches so the scheduler interleaves them (padding lanes draw too)
 #pragma unroll
         for (int q = 0; q < ZQ; ++q) {
-            const int il = q * NT + tid;
-            if (q < PPT && il < Pc) draw_normals<NX>(a, chain, t, base + il, zreg[q]);
+            if (q < PPT) draw_normals<NX>(a, chain, t, min(base + q * NT + tid, N - 1), zreg[q]);
         }
         if (C > 1) cluster_wait();
         double* st_row = a.state_trace + (((size_t)chain * a.trace_rows + (t - a.row_off)) * N) * NX;
