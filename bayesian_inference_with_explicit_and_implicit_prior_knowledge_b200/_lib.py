@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(sp)
                 and os.path.getmtime(obj) > hdr_t):
             return obj
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", sp, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("PGAS_NVCC_EXTRA", "").split() + ["-c", sp, "-o", obj]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         r = subprocess.run(cmd, capture_output=True, text=True)

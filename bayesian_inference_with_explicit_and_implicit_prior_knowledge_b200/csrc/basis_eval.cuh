@@ -31,6 +31,16 @@ __device__ __forceinline__ void sine_seed(double t, int f_start, int f_step, dou
     }
 }
 
+#ifndef PGAS_FINE_TICKS
+#define PGAS_FINE_TICKS 0
+#endif
+#if PGAS_FINE_TICKS
+__device__ long long g_fine[64];
+#define PGAS_FTICK(K) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_fine[K] = clock64(); } while (0)
+#else
+#define PGAS_FTICK(K) do { } while (0)
+#endif
+
 constexpr int QUART = 8;        // particles per shared sine tile (one DMMA fragment row group)
 constexpr int TILE_PS = 8;      // tile row pitch in doubles: a 4x8 fragment read covers 256 contiguous bytes
 constexpr int NTB = 5;          // column tiles accumulated per pass (accumulators: NTB x 2 doubles)
@@ -41,8 +51,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 
 // doubles of shared memory one warp needs for its sine tile
 __host__ __device__ __forceinline__ int sine_tile_doubles(const DevModel& m) {
-    int rows = m.jmax;
-    for (int d = 0; d + 1 < m.D; ++d) rows += m.npos_d[d];
+    int rows = m.jmax + 4;                                   // +4: the A prefetch of the pipelined loop reads one step ahead
+    for (int d = 0; d + 1 < m.D; ++d) rows += (m.npos_d[d] + 3) & ~3;
     return rows * TILE_PS;
 }
 
@@ -58,7 +68,7 @@ __host__ __device__ __forceinline__ int sine_tile_doubles(const DevModel& m) {
 // mus[k*P + particle]; after the closing __syncwarp every owner can read its own entry.
 template <int NX, int D>
 __device__ __forceinline__ void eval_mu_warp(const DevModel& m, const double* __restrict__ bfrag, const int* __restrict__ rowpos,
-                                             double* __restrict__ tile, const double tz[D],
+                                             const int* __restrict__ ntc_s, double* __restrict__ tile, const double tz[D],
                                              int lane, double* __restrict__ mus, int P, int il0) {
     const int q = lane & 3, r = lane >> 2;
     const int KS = m.KS, NTNP = m.NTNP;
@@ -66,39 +76,57 @@ __device__ __forceinline__ void eval_mu_warp(const DevModel& m, const double* __
     int dim_off[D];
     dim_off[D - 1] = 0;
     {
-        int o = m.jmax;
+        int o = m.jmax + 4;
 #pragma unroll
-        for (int d = 0; d + 1 < D; ++d) { dim_off[d] = o; o += m.npos_d[d]; }
+        for (int d = 0; d + 1 < D; ++d) { dim_off[d] = o; o += (m.npos_d[d] + 3) & ~3; }
     }
+    PGAS_FTICK(1);
     double cur0[D], prev0[D], twoc[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) sine_seed(tz[d], m.f_start, m.f_step, cur0[d], prev0[d], twoc[d]);
+    PGAS_FTICK(2);
     const int dsel = (lane >> 3) & 1, par = lane >> 4;
+    int npos[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) npos[d] = (d == D - 1) ? m.jmax : ((m.npos_d[d] + 3) & ~3);
 
     for (int h = 0; h < 4; ++h) {
-        // ---- sines of this pass's 8 particles -> tile[dim][pos][8]
+        // ---- sines of this pass's 8 particles -> tile[dim][pos][8].  One instruction stream for all lanes:
+        //      lane group g = (lane>>3)&1 handles dimension D-1-g-2s in slot s (selected by data, not by
+        //      branches, so the two groups do not serialise), position parity = lane>>4.
         {
             const int src = QUART * h + (lane & 7);
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const double c = __shfl_sync(0xffffffffu, cur0[d], src), pv = __shfl_sync(0xffffffffu, prev0[d], src);
-                const double tc = __shfl_sync(0xffffffffu, twoc[d], src);
-                const bool mine = (D == 1) ? (dsel == 0) : ((d == D - 1) == (dsel == 0));
-                if (mine) {
-                    const int np = (d == D - 1) ? m.jmax : m.npos_d[d];
-                    double* col = tile + (size_t)dim_off[d] * TILE_PS + (lane & 7);
-                    const double tc2 = fma(tc, tc, -2.0);
-                    double cur = par ? fma(tc, c, -pv) : c;            // s[1] : s[0]
-                    double prev = par ? pv : fma(tc, pv, -c);          // s[-1] : s[-2]
-                    for (int p = par; p < np; p += 2) {
-                        col[(size_t)p * TILE_PS] = cur;
-                        const double n = fma(tc2, cur, -prev);
-                        prev = cur; cur = n;
+            for (int s = 0; 2 * s < D; ++s) {
+                const int d0 = D - 1 - 2 * s, d1 = D - 2 - 2 * s;       // dimension of group 0 / group 1 in this slot
+                const int dA = d0, dB = d1 >= 0 ? d1 : d0;
+                const bool active = (dsel == 0) || (d1 >= 0);
+                // the seeds live in the OWNER lane (src): fetch both groups' dimensions, select by this lane's group
+                const double cA = __shfl_sync(0xffffffffu, cur0[dA], src), cB = __shfl_sync(0xffffffffu, cur0[dB], src);
+                const double pA = __shfl_sync(0xffffffffu, prev0[dA], src), pB = __shfl_sync(0xffffffffu, prev0[dB], src);
+                const double tA = __shfl_sync(0xffffffffu, twoc[dA], src), tB = __shfl_sync(0xffffffffu, twoc[dB], src);
+                const double c = dsel ? cB : cA, pv = dsel ? pB : pA, tc = dsel ? tB : tA;
+                const int np = active ? (dsel ? npos[dB] : npos[dA]) : 0;
+                const int npmax = max(npos[dA], npos[dB]);
+                double* col = tile + (size_t)(dsel ? dim_off[dB] : dim_off[dA]) * TILE_PS + (lane & 7) + (size_t)par * TILE_PS;
+                const double tc2 = fma(tc, tc, -2.0);
+                double cur = par ? fma(tc, c, -pv) : c;            // s[1] : s[0]
+                double prev = par ? pv : fma(tc, pv, -c);          // s[-1] : s[-2]
+                // two positions of this lane's parity per iteration (np is a multiple of 4: tiles are padded)
+                for (int p = 0; p < npmax; p += 4) {
+                    const double n1 = fma(tc2, cur, -prev);
+                    const double n2 = fma(tc2, n1, -cur);
+                    if (p < np) {
+                        col[0] = cur;
+                        col[2 * TILE_PS] = n1;
                     }
+                    col += 4 * TILE_PS;
+                    prev = n1; cur = n2;
                 }
             }
         }
         __syncwarp();
+        PGAS_FTICK(3 + 4 * h);
         double mup[NX];
 #pragma unroll
         for (int k = 0; k < NX; ++k) mup[k] = 0.0;
@@ -107,22 +135,37 @@ __device__ __forceinline__ void eval_mu_warp(const DevModel& m, const double* __
             double acc[NTB][2];
 #pragma unroll
             for (int j = 0; j < NTB; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
-            for (int ks = 0; ks < KS; ++ks) {
-                const int ntc = m.ntcount[ks] - nb;           // kernel-parameter data: warp-uniform
-                if (ntc <= 0) continue;
-                const double a0 = tile[(size_t)(4 * ks + q) * TILE_PS + r];
-                const double* bp = bfrag + ((size_t)ks * NTNP + nb) * 32 + lane;
-                double bv[NTB];
+            // software-pipelined: the fragments and the tile count of position step ks+1 are loaded while the
+            // DMMAs of step ks issue (the count table is padded by one entry, the B array by one step of zeros)
+            const double* ap = tile + (size_t)q * TILE_PS + r;
+            const double* bp = bfrag + (size_t)nb * 32 + lane;
+            const size_t bstep = (size_t)NTNP * 32;
+            double a0 = ap[0], bv[NTB];
 #pragma unroll
-                for (int j = 0; j < NTB; ++j) bv[j] = bp[j * 32];   // tiles past ntcount hold zeros: always loadable
+            for (int j = 0; j < NTB; ++j) bv[j] = bp[j * 32];
+            int ntc = ntc_s[0] - nb;
+            for (int ks = 0; ks < KS; ++ks) {
+                ap += 4 * TILE_PS;
+                bp += bstep;
+                const double a_n = ap[0];
+                double b_n[NTB];
+#pragma unroll
+                for (int j = 0; j < NTB; ++j) b_n[j] = bp[j * 32];
+                const int ntc_n = ntc_s[ks + 1] - nb;
                 switch (ntc) {                                   // warp-uniform: straight-line DMMAs, no predication
                     default: dmma_m8n8k4(acc[4][0], acc[4][1], a0, bv[4]);
                     case 4: dmma_m8n8k4(acc[3][0], acc[3][1], a0, bv[3]);
                     case 3: dmma_m8n8k4(acc[2][0], acc[2][1], a0, bv[2]);
                     case 2: dmma_m8n8k4(acc[1][0], acc[1][1], a0, bv[1]);
                     case 1: dmma_m8n8k4(acc[0][0], acc[0][1], a0, bv[0]);
+                    case 0: break;
                 }
+                a0 = a_n;
+#pragma unroll
+                for (int j = 0; j < NTB; ++j) bv[j] = b_n[j];
+                ntc = ntc_n;
             }
+            PGAS_FTICK(4 + 4 * h);
             // ---- per-row scaling by the leading-dimension sines (padding rows have zero accumulators)
 #pragma unroll
             for (int j = 0; j < NTB; ++j) {
@@ -145,6 +188,7 @@ __device__ __forceinline__ void eval_mu_warp(const DevModel& m, const double* __
                 }
             }
         }
+        PGAS_FTICK(5 + 4 * h);
         // ---- reduce over the 4 lanes of a fragment row, row leaders publish
 #pragma unroll
         for (int k = 0; k < NX; ++k) {
@@ -155,8 +199,47 @@ __device__ __forceinline__ void eval_mu_warp(const DevModel& m, const double* __
             if (q == 0 && il < P) mus[(size_t)k * P + il] = v;
         }
         __syncwarp();
+        PGAS_FTICK(6 + 4 * h);
     }
 }
+
+// GP-input map with the model constants hoisted into registers once per kernel (kernel-parameter reads
+// with run-time indices cost ~100 cycles each on the critical path of every step)
+template <int NX, int D>
+struct MapRegs {
+    double A[D][NX], off[D], sc[D], lf, lr;
+    int kind;
+    __device__ __forceinline__ void init(const DevModel& m) {
+        kind = m.map_kind; lf = m.slip_lf; lr = m.slip_lr;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            off[d] = m.L[d] - m.center[d];
+            sc[d] = m.inv2L[d];
+#pragma unroll
+            for (int k = 0; k < NX; ++k) A[d][k] = m.Az[d][k];
+        }
+    }
+    // cz[d] = bz[d] + sum_k Az[d][n_x+k] u[k] is the per-step constant part (StepConst)
+    __device__ __forceinline__ void apply(const double x[NX], const double* __restrict__ cz, const double* __restrict__ u, double tz[D]) const {
+        double z[D];
+        if (kind == PGAS_MAP_VEHICLE_SLIP) {
+            const double x0 = x[0], x1 = x[NX > 1 ? 1 : 0];
+            z[0] = u[0] - atan((x1 + x0 * lf) / u[1]);
+            if constexpr (D >= 2) z[1] = -atan((x1 - x0 * lr) / u[1]);
+            if constexpr (D >= 3) z[2] = 0.0;
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                double acc = cz[d];
+#pragma unroll
+                for (int k = 0; k < NX; ++k) acc = fma(A[d][k], x[k], acc);
+                z[d] = acc;
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) tz[d] = (z[d] + off[d]) * sc[d];
+    }
+};
 
 // GP-input map (state, input) -> normalised lattice coordinate t_d = (z_d - c_d + L_d)/(2 L_d)
 template <int NX, int D>

@@ -65,7 +65,7 @@ __device__ __forceinline__ double exp_neg_bf(double x) {
     const int e = (int)n;
     const double scale = __longlong_as_double((long long)(e + 1023) << 52);
     const double v = p * scale;
-    return (x < -708.0) ? 0.0 : ((x > 0.0) ? exp(x) : v);     // x > 0 never happens after max subtraction
+    return (x < -708.0) ? 0.0 : v;        // valid for x <= ~+700 as well (the shift may undershoot the max slightly)
 }
 
 // 1/d for normal positive d: float seed + two Newton steps (~1 ulp)
@@ -118,4 +118,19 @@ __device__ __forceinline__ double sqrt_bf(double a) {
 __device__ __forceinline__ double div_by_count(double a, double dN, double rN) {
     const double q = a * rN;
     return fma(fma(-q, dN, a), rN, q);
+}
+
+// upper bound-ish of max over the warp for use as a softmax SHIFT: exact maximum of the values with
+// their low 32 mantissa bits cleared (one 32-bit redux instead of a 5-level 64-bit shuffle tree).
+// The result differs from the true maximum by < 2^-20 relative, which only rescales numerator and
+// denominator of the softmax identically.  NaNs are ignored like fmax does.
+__device__ __forceinline__ double warp_shift_max(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v);
+    const bool isnan_ = v != v;
+    // order-preserving map of the sign-magnitude high word to unsigned
+    unsigned key = (hi & 0x80000000u) ? ~hi : (hi | 0x80000000u);
+    key = isnan_ ? 0u : key;
+    const unsigned best = __reduce_max_sync(0xffffffffu, key);
+    const unsigned bh = (best & 0x80000000u) ? (best & 0x7fffffffu) : ~best;
+    return __hiloint2double((int)bh, 0);
 }

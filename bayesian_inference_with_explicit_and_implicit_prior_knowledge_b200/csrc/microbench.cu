@@ -73,6 +73,29 @@ __global__ void dfma_issue_kernel(double* out, int iters, double a, double b) {
     if (s == 123.456) out[1] = s;
 }
 
+// single warp DMMA: ILP independent accumulator chains; cycles per DMMA
+template <int ILP>
+__global__ void dmma_chain_kernel(double* out, int iters, double a, double b) {
+    double c0[ILP], c1[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { c0[i] = 0.0; c1[i] = 0.0; }
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < ILP; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+    }
+    long long t1 = clock64();
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += c0[i] + c1[i];
+    if (threadIdx.x == 0) out[0] = (double)(t1 - t0) / ((double)iters * 4.0 * ILP);
+    if (s == 123.456) out[1] = s;
+}
+
 // cluster barrier round trip (arrive.release + wait.acquire), cycles
 __global__ void __launch_bounds__(256) cluster_barrier_kernel(double* out, int iters) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -131,10 +154,29 @@ extern "C" int pgas_measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops,
     return 0;
 }
 
+// out[5] = dependent DMMA latency (cycles), out[6] = cycles per DMMA of one warp with 5 independent chains,
+// out[7] = cycles per DMMA with 4 warps on one SM sub-partition each running 5 chains (16 warps/SM)
 // out[0] = dependent DFMA latency (cycles), out[1] = single-warp DFMA issue interval (cycles),
 // out[2] = cluster barrier round trip at cluster size 16 (cycles; -1 if not launchable),
 // out[3] = same at cluster size 8, out[4] = DFMA TFLOP/s with 2 warps/SMSP x ILP 4 (the sweep's shape)
 extern "C" int pgas_microbench_f64(double* out5, void* stream) {
+    {
+        cudaStream_t st0 = (cudaStream_t)stream;
+        if (!g_scratch) PGAS_CUDA(cudaMalloc((void**)&g_scratch, 64 * sizeof(double)));
+        double hh[2];
+        dmma_chain_kernel<1><<<1, 32, 0, st0>>>(g_scratch, 2000, 1.0000001, 1e-9);
+        PGAS_CUDA(cudaMemcpyAsync(hh, g_scratch, sizeof(hh), cudaMemcpyDeviceToHost, st0));
+        PGAS_CUDA(cudaStreamSynchronize(st0));
+        out5[5] = hh[0];
+        dmma_chain_kernel<5><<<1, 32, 0, st0>>>(g_scratch, 2000, 1.0000001, 1e-9);
+        PGAS_CUDA(cudaMemcpyAsync(hh, g_scratch, sizeof(hh), cudaMemcpyDeviceToHost, st0));
+        PGAS_CUDA(cudaStreamSynchronize(st0));
+        out5[6] = hh[0];
+        dmma_chain_kernel<5><<<1, 512, 0, st0>>>(g_scratch, 2000, 1.0000001, 1e-9);
+        PGAS_CUDA(cudaMemcpyAsync(hh, g_scratch, sizeof(hh), cudaMemcpyDeviceToHost, st0));
+        PGAS_CUDA(cudaStreamSynchronize(st0));
+        out5[7] = hh[0];
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0;
     PGAS_CUDA(cudaGetDevice(&dev));

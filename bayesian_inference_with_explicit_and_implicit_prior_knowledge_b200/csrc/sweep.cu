@@ -119,6 +119,7 @@ struct StepConst {
     double y[PGAS_MAX_NY];
     double u[PGAS_MAX_NU];
     double ref[PGAS_MAX_NX];
+    double cz[PGAS_MAX_D];       // input-dependent constant part of the affine GP-input map
     double ures, uanc;
 };
 
@@ -145,6 +146,11 @@ __device__ __forceinline__ void load_step_const(const SweepArgs& a, int chain, i
     const int tin = (m.flags & PGAS_FLAG_INPUT_PREV) ? t - 1 : t;     // quirk (ii), src/PGAS.py:52-54
     for (int r = 0; r < m.n_y; ++r) sc->y[r] = m.obs[(size_t)t * m.n_y + r];
     for (int k = 0; k < m.n_u; ++k) sc->u[k] = m.inputs[(size_t)tin * m.n_u + k];
+    for (int d = 0; d < m.D; ++d) {
+        double acc = m.bz[d];
+        for (int k = 0; k < m.n_u; ++k) acc = fma(m.Az[d][m.n_x + k], sc->u[k], acc);
+        sc->cz[d] = acc;
+    }
     for (int k = 0; k < m.n_x; ++k) sc->ref[k] = a.ref[(size_t)chain * a.ref_stride + (size_t)(t - a.row_off) * m.n_x + k];
     if (a.rng_mode == 1) {
         const double* up = a.U + ((size_t)chain * a.var_rows + (t - a.row_off)) * 2;
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
     // ------------------------------------------------------------------ shared memory carve
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sp = reinterpret_cast<double*>(smem_raw);
-    double* bfrag = sp;         sp += m.n_packed;                          // Theta' in DMMA B-fragment order
+    double* bfrag = sp;         sp += m.n_packed + (size_t)m.NTNP * 32;    // Theta' in DMMA B-fragment order (+1 zero step: prefetch)
     double* tiles = sp;         sp += (size_t)NW * sine_tile_doubles(m);   // per-warp sine tiles
     double* xs = sp;            sp += (size_t)NX * P;          // [k][i]
     double* mus = sp;           sp += (size_t)NX * P;          // [k][i] auxiliary mean
@@ -197,14 +203,18 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
     int* ip = reinterpret_cast<int*>(sp);
     int* rowpos = ip;           ip += ((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD;
     int* cnt = ip;              ip += 2;
+    int* ntc_s = ip;            ip += 18;                      // per position step: non-zero column tiles (+1 pad)
 
     // ------------------------------------------------------------------ prologue
     for (int r = tid; r < ((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD; r += NT) rowpos[r] = m.row_pos[r];
     for (int r = Pc + tid; r < nblk * 256; r += NT) b1[r] = INFINITY;
+    if (tid < 18) ntc_s[tid] = (tid < m.KS) ? m.ntcount[tid] : 0;
+    MapRegs<NX, D> mapr;
+    mapr.init(m);
     {   // Theta' = norm * Theta scattered into B-fragment order
         const double* Th = a.Theta + (size_t)chain * NX * m.M;
-        for (int s = tid; s < m.n_packed; s += NT) {
-            const int e = m.perm[s];
+        for (int s = tid; s < m.n_packed + m.NTNP * 32; s += NT) {
+            const int e = (s < m.n_packed) ? m.perm[s] : -1;
             bfrag[s] = (e >= 0) ? m.norm * Th[(size_t)(e & 3) * m.M + (e >> 2)] : 0.0;
         }
     }
@@ -283,6 +293,8 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
         StepConst nxt;                                       // prefetch of step t+1 (thread 0)
         if (tid == 0 && t + 1 < a.t_end) load_step_const(a, chain, t + 1, &nxt);
 
+#define PGAS_TICK(K) do { if (a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 64)) a.dbg[((size_t)(t - a.t_begin) * 2 + (tid ? 1 : 0)) * 8 + (K)] = clock64(); } while (0)
+        PGAS_TICK(0);
         // ---- A: auxiliary mean (DMMA), first-stage log-weights (src/PGAS.py:89-101, :109-117), and the
         //      softmax numerators (:102,:118) with a WARP-local shift: exp(lw - max_warp) and its in-warp
         //      inclusive scan need no block-wide reduction; the (max, sum) pair of every warp is combined
@@ -294,13 +306,14 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
                 double tz[D];
 #pragma unroll
                 for (int d = 0; d < D; ++d) tz[d] = 0.0;
+                PGAS_FTICK(0);
                 if (il < Pc) {
                     double x[NX];
 #pragma unroll
                     for (int k = 0; k < NX; ++k) x[k] = xs[(size_t)k * P + il];
-                    gp_input<NX, D>(m, x, k_t.u, tz);
+                    mapr.apply(x, k_t.cz, k_t.u, tz);
                 }
-                eval_mu_warp<NX, D>(m, bfrag, rowpos, tiles + (size_t)warp * sine_tile_doubles(m), tz, lane, mus, P, il0);
+                eval_mu_warp<NX, D>(m, bfrag, rowpos, ntc_s, tiles + (size_t)warp * sine_tile_doubles(m), tz, lane, mus, P, il0);
                 if (il < Pc) {
                     double mu[NX];
 #pragma unroll
@@ -310,10 +323,14 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
                     lwr = lwa + gauss_logpdf_state<NX>(sw, slogc[0], k_t.ref, mu);
                     laux[il] = la;
                 }
-                const double m1w = warp_max(lwa), m2w = warp_max(lwr);
+                PGAS_FTICK(20);
+                const double m1w = warp_shift_max(lwa), m2w = warp_shift_max(lwr);
+                PGAS_FTICK(21);
                 const double e1 = (il < Pc) ? exp_neg_bf(lwa - m1w) : 0.0;
                 const double e2 = (il < Pc) ? exp_neg_bf(lwr - m2w) : 0.0;
+                PGAS_FTICK(22);
                 const double s1 = warp_scan_incl(e1, lane), s2 = warp_scan_incl(e2, lane);
+                PGAS_FTICK(23);
                 if (il < Pc) { b1[il] = s1; b2[il] = s2; }
                 if (lane == 31) {
                     double* up = unit + (size_t)(q * NW + warp) * 4;
@@ -324,7 +341,9 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
                 up[0] = -INFINITY; up[1] = 0.0; up[2] = -INFINITY; up[3] = 0.0;
             }
         }
+        PGAS_TICK(1);
         __syncthreads();
+        PGAS_TICK(2);
 
         // ---- X1: warp 0 folds the warp pairs into the CTA pair; all-gather across the cluster; fold again
         const int c_last = (N - 1) / P;                       // CTA owning particle N-1 (later CTAs are empty)
@@ -395,8 +414,10 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
                 cnt[1] = __popc(below);
             }
         }
+        PGAS_TICK(3);
         if (tid == 0 && t + 1 < a.t_end) sc[(t + 1) & 1] = nxt;
         __syncthreads();
+        PGAS_TICK(4);
         const double myg1 = gsum[rank * 2], myg2 = gsum[rank * 2 + 1], g1hi = gsum[(rank + 1) * 2];
         const double myf1 = fx[rank * 2], myf2 = fx[rank * 2 + 1];
         const double S1 = fx[2 * MAXC], S2 = fx[2 * MAXC + 1];      // reciprocals of the normalisers
@@ -421,6 +442,7 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
         }
         __syncthreads();
 
+        PGAS_TICK(5);
         // ---- B2: systematic resampling (src/Filtering.py:28-35) by the owner of the CDF segment
         {
             const double blo = clip01(__dmul_rn(myg1, S1)), bhi = clip01(__dmul_rn(g1hi, S1));
@@ -460,6 +482,7 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
             }
         }
 
+        PGAS_TICK(6);
         // ---- X2 + C: barrier #2 overlapped with the noise draw; new state, new log-weights
         if (C > 1) cluster_arrive(); else __syncthreads();
         const bool last_step = (t + 1 == a.t_end);
@@ -507,6 +530,7 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
                 finish(il, z);
             }
         }
+        PGAS_TICK(7);
         // next step's A1 only touches this thread's own xs/logw entries and arrays whose previous
         // readers are fenced by the barriers above; b1/b2/laux/mus are rewritten after every
         // thread of the CTA has left B2, which the X2 barrier guarantees.
@@ -517,10 +541,10 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
 // ------------------------------------------------------------------------------------ launch
 static size_t sweep_smem_bytes(const DevModel& m, int NX, int P, bool gather, int NT) {
     const int NW = NT / 32;
-    size_t d = (size_t)m.n_packed + (size_t)NW * sine_tile_doubles(m) + (size_t)NX * P * 2 + (size_t)P * 4 + (size_t)((P + 255) / 256) * 256 +
+    size_t d = (size_t)m.n_packed + (size_t)m.NTNP * 32 + (size_t)NW * sine_tile_doubles(m) + (size_t)NX * P * 2 + (size_t)P * 4 + (size_t)((P + 255) / 256) * 256 +
                (gather ? (size_t)NX * P : 0) + MAXC * 4 + 2 * (MAXC + 1) + 2 * MAXC + 2 + (size_t)((P + NT - 1) / NT) * NW * 8 + 2 * NX * NX + 2 +
                2 * ((sizeof(StepConst) + 7) / 8);
-    return d * 8 + (size_t)(((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD + 2) * 4 + 32;
+    return d * 8 + (size_t)(((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD + 2 + 18) * 4 + 32;
 }
 
 // threads per CTA: 512 (16 warps hide the dependent-FP64 latency best) when the per-warp sine tiles
@@ -611,3 +635,26 @@ extern "C" int pgas_debug_max_active_clusters(const pgas_model* model, int32_t N
     g_query_clusters = nullptr;
     return rc ? -rc : n;
 }
+
+// developer aid: run a sweep with phase clocks of CTA 0 recorded into dbg (2 threads x 8 ticks per step)
+extern "C" int pgas_debug_sweep_ticks(const pgas_model* model, int32_t N, int32_t n_chains, const double* ref, const double* Theta,
+                                      const double* Sigma, double* state_trace, int32_t* anc_trace, double* logw_last,
+                                      int32_t cluster_size, long long* dbg, void* stream) {
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = model->dev;
+    a.N = N; a.n_chains = n_chains; a.C = pgas_choose_cluster(a.m, N, n_chains, cluster_size); a.P = (N + a.C - 1) / a.C;
+    a.t_begin = 1; a.t_end = a.m.T;
+    a.ref_rows = a.m.T; a.trace_rows = a.m.T; a.anc_rows = a.m.T - 1; a.var_rows = a.m.T;
+    a.ref = ref; a.ref_stride = (long long)a.m.T * a.m.n_x; a.Theta = Theta; a.Sigma = Sigma;
+    a.state_trace = state_trace; a.anc_trace = anc_trace; a.logw_last = logw_last;
+    a.rng_mode = 0; a.seed = 1234;
+    a.dbg = dbg;
+    return pgas_launch_sweep(a, (cudaStream_t)stream);
+}
+
+#if PGAS_FINE_TICKS
+extern "C" int pgas_debug_fine_ticks(long long* host64) {
+    return (int)cudaMemcpyFromSymbol(host64, g_fine, sizeof(long long) * 64);
+}
+#endif

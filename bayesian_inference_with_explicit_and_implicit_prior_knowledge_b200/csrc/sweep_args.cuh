@@ -22,6 +22,7 @@ struct SweepArgs {
     unsigned chain_base, iteration;
     const double* Z;             // (n_chains, var_rows, N, NX)
     const double* U;             // (n_chains, var_rows, 2)
+    long long* dbg;              // optional phase clocks of CTA 0 (8 per step), developer aid
 };
 
 int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream);

@@ -29,6 +29,7 @@ PKG = "bayesian_inference_with_explicit_and_implicit_prior_knowledge_b200"
 
 N_PART, T_STEPS, M_BASIS, CHAINS_TOTAL = 4096, 2000, 256, 64
 FLOP_PER_PSTEP = 2 * M_BASIS * 2 + M_BASIS * 2          # 2 M n_x + M D  (SURVEY.md 8d), n_x = D = 2
+NCU_DRAM_BYTES_PER_PSTEP = (1.871104e6 + 472.886016e6) / (64 * 4096 * 100)   # profiles/r01_sweep_full_raw.csv
 SEED = 12345678                                          # the reference's seed (src/SingleMassOscillator.py:82)
 
 
@@ -319,7 +320,9 @@ def run_gpu_arm(args):
                        f"{count * T * N * 20 / 1e9:.1f} GB on rank 0) exceeds the 126 MB L2", "rng": "Philox-4x32-10 in-kernel"},
             "sweeps_per_s": args.chains * args.steps / (ms * 1e-3),
             "roofline": {"bound": "tensor", "kernel": "csmc_sweep_kernel (FP64 DMMA m8n8k4 + FP64 FMA)", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_PSTEP * count * N * (T - 1),
+                         "traffic_note": "dram__bytes_read+write of this kernel from the ncu --set full capture in profiles/r01_sweep_full_summary.md "
+                                         "(18.1 B per particle-step measured at T=101, scaled to this launch; algorithmic 20 B)",
                          "note": f"algorithmic flops = {FLOP_PER_PSTEP} per particle-step (2 M n_x + M D) x {count * N * (T - 1)} particle-steps "
                                  f"per launch; peak = FP64 measured on this GPU in this run (register-resident DFMA {dfma.value:.1f}, DMMA "
                                  f"{dmma.value:.1f} TFLOP/s; MEASURED_PEAKS.json has no FP64 figure); sweep launch {sweep_avg:.2f} ms",

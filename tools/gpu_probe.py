@@ -24,10 +24,11 @@ L.check(lib.pgas_measure_fp64_peaks(C.byref(a), C.byref(b), L.stream_ptr()))
 out["dfma_tflops"], out["dmma_tflops"] = a.value, b.value
 lib.pgas_microbench_f64.restype = C.c_int
 lib.pgas_microbench_f64.argtypes = [C.POINTER(C.c_double), C.c_void_p]
-arr = (C.c_double * 5)()
+arr = (C.c_double * 8)()
 L.check(lib.pgas_microbench_f64(arr, L.stream_ptr()))
-out["dfma_latency_cyc"], out["dfma_issue_cyc"], out["cluster16_barrier_cyc"], out["cluster8_barrier_cyc"], out["dfma_2w_ilp4_tflops"] = list(arr)
+out["dfma_latency_cyc"], out["dfma_issue_cyc"], out["cluster16_barrier_cyc"], out["cluster8_barrier_cyc"], out["dfma_2w_ilp4_tflops"], out["dmma_latency_cyc"], out["dmma_1w_ilp5_cyc"], out["dmma_16w_ilp5_cyc"] = list(arr)
 print(json.dumps(out), flush=True)
+if len(sys.argv) > 1: sys.exit(0)
 
 
 def time_sweep(kind, N, T, M, n_chains, cluster, reps=3):
