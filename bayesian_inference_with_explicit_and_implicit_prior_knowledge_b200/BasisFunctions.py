@@ -12,6 +12,7 @@ import numpy as np
 
 from . import _lib
 from . import models as _models
+from . import tracing as _tracing
 
 
 def _lattice_search(num_fcn, size, idx_start, idx_step):
@@ -71,6 +72,8 @@ class HilbertBasis:
         return self._eval_model
 
     def __call__(self, x):
+        if isinstance(x, _tracing.Expr):                 # marginalised filters (Algorithm1/2/3): per-step tracer
+            return _tracing.BasisCall(self, x)
         if isinstance(x, _models.Affine):
             if len(x) != self.D:
                 raise ValueError(f"basis expects {self.D} inputs, traced value has {len(x)}")

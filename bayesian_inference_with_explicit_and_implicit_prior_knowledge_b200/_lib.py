@@ -18,7 +18,8 @@ _SOURCES = ["model.cu", "sweep.cu", "sweep_api.cu", "suffstats.cu", "mniw_draw.c
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
-PGAS_MAX_NX, PGAS_MAX_NY, PGAS_MAX_NU, PGAS_MAX_D = 4, 2, 4, 3
+PGAS_MAX_NX, PGAS_MAX_NY, PGAS_MAX_NU, PGAS_MAX_D, PGAS_MAX_GP = 4, 2, 4, 3, 2
+LINK_IDENTITY, LINK_ATAN, LINK_TANH = 0, 1, 2
 MAP_AFFINE, MAP_VEHICLE_SLIP = 0, 1
 FLAG_ANCESTOR_GATHER, FLAG_INPUT_PREV, FLAG_VCHOL_TRANSPOSE = 1, 2, 4
 
@@ -104,6 +105,42 @@ class Rng(C.Structure):
     ]
 
 
+class MargGP(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("D", C.c_int32),
+        ("sqrt_eig", C.POINTER(C.c_double)),
+        ("center", C.c_double * PGAS_MAX_D), ("half_width", C.c_double * PGAS_MAX_D),
+        ("link", C.c_int32),
+        ("gp_in", C.POINTER(C.c_double)), ("gp_post", C.POINTER(C.c_double)),
+        ("eta0", C.POINTER(C.c_double)), ("eta1", C.POINTER(C.c_double)),
+        ("eta2", C.c_double), ("eta3", C.c_double),
+        ("xi_mean", C.c_double), ("xi_var", C.c_double),
+    ]
+
+
+class MargParams(C.Structure):
+    _fields_ = [
+        ("n_x", C.c_int32), ("n_y", C.c_int32), ("n_gp", C.c_int32), ("T", C.c_int32),
+        ("gp", MargGP * PGAS_MAX_GP),
+        ("trans", C.POINTER(C.c_double)), ("outp", C.POINTER(C.c_double)),
+        ("out_link", C.c_int32),
+        ("observations", C.POINTER(C.c_double)),
+        ("Q", (C.c_double * PGAS_MAX_NX) * PGAS_MAX_NX),
+        ("R", (C.c_double * PGAS_MAX_NY) * PGAS_MAX_NY),
+        ("m0", C.c_double * PGAS_MAX_NX),
+        ("P0", (C.c_double * PGAS_MAX_NX) * PGAS_MAX_NX),
+    ]
+
+
+class MargRng(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("seed", C.c_uint64), ("chain_base", C.c_uint32), ("iteration", C.c_uint32),
+        ("Z", C.c_void_p), ("ZXI0", C.c_void_p), ("U", C.c_void_p), ("TS", C.c_void_p),
+    ]
+
+
+_PP = C.POINTER(C.c_void_p)      # array of device pointers (double* const*)
+
 EXPORTS = {
     # name: (restype, argtypes)
     "pgas_last_error": (C.c_char_p, []),
@@ -133,6 +170,24 @@ EXPORTS = {
                                       C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "pgas_philox_sweep_variates_f64": (C.c_int, [C.POINTER(Rng), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pgas_marg_model_create": (C.c_int, [C.POINTER(MargParams), C.POINTER(C.c_void_p)]),
+    "pgas_marg_model_destroy": (C.c_int, [C.c_void_p]),
+    "pgas_marg_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
+    "pgas_marg_filter_f64": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.POINTER(MargRng), C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, _PP, _PP, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "pgas_marg_refstats_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, _PP,
+                                         C.c_void_p]),
+    "pgas_marg_csmc_f64": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, _PP, C.POINTER(MargRng), C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                     C.c_void_p, C.c_size_t, C.c_void_p]),
+    "pgas_marg_run_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
+    "pgas_marg_run_f64": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(MargRng),
+                                    C.c_void_p, C.c_void_p, _PP, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "pgas_marg_outputs_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pgas_mniw_log_base_measure_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                                 C.c_void_p]),
+    "pgas_philox_marg_variates_f64": (C.c_int, [C.POINTER(MargRng), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pgas_measure_fp64_peaks": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]),
 }
 
@@ -175,6 +230,14 @@ def require_cuda():
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr_array(tensors):
+    """ctypes array of device pointers (double* const*) for a list of CUDA tensors; None -> NULL array pointer"""
+    if tensors is None:
+        return C.cast(None, _PP)
+    arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return C.cast(arr, _PP)
 
 
 def ptr(t):

@@ -1,0 +1,110 @@
+// marginal.cuh — device model, workspace layout and argument block of the marginalised particle
+// filters (marginal.cu): Algorithm1 / Algorithm3 / Algorithm2 of the reference
+// (src/Algorithm1.py, src/Algorithm3.py, src/Algorithm2.py), SURVEY.md 8a group B.
+#pragma once
+#include "common.cuh"
+
+constexpr int MG_GP = PGAS_MAX_GP;
+constexpr int MG_NX = PGAS_MAX_NX;
+constexpr int MG_NY = PGAS_MAX_NY;
+constexpr int MG_D = PGAS_MAX_D;
+constexpr int MG_MAX_M = 128;          // 4 register rows per lane in the triangular solve
+
+enum { PURPOSE_XI0 = 5, PURPOSE_TVAR = 6 /* + GP index */ };
+
+struct MargGP {
+    int M, D, link, npk;               // npk = M (M + 1) / 2 packed lower-triangular entries
+    double center[MG_D], L[MG_D], sqrt_invL[MG_D];
+    const double* sqrt_eig;            // (M, D)
+    const double* gp_in;               // (T, D, n_x + 1)
+    const double* gp_post;             // (T, D, 2)
+    const double* p0;                  // (M)    prior eta0
+    const double* p1;                  // (npk)  prior eta1, packed lower triangle of its symmetric part
+    double p2, p3;
+    double xi_mean, xi_sd;
+};
+
+struct MargDev {
+    int n_x, n_y, G, T, out_link, deterministic;
+    MargGP gp[MG_GP];
+    const double* trans;               // (T, n_x, n_x + G + 1)
+    const double* outp;                // (T, n_y, n_x + G + 1)
+    const double* obs;                 // (T, n_y)
+    double Qc[MG_NX][MG_NX];           // chol(Q) lower (zero when deterministic)
+    double Qw[MG_NX][MG_NX];           // inverse of chol(Q): e = Qw (x - mean)
+    double Q_logc;                     // -n_x/2 log(2 pi) - sum log diag chol(Q)
+    double Rw[MG_NY][MG_NY], R_logc;
+    double m0[MG_NX], P0c[MG_NX][MG_NX];
+};
+
+struct pgas_marg_model {
+    MargDev dev;
+    void* arena;
+    size_t arena_bytes;
+};
+
+// Per-chain, per-parity block of the per-particle workspace (element offsets in doubles).  Two
+// parities: pass t writes parity t & 1 and gathers, by ancestor, from parity (t - 1) & 1.
+struct MargWs {
+    size_t auxx, ellaux, lwaux, lwanc;
+    size_t yv[MG_GP], psi[MG_GP], Lp[MG_GP], T1p[MG_GP], T0[MG_GP], T2[MG_GP], T3[MG_GP];
+    size_t parity_stride, chain_stride;
+};
+
+__host__ __device__ inline MargWs marg_ws_layout(const MargDev& m, int N) {
+    MargWs w;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
+    w.auxx = take((size_t)N * m.n_x);
+    w.ellaux = take(N);
+    w.lwaux = take(N);
+    w.lwanc = take(N);
+    for (int g = 0; g < MG_GP; ++g) {
+        const bool on = g < m.G;
+        const size_t M = on ? m.gp[g].M : 0, npk = on ? m.gp[g].npk : 0;
+        w.yv[g] = take((size_t)N * M);
+        w.psi[g] = take(on ? N : 0);
+        w.Lp[g] = take((size_t)N * npk);
+        w.T1p[g] = take((size_t)N * npk);
+        w.T0[g] = take((size_t)N * M);
+        w.T2[g] = take(on ? N : 0);
+        w.T3[g] = take(on ? N : 0);
+    }
+    w.parity_stride = o;
+    w.chain_stride = 2 * o;
+    return w;
+}
+
+// prior + remaining reference statistics after step t (src/Algorithm3.py:235-246, :163-174), one row
+// per time step: PR1 packed (T, npk), PR0 (T, M), PR2 (T), PR3 (T); per chain.
+struct MargRefTab {
+    const double* PR0[MG_GP];
+    const double* PR1[MG_GP];
+    const double* PR2[MG_GP];
+    const double* PR3[MG_GP];
+};
+
+struct MargArgs {
+    MargDev m;
+    int N, n_chains, CS, NW;           // cluster size (CTAs per chain), warps per CTA
+    int mode;                          // 0 = Algorithm1 (filter), 1 = Algorithm3 (conditional)
+    double lambda;                     // forgetting factor (1 in mode 1)
+    size_t warp_doubles, cta_doubles;  // shared-memory carve-up
+    // reference trajectory (mode 1)
+    const double* ref_x;  long long ref_x_stride;                       // (n_chains, T, n_x)
+    const double* ref_xi; long long ref_xi_stride, ref_xi_gstride;      // xi[c][g][t]
+    MargRefTab tab;                    // chain stride = T * (row length)
+    // traces
+    double* state_trace;               // (n_chains, T, N, n_x)
+    double* xi_trace;                  // (n_chains, G, T, N)
+    double* logw_trace;                // (n_chains, T, N)
+    int* anc_trace;                    // (n_chains, T-1, N)
+    double* sst[4 * MG_GP];            // optional weighted statistics trace (mode 0)
+    double* ws;                        // per-particle workspace (n_chains * chain_stride doubles)
+    int* status;                       // (n_chains)
+    // variates
+    int rng_mode;
+    unsigned long long seed;
+    unsigned chain_base, iteration;
+    const double *Z, *ZXI0, *U, *TS;
+};

@@ -73,3 +73,12 @@ def as_key(k):
     if isinstance(k, (int, np.integer)):
         return PhiloxKey(k)
     raise TypeError(f"expected a PhiloxKey (see {__name__}.key), got {type(k).__name__}")
+
+
+def normal(k, shape=()):
+    """jax.random.normal stand-in for the example modules' data synthesis (host side, Box-Muller)."""
+    n = int(np.prod(shape)) if shape != () else 1
+    o = philox4x32(np.arange(n, dtype=np.uint64), 0, 0, 0xFFFFFFFD, k.seed & 0xFFFFFFFF, k.seed >> 32)
+    u1, u2 = u53(o[0], o[1]) + 1.0 / 9007199254740992.0, u53(o[2], o[3])
+    z = np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+    return float(z[0]) if shape == () else z.reshape(shape)

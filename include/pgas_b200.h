@@ -185,6 +185,130 @@ int pgas_run_chains_f64(const pgas_model* model, int32_t N, int32_t K, int32_t n
 int pgas_philox_sweep_variates_f64(const pgas_rng* rng, int32_t n_chains, int32_t T, int32_t N,
                                    int32_t n_x, double* Z_out, double* U_out, void* stream);
 
+/* ====================================================================================
+ * Group B — the marginalised particle filters: Algorithm1 (online
+ * marginalised auxiliary particle filter, src/Algorithm1.py), Algorithm3 (marginalised conditional
+ * SMC with ancestor sampling, src/Algorithm3.py) and Algorithm2 (the PGAS outer loop,
+ * src/Algorithm2.py).  Every particle carries the MNIW sufficient statistics of each GP.
+ *
+ * The reference's StateSpaceModel callables (src/StateSpaceModel.py:19-30) are arbitrary Python.
+ * The host layer traces them once per time step (the input u_t is concrete there) and reduces them to
+ * per-step coefficient tables of the compiled-in family
+ *   transition   x' = A_t x + B_t xi + c_t                              (trans, row t moves t -> t+1)
+ *   output       y  = link(C_t x + D_t xi + e_t),  link = identity | tanh (outp, row t)
+ *   GP input g   z_d = p_t,d * link(a_t,d . x + b_t,d) + q_t,d, link = identity | atan
+ * which covers every shipped example (RK4 of src/SingleMassOscillator.py:32-44 and src/EMPS.py:177-183
+ * is affine in (x, xi); src/Vehicle.py:60-128 is affine in (x, xi) given u_t, with a tanh output and
+ * the atan slip angles of :50-57).  Interface variables are scalar (n_xi = 1), as in every example.
+ * ==================================================================================== */
+enum { PGAS_LINK_IDENTITY = 0, PGAS_LINK_ATAN = 1, PGAS_LINK_TANH = 2 };
+
+typedef struct pgas_marg_gp {
+    int32_t M, D;
+    const double* sqrt_eig;        /* (M, D) host: sqrt(eigenvalue) = pi j / size  (src/BasisFunctions.py:60,79) */
+    double center[PGAS_MAX_D];
+    double half_width[PGAS_MAX_D];
+    int32_t link;                  /* PGAS_LINK_IDENTITY or PGAS_LINK_ATAN */
+    const double* gp_in;           /* (T, D, n_x + 1) host: a_t,d (n_x) then b_t,d */
+    const double* gp_post;         /* (T, D, 2) host: p_t,d, q_t,d */
+    const double* eta0;            /* (M) host      prior natural parameters (src/BayesianInferrence.py:18-32) */
+    const double* eta1;            /* (M, M) host */
+    double eta2, eta3;
+    double xi_mean, xi_var;        /* init_int_var_mean / init_int_var_cov (src/Algorithm1.py:36-37) */
+} pgas_marg_gp;
+
+typedef struct pgas_marg_params {
+    int32_t n_x, n_y, n_gp, T;
+    pgas_marg_gp gp[PGAS_MAX_GP];
+    const double* trans;           /* (T, n_x, n_x + n_gp + 1) host */
+    const double* outp;            /* (T, n_y, n_x + n_gp + 1) host */
+    int32_t out_link;              /* PGAS_LINK_IDENTITY or PGAS_LINK_TANH */
+    const double* observations;    /* (T, n_y) host */
+    double Q[PGAS_MAX_NX][PGAS_MAX_NX];   /* process noise (src/StateSpaceModel.py:9) */
+    double R[PGAS_MAX_NY][PGAS_MAX_NY];   /* output noise */
+    double m0[PGAS_MAX_NX];
+    double P0[PGAS_MAX_NX][PGAS_MAX_NX];
+} pgas_marg_params;
+
+typedef struct pgas_marg_model pgas_marg_model;
+
+/* Variates of the marginalised filters.  Injected mode (device arrays):
+ *   Z (n_chains,T,N,n_x) normals [row 0: initial states], ZXI0 (n_chains,n_gp,N) normals,
+ *   U (n_chains,T,2) uniforms [U[t,0]=u_res(t), U[t,1]=u_anc(t) for t>=1; U[0,0]=u_idx],
+ *   TS (n_chains,n_gp,T,N) Student-t variates with the predictive's degrees of freedom
+ *   (jax.random.t, src/BayesianInferrence.py:103).
+ * Philox mode generates the same slots in-kernel (t = z sqrt(a/g), g ~ Gamma(a), a = df/2). */
+typedef struct pgas_marg_rng {
+    int32_t mode;                  /* 0 = Philox, 1 = injected */
+    uint64_t seed;
+    uint32_t chain_base, iteration;
+    const double* Z;
+    const double* ZXI0;
+    const double* U;
+    const double* TS;
+} pgas_marg_rng;
+
+int pgas_marg_model_create(const pgas_marg_params* params, pgas_marg_model** out);
+int pgas_marg_model_destroy(pgas_marg_model* model);
+size_t pgas_marg_workspace_bytes(const pgas_marg_model* model, int32_t N, int32_t n_chains);
+
+/* Statistic arrays are passed as arrays of 4*n_gp device pointers, entry 4g+j = statistic j of GP g:
+ * j=0: T0 (.., M), j=1: T1 (.., M, M), j=2: T2 (..), j=3: T3 (..)   [n_xi = 1]. */
+
+/* Algorithm1.__call__ (src/Algorithm1.py:399-492): one persistent kernel for all T steps.
+ *   -> state_trace (n_chains,T,N,n_x), xi_trace (n_chains,n_gp,T,N), logw_trace (n_chains,T,N),
+ *      anc_trace (n_chains,T-1,N) int32; optional sst_trace[4g+j] (n_chains,T,...) = weighted means
+ *      of the per-particle statistics (:445-457); optional final_stats[4g+j] (n_chains,N,...) (:488).
+ * status (n_chains) int32 device: 0 or the first time step at which a factorisation lost positive
+ * definiteness (the reference would propagate NaN). */
+int pgas_marg_filter_f64(const pgas_marg_model* model, int32_t N, int32_t n_chains, double forgetting_factor,
+                         const pgas_marg_rng* rng, double* state_trace, double* xi_trace, double* logw_trace,
+                         int32_t* anc_trace, double* const* sst_trace, double* const* final_stats,
+                         int32_t* status, int32_t cluster_size, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Reference-trajectory statistics of Algorithm2 (src/Algorithm2.py:83-96, :139-152): sums over ALL T
+ * steps.  x_traj (n_chains,T,n_x) with chain stride x_stride, xi_traj (n_chains,n_gp,T) with chain
+ * stride xi_stride and GP stride xi_gstride (elements) -> stats_out[4g+j] (n_chains, ...). */
+int pgas_marg_refstats_f64(const pgas_marg_model* model, const double* x_traj, int64_t x_stride, const double* xi_traj,
+                           int64_t xi_stride, int64_t xi_gstride, int32_t n_chains, double* const* stats_out,
+                           void* stream);
+
+/* Algorithm3.__call__ (src/Algorithm3.py:199-303): ref_x (n_chains,T,n_x), ref_xi (n_chains,n_gp,T),
+ * ref_stats[4g+j] (n_chains,...) -> traces as above, final_idx (n_chains) int32 (may be NULL),
+ * traj_x_out (n_chains,T,n_x), traj_xi_out (n_chains,n_gp,T). */
+int pgas_marg_csmc_f64(const pgas_marg_model* model, int32_t N, int32_t n_chains, const double* ref_x,
+                       const double* ref_xi, const double* const* ref_stats, const pgas_marg_rng* rng,
+                       double* state_trace, double* xi_trace, double* logw_trace, int32_t* anc_trace,
+                       int32_t* final_idx, double* traj_x_out, double* traj_xi_out, int32_t* status,
+                       int32_t cluster_size, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Algorithm2.__call__ (src/Algorithm2.py:106-187), K iterations stream-ordered on the device:
+ * init_x (n_chains,T,n_x), init_xi (n_chains,n_gp,T) -> x_trace_out (n_chains,K,T,n_x),
+ * xi_trace_out (n_chains,n_gp,K,T), sst_out[4g+j] (n_chains,K,...) reference statistics per iteration.
+ * Injected mode: rng arrays carry a leading K axis (block k feeds sweep k; block 0 unused). */
+size_t pgas_marg_run_workspace_bytes(const pgas_marg_model* model, int32_t N, int32_t n_chains);
+int pgas_marg_run_f64(const pgas_marg_model* model, int32_t N, int32_t K, int32_t n_chains, const double* init_x,
+                      const double* init_xi, const pgas_marg_rng* rng, double* x_trace_out, double* xi_trace_out,
+                      double* const* sst_out, int32_t* status, int32_t cluster_size, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* vmap(vmap(output_mdl)) and vmap(vmap(log_likelihood)) over a (T, n) table (src/Algorithm1.py:463-480,
+ * src/Algorithm2.py:160-178): states (T,n,n_x), xi (n_gp,T,n) -> obs_out (T,n,n_y), loglik_out (T,n). */
+int pgas_marg_outputs_f64(const pgas_marg_model* model, const double* states, const double* xi, int32_t n,
+                          double* obs_out, double* loglik_out, void* stream);
+
+/* vmap(prior_mniw_log_base_measure) (src/BayesianInferrence.py:111-124) for n_xi = 1:
+ * T0 (n,M), T1 (n,M,M), T2 (n), T3 (n) -> out (n). */
+int pgas_mniw_log_base_measure_f64(const double* T0, const double* T1, const double* T2, const double* T3,
+                                   int32_t n, int32_t M, double* out, void* stream);
+
+/* The variates the Philox mode of the marginalised filters uses for sweep `rng->iteration`:
+ * Z (n_chains,T,N,n_x), ZXI0 (n_chains,n_gp,N), U (n_chains,T,2), TS (n_chains,n_gp,T,N) with
+ * df (n_gp,T) host = degrees of freedom of the predictive at each step. */
+int pgas_philox_marg_variates_f64(const pgas_marg_rng* rng, int32_t n_chains, int32_t n_gp, int32_t T, int32_t N,
+                                  int32_t n_x, const double* df_host, double* Z_out, double* ZXI0_out,
+                                  double* U_out, double* TS_out, void* stream);
+
 /* Machine denominators for the FP64 rooflines: a register-resident DFMA loop and
  * a register-resident DMMA (mma.sync m8n8k4 f64) loop on all SMs.  Results in TFLOP/s (host). */
 int pgas_measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops, void* stream);

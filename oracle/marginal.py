@@ -129,7 +129,8 @@ def alg1_run(model, N, lam, V):
         for j in range(4):
             sst[g][j][0] = np.einsum("n...,n->...", st[g][j], w)                              # :165-169
     for t in range(1, T):
-        lw, x, xi, st, a = alg1_step(model, t, lws[t - 1], xs[t - 1], [v[t - 1] for v in xis], st, lam, V["U"][t],
+        u_res = V["U"][t, 0] if np.ndim(V["U"]) == 2 else V["U"][t]
+        lw, x, xi, st, a = alg1_step(model, t, lws[t - 1], xs[t - 1], [v[t - 1] for v in xis], st, lam, u_res,
                                      V["Z"][t], [V["TS"][g][t] for g in range(G)])
         xs[t], lws[t], anc[t - 1] = x, lw, a
         w = F.softmax(lw)

@@ -1,0 +1,178 @@
+"""GPU parity of the marginalised filters (SURVEY.md 8a group B) against the CPU oracle under injected
+variates: ancestor indices exact, float64 traces / statistics within 1e-9 relative (BASELINE.json)."""
+import numpy as np
+import pytest
+
+import helpers
+import helpers_marginal as HM
+
+pytestmark = pytest.mark.gpu
+REL = helpers.REL_TOL
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("kind,T,N,M,cs", [("smo", 24, 32, 12, 0), ("smo", 12, 200, 41, 0), ("emps", 30, 48, 9, 1),
+                                           ("vehicle", 24, 40, 8, 0), ("smo", 16, 70, 12, 4)])
+def test_algorithm1_matches_oracle(kind, T, N, M, cs):
+    from oracle import marginal as OMg
+    prob = HM.make_marg_problem(kind, T=T, N=N, M=M, seed=3)
+    lam = prob["lam"]
+    V = HM.make_variates(prob, lam, seed=11)
+    ref = OMg.alg1_run(prob["oracle"], N, lam, HM.oracle_variates(V))
+    A1 = helpers.pkg("Algorithm1").Algorithm1(forgetting_factor=lam, cluster_size=cs, **prob["prod_kwargs"])
+    r = A1.filter(variates=HM.device_variates(V))
+    assert int(r["status"][0]) == 0
+    np.testing.assert_array_equal(_np(r["anc_trace"][0]), ref["anc_trace"] if "anc_trace" in ref else ref["ancestor_trace"])
+    assert HM.rel_err(_np(r["state_trace"][0]), ref["state_trace"]) < REL
+    for g in range(prob["G"]):
+        assert HM.rel_err(_np(r["xi_trace"][0, g]), ref["int_var_trace"][g][..., 0]) < REL
+        for j, sh in enumerate([(T, M), (T, M, M), (T,), (T,)]):
+            assert HM.rel_err(_np(r["sst_trace"][4 * g + j][0]).reshape(sh), np.asarray(ref["suff_stats_trace"][g][j]).reshape(sh)) < REL
+        for j, sh in enumerate([(N, M), (N, M, M), (N,), (N,)]):
+            assert HM.rel_err(_np(r["final_stats"][4 * g + j][0]).reshape(sh), np.asarray(ref["suff_stats"][g][j]).reshape(sh)) < REL
+    assert HM.rel_err(_np(r["logw_trace"][0]), ref["logw_trace"]) < REL
+
+
+@pytest.mark.parametrize("kind,T,N,M,cs", [("smo", 24, 32, 12, 0), ("smo", 10, 200, 41, 0), ("emps", 30, 48, 9, 2),
+                                           ("vehicle", 24, 40, 8, 0)])
+def test_algorithm3_matches_oracle(kind, T, N, M, cs):
+    import torch
+    from oracle import marginal as OMg
+    prob = HM.make_marg_problem(kind, T=T, N=N, M=M, seed=5)
+    # reference trajectory: particle 0's path of an oracle filter run
+    V1 = HM.make_variates(prob, 1.0, seed=21)
+    f = OMg.alg1_run(prob["oracle"], N, 1.0, HM.oracle_variates(V1))
+    ref_x = f["state_trace"][:, 0]
+    ref_xi = [f["int_var_trace"][g][:, 0, 0] for g in range(prob["G"])]
+    rs = OMg.reference_stats(prob["oracle"], ref_x, ref_xi)
+    V = HM.make_variates(prob, 1.0, seed=22)
+    ref = OMg.alg3_run(prob["oracle"], N, ref_x, ref_xi, rs, HM.oracle_variates(V))
+    A3 = helpers.pkg("Algorithm3").Algorithm3(cluster_size=cs, **prob["prod_kwargs"])
+    f64 = dict(dtype=torch.float64, device="cuda")
+    rx = torch.as_tensor(ref_x[None], **f64)
+    rxi = torch.as_tensor(np.stack(ref_xi)[None], **f64)
+    # (a) reference statistics computed on the device
+    dev_rs = A3.reference_stats(rx, rxi)
+    for g in range(prob["G"]):
+        for j in range(4):
+            assert HM.rel_err(_np(dev_rs[4 * g + j][0]).reshape(-1), np.asarray(rs[g][j], dtype=np.float64).reshape(-1)) < REL
+    # (b) the sweep, with the statistics passed in (Algorithm3.__call__ signature) and computed internally
+    for stats in (dev_rs, None):
+        r = A3.csmc(rx, rxi, stats, variates=HM.device_variates(V))
+        assert int(r["status"][0]) == 0
+        np.testing.assert_array_equal(_np(r["anc_trace"][0]), ref["anc_trace"])
+        assert HM.rel_err(_np(r["state_trace"][0]), ref["state_trace"]) < REL
+        assert HM.rel_err(_np(r["logw_trace"][0]), ref["logw_trace"]) < REL
+        assert int(r["idx"][0]) == ref["idx"]
+        assert HM.rel_err(_np(r["traj"][0]), ref["traj"]) < REL
+        for g in range(prob["G"]):
+            assert HM.rel_err(_np(r["xi_trace"][0, g]), ref["int_var_trace"][g][..., 0]) < REL
+            assert HM.rel_err(_np(r["xi_traj"][0, g]), ref["xi_traj"][g][:, 0]) < REL
+
+
+@pytest.mark.parametrize("kind", ["smo", "vehicle"])
+def test_algorithm2_matches_oracle(kind):
+    import torch
+    from oracle import marginal as OMg
+    T, N, M, K = 16, 24, 8, 4
+    prob = HM.make_marg_problem(kind, T=T, N=N, M=M, seed=7)
+    V1 = HM.make_variates(prob, 1.0, seed=31)
+    f = OMg.alg1_run(prob["oracle"], N, 1.0, HM.oracle_variates(V1))
+    init_x = f["state_trace"][:, 1]
+    init_xi = [f["int_var_trace"][g][:, 1, 0] for g in range(prob["G"])]
+    V = HM.make_variates(prob, 1.0, seed=32, K=K)
+    ref = OMg.alg2_run(prob["oracle"], N, K, init_x, init_xi, lambda k: HM.oracle_variates(V, k))
+    A2 = helpers.pkg("Algorithm2").Algorithm2(N_iterations=K, **prob["prod_kwargs"])
+    f64 = dict(dtype=torch.float64, device="cuda")
+    r = A2.run(torch.as_tensor(init_x[None], **f64), torch.as_tensor(np.stack(init_xi)[None], **f64), variates=HM.device_variates(V))
+    assert int(r["status"][0]) == 0
+    assert HM.rel_err(_np(r["x_trace"][0]).transpose(1, 0, 2), ref["state_trace"]) < REL
+    for g in range(prob["G"]):
+        assert HM.rel_err(_np(r["xi_trace"][0, g]).T, ref["int_var_trace"][g][..., 0]) < REL
+        for k in range(K):
+            for j in range(4):
+                assert HM.rel_err(_np(r["sst"][4 * g + j][0, k]).reshape(-1), np.asarray(ref["suff_stats_trace"][k][g][j], dtype=np.float64).reshape(-1)) < REL
+
+
+def test_marginal_philox_mode_matches_oracle_fed_with_the_library_stream():
+    """Philox mode: export the library's own variates (pgas_philox_marg_variates_f64) and feed them to the oracle."""
+    import ctypes as C
+    import torch
+    from oracle import marginal as OMg
+    L = helpers.pkg("_lib")
+    A1m = helpers.pkg("Algorithm1")
+    T, N, M = 20, 48, 10
+    prob = HM.make_marg_problem("smo", T=T, N=N, M=M, seed=9)
+    lam = 0.98
+    A1 = A1m.Algorithm1(forgetting_factor=lam, **prob["prod_kwargs"])
+    key = helpers.pkg("random").key(2024)
+    r = A1.filter(key=key, chain_base=3)
+    df = np.ascontiguousarray(HM.predictive_df(prob, lam))
+    f64 = dict(dtype=torch.float64, device="cuda")
+    Z, ZX, U, TS = torch.empty((1, T, N, 2), **f64), torch.empty((1, 1, N), **f64), torch.empty((1, T, 2), **f64), torch.empty((1, 1, T, N), **f64)
+    rng = A1m.make_marg_rng(key, 3, 0)
+    L.check(L.lib().pgas_philox_marg_variates_f64(C.byref(rng), 1, 1, T, N, 2, df.ctypes.data_as(C.POINTER(C.c_double)), L.ptr(Z), L.ptr(ZX),
+                                                  L.ptr(U), L.ptr(TS), L.stream_ptr()))
+    V = dict(Z=_np(Z[0]), ZXI0=_np(ZX[0]), U=_np(U[0]), TS=_np(TS[0]))
+    assert abs(V["Z"].mean()) < 0.1 and abs(V["Z"].std() - 1) < 0.1 and 0.2 < V["U"].mean() < 0.8
+    ref = OMg.alg1_run(prob["oracle"], N, lam, HM.oracle_variates(V))
+    np.testing.assert_array_equal(_np(r["anc_trace"][0]), ref["ancestor_trace"])
+    assert HM.rel_err(_np(r["state_trace"][0]), ref["state_trace"]) < REL
+    assert HM.rel_err(_np(r["xi_trace"][0, 0]), ref["int_var_trace"][0][..., 0]) < REL
+
+
+def test_marginal_chains_are_independent_of_batching():
+    """chain ids, not launch geometry, define the streams: 3 chains at once == chain 2 alone"""
+    A1m = helpers.pkg("Algorithm1")
+    prob = HM.make_marg_problem("emps", T=16, N=32, M=9, seed=2)
+    A1 = A1m.Algorithm1(forgetting_factor=0.999, **prob["prod_kwargs"])
+    key = helpers.pkg("random").key(77)
+    a = A1.filter(key=key, n_chains=3, chain_base=0)
+    b = A1.filter(key=key, n_chains=1, chain_base=2)
+    np.testing.assert_array_equal(_np(a["anc_trace"][2]), _np(b["anc_trace"][0]))
+    np.testing.assert_array_equal(_np(a["state_trace"][2]), _np(b["state_trace"][0]))
+
+
+def test_log_base_measure_batched():
+    import torch
+    from oracle import mniw as OM
+    L = helpers.pkg("_lib")
+    rng = np.random.default_rng(0)
+    n, M = 9, 17
+    Phi = rng.normal(size=(n, 40, M))
+    y = rng.normal(size=(n, 40))
+    T1 = np.einsum("ntm,ntk->nmk", Phi, Phi) + np.eye(M)
+    T0 = np.einsum("ntm,nt->nm", Phi, y)
+    T2 = np.einsum("nt,nt->n", y, y) + 1.0
+    T3 = 40.0 + rng.integers(0, 5, size=n)
+    ref = np.array([OM.prior_mniw_log_base_measure(T0[i][:, None], T1[i], np.array([[T2[i]]]), T3[i]) for i in range(n)])
+    f64 = dict(dtype=torch.float64, device="cuda")
+    out = torch.empty(n, **f64)
+    d = [torch.as_tensor(np.ascontiguousarray(a), **f64) for a in (T0, T1, T2, T3)]
+    L.check(L.lib().pgas_mniw_log_base_measure_f64(*[L.ptr(t) for t in d], n, M, L.ptr(out), L.stream_ptr()))
+    assert HM.rel_err(_np(out), ref) < REL
+
+
+def test_reference_api_tuples():
+    """Algorithm1.__call__ / Algorithm3.__call__ / Algorithm2.__call__ return the reference's tuples and shapes"""
+    A1m, A2m, A3m = helpers.pkg("Algorithm1"), helpers.pkg("Algorithm2"), helpers.pkg("Algorithm3")
+    T, N, M, K = 12, 24, 8, 3
+    prob = HM.make_marg_problem("vehicle", T=T, N=N, M=M, seed=4)
+    key = helpers.pkg("random").key(5)
+    out = A1m.Algorithm1(forgetting_factor=0.999, **prob["prod_kwargs"])(key)
+    st, iv, sst, w, anc, fin, obs, ll = out
+    assert st.shape == (T, N, 2) and len(iv) == 2 and iv[0].shape == (T, N, 1) and w.shape == (T, N)
+    assert anc.shape == (T - 1, N) and anc.dtype == np.int32 and obs.shape == (T, N, 2) and ll.shape == (T, N)
+    assert sst[1][0].shape == (T, M, 1) and sst[1][1].shape == (T, M, M) and sst[1][2].shape == (T, 1, 1) and sst[1][3].shape == (T,)
+    assert fin[0][1].shape == (N, M, M) and np.allclose(w.sum(axis=1), 1.0)
+    ref_x, ref_xi = st[:, 0], [iv[g][:, 0, 0] for g in range(2)]
+    A2 = A2m.Algorithm2(N_iterations=K, **prob["prod_kwargs"])
+    s2, iv2, w2, sst2, obs2, ll2 = A2(key, ref_x, ref_xi)
+    assert s2.shape == (T, K, 2) and iv2[1].shape == (T, K, 1) and w2.shape == (T, K) and obs2.shape == (T, K, 2) and ll2.shape == (T, K)
+    assert sst2[0][1].shape == (K, M, M) and np.allclose(s2[:, 0], ref_x) and np.all(np.isfinite(s2))
+    A3 = A3m.Algorithm3(**prob["prod_kwargs"])
+    traj, xit = A3(key, ref_x, ref_xi, [[sst2[g][j][0] for j in range(4)] for g in range(2)])
+    assert traj.shape == (T, 2) and len(xit) == 2 and xit[0].shape == (T,)
