@@ -159,42 +159,154 @@ __device__ double philox_student_t(unsigned long long seed, unsigned purpose, un
     return z * sqrt(a0 / g);
 }
 
+// The Philox blocks one particle needs in a step, evaluated in parallel across lanes (the serial versions
+// above define the stream; this only changes who computes which block):
+//   lanes 3g, 3g+1, 3g+2 : GP g — Student-t normal (slot 0), first Marsaglia-Tsang attempt normal / uniform (slots 2, 3)
+//   lanes 3G + p         : state normals of pair p
+struct StepVariates {
+    double zs[MG_NX];
+    double tz[MG_GP], tx[MG_GP], tu[MG_GP];
+};
+__device__ __forceinline__ StepVariates philox_step_variates(unsigned long long seed, unsigned chain, unsigned iter, unsigned t, unsigned i,
+                                                             int G, int nx, int lane) {
+    const int ng = 3 * G, npair = (nx + 1) >> 1;
+    const int g = lane / 3, slot = lane - 3 * g;
+    const bool is_t = lane < ng;
+    const unsigned purpose = is_t ? (unsigned)(PURPOSE_TVAR + g) : (unsigned)PURPOSE_STATE;
+    const unsigned code = slot == 0 ? 0u : (slot == 1 ? 2u : 3u);
+    const unsigned c1 = is_t ? (t | (code << 20)) : (t | ((unsigned)(lane - ng) << 28));
+    uint32_t o[4];
+    philox4x32_10(i, c1, iter, (purpose << 24) | (chain & 0xFFFFFFu), (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    const double ua = u53(o[0], o[1]), ub = u53(o[2], o[3]);
+    const double r = sqrt_bf(fmax(-2.0 * log_unit_bf(ua + (1.0 / 9007199254740992.0)), 1e-300));
+    double sn, cs;
+    sincospi_bf(2.0 * ub, sn, cs);
+    const double za = r * cs, zb = r * sn;
+    StepVariates v;
+    for (int gg = 0; gg < MG_GP; ++gg) {
+        v.tz[gg] = __shfl_sync(FULL, za, min(3 * gg, 31));
+        v.tx[gg] = __shfl_sync(FULL, za, min(3 * gg + 1, 31));
+        v.tu[gg] = __shfl_sync(FULL, ua, min(3 * gg + 2, 31));
+    }
+    for (int p = 0; p < (MG_NX >> 1); ++p) {
+        v.zs[2 * p] = __shfl_sync(FULL, za, min(ng + p, 31));
+        v.zs[2 * p + 1] = __shfl_sync(FULL, zb, min(ng + p, 31));
+    }
+    (void)npair;
+    return v;
+}
+
+// Student-t variate from pre-computed first-attempt pieces; falls back to the serial stream when the first
+// attempt is rejected or the shape is below one (identical values by construction).
+__device__ __forceinline__ double student_t_from(const StepVariates& v, int g, unsigned long long seed, unsigned purpose, unsigned chain,
+                                                 unsigned iter, unsigned t, unsigned i, double df) {
+    const double a = 0.5 * df;
+    if (a >= 1.0) {
+        const double tiny = 1.0 / 9007199254740992.0;
+        const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+        const double x = v.tx[g];
+        double w = 1.0 + c * x;
+        if (w > 0.0) {
+            w = w * w * w;
+            if (log(v.tu[g] + tiny) < 0.5 * x * x + d - d * w + d * log(w)) return v.tz[g] * sqrt(a / (d * w));
+        }
+    }
+    return philox_student_t(seed, purpose, chain, iter, t, i, df);
+}
+
 // ---------------------------------------------------------------------------------- warp linear algebra
 // In-place left-looking Cholesky of a packed (row-major, lower) matrix in shared memory by one warp.
 // The leading M x M block is factored; rows M .. R-1 ride along as right-hand sides (row M+e becomes
 // (L^-1 b_e)^T in its first M entries; entries beyond column M-1 are left untouched).  Diagonal slots
 // receive 1 / L_jj.  Returns log det = sum_j log(pivot_j) (identical on all lanes).
+//
+// Columns are processed in panels of four: a lane owns row J + lane (+32 per pass) and accumulates the
+// four dot products of the panel at once — one load of its own row entry and four broadcast loads feed
+// four independent DFMAs — then the 4 x 4 diagonal block is resolved with shuffles from the lanes that
+// own the panel's rows.  Pivots are parked in registers (lane j % 32) so that the logarithms of the
+// determinant run once, in parallel, after the sweep.
 __device__ double warp_chol_packed(double* A, int M, int R, int lane, int& fail) {
-    double logdet = 0.0;
-    for (int j = 0; j < M; ++j) {
-        const double* rj = A + tri(j);
-        double invd = 0.0;
-        for (int i0 = j; i0 < R; i0 += 32) {
-            const int i = i0 + lane;
-            double s = 0.0;
-            if (i < R) {
-                const double* ri = A + tri(i);
-                double s0 = ri[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int k = 0;
-                for (; k + 3 < j; k += 4) {
-                    s0 = fma(-ri[k], rj[k], s0);
-                    s1 = fma(-ri[k + 1], rj[k + 1], s1);
-                    s2 = fma(-ri[k + 2], rj[k + 2], s2);
-                    s3 = fma(-ri[k + 3], rj[k + 3], s3);
-                }
-                for (; k < j; ++k) s0 = fma(-ri[k], rj[k], s0);
-                s = (s0 + s1) + (s2 + s3);
+    double pv0 = 1.0, pv1 = 1.0, pv2 = 1.0, pv3 = 1.0;        // pivot of column lane + 32 q
+#define MG_SAVE_PIVOT(col, d) do { if (lane == ((col) & 31)) { const int q_ = (col) >> 5; \
+    pv0 = q_ == 0 ? (d) : pv0; pv1 = q_ == 1 ? (d) : pv1; pv2 = q_ == 2 ? (d) : pv2; pv3 = q_ == 3 ? (d) : pv3; } } while (0)
+    for (int J = 0; J < M; J += 4) {
+        const int nc = min(4, M - J);
+        const double* r0 = A + tri(J);
+        const double* r1 = A + tri(J + (nc > 1 ? 1 : 0));
+        const double* r2 = A + tri(J + (nc > 2 ? 2 : 0));
+        const double* r3 = A + tri(J + (nc > 3 ? 3 : 0));
+        double i0v = 0.0, i1v = 0.0, i2v = 0.0, i3v = 0.0;             // 1 / L_jj of the panel columns
+        double b10 = 0.0, b20 = 0.0, b21 = 0.0, b30 = 0.0, b31 = 0.0, b32 = 0.0;   // L[J+c][J+c'] of the diagonal block
+        for (int ib = J; ib < R; ib += 32) {
+            const int i = ib + lane;
+            const bool act = i < R;
+            const double* ri = A + tri(act ? i : R - 1);
+            double s0 = ri[J], s1 = ri[J + (nc > 1 ? 1 : 0)], s2 = ri[J + (nc > 2 ? 2 : 0)], s3 = ri[J + (nc > 3 ? 3 : 0)];
+            int k = 0;
+            for (; k + 1 < J; k += 2) {
+                const double a0 = ri[k], a1 = ri[k + 1];
+                s0 = fma(-a0, r0[k], s0); s1 = fma(-a0, r1[k], s1); s2 = fma(-a0, r2[k], s2); s3 = fma(-a0, r3[k], s3);
+                s0 = fma(-a1, r0[k + 1], s0); s1 = fma(-a1, r1[k + 1], s1); s2 = fma(-a1, r2[k + 1], s2); s3 = fma(-a1, r3[k + 1], s3);
             }
-            if (i0 == j) {
-                const double d = __shfl_sync(FULL, s, 0);
+            if (k < J) {
+                const double a0 = ri[k];
+                s0 = fma(-a0, r0[k], s0); s1 = fma(-a0, r1[k], s1); s2 = fma(-a0, r2[k], s2); s3 = fma(-a0, r3[k], s3);
+            }
+            const bool first = ib == J;
+            // column J
+            if (first) {
+                const double d = __shfl_sync(FULL, s0, 0);
                 if (!(d > 0.0)) fail = 1;
-                invd = rsqrt(d);
-                if (lane == (j & 31)) logdet += log(d);
+                i0v = rsqrt(d);
+                MG_SAVE_PIVOT(J, d);
             }
-            if (i < R) A[tri(i) + j] = (i == j) ? invd : s * invd;
+            const double l0 = s0 * i0v;
+            // column J + 1
+            if (first) b10 = __shfl_sync(FULL, l0, 1);
+            s1 = fma(-l0, b10, s1);
+            if (first && nc > 1) {
+                const double d = __shfl_sync(FULL, s1, 1);
+                if (!(d > 0.0)) fail = 1;
+                i1v = rsqrt(d);
+                MG_SAVE_PIVOT(J + 1, d);
+            }
+            const double l1 = s1 * i1v;
+            // column J + 2
+            if (first) { b20 = __shfl_sync(FULL, l0, 2); b21 = __shfl_sync(FULL, l1, 2); }
+            s2 = fma(-l1, b21, fma(-l0, b20, s2));
+            if (first && nc > 2) {
+                const double d = __shfl_sync(FULL, s2, 2);
+                if (!(d > 0.0)) fail = 1;
+                i2v = rsqrt(d);
+                MG_SAVE_PIVOT(J + 2, d);
+            }
+            const double l2 = s2 * i2v;
+            // column J + 3
+            if (first) { b30 = __shfl_sync(FULL, l0, 3); b31 = __shfl_sync(FULL, l1, 3); b32 = __shfl_sync(FULL, l2, 3); }
+            s3 = fma(-l2, b32, fma(-l1, b31, fma(-l0, b30, s3)));
+            if (first && nc > 3) {
+                const double d = __shfl_sync(FULL, s3, 3);
+                if (!(d > 0.0)) fail = 1;
+                i3v = rsqrt(d);
+                MG_SAVE_PIVOT(J + 3, d);
+            }
+            const double l3 = s3 * i3v;
+            if (act) {
+                double* wi = A + tri(i) + J;
+                if (i >= J) wi[0] = (i == J) ? i0v : l0;
+                if (nc > 1 && i >= J + 1) wi[1] = (i == J + 1) ? i1v : l1;
+                if (nc > 2 && i >= J + 2) wi[2] = (i == J + 2) ? i2v : l2;
+                if (nc > 3 && i >= J + 3) wi[3] = (i == J + 3) ? i3v : l3;
+            }
         }
         __syncwarp();
     }
+#undef MG_SAVE_PIVOT
+    double logdet = 0.0;
+    if (lane < M) logdet += log(pv0);
+    if (lane + 32 < M) logdet += log(pv1);
+    if (lane + 64 < M) logdet += log(pv2);
+    if (lane + 96 < M) logdet += log(pv3);
     return warp_sum(logdet);
 }
 
@@ -359,6 +471,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
         const int ac = min(max(anc, 0), N - 1);                      // JAX gathers clamp
         const bool pinned = (MODE == 1) && (i == N - 1);
         double x[MG_NX], xi[MG_GP], z[MG_D], T2v[MG_GP], T3v[MG_GP];
+        StepVariates sv;
         // ---- new state
         if (t == 0) {
             double zz[MG_NX];
@@ -376,16 +489,11 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             }
         } else {
             double zz[MG_NX];
-            for (int k = 0; k < nx; k += 2) {
-                double za = 0.0, zb = 0.0;
-                if (!m.deterministic) {
-                    if (a.rng_mode == 1) {
-                        za = Zc[((size_t)t * N + i) * nx + k];
-                        zb = (k + 1 < nx) ? Zc[((size_t)t * N + i) * nx + k + 1] : 0.0;
-                    } else philox_normal2(a.seed, PURPOSE_STATE, pchain, a.iteration, (unsigned)t | ((unsigned)(k >> 1) << 28), (unsigned)i, za, zb);
-                }
+            if (a.rng_mode != 1) sv = philox_step_variates(a.seed, pchain, a.iteration, (unsigned)t, (unsigned)i, G, nx, lane);
+            for (int k = 0; k < nx; ++k) {
+                double za = 0.0;
+                if (!m.deterministic) za = (a.rng_mode == 1) ? Zc[((size_t)t * N + i) * nx + k] : sv.zs[k];
                 zz[k] = za;
-                if (k + 1 < nx) zz[k + 1] = zb;
             }
             for (int r = 0; r < nx; ++r) {
                 double s = ldcg(wq + L.auxx + (size_t)ac * nx + r);     // f(x[a], u_{t-1}, xi[a]) = aux state of the ancestor
@@ -428,7 +536,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                 const double df = (gp.p3 + lam * T3a) + 1.0 - 1.0;        // df + 1 - n_xi (src/BayesianInferrence.py:78)
                 double tv;
                 if (a.rng_mode == 1) tv = TSc[((size_t)g * T + t) * N + i];
-                else tv = philox_student_t(a.seed, PURPOSE_TVAR + g, pchain, a.iteration, (unsigned)t, (unsigned)i, df);
+                else tv = student_t_from(sv, g, a.seed, PURPOSE_TVAR + g, pchain, a.iteration, (unsigned)t, (unsigned)i, df);
                 xiv = ms + sqrt(psia / df) * tv * sqrt(cs);               // src/BayesianInferrence.py:98-108
             }
             if (pinned) xiv = refxi[(size_t)g * a.ref_xi_gstride + t];
@@ -500,7 +608,11 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             if (MODE == 1) {
                 // g_t - g_T (src/Algorithm3.py:92-106); lambda = 1 here
                 const double T3n = T3v[g], T2n = T2v[g];
-                const double gt = log_base_measure(M, logdet, psi, gp.p3 + T3n);
+                // Only the particle-dependent terms of prior_mniw_log_base_measure are kept: -n m/2 log(2 pi)
+                // cancels between g_t and g_T, and -nu n/2 log 2 - multigammaln(nu/2, n) depend on T3 alone, which
+                // is the same for every particle (T3 = lambda T3[a] + 1 from a common start), so they shift all
+                // ancestor log-weights equally and vanish in the softmax (src/Algorithm3.py:115-118).
+                const double gt = 0.5 * logdet + log(psi) * (0.5 * (gp.p3 + T3n));
                 const size_t trow = (size_t)chain * T + t;
                 const double* PR1 = a.tab.PR1[g] + trow * npk;
                 const double* PR0 = a.tab.PR0[g] + trow * M;
@@ -514,7 +626,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                 double y2 = 0.0;
                 for (int k = lane; k < M; k += 32) { const double y = wc.B[rowM + k]; y2 = fma(y, y, y2); }
                 const double psi2 = wc.B[rowM + M] - warp_sum(y2);
-                const double gT = log_base_measure(M, logdet2, psi2, a.tab.PR3[g][trow] + T3n);
+                const double gT = 0.5 * logdet2 + log(psi2) * (0.5 * (a.tab.PR3[g][trow] + T3n));
                 gdiff += gt - gT;
             }
             __syncwarp();
@@ -560,30 +672,32 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
         __syncthreads();
     };
 
-    // ------------------------------------------------------------------ t = 0
-    for (int i = wg; i < N; i += WT) particle_pass(0, i, 0);
-
-    // ------------------------------------------------------------------ t = 1 .. T-1
+    // ------------------------------------------------------------------ t = 0 .. T-1
     const bool want_sst = (MODE == 0) && a.sst[0] != nullptr;
     const int last_owner_rank = ((N - 1) % WT) / NW;
-    for (int t = 1; t < T; ++t) {
-        mg_cluster_barrier(multi);
-        const double* wq = wsc + (size_t)((t - 1) & 1) * L.parity_stride;
-        if (want_sst) weighted_trace(t - 1);
-        double u_res, u_anc;
-        if (a.rng_mode == 1) { u_res = Uc[(size_t)t * 2]; u_anc = Uc[(size_t)t * 2 + 1]; }
-        else philox_uniform2(a.seed, PURPOSE_STEP_U, pchain, a.iteration, (unsigned)t, 0u, u_res, u_anc);
-        if (MODE == 1 && rank == last_owner_rank) {
-            // ancestor of the conditioned path (src/Algorithm3.py:115-125); not clipped in the reference
-            cta_softmax_cdf(wq + L.lwanc, N, false, true, cdf, red, tid, nthr);
-            if (tid == 0) s_refidx = count_below(cdf, N, u_anc);
-            __syncthreads();
+    const double dN = (double)N;
+    for (int t = 0; t < T; ++t) {
+        double u_res = 0.0, u_anc = 0.0;
+        if (t > 0) {
+            mg_cluster_barrier(multi);
+            const double* wq = wsc + (size_t)((t - 1) & 1) * L.parity_stride;
+            if (want_sst) weighted_trace(t - 1);
+            if (a.rng_mode == 1) { u_res = Uc[(size_t)t * 2]; u_anc = Uc[(size_t)t * 2 + 1]; }
+            else philox_uniform2(a.seed, PURPOSE_STEP_U, pchain, a.iteration, (unsigned)t, 0u, u_res, u_anc);
+            if (MODE == 1 && rank == last_owner_rank) {
+                // ancestor of the conditioned path (src/Algorithm3.py:115-125); not clipped in the reference
+                cta_softmax_cdf(wq + L.lwanc, N, false, true, cdf, red, tid, nthr);
+                if (tid == 0) s_refidx = count_below(cdf, N, u_anc);
+                __syncthreads();
+            }
+            cta_softmax_cdf(wq + L.lwaux, N, true, true, cdf, red, tid, nthr);
         }
-        cta_softmax_cdf(wq + L.lwaux, N, true, true, cdf, red, tid, nthr);
-        const double dN = (double)N;
         for (int i = wg; i < N; i += WT) {
-            int anc = min(count_below(cdf, N, __ddiv_rn(__dadd_rn(u_res, (double)i), dN)), N - 1);   // src/Filtering.py:28-35
-            if (MODE == 1 && i == N - 1) anc = s_refidx;
+            int anc = 0;
+            if (t > 0) {
+                anc = min(count_below(cdf, N, __ddiv_rn(__dadd_rn(u_res, (double)i), dN)), N - 1);   // src/Filtering.py:28-35
+                if (MODE == 1 && i == N - 1) anc = s_refidx;
+            }
             particle_pass(t, i, anc);
         }
     }
