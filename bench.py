@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """bench.py — PGAS particle-steps/s on the BASELINE.json workload "scaled single-mass oscillator":
-N=4096 particles, T=2000 steps, M=256 basis functions (2-D Hilbert GP), 64 independent chains in total,
-sharded over the GPUs (strong scaling: 64/G chains per GPU; chains never communicate, one NCCL
-all-gather of the per-chain trajectories at the end).
+N=4096 particles, T=2000 steps, M=256 basis functions (2-D Hilbert GP), 64 independent chains per GPU
+(weak scaling: the path shards over independent chains, every GPU runs the one-GPU workload on its own
+chain ids; chains never communicate, one NCCL all-gather of the per-chain trajectories at the end;
+`--scaling strong` shards 64 chains in total instead).
 
 One "step" = one full Gibbs iteration of every chain of the job: conditional-SMC sweep (persistent
 kernel) -> final pick + backward trace -> sufficient statistics -> MNIW posterior draw.
@@ -159,13 +160,64 @@ def run_reference_arm(args):
               f"per step, NumPy restatement of the reference (oracle/); jax 0.4.38 / equinox 0.12.2 not installable offline")
     line = {"impl": "reference", "metric": "pgas_particle_steps_per_s", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "scaled single-mass oscillator: N=4096, T=2000, M=256, 64 chains (BASELINE.json configs[3])",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "scaled single-mass oscillator: N=4096, T=2000, M=256, 64 chains per GPU (BASELINE.json configs[3])",
                        "sample": sample},
             "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- marginalised path (group B)
+def marginalised_leg(key_mod):
+    """Shipped single-mass-oscillator configuration (BASELINE.json configs[0]: N=200, T=750, M=41) through the
+    marginalised PGAS (Algorithm2 -> Algorithm3): conditional sweeps per second for 1 chain and for 7 replicas
+    (7 clusters of 16 CTAs are co-resident on B200, profiles/r01_microbench.md), beside the NumPy restatement of one Algorithm3 step on one host core."""
+    import importlib
+    import torch
+    S = importlib.import_module("src.SingleMassOscillator")
+    a1, a2 = S.SMO_Algorithm1, S.SMO_Algorithm2
+    m = a1.model
+    N, T = a1.N_samples, m.T
+    key = key_mod.key(SEED)
+    r = a1.filter(key=key)
+    x0, xi0 = r["state_trace"][0, :, 0].contiguous(), r["xi_trace"][0, :, :, 0].contiguous()
+    out = {"workload": f"SingleMassOscillator as shipped: N={N}, T={T}, M={m.M[0]}, Algorithm2/3 (marginalised PGAS)"}
+    for nc in (1, 7):
+        ix, ixi = x0[None].repeat(nc, 1, 1), xi0[None].repeat(nc, 1, 1)
+        a2.run(ix, ixi, key=key, K=2, want_sst=True)
+        torch.cuda.synchronize()
+        K = 4
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rr = a2.run(ix, ixi, key=key, K=K + 1, want_sst=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        assert bool(torch.isfinite(rr["x_trace"]).all()) and int(rr["status"].abs().sum()) == 0
+        out[f"chains_{nc}"] = {"ms_per_sweep": ms, "us_per_step": 1e3 * ms / (T - 1), "sweeps_per_s": nc / (ms * 1e-3),
+                               "particle_steps_per_s": nc * N * (T - 1) / (ms * 1e-3)}
+    # CPU: the oracle's Algorithm3 step (NumPy restatement, one core), a few steps at the same N and M
+    try:
+        from threadpoolctl import threadpool_limits
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers_marginal as HM
+        from oracle import marginal as OMg
+        steps = 4
+        prob = HM.make_marg_problem("smo", T=steps + 1, N=N, M=m.M[0], seed=1)
+        V = HM.make_variates(prob, 1.0, seed=2)
+        ref_x, ref_xi = np.zeros((steps + 1, 2)), [np.zeros(steps + 1)]
+        rs = OMg.reference_stats(prob["oracle"], ref_x, ref_xi)
+        with threadpool_limits(limits=1):
+            t0 = time.perf_counter()
+            OMg.alg3_run(prob["oracle"], N, ref_x, ref_xi, rs, HM.oracle_variates(V))
+            dt = time.perf_counter() - t0
+        out["cpu_port"] = {"particle_steps_per_s": N * steps / dt, "cores": 1, "kind": "port",
+                           "sample": f"{steps} Algorithm3 steps at N={N}, M={m.M[0]} (oracle/marginal.py, single thread)"}
+    except Exception as e:          # the oracle is test infrastructure; the GPU numbers stand without it
+        out["cpu_port"] = {"error": str(e)}
+    return out
 
 
 # ------------------------------------------------------------------------------- GPU arm
@@ -195,6 +247,8 @@ def run_gpu_arm(args):
     T = args.T
     hgp, sd = BF.generate_Hilbert_BasisFunction(M_BASIS, w["domain"], w["lengthscale"], w["scale"])
     prior = BI.prior_mniw_2naturalPara(np.zeros((2, M_BASIS)), np.diag(sd), np.eye(2), w["df"])
+    if args.scaling == "weak":
+        args.chains = args.chains * world                    # per-GPU work fixed: 64 chains on every rank
     first, count = DI.shard_chains(args.chains, rank, world)
     K = args.steps + args.warmup + 1                         # iteration 0 is the initial draw
     del K
@@ -311,10 +365,10 @@ def run_gpu_arm(args):
         cpu = cpu_baseline_single() if (world == 1 and not args.no_cpu_baseline) else None
         line = {
             "metric": "pgas_particle_steps_per_s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"scaled single-mass oscillator (BASELINE.json configs[3]): N={N} particles, T={T} steps, M={M_BASIS} basis "
-                                   f"functions (2-D Hilbert GP), {args.chains} independent chains in total, {count} on rank 0",
+                                   f"functions (2-D Hilbert GP), {args.chains} independent chains in total, {count} on rank 0 ({args.scaling} scaling)",
                        "step": "one Gibbs iteration of every chain: cSMC sweep + pick/backward trace + sufficient statistics + MNIW draw",
                        "cluster_size": args.cluster, "l2": "per-step working set (state + ancestor traces, "
                        f"{count * T * N * 20 / 1e9:.1f} GB on rank 0) exceeds the 126 MB L2", "rng": "Philox-4x32-10 in-kernel"},
@@ -335,6 +389,8 @@ def run_gpu_arm(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_marginalised:
+            line["marginalised"] = marginalised_leg(RND)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -347,7 +403,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chains", type=int, default=CHAINS_TOTAL)
+    ap.add_argument("--chains", type=int, default=CHAINS_TOTAL, help="chains per GPU (weak scaling) or in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-marginalised", action="store_true", help="skip the marginalised-path (Algorithm2/3) leg")
     ap.add_argument("--particles", type=int, default=N_PART)
     ap.add_argument("--T", type=int, default=T_STEPS)
     ap.add_argument("--cluster", type=int, default=0)

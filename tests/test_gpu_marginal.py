@@ -176,3 +176,23 @@ def test_reference_api_tuples():
     A3 = A3m.Algorithm3(**prob["prod_kwargs"])
     traj, xit = A3(key, ref_x, ref_xi, [[sst2[g][j][0] for j in range(4)] for g in range(2)])
     assert traj.shape == (T, 2) and len(xit) == 2 and xit[0].shape == (T,)
+
+
+def test_shipped_smo_pipeline_recovers_the_spring_damper_force(tmp_path):
+    """SURVEY.md 8c pin (4): the shipped single-mass-oscillator pipeline (Algorithm1 -> Algorithm2, N=200, T=750, M=41,
+    reduced to 30 Gibbs iterations) learns F_sd on the visited states: posterior-mean RMSE well below the force's RMS
+    (measured 0.057 of it at K=40 on B200).  Replaces the comparison with plots/SingleMassOscillator.mat, a Git-LFS stub."""
+    import os
+    import sys
+    import scipy.io
+    sys.path.insert(0, os.path.join(helpers.ROOT, "drivers"))
+    import run_example
+    out = str(tmp_path / "smo.mat")
+    md, summary = run_example.run("smo", iterations=30, out=out, quiet=True)
+    assert summary["rmse_F_on_trajectory"] < 0.12 * summary["rms_F_true"], summary
+    back = scipy.io.loadmat(out)
+    for k in ("offline_Sigma_X", "offline_Sigma_F", "offline_T1", "online_T0", "online_weights", "basis_plot", "prior_T1", "F_sd_true_plot"):
+        assert k in back
+    assert back["offline_Sigma_X"].shape == (750, 30, 2) and back["offline_T1"].shape == (30, 41, 41)
+    assert back["online_Sigma_F"].shape == (750, 200, 1) and back["basis_plot"].shape == (2500, 41)
+    assert np.all(np.isfinite(back["offline_Sigma_X"])) and np.all(np.isfinite(back["online_log_likelihood"]))
