@@ -66,29 +66,40 @@ __host__ __device__ __forceinline__ int sine_tile_doubles(const DevModel& m) {
 // on the FP64 tensor pipe (mma.sync m8n8k4: A = sines, B = Theta' fragments from shared memory);
 // the per-row scaling and a 4-lane reduction finish it.  Row leaders (lane%4 == 0) write mu to
 // mus[k*P + particle]; after the closing __syncwarp every owner can read its own entry.
-template <int NX, int D>
-__device__ __forceinline__ void eval_mu_warp(const DevModel& m, const double* __restrict__ bfrag, const int* __restrict__ rowpos,
-                                             const int* __restrict__ ntc_s, double* __restrict__ tile, const double tz[D],
-                                             int lane, double* __restrict__ mus, int P, int il0) {
-    const int q = lane & 3, r = lane >> 2;
-    const int KS = m.KS, NTNP = m.NTNP;
-    // tile layout: last dimension first (jmax rows), then the leading dimensions
-    int dim_off[D];
-    dim_off[D - 1] = 0;
-    {
+// constants of the contraction, derived from the model ONCE per kernel and kept in registers (reading
+// kernel parameters with run-time indices inside the time loop costs issue slots on every step)
+template <int D>
+struct EvalCtx {
+    int NTNP, f_start, f_step;
+    int dim_off[D], npos[D];       // tile layout: last dimension first (jmax rows), then the leading dimensions
+    __device__ __forceinline__ void init(const DevModel& m) {
+        NTNP = m.NTNP; f_start = m.f_start; f_step = m.f_step;
+        dim_off[D - 1] = 0;
         int o = m.jmax + 4;
 #pragma unroll
         for (int d = 0; d + 1 < D; ++d) { dim_off[d] = o; o += (m.npos_d[d] + 3) & ~3; }
+#pragma unroll
+        for (int d = 0; d < D; ++d) npos[d] = (d == D - 1) ? m.jmax : ((m.npos_d[d] + 3) & ~3);
     }
+};
+
+// kcb[b] = number of position steps whose non-zero column tiles reach into column block b (rows are sorted
+// by decreasing length, so the non-zero (step, block) pairs of a block are a prefix of the steps): the
+// contraction runs DENSE, branch-free DMMAs over exactly those steps.
+template <int NX, int D>
+__device__ __forceinline__ void eval_mu_warp(const EvalCtx<D>& cx, const double* __restrict__ bfrag, const int* __restrict__ rowpos,
+                                             const int* __restrict__ kcb, double* __restrict__ tile, const double tz[D],
+                                             int lane, double* __restrict__ mus, int P, int il0) {
+    const int q = lane & 3, r = lane >> 2;
+    const int NTNP = cx.NTNP;
     PGAS_FTICK(1);
     double cur0[D], prev0[D], twoc[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) sine_seed(tz[d], m.f_start, m.f_step, cur0[d], prev0[d], twoc[d]);
+    for (int d = 0; d < D; ++d) sine_seed(tz[d], cx.f_start, cx.f_step, cur0[d], prev0[d], twoc[d]);
     PGAS_FTICK(2);
     const int dsel = (lane >> 3) & 1, par = lane >> 4;
-    int npos[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) npos[d] = (d == D - 1) ? m.jmax : ((m.npos_d[d] + 3) & ~3);
+    const int* dim_off = cx.dim_off;
+    const int* npos = cx.npos;
 
     for (int h = 0; h < 4; ++h) {
         // ---- sines of this pass's 8 particles -> tile[dim][pos][8].  One instruction stream for all lanes:
@@ -143,27 +154,19 @@ __device__ __forceinline__ void eval_mu_warp(const DevModel& m, const double* __
             double a0 = ap[0], bv[NTB];
 #pragma unroll
             for (int j = 0; j < NTB; ++j) bv[j] = bp[j * 32];
-            int ntc = ntc_s[0] - nb;
-            for (int ks = 0; ks < KS; ++ks) {
+            const int kc = kcb[nb / NTB];
+            for (int ks = 0; ks < kc; ++ks) {
                 ap += 4 * TILE_PS;
                 bp += bstep;
                 const double a_n = ap[0];
                 double b_n[NTB];
 #pragma unroll
                 for (int j = 0; j < NTB; ++j) b_n[j] = bp[j * 32];
-                const int ntc_n = ntc_s[ks + 1] - nb;
-                switch (ntc) {                                   // warp-uniform: straight-line DMMAs, no predication
-                    default: dmma_m8n8k4(acc[4][0], acc[4][1], a0, bv[4]);
-                    case 4: dmma_m8n8k4(acc[3][0], acc[3][1], a0, bv[3]);
-                    case 3: dmma_m8n8k4(acc[2][0], acc[2][1], a0, bv[2]);
-                    case 2: dmma_m8n8k4(acc[1][0], acc[1][1], a0, bv[1]);
-                    case 1: dmma_m8n8k4(acc[0][0], acc[0][1], a0, bv[0]);
-                    case 0: break;
-                }
+#pragma unroll
+                for (int j = 0; j < NTB; ++j) dmma_m8n8k4(acc[j][0], acc[j][1], a0, bv[j]);
                 a0 = a_n;
 #pragma unroll
                 for (int j = 0; j < NTB; ++j) bv[j] = b_n[j];
-                ntc = ntc_n;
             }
             PGAS_FTICK(4 + 4 * h);
             // ---- per-row scaling by the leading-dimension sines (padding rows have zero accumulators)

@@ -203,12 +203,19 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
     int* ip = reinterpret_cast<int*>(sp);
     int* rowpos = ip;           ip += ((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD;
     int* cnt = ip;              ip += 2;
-    int* ntc_s = ip;            ip += 18;                      // per position step: non-zero column tiles (+1 pad)
+    int* ntc_s = ip;            ip += 18;                      // per column block: position steps with non-zero tiles (basis_eval.cuh: kcb)
 
     // ------------------------------------------------------------------ prologue
     for (int r = tid; r < ((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD; r += NT) rowpos[r] = m.row_pos[r];
     for (int r = Pc + tid; r < nblk * 256; r += NT) b1[r] = INFINITY;
-    if (tid < 18) ntc_s[tid] = (tid < m.KS) ? m.ntcount[tid] : 0;
+    if (tid < 18) {
+        int kc = 0;
+        for (int ks = 0; ks < m.KS; ++ks) kc += (m.ntcount[ks] > tid * NTB) ? 1 : 0;
+        ntc_s[tid] = kc;
+    }
+    EvalCtx<D> ecx;
+    ecx.init(m);
+    const int tile_doubles = sine_tile_doubles(m);
     MapRegs<NX, D> mapr;
     mapr.init(m);
     {   // Theta' = norm * Theta scattered into B-fragment order
@@ -313,7 +320,7 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
                     for (int k = 0; k < NX; ++k) x[k] = xs[(size_t)k * P + il];
                     mapr.apply(x, k_t.cz, k_t.u, tz);
                 }
-                eval_mu_warp<NX, D>(m, bfrag, rowpos, ntc_s, tiles + (size_t)warp * sine_tile_doubles(m), tz, lane, mus, P, il0);
+                eval_mu_warp<NX, D>(ecx, bfrag, rowpos, ntc_s, tiles + (size_t)warp * tile_doubles, tz, lane, mus, P, il0);
                 if (il < Pc) {
                     double mu[NX];
 #pragma unroll
