@@ -1,0 +1,79 @@
+// basis_rowwalk.cuh — mu = Theta phi(z) for TWO-dimensional Hilbert bases, one particle per thread, on the
+// FP64 FMA pipe.
+//
+// Replaces vmap(basis_fcn) + einsum("kj,ij->ik") (reference src/BasisFunctions.py:77-80, src/PGAS.py:52-55,
+// :67-70) without forming phi:
+//   mu_k = sum_i s0_i * ( sum_j Theta'[k, m(i,j)] s1_j ),   s0_i = sin(pi f_i t_0), s1_j = sin(pi f_j t_1)
+// with both sine families produced by the three-term recurrence (one sincospi per dimension and particle
+// instead of M*D libm sines).  A thread owns PP particles and walks the lattice in blocks of RW_RB first-
+// dimension positions (common.cuh): every Theta' pair is fetched ONCE per warp with a broadcast LDS.128 and
+// feeds PP * n_x independent DFMAs — no shared-memory staging of sines, no shuffles, no warp-level
+// synchronisation.  On B200 the FP64 tensor pipe (DMMA m8n8k4: 512 flops / 16 pipe cycles) and the FP64
+// FMA pipe (64 flops / 2 cycles) have the same flop rate; the tile form (basis_eval.cuh) spends its issue
+// slots on fragment traffic, this form spends them on the FMAs themselves and is bound by the FP64 pipe
+// (profiles/r01_sweep_history.md).
+#pragma once
+#include "basis_eval.cuh"
+
+template <int NX, int PP>
+__device__ __forceinline__ void rowwalk_mu(const double* __restrict__ bd, const int* __restrict__ blen, int nblk, int f_start, int f_step,
+                                           const double (&t0)[PP], const double (&t1)[PP], double (&mu)[PP][NX]) {
+    double a_cur[PP], a_prev[PP], a_2c[PP], b_cur[PP], b_prev[PP], b_2c[PP];
+#pragma unroll
+    for (int p = 0; p < PP; ++p) {
+        sine_seed(t0[p], f_start, f_step, a_cur[p], a_prev[p], a_2c[p]);
+        sine_seed(t1[p], f_start, f_step, b_cur[p], b_prev[p], b_2c[p]);
+#pragma unroll
+        for (int k = 0; k < NX; ++k) mu[p][k] = 0.0;
+    }
+    const double* th = bd;
+    for (int b = 0; b < nblk; ++b) {
+        double acc[PP][RW_RB][NX];
+        double c[PP], pv[PP];
+#pragma unroll
+        for (int p = 0; p < PP; ++p) {
+            c[p] = b_cur[p];
+            pv[p] = b_prev[p];
+#pragma unroll
+            for (int i = 0; i < RW_RB; ++i)
+#pragma unroll
+                for (int k = 0; k < NX; ++k) acc[p][i][k] = 0.0;
+        }
+        const int L = blen[b];
+#pragma unroll 2
+        for (int j = 0; j < L; ++j) {
+#pragma unroll
+            for (int i = 0; i < RW_RB; ++i) {
+                double w[NX];
+                if constexpr (NX == 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(th + i * 2);
+                    w[0] = v.x; w[1] = v.y;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NX; ++k) w[k] = th[i * NX + k];
+                }
+#pragma unroll
+                for (int p = 0; p < PP; ++p)
+#pragma unroll
+                    for (int k = 0; k < NX; ++k) acc[p][i][k] = fma(w[k], c[p], acc[p][i][k]);
+            }
+            th += RW_RB * NX;
+#pragma unroll
+            for (int p = 0; p < PP; ++p) {
+                const double n = fma(b_2c[p], c[p], -pv[p]);
+                pv[p] = c[p];
+                c[p] = n;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RW_RB; ++i)
+#pragma unroll
+            for (int p = 0; p < PP; ++p) {
+#pragma unroll
+                for (int k = 0; k < NX; ++k) mu[p][k] = fma(a_cur[p], acc[p][i][k], mu[p][k]);
+                const double n = fma(a_2c[p], a_cur[p], -a_prev[p]);
+                a_prev[p] = a_cur[p];
+                a_cur[p] = n;
+            }
+    }
+}

@@ -33,6 +33,15 @@ extern long long g_pgas_launches;
 // lattice search selects are the trailing column tiles of each position step: ntcount[ks].
 constexpr int MAX_LEAD = PGAS_MAX_D - 1;
 
+// Row-walk layout of a TWO-dimensional basis for the thread-per-particle FP64-FMA contraction
+// (basis_rowwalk.cuh): first-dimension lattice positions are grouped into blocks of RW_RB; inside a block
+// the last-dimension positions j = 0 .. blen-1 are walked once while RW_RB x n_x accumulators collect
+//   T[i][k] = sum_j Theta'[k, m(i, j)] sin(pi f_j t_last),
+// then mu_k += sin(pi f_i t_first) T[i][k].  Storage order: [block][j][i][k], zero where the lattice
+// search did not select (i, j).
+constexpr int RW_RB = 4;
+constexpr int RW_MAXBLK = 24;
+
 struct DevModel {
     int n_x, n_y, n_u, D, M, T;
     int R, NTN, KS, n_packed;     // rows, column tiles (8 wide), position steps (4 deep), KS*NTNP*32 fragment slots
@@ -51,6 +60,9 @@ struct DevModel {
     double Rw[PGAS_MAX_NY][PGAS_MAX_NY];            // inverse of chol(R) (lower): e = Rw (y - mean)
     double R_logc;                                  // -n_y/2 log(2 pi) - sum log diag chol(R)
     double m0[PGAS_MAX_NX], P0c[PGAS_MAX_NX][PGAS_MAX_NX];   // chol(P0) lower
+    int rw_ok, rw_nblk, rw_slots;                   // row-walk layout (D == 2): available, blocks, doubles
+    int rw_blen[RW_MAXBLK];                         // last-dimension positions walked per block
+    const int* rw_perm;     // [rw_slots] slot -> m * 4 + k of the Theta entry it holds, or -1 (zero)
     const int* perm;        // [n_packed] fragment slot -> m * 4 + k of the Theta entry it holds, or -1 (zero)
     const int* row_pos;     // [8*NTN / n_x rounded up][MAX_LEAD] leading-dimension positions of each row (0 for padding rows)
     const int* freq;        // [M*D] integer frequencies, reference order

@@ -173,11 +173,33 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
     for (int r = 0; r < dm.R; ++r)
         for (int d = 0; d < D - 1; ++d) row_pos[(size_t)rank[r] * MAX_LEAD + d] = row_lead[r][d];
 
+    // ---- row-walk layout (two-dimensional bases): [block][j][i][k] --------------------------
+    std::vector<int> rw_perm;
+    dm.rw_ok = 0; dm.rw_nblk = 0; dm.rw_slots = 0;
+    if (D == 2 && (dm.npos_d[0] + RW_RB - 1) / RW_RB <= RW_MAXBLK) {
+        const int nb = (dm.npos_d[0] + RW_RB - 1) / RW_RB;
+        std::vector<int> off(nb + 1, 0);
+        for (int b = 0; b < RW_MAXBLK; ++b) dm.rw_blen[b] = 0;
+        for (int mI = 0; mI < M; ++mI) {
+            const int b = pos[(size_t)mI * D] / RW_RB;
+            dm.rw_blen[b] = std::max(dm.rw_blen[b], pos[(size_t)mI * D + 1] + 1);
+        }
+        for (int b = 0; b < nb; ++b) off[b + 1] = off[b] + dm.rw_blen[b] * RW_RB * nx;
+        rw_perm.assign((size_t)off[nb], -1);
+        for (int mI = 0; mI < M; ++mI) {
+            const int p0 = pos[(size_t)mI * D], j = pos[(size_t)mI * D + 1];
+            const int b = p0 / RW_RB, i = p0 % RW_RB;
+            for (int k = 0; k < nx; ++k) rw_perm[(size_t)off[b] + ((size_t)j * RW_RB + i) * nx + k] = mI * 4 + k;
+        }
+        dm.rw_ok = 1; dm.rw_nblk = nb; dm.rw_slots = off[nb];
+    }
+
     // ---- one device arena ---------------------------------------------------------------
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_rows = al(sizeof(int) * row_pos.size()), b_perm = al(sizeof(int) * dm.n_packed), b_freq = al(sizeof(int) * M * D);
     const size_t b_obs = al(sizeof(double) * (size_t)p->T * p->n_y), b_in = al(sizeof(double) * (size_t)p->T * std::max(p->n_u, 1));
-    const size_t total = b_rows + b_perm + b_freq + b_obs + b_in;
+    const size_t b_rw = al(sizeof(int) * std::max<size_t>(rw_perm.size(), 1));
+    const size_t total = b_rows + b_perm + b_freq + b_obs + b_in + b_rw;
     char* arena = nullptr;
     PGAS_CUDA(cudaMalloc((void**)&arena, total));
     size_t o = 0;
@@ -192,6 +214,7 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
     dm.freq = (const int*)up(p->freq, sizeof(int) * M * D, b_freq);
     dm.obs = (const double*)up(p->observations, sizeof(double) * (size_t)p->T * p->n_y, b_obs);
     dm.inputs = (const double*)up(p->inputs, p->n_u ? sizeof(double) * (size_t)p->T * p->n_u : 0, b_in);
+    dm.rw_perm = (const int*)up(rw_perm.data(), sizeof(int) * rw_perm.size(), b_rw);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { cudaFree(arena); PGAS_FAIL((int)e, "model upload failed: %s", cudaGetErrorString(e)); }
 

@@ -13,6 +13,7 @@
 //   C  x_t^i = mu + chol(Sigma) z,  logw_t^i = log p(y_t|x_t^i) - l_aux[a_i],  trace row written
 #include <cooperative_groups.h>
 #include "basis_eval.cuh"
+#include "basis_rowwalk.cuh"
 #include "sweep_args.cuh"
 
 namespace cg = cooperative_groups;
@@ -180,8 +181,10 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
     // ------------------------------------------------------------------ shared memory carve
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sp = reinterpret_cast<double*>(smem_raw);
-    double* bfrag = sp;         sp += m.n_packed + (size_t)m.NTNP * 32;    // Theta' in DMMA B-fragment order (+1 zero step: prefetch)
-    double* tiles = sp;         sp += (size_t)NW * sine_tile_doubles(m);   // per-warp sine tiles
+    const bool rw = (D == 2) && m.rw_ok;                    // thread-per-particle FMA row walk (basis_rowwalk.cuh)
+    double* bfrag = sp;         sp += rw ? (size_t)((m.rw_slots + 1) & ~1)      // Theta' in row-walk order, or
+                                         : m.n_packed + (size_t)m.NTNP * 32;    // in DMMA B-fragment order (+1 zero step: prefetch)
+    double* tiles = sp;         sp += rw ? 0 : (size_t)NW * sine_tile_doubles(m);   // per-warp sine tiles (tile form only)
     double* xs = sp;            sp += (size_t)NX * P;          // [k][i]
     double* mus = sp;           sp += (size_t)NX * P;          // [k][i] auxiliary mean
     double* logw = sp;          sp += P;
@@ -204,10 +207,12 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
     int* rowpos = ip;           ip += ((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD;
     int* cnt = ip;              ip += 2;
     int* ntc_s = ip;            ip += 18;                      // per column block: position steps with non-zero tiles (basis_eval.cuh: kcb)
+    int* rwlen = ip;            ip += RW_MAXBLK;               // row-walk block lengths
 
     // ------------------------------------------------------------------ prologue
     for (int r = tid; r < ((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD; r += NT) rowpos[r] = m.row_pos[r];
     for (int r = Pc + tid; r < nblk * 256; r += NT) b1[r] = INFINITY;
+    if (tid < RW_MAXBLK) rwlen[tid] = m.rw_blen[tid];
     if (tid < 18) {
         int kc = 0;
         for (int ks = 0; ks < m.KS; ++ks) kc += (m.ntcount[ks] > tid * NTB) ? 1 : 0;
@@ -220,9 +225,16 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
     mapr.init(m);
     {   // Theta' = norm * Theta scattered into B-fragment order
         const double* Th = a.Theta + (size_t)chain * NX * m.M;
-        for (int s = tid; s < m.n_packed + m.NTNP * 32; s += NT) {
-            const int e = (s < m.n_packed) ? m.perm[s] : -1;
-            bfrag[s] = (e >= 0) ? m.norm * Th[(size_t)(e & 3) * m.M + (e >> 2)] : 0.0;
+        if (rw) {
+            for (int s = tid; s < m.rw_slots; s += NT) {
+                const int e = m.rw_perm[s];
+                bfrag[s] = (e >= 0) ? m.norm * Th[(size_t)(e & 3) * m.M + (e >> 2)] : 0.0;
+            }
+        } else {
+            for (int s = tid; s < m.n_packed + m.NTNP * 32; s += NT) {
+                const int e = (s < m.n_packed) ? m.perm[s] : -1;
+                bfrag[s] = (e >= 0) ? m.norm * Th[(size_t)(e & 3) * m.M + (e >> 2)] : 0.0;
+            }
         }
     }
     if (tid == 0) {
@@ -306,6 +318,45 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
         //      softmax numerators (:102,:118) with a WARP-local shift: exp(lw - max_warp) and its in-warp
         //      inclusive scan need no block-wide reduction; the (max, sum) pair of every warp is combined
         //      once per step by warp 0 (online-softmax rescaling), first across the CTA, then across the cluster.
+        if constexpr (D == 2) {
+            if (rw) {
+                // mu of every particle of this thread, two particles at a time (each Theta' pair read once per warp
+                // feeds 2 n_x DFMAs)
+                const int nblk_rw = m.rw_nblk;
+                int q0 = 0;
+                for (; q0 + 1 < PPT; q0 += 2) {
+                    const int ila = q0 * NT + tid, ilb = ila + NT;
+                    if (q0 * NT + warp * 32 >= Pc) break;     // warp-uniform
+                    double xa[NX], xb[NX], ta[D], tb[D];
+#pragma unroll
+                    for (int k = 0; k < NX; ++k) { xa[k] = (ila < Pc) ? xs[(size_t)k * P + ila] : 0.0; xb[k] = (ilb < Pc) ? xs[(size_t)k * P + ilb] : 0.0; }
+                    mapr.apply(xa, k_t.cz, k_t.u, ta);
+                    mapr.apply(xb, k_t.cz, k_t.u, tb);
+                    const double t0[2] = {ta[0], tb[0]}, t1[2] = {ta[1], tb[1]};
+                    double mu2[2][NX];
+                    rowwalk_mu<NX, 2>(bfrag, rwlen, nblk_rw, ecx.f_start, ecx.f_step, t0, t1, mu2);
+#pragma unroll
+                    for (int k = 0; k < NX; ++k) {
+                        if (ila < Pc) mus[(size_t)k * P + ila] = mu2[0][k];
+                        if (ilb < Pc) mus[(size_t)k * P + ilb] = mu2[1][k];
+                    }
+                }
+                for (; q0 < PPT; ++q0) {
+                    const int ila = q0 * NT + tid;
+                    if (q0 * NT + warp * 32 >= Pc) break;
+                    double xa[NX], ta[D];
+#pragma unroll
+                    for (int k = 0; k < NX; ++k) xa[k] = (ila < Pc) ? xs[(size_t)k * P + ila] : 0.0;
+                    mapr.apply(xa, k_t.cz, k_t.u, ta);
+                    const double t0[1] = {ta[0]}, t1[1] = {ta[1]};
+                    double mu1[1][NX];
+                    rowwalk_mu<NX, 1>(bfrag, rwlen, nblk_rw, ecx.f_start, ecx.f_step, t0, t1, mu1);
+#pragma unroll
+                    for (int k = 0; k < NX; ++k)
+                        if (ila < Pc) mus[(size_t)k * P + ila] = mu1[0][k];
+                }
+            }
+        }
         for (int q = 0; q < PPT; ++q) {
             const int il = q * NT + tid, il0 = q * NT + warp * 32;
             double lwa = -INFINITY, lwr = -INFINITY;
@@ -314,13 +365,15 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
 #pragma unroll
                 for (int d = 0; d < D; ++d) tz[d] = 0.0;
                 PGAS_FTICK(0);
-                if (il < Pc) {
-                    double x[NX];
+                if (!rw) {
+                    if (il < Pc) {
+                        double x[NX];
 #pragma unroll
-                    for (int k = 0; k < NX; ++k) x[k] = xs[(size_t)k * P + il];
-                    mapr.apply(x, k_t.cz, k_t.u, tz);
+                        for (int k = 0; k < NX; ++k) x[k] = xs[(size_t)k * P + il];
+                        mapr.apply(x, k_t.cz, k_t.u, tz);
+                    }
+                    eval_mu_warp<NX, D>(ecx, bfrag, rowpos, ntc_s, tiles + (size_t)warp * tile_doubles, tz, lane, mus, P, il0);
                 }
-                eval_mu_warp<NX, D>(ecx, bfrag, rowpos, ntc_s, tiles + (size_t)warp * tile_doubles, tz, lane, mus, P, il0);
                 if (il < Pc) {
                     double mu[NX];
 #pragma unroll
@@ -548,10 +601,11 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
 // ------------------------------------------------------------------------------------ launch
 static size_t sweep_smem_bytes(const DevModel& m, int NX, int P, bool gather, int NT) {
     const int NW = NT / 32;
-    size_t d = (size_t)m.n_packed + (size_t)m.NTNP * 32 + (size_t)NW * sine_tile_doubles(m) + (size_t)NX * P * 2 + (size_t)P * 4 + (size_t)((P + 255) / 256) * 256 +
+    const bool rw = (m.D == 2) && m.rw_ok;
+    size_t d = (rw ? (size_t)((m.rw_slots + 1) & ~1) : (size_t)m.n_packed + (size_t)m.NTNP * 32 + (size_t)NW * sine_tile_doubles(m)) + (size_t)NX * P * 2 + (size_t)P * 4 + (size_t)((P + 255) / 256) * 256 +
                (gather ? (size_t)NX * P : 0) + MAXC * 4 + 2 * (MAXC + 1) + 2 * MAXC + 2 + (size_t)((P + NT - 1) / NT) * NW * 8 + 2 * NX * NX + 2 +
                2 * ((sizeof(StepConst) + 7) / 8);
-    return d * 8 + (size_t)(((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD + 2 + 18) * 4 + 32;
+    return d * 8 + (size_t)(((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD + 2 + 18 + RW_MAXBLK) * 4 + 32;
 }
 
 // threads per CTA: 512 (16 warps hide the dependent-FP64 latency best) when the per-warp sine tiles
