@@ -75,9 +75,12 @@ class condSequentialMonteCarlo:
         idx = torch.empty((nc,), dtype=torch.int32, device="cuda")
         traj = torch.empty((nc, m.T, m.n_x), dtype=torch.float64, device="cuda")
         rng = _make_rng(key, chain_base, iteration, variates)
+        nbytes = int(_lib.lib().pgas_csmc_sweep_workspace_bytes(m.handle, N, nc))
+        if getattr(self, "_sweep_ws", None) is None or self._sweep_ws.numel() < nbytes:
+            self._sweep_ws = torch.empty((nbytes,), dtype=torch.uint8, device="cuda")
         _lib.check(_lib.lib().pgas_csmc_sweep_f64(m.handle, N, nc, _lib.ptr(ref), _lib.ptr(Theta), _lib.ptr(Sigma),
                                                   C.byref(rng), _lib.ptr(st), _lib.ptr(anc), _lib.ptr(lw), _lib.ptr(idx),
-                                                  _lib.ptr(traj), self.cluster_size, C.c_void_p(0), 0, _lib.stream_ptr()))
+                                                  _lib.ptr(traj), self.cluster_size, _lib.ptr(self._sweep_ws), nbytes, _lib.stream_ptr()))
         return dict(traj=traj, state_trace=st, anc_trace=anc, logw_last=lw, idx=idx)
 
     def step(self, time, log_weights, state, coeff_mat, error_cov, ref_state, u2, z):

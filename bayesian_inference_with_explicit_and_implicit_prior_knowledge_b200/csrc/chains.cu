@@ -24,7 +24,8 @@ struct ChainWs {
     double *state, *logw, *T0, *T1, *T2, *e0, *e1, *e2, *A, *S;
     int *anc, *status;
     void* draw;
-    size_t draw_bytes, total;
+    void* sweep;
+    size_t draw_bytes, sweep_bytes, total;
 };
 
 static ChainWs carve(const DevModel& m, int N, int n_chains, char* base) {
@@ -46,6 +47,8 @@ static ChainWs carve(const DevModel& m, int N, int n_chains, char* base) {
     w.status = (int*)take(sizeof(int) * C);
     w.draw_bytes = pgas_mniw_draw_workspace_bytes((int)M, (int)nx, n_chains);
     w.draw = take(w.draw_bytes);
+    w.sweep_bytes = pgas_sweep_split_workspace(m, N, n_chains);
+    w.sweep = take(w.sweep_bytes);
     w.total = o + 256;
     return w;
 }
@@ -98,6 +101,7 @@ extern "C" int pgas_run_chains_f64(const pgas_model* model, int32_t N, int32_t K
             a.state_trace = w.state; a.anc_trace = w.anc; a.logw_last = w.logw;
             a.rng_mode = r.mode; a.seed = r.seed; a.chain_base = r.chain_base; a.iteration = r.iteration;
             a.Z = r.Z; a.U = r.U;
+            a.ws = w.sweep; a.ws_bytes = w.sweep_bytes;
             if (int rc = pgas_launch_sweep(a, st)) return rc;
             if (int rc = pgas_launch_pick_and_trace(w.logw, w.state, w.anc, nullptr, n_chains, m.T, N, m.n_x, &r, m.T, nullptr, traj_k,
                                                     tstride, st))

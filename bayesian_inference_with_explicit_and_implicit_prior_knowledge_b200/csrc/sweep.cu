@@ -12,6 +12,8 @@
 //   X2 cluster barrier #2 — its latency is covered by the noise draw and the new state
 //   C  x_t^i = mu + chol(Sigma) z,  logw_t^i = log p(y_t|x_t^i) - l_aux[a_i],  trace row written
 #include <cooperative_groups.h>
+#include <algorithm>
+#include <stdlib.h>
 #include "basis_eval.cuh"
 #include "basis_rowwalk.cuh"
 #include "sweep_args.cuh"
@@ -152,7 +154,7 @@ __device__ __forceinline__ void load_step_const(const SweepArgs& a, int chain, i
         for (int k = 0; k < m.n_u; ++k) acc = fma(m.Az[d][m.n_x + k], sc->u[k], acc);
         sc->cz[d] = acc;
     }
-    for (int k = 0; k < m.n_x; ++k) sc->ref[k] = a.ref[(size_t)chain * a.ref_stride + (size_t)(t - a.row_off) * m.n_x + k];
+    for (int k = 0; k < m.n_x; ++k) sc->ref[k] = a.ref ? a.ref[(size_t)chain * a.ref_stride + (size_t)(t - a.row_off) * m.n_x + k] : 0.0;
     if (a.rng_mode == 1) {
         const double* up = a.U + ((size_t)chain * a.var_rows + (t - a.row_off)) * 2;
         sc->ures = up[0];
@@ -162,8 +164,8 @@ __device__ __forceinline__ void load_step_const(const SweepArgs& a, int chain, i
     }
 }
 
-template <int NX, int NY, int D, int NT>
-__global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant__ SweepArgs a) {
+template <int NX, int NY, int D, int NT, bool PRE>
+__global__ void __launch_bounds__(NT, (NT == 256 || PRE) ? 2 : 1) csmc_sweep_kernel(const __grid_constant__ SweepArgs a) {
     constexpr int NW = NT / 32;
     const DevModel& m = a.m;
     cg::cluster_group cluster = cg::this_cluster();
@@ -182,18 +184,18 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sp = reinterpret_cast<double*>(smem_raw);
     const bool rw = (D == 2) && m.rw_ok;                    // thread-per-particle FMA row walk (basis_rowwalk.cuh)
-    double* bfrag = sp;         sp += rw ? (size_t)((m.rw_slots + 1) & ~1)      // Theta' in row-walk order, or
+    double* bfrag = sp;         sp += PRE ? 0 : rw ? (size_t)((m.rw_slots + 1) & ~1)      // Theta' in row-walk order, or
                                          : m.n_packed + (size_t)m.NTNP * 32;    // in DMMA B-fragment order (+1 zero step: prefetch)
-    double* tiles = sp;         sp += rw ? 0 : (size_t)NW * sine_tile_doubles(m);   // per-warp sine tiles (tile form only)
-    double* xs = sp;            sp += (size_t)NX * P;          // [k][i]
-    double* mus = sp;           sp += (size_t)NX * P;          // [k][i] auxiliary mean
+    double* tiles = sp;         sp += (PRE || rw) ? 0 : (size_t)NW * sine_tile_doubles(m);   // per-warp sine tiles (tile form only)
+    double* xs = sp;            sp += PRE ? 0 : (size_t)NX * P;          // [k][i]
+    double* mus = sp;           sp += PRE ? 0 : (size_t)NX * P;          // [k][i] auxiliary mean
     double* logw = sp;          sp += P;
     double* laux = sp;          sp += P;
     const int nblk = (P + 255) / 256;
     double* b1 = sp;            sp += nblk * 256;              // lw_aux -> prefix -> CDF (padded with +inf for the search)
     double* b2 = sp;            sp += P;                       // lw_anc -> prefix
     double* lauxg = sp;         sp += P;                       // l_aux[a_i], pushed by the CDF owner
-    double* mug = sp;           sp += gather ? (size_t)NX * P : 0;
+    double* mug = sp;           sp += (gather && !PRE) ? (size_t)NX * P : 0;
     double* exch = sp;          sp += MAXC * 4;                // per-CTA (m1,s1,m2,s2), all-gathered
     double* gsum = sp;          sp += 2 * (MAXC + 1);          // exclusive CDF offsets G1[c], G2[c], c = 0..C
     double* fx = sp;            sp += 2 * MAXC + 2;            // rescale factors exp(m_c - M); then 1/S1, 1/S2
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
     const int tile_doubles = sine_tile_doubles(m);
     MapRegs<NX, D> mapr;
     mapr.init(m);
-    {   // Theta' = norm * Theta scattered into B-fragment order
+    if constexpr (!PRE) {   // Theta' = norm * Theta scattered into B-fragment order
         const double* Th = a.Theta + (size_t)chain * NX * m.M;
         if (rw) {
             for (int s = tid; s < m.rw_slots; s += NT) {
@@ -237,7 +239,11 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
             }
         }
     }
-    if (tid == 0) {
+    if (PRE && tid == 0) {
+        cnt[0] = 0;
+        load_step_const(a, chain, a.t_begin, &sc[a.t_begin & 1]);
+    }
+    if (!PRE && tid == 0) {
         // chol(Sigma) and its inverse (src/PGAS.py:72-75 multivariate_normal; :109-116 logpdf)
         const double* S = a.Sigma + (size_t)chain * NX * NX;
         double Lc[NX][NX], Li[NX][NX];
@@ -273,6 +279,10 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
     // initial particles
     for (int q = 0; q < PPT; ++q) {
         const int il = q * NT + tid;
+        if constexpr (PRE) {
+            if (il < Pc) logw[il] = a.init_logw ? a.init_logw[(size_t)chain * N + base + il] : 0.0;
+            continue;
+        }
         if (il < Pc) {
             const int i = base + il;
             double x[NX];
@@ -318,46 +328,116 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
         //      softmax numerators (:102,:118) with a WARP-local shift: exp(lw - max_warp) and its in-warp
         //      inclusive scan need no block-wide reduction; the (max, sum) pair of every warp is combined
         //      once per step by warp 0 (online-softmax rescaling), first across the CTA, then across the cluster.
-        if constexpr (D == 2) {
-            if (rw) {
-                // mu of every particle of this thread, two particles at a time (each Theta' pair read once per warp
-                // feeds 2 n_x DFMAs)
-                const int nblk_rw = m.rw_nblk;
-                int q0 = 0;
-                for (; q0 + 1 < PPT; q0 += 2) {
-                    const int ila = q0 * NT + tid, ilb = ila + NT;
-                    if (q0 * NT + warp * 32 >= Pc) break;     // warp-uniform
-                    double xa[NX], xb[NX], ta[D], tb[D];
+        // softmax numerators of four particles of this thread: warp-local shift, exp, in-warp inclusive scan —
+        // eight independent sequences interleaved; lane 31 publishes the (max, sum) pairs of the warp
+        auto softmax4 = [&](int qc, const double (&lwa)[4], const double (&lwr)[4]) {
+            double m1w[4], m2w[4], e1[4], e2[4], s1[4], s2[4];
 #pragma unroll
-                    for (int k = 0; k < NX; ++k) { xa[k] = (ila < Pc) ? xs[(size_t)k * P + ila] : 0.0; xb[k] = (ilb < Pc) ? xs[(size_t)k * P + ilb] : 0.0; }
-                    mapr.apply(xa, k_t.cz, k_t.u, ta);
-                    mapr.apply(xb, k_t.cz, k_t.u, tb);
-                    const double t0[2] = {ta[0], tb[0]}, t1[2] = {ta[1], tb[1]};
-                    double mu2[2][NX];
-                    rowwalk_mu<NX, 2>(bfrag, rwlen, nblk_rw, ecx.f_start, ecx.f_step, t0, t1, mu2);
+            for (int u = 0; u < 4; ++u) { m1w[u] = warp_shift_max(lwa[u]); m2w[u] = warp_shift_max(lwr[u]); }
 #pragma unroll
-                    for (int k = 0; k < NX; ++k) {
-                        if (ila < Pc) mus[(size_t)k * P + ila] = mu2[0][k];
-                        if (ilb < Pc) mus[(size_t)k * P + ilb] = mu2[1][k];
+            for (int u = 0; u < 4; ++u) {
+                const bool v = (qc + u) * NT + tid < Pc && qc + u < PPT;
+                e1[u] = v ? exp_neg_bf(lwa[u] - m1w[u]) : 0.0;
+                e2[u] = v ? exp_neg_bf(lwr[u] - m2w[u]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { s1[u] = e1[u]; s2[u] = e2[u]; }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {                          // eight interleaved Kogge-Stone scans
+                double n1[4], n2[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { n1[u] = __shfl_up_sync(0xffffffffu, s1[u], o); n2[u] = __shfl_up_sync(0xffffffffu, s2[u], o); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (lane >= o) { s1[u] += n1[u]; s2[u] += n2[u]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = qc + u, il = q * NT + tid;
+                if (q < PPT) {
+                    if (il < Pc) { b1[il] = s1[u]; b2[il] = s2[u]; }
+                    if (lane == 31) {
+                        double* up = unit + (size_t)(q * NW + warp) * 4;
+                        const bool any = q * NT + warp * 32 < Pc;
+                        up[0] = any ? m1w[u] : -INFINITY; up[1] = any ? s1[u] : 0.0;
+                        up[2] = any ? m2w[u] : -INFINITY; up[3] = any ? s2[u] : 0.0;
                     }
                 }
-                for (; q0 < PPT; ++q0) {
-                    const int ila = q0 * NT + tid;
-                    if (q0 * NT + warp * 32 >= Pc) break;
-                    double xa[NX], ta[D];
+            }
+        };
+        if constexpr (PRE) {
+            // log-densities were left by the state kernel (sweep_split.cu): l_aux, h; only the weight recursion runs here
+            const size_t prow = ((size_t)chain * a.pre_rows + (size_t)(t - a.pre_off)) * N + base;
+            for (int qc = 0; qc < PPT; qc += 4) {
+                double lwa[4], lwr[4];
 #pragma unroll
-                    for (int k = 0; k < NX; ++k) xa[k] = (ila < Pc) ? xs[(size_t)k * P + ila] : 0.0;
-                    mapr.apply(xa, k_t.cz, k_t.u, ta);
-                    const double t0[1] = {ta[0]}, t1[1] = {ta[1]};
-                    double mu1[1][NX];
-                    rowwalk_mu<NX, 1>(bfrag, rwlen, nblk_rw, ecx.f_start, ecx.f_step, t0, t1, mu1);
+                for (int u = 0; u < 4; ++u) {
+                    const int q = qc + u, il = q * NT + tid;
+                    lwa[u] = lwr[u] = -INFINITY;
+                    if (q < PPT && il < Pc) {
+                        const double la = a.pre_la[prow + il];
+                        lwa[u] = la + logw[il];
+                        lwr[u] = lwa[u] + a.pre_lr[prow + il];
+                        laux[il] = la;
+                    }
+                }
+                softmax4(qc, lwa, lwr);
+            }
+        }
+        if constexpr (D == 2 && !PRE) {
+            if (rw) {
+                // Row-walk form.  A thread's particles are handled four at a time so that the dependent chains of
+                // the weights (log-densities, softmax shift, exp, in-warp scan) of the four are interleaved: first
+                // the contraction two particles at a time (each Theta' pair read once per warp feeds 2 n_x DFMAs),
+                // then eight independent shift-max / exp / scan sequences.
+                const int nblk_rw = m.rw_nblk;
+                auto weights = [&](int il, const double (&mu)[NX], double& lwa, double& lwr) {
 #pragma unroll
-                    for (int k = 0; k < NX; ++k)
-                        if (ila < Pc) mus[(size_t)k * P + ila] = mu1[0][k];
+                    for (int k = 0; k < NX; ++k) mus[(size_t)k * P + il] = mu[k];
+                    const double la = gauss_loglik<NX, NY>(m, k_t.y, mu);
+                    lwa = la + logw[il];
+                    lwr = lwa + gauss_logpdf_state<NX>(sw, slogc[0], k_t.ref, mu);
+                    laux[il] = la;
+                };
+                for (int qc = 0; qc < PPT; qc += 4) {
+                    double lwa[4], lwr[4];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int q0 = qc + 2 * h;
+                        const int ila = q0 * NT + tid, ilb = ila + NT;
+                        lwa[2 * h] = lwr[2 * h] = lwa[2 * h + 1] = lwr[2 * h + 1] = -INFINITY;
+                        if (q0 < PPT && q0 * NT + warp * 32 < Pc) {            // warp-uniform
+                            if (q0 + 1 < PPT) {
+                                double xa[NX], xb[NX], ta[D], tb[D];
+#pragma unroll
+                                for (int k = 0; k < NX; ++k) {
+                                    xa[k] = (ila < Pc) ? xs[(size_t)k * P + ila] : 0.0;
+                                    xb[k] = (ilb < Pc) ? xs[(size_t)k * P + ilb] : 0.0;
+                                }
+                                mapr.apply(xa, k_t.cz, k_t.u, ta);
+                                mapr.apply(xb, k_t.cz, k_t.u, tb);
+                                const double t0[2] = {ta[0], tb[0]}, t1[2] = {ta[1], tb[1]};
+                                double mu2[2][NX];
+                                rowwalk_mu<NX, 2>(bfrag, rwlen, nblk_rw, ecx.f_start, ecx.f_step, t0, t1, mu2);
+                                if (ila < Pc) weights(ila, mu2[0], lwa[2 * h], lwr[2 * h]);
+                                if (ilb < Pc) weights(ilb, mu2[1], lwa[2 * h + 1], lwr[2 * h + 1]);
+                            } else {
+                                double xa[NX], ta[D];
+#pragma unroll
+                                for (int k = 0; k < NX; ++k) xa[k] = (ila < Pc) ? xs[(size_t)k * P + ila] : 0.0;
+                                mapr.apply(xa, k_t.cz, k_t.u, ta);
+                                const double t0[1] = {ta[0]}, t1[1] = {ta[1]};
+                                double mu1[1][NX];
+                                rowwalk_mu<NX, 1>(bfrag, rwlen, nblk_rw, ecx.f_start, ecx.f_step, t0, t1, mu1);
+                                if (ila < Pc) weights(ila, mu1[0], lwa[2 * h], lwr[2 * h]);
+                            }
+                        }
+                    }
+                    softmax4(qc, lwa, lwr);
                 }
             }
         }
-        for (int q = 0; q < PPT; ++q) {
+        for (int q = 0; q < ((rw || PRE) ? 0 : PPT); ++q) {
             const int il = q * NT + tid, il0 = q * NT + warp * 32;
             double lwa = -INFINITY, lwr = -INFINITY;
             if (il0 < Pc) {                                   // warp-uniform: the whole warp takes part in the DMMA
@@ -518,7 +598,7 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
                 const int cj = j / P, jl = j - cj * P;
                 double* dl = (C > 1 && cj != rank) ? cluster.map_shared_rank(lauxg, cj) : lauxg;
                 dl[jl] = laux[k];
-                if (gather) {
+                if (gather && !PRE) {
                     double* dm = (C > 1 && cj != rank) ? cluster.map_shared_rank(mug, cj) : mug;
 #pragma unroll
                     for (int kk = 0; kk < NX; ++kk) dm[(size_t)kk * P + jl] = mus[(size_t)kk * P + k];
@@ -534,7 +614,7 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
                 const int cj = c_last, jl = (N - 1) - cj * P;
                 double* dl = (C > 1 && cj != rank) ? cluster.map_shared_rank(lauxg, cj) : lauxg;
                 dl[jl] = laux[k];
-                if (gather) {
+                if (gather && !PRE) {
                     double* dm = (C > 1 && cj != rank) ? cluster.map_shared_rank(mug, cj) : mug;
 #pragma unroll
                     for (int kk = 0; kk < NX; ++kk) dm[(size_t)kk * P + jl] = mus[(size_t)kk * P + k];
@@ -546,48 +626,61 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
         // ---- X2 + C: barrier #2 overlapped with the noise draw; new state, new log-weights
         if (C > 1) cluster_arrive(); else __syncthreads();
         const bool last_step = (t + 1 == a.t_end);
-        constexpr int ZQ = 4;                                 // particles per thread whose noise is drawn under the barrier
-        double zreg[ZQ][NX];
-        // the draws of a thread's particles are independent chains (Philox -> log/sqrt/sincospi): issued
-        // back to back without per-lane branches so the scheduler interleaves them (padding lanes draw too)
-#pragma unroll
-        for (int q = 0; q < ZQ; ++q) {
-            if (q < PPT) draw_normals<NX>(a, chain, t, min(base + q * NT + tid, N - 1), zreg[q]);
-        }
-        if (C > 1) cluster_wait();
-        double* st_row = a.state_trace + (((size_t)chain * a.trace_rows + (t - a.row_off)) * N) * NX;
-        const double* msrc = gather ? mug : mus;              // quirk (i): own particle unless gather mode
-        auto finish = [&](int il, const double z[NX]) {
-            const int i = base + il;
-            double x[NX];
-#pragma unroll
-            for (int r = 0; r < NX; ++r) {
-                double v = msrc[(size_t)r * P + il];
-#pragma unroll
-                for (int c = 0; c <= r; ++c) v = fma(chol[r * NX + c], z[c], v);
-                x[r] = v;
+        if constexpr (PRE) {
+            if (C > 1) cluster_wait();
+            const size_t prow = ((size_t)chain * a.pre_rows + (size_t)(t - a.pre_off)) * N + base;
+            for (int q = 0; q < PPT; ++q) {
+                const int il = q * NT + tid;
+                if (il < Pc) {
+                    const double lw = a.pre_ll[prow + il] - lauxg[il];             // src/PGAS.py:137-147
+                    logw[il] = lw;
+                    if (last_step && a.logw_last) a.logw_last[(size_t)chain * N + base + il] = lw;
+                }
             }
-            if (i == N - 1) {
-#pragma unroll
-                for (int k = 0; k < NX; ++k) x[k] = k_t.ref[k];               // src/PGAS.py:134
+        } else {
+            constexpr int ZQ = 4;                                 // particles per thread whose noise is drawn under the barrier
+            double zreg[ZQ][NX];
+            // the draws of a thread's particles are independent chains (Philox -> log/sqrt/sincospi): issued
+            // back to back without per-lane branches so the scheduler interleaves them (padding lanes draw too)
+    #pragma unroll
+            for (int q = 0; q < ZQ; ++q) {
+                if (q < PPT) draw_normals<NX>(a, chain, t, min(base + q * NT + tid, N - 1), zreg[q]);
             }
-            const double lw = gauss_loglik<NX, NY>(m, k_t.y, x) - lauxg[il];   // :137-147
-            logw[il] = lw;
-#pragma unroll
-            for (int k = 0; k < NX; ++k) { xs[(size_t)k * P + il] = x[k]; st_row[(size_t)i * NX + k] = x[k]; }
-            if (last_step && a.logw_last) a.logw_last[(size_t)chain * N + i] = lw;
-        };
-#pragma unroll
-        for (int q = 0; q < ZQ; ++q) {
-            const int il = q * NT + tid;
-            if (q < PPT && il < Pc) finish(il, zreg[q]);
-        }
-        for (int q = ZQ; q < PPT; ++q) {
-            const int il = q * NT + tid;
-            if (il < Pc) {
-                double z[NX];
-                draw_normals<NX>(a, chain, t, base + il, z);
-                finish(il, z);
+            if (C > 1) cluster_wait();
+            double* st_row = a.state_trace + (((size_t)chain * a.trace_rows + (t - a.row_off)) * N) * NX;
+            const double* msrc = gather ? mug : mus;              // quirk (i): own particle unless gather mode
+            auto finish = [&](int il, const double z[NX]) {
+                const int i = base + il;
+                double x[NX];
+    #pragma unroll
+                for (int r = 0; r < NX; ++r) {
+                    double v = msrc[(size_t)r * P + il];
+    #pragma unroll
+                    for (int c = 0; c <= r; ++c) v = fma(chol[r * NX + c], z[c], v);
+                    x[r] = v;
+                }
+                if (i == N - 1) {
+    #pragma unroll
+                    for (int k = 0; k < NX; ++k) x[k] = k_t.ref[k];               // src/PGAS.py:134
+                }
+                const double lw = gauss_loglik<NX, NY>(m, k_t.y, x) - lauxg[il];   // :137-147
+                logw[il] = lw;
+    #pragma unroll
+                for (int k = 0; k < NX; ++k) { xs[(size_t)k * P + il] = x[k]; st_row[(size_t)i * NX + k] = x[k]; }
+                if (last_step && a.logw_last) a.logw_last[(size_t)chain * N + i] = lw;
+            };
+    #pragma unroll
+            for (int q = 0; q < ZQ; ++q) {
+                const int il = q * NT + tid;
+                if (q < PPT && il < Pc) finish(il, zreg[q]);
+            }
+            for (int q = ZQ; q < PPT; ++q) {
+                const int il = q * NT + tid;
+                if (il < Pc) {
+                    double z[NX];
+                    draw_normals<NX>(a, chain, t, base + il, z);
+                    finish(il, z);
+                }
             }
         }
         PGAS_TICK(7);
@@ -599,11 +692,11 @@ __global__ void __launch_bounds__(NT, 1) csmc_sweep_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------ launch
-static size_t sweep_smem_bytes(const DevModel& m, int NX, int P, bool gather, int NT) {
+static size_t sweep_smem_bytes(const DevModel& m, int NX, int P, bool gather, int NT, bool pre = false) {
     const int NW = NT / 32;
     const bool rw = (m.D == 2) && m.rw_ok;
-    size_t d = (rw ? (size_t)((m.rw_slots + 1) & ~1) : (size_t)m.n_packed + (size_t)m.NTNP * 32 + (size_t)NW * sine_tile_doubles(m)) + (size_t)NX * P * 2 + (size_t)P * 4 + (size_t)((P + 255) / 256) * 256 +
-               (gather ? (size_t)NX * P : 0) + MAXC * 4 + 2 * (MAXC + 1) + 2 * MAXC + 2 + (size_t)((P + NT - 1) / NT) * NW * 8 + 2 * NX * NX + 2 +
+    size_t d = (pre ? 0 : (rw ? (size_t)((m.rw_slots + 1) & ~1) : (size_t)m.n_packed + (size_t)m.NTNP * 32 + (size_t)NW * sine_tile_doubles(m)) + (size_t)NX * P * 2) + (size_t)P * 4 + (size_t)((P + 255) / 256) * 256 +
+               ((gather && !pre) ? (size_t)NX * P : 0) + MAXC * 4 + 2 * (MAXC + 1) + 2 * MAXC + 2 + (size_t)((P + NT - 1) / NT) * NW * 8 + 2 * NX * NX + 2 +
                2 * ((sizeof(StepConst) + 7) / 8);
     return d * 8 + (size_t)(((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD + 2 + 18 + RW_MAXBLK) * 4 + 32;
 }
@@ -611,15 +704,16 @@ static size_t sweep_smem_bytes(const DevModel& m, int NX, int P, bool gather, in
 // threads per CTA: 512 (16 warps hide the dependent-FP64 latency best) when the per-warp sine tiles
 // still fit shared memory, else 256
 static int sweep_threads(const DevModel& m, int P) {
+    if (const char* e = getenv("PGAS_SWEEP_THREADS")) { const int v = atoi(e); if (v == 256 || v == 512) return v; }   // developer override
     const bool gather = (m.flags & PGAS_FLAG_ANCESTOR_GATHER) != 0;
     return (sweep_smem_bytes(m, m.n_x, P, gather, 512) <= 227 * 1024 && P > 128) ? 512 : 256;
 }
 
 static int* g_query_clusters = nullptr;      // debug: when set, launch_variant reports occupancy instead of launching
 
-template <int NX, int NY, int D, int NT>
+template <int NX, int NY, int D, int NT, bool PRE = false>
 static int launch_variant(const SweepArgs& a, size_t smem, cudaStream_t stream) {
-    auto kern = csmc_sweep_kernel<NX, NY, D, NT>;
+    auto kern = csmc_sweep_kernel<NX, NY, D, NT, PRE>;
     PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (a.C > 8) PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
@@ -643,7 +737,15 @@ static int launch_variant(const SweepArgs& a, size_t smem, cudaStream_t stream) 
     return 0;
 }
 
-int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
+// resampling recursion on precomputed log-densities (split form); the model dimensions do not matter here
+int pgas_launch_sweep_pre(const SweepArgs& a, cudaStream_t stream) {
+    const DevModel& m = a.m;
+    const size_t smem = sweep_smem_bytes(m, m.n_x, a.P, false, 512, true);
+    if (smem > 227 * 1024) PGAS_FAIL(-21, "resampling kernel needs %zu bytes of shared memory per CTA", smem);
+    return launch_variant<2, 1, 2, 512, true>(a, smem, stream);
+}
+
+int pgas_launch_sweep_fused(const SweepArgs& a, cudaStream_t stream) {
     const DevModel& m = a.m;
     const bool gather = (m.flags & PGAS_FLAG_ANCESTOR_GATHER) != 0;
     const int nt = sweep_threads(m, a.P);
@@ -692,7 +794,7 @@ extern "C" int pgas_debug_max_active_clusters(const pgas_model* model, int32_t N
     a.N = N; a.n_chains = 1; a.C = cluster_size; a.P = (N + cluster_size - 1) / cluster_size;
     int n = -1;
     g_query_clusters = &n;
-    const int rc = pgas_launch_sweep(a, 0);
+    const int rc = pgas_launch_sweep_fused(a, 0);
     g_query_clusters = nullptr;
     return rc ? -rc : n;
 }
@@ -711,7 +813,7 @@ extern "C" int pgas_debug_sweep_ticks(const pgas_model* model, int32_t N, int32_
     a.state_trace = state_trace; a.anc_trace = anc_trace; a.logw_last = logw_last;
     a.rng_mode = 0; a.seed = 1234;
     a.dbg = dbg;
-    return pgas_launch_sweep(a, (cudaStream_t)stream);
+    return pgas_launch_sweep_fused(a, (cudaStream_t)stream);
 }
 
 #if PGAS_FINE_TICKS
@@ -719,3 +821,292 @@ extern "C" int pgas_debug_fine_ticks(long long* host64) {
     return (int)cudaMemcpyFromSymbol(host64, g_fine, sizeof(long long) * 64);
 }
 #endif
+
+
+// ====================================================================================== split form
+// In the reference's semantics the state recursion is independent of the resampling: _draw_states propagates
+// particle i from particle i (src/PGAS.py:131-133), so x_t^i = Theta phi(x_{t-1}^i, u_t) + chol(Sigma) z_t^i never
+// sees an ancestor index; only the WEIGHT recursion does (logw_t^i = log p(y_t|x_t^i) - l_aux[a_i], :137-147).
+// The sweep therefore splits into
+//   csmc_state_kernel      all particles, all steps of a chunk, no synchronisation at all: two particles per
+//                          thread stay in registers; FP64-FMA row walk (basis_rowwalk.cuh), log-densities,
+//                          Philox / Box-Muller, trace row; bound by the FP64 pipe;
+//   csmc_sweep_kernel<PRE> the resampling recursion on the three log-densities the state kernel left per
+//                          particle and step (24 B), latency-bound (barriers, scans, searches),
+// run chunk-wise on two streams so that the FP64-bound kernel of chunk c+1 shares the SMs with the latency-
+// bound kernel of chunk c.  With PGAS_FLAG_ANCESTOR_GATHER (textbook move) the state depends on the
+// ancestors and the fused kernel is used.
+struct StateArgs {
+    SweepArgs a;
+    double* x_carry;             // (n_chains, N, NX): state at step t0-1 on entry (unless first), at t1-1 on exit
+    double *la, *lr, *ll;        // (n_chains, rows, N), row t - t0
+    int t0, t1, rows, first, bpc;
+};
+
+constexpr int ST_NT = 256;
+
+template <int NX, int NY>
+__global__ void __launch_bounds__(ST_NT, 2) csmc_state_kernel(const __grid_constant__ StateArgs s) {
+    constexpr int D = 2;
+    const SweepArgs& a = s.a;
+    const DevModel& m = a.m;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* bd = reinterpret_cast<double*>(smem_raw);
+    double* chol = bd + ((m.rw_slots + 1) & ~1);
+    double* sw = chol + NX * NX;
+    double* slogc = sw + NX * NX;
+    int* rwlen = reinterpret_cast<int*>(slogc + 2);
+    const int tid = threadIdx.x, N = a.N;
+    const int chain = blockIdx.x / s.bpc, blk = blockIdx.x % s.bpc;
+    {
+        const double* Th = a.Theta + (size_t)chain * NX * m.M;
+        for (int e = tid; e < m.rw_slots; e += ST_NT) {
+            const int q = m.rw_perm[e];
+            bd[e] = (q >= 0) ? m.norm * Th[(size_t)(q & 3) * m.M + (q >> 2)] : 0.0;
+        }
+        if (tid < RW_MAXBLK) rwlen[tid] = m.rw_blen[tid];
+        if (tid == 0) {
+            const double* S = a.Sigma + (size_t)chain * NX * NX;
+            double Lc[NX][NX], Li[NX][NX], logdet = 0.0;
+            for (int i = 0; i < NX; ++i)
+                for (int j = 0; j < NX; ++j) { Lc[i][j] = 0.0; Li[i][j] = 0.0; }
+            for (int j = 0; j < NX; ++j) {
+                double d = S[j * NX + j];
+                for (int k = 0; k < j; ++k) d -= Lc[j][k] * Lc[j][k];
+                d = sqrt(d);
+                Lc[j][j] = d;
+                logdet += log(d);
+                for (int i = j + 1; i < NX; ++i) {
+                    double v = S[i * NX + j];
+                    for (int k = 0; k < j; ++k) v -= Lc[i][k] * Lc[j][k];
+                    Lc[i][j] = v / d;
+                }
+            }
+            for (int j = 0; j < NX; ++j) {
+                Li[j][j] = 1.0 / Lc[j][j];
+                for (int i = j + 1; i < NX; ++i) {
+                    double v = 0.0;
+                    for (int k = j; k < i; ++k) v -= Lc[i][k] * Li[k][j];
+                    Li[i][j] = v / Lc[i][i];
+                }
+            }
+            for (int i = 0; i < NX; ++i)
+                for (int j = 0; j < NX; ++j) { chol[i * NX + j] = Lc[i][j]; sw[i * NX + j] = Li[i][j]; }
+            slogc[0] = -0.5 * NX * 1.8378770664093453 - logdet;
+        }
+    }
+    __syncthreads();
+    MapRegs<NX, D> mapr;
+    mapr.init(m);
+    const int f_start = m.f_start, f_step = m.f_step, nblk = m.rw_nblk;
+    const int ip[2] = {blk * 2 * ST_NT + tid, blk * 2 * ST_NT + ST_NT + tid};
+    const bool val[2] = {ip[0] < N, ip[1] < N};
+    double x[2][NX];
+    const double* refc = a.ref + (size_t)chain * a.ref_stride;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        if (s.first) {
+            // x_0 ~ N(m0, P0) (src/PGAS.py:167-172), particle N-1 = reference (:194)
+            double z[NX];
+            draw_normals<NX>(a, chain, 0, min(ip[p], N - 1), z);
+#pragma unroll
+            for (int r = 0; r < NX; ++r) {
+                double v = m.m0[r];
+#pragma unroll
+                for (int c = 0; c <= r; ++c) v = fma(m.P0c[r][c], z[c], v);
+                x[p][r] = v;
+            }
+            if (ip[p] == N - 1) {
+#pragma unroll
+                for (int k = 0; k < NX; ++k) x[p][k] = refc[k];
+            }
+            if (val[p]) {
+                double* out = a.state_trace + (((size_t)chain * a.trace_rows + 0) * N + ip[p]) * NX;
+#pragma unroll
+                for (int k = 0; k < NX; ++k) out[k] = x[p][k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NX; ++k) x[p][k] = val[p] ? s.x_carry[((size_t)chain * N + ip[p]) * NX + k] : 0.0;
+        }
+    }
+    for (int t = s.t0; t < s.t1; ++t) {
+        // per-step constants (uniform addresses: broadcast loads)
+        const int tin = (m.flags & PGAS_FLAG_INPUT_PREV) ? t - 1 : t;          // quirk (ii), src/PGAS.py:52-54
+        double y[NY], u[PGAS_MAX_NU], cz[D], ref[NX];
+#pragma unroll
+        for (int r = 0; r < NY; ++r) y[r] = m.obs[(size_t)t * NY + r];
+#pragma unroll
+        for (int k = 0; k < PGAS_MAX_NU; ++k) u[k] = (k < m.n_u) ? m.inputs[(size_t)tin * m.n_u + k] : 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            double acc = m.bz[d];
+#pragma unroll
+            for (int k = 0; k < PGAS_MAX_NU; ++k) acc = (k < m.n_u) ? fma(m.Az[d][NX + k], u[k], acc) : acc;
+            cz[d] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < NX; ++k) ref[k] = refc[(size_t)t * NX + k];
+        double ta[D], tb[D];
+        mapr.apply(x[0], cz, u, ta);
+        mapr.apply(x[1], cz, u, tb);
+        const double t0v[2] = {ta[0], tb[0]}, t1v[2] = {ta[1], tb[1]};
+        double mu[2][NX];
+        rowwalk_mu<NX, 2>(bd, rwlen, nblk, f_start, f_step, t0v, t1v, mu);
+        const size_t prow = ((size_t)chain * s.rows + (size_t)(t - s.t0)) * N;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int i = min(ip[p], N - 1);
+            const double la = gauss_loglik<NX, NY>(m, y, mu[p]);
+            const double lr = gauss_logpdf_state<NX>(sw, slogc[0], ref, mu[p]);
+            double z[NX];
+            draw_normals<NX>(a, chain, t, i, z);
+#pragma unroll
+            for (int r = 0; r < NX; ++r) {
+                double v = mu[p][r];
+#pragma unroll
+                for (int c = 0; c <= r; ++c) v = fma(chol[r * NX + c], z[c], v);
+                x[p][r] = v;
+            }
+            if (ip[p] == N - 1) {
+#pragma unroll
+                for (int k = 0; k < NX; ++k) x[p][k] = ref[k];                 // src/PGAS.py:134
+            }
+            const double ll = gauss_loglik<NX, NY>(m, y, x[p]);
+            if (val[p]) {
+                double* out = a.state_trace + (((size_t)chain * a.trace_rows + t) * N + ip[p]) * NX;
+#pragma unroll
+                for (int k = 0; k < NX; ++k) out[k] = x[p][k];
+                s.la[prow + ip[p]] = la;
+                s.lr[prow + ip[p]] = lr;
+                s.ll[prow + ip[p]] = ll;
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+        if (val[p]) {
+#pragma unroll
+            for (int k = 0; k < NX; ++k) s.x_carry[((size_t)chain * N + ip[p]) * NX + k] = x[p][k];
+        }
+}
+
+static int split_chunk_rows(const DevModel& m, int N, int n_chains) {
+    // rows per chunk: enough work to amortise two launches, small enough that the 24 B per particle-step stay modest
+    const size_t per_row = (size_t)n_chains * N * 3 * sizeof(double);
+    size_t rows = (size_t)(768ull << 20) / std::max<size_t>(per_row, 1);      // <= 768 MB per buffer
+    rows = std::min<size_t>(std::max<size_t>(rows, 8), 64);
+    if (const char* e = getenv("PGAS_SPLIT_ROWS")) { const int v = atoi(e); if (v >= 8) rows = std::min<size_t>(rows, (size_t)v); }   // developer override
+    return (int)std::min<size_t>(rows, (size_t)std::max(m.T - 1, 1));
+}
+
+size_t pgas_sweep_split_workspace(const DevModel& m, int N, int n_chains) {
+    if (!(m.D == 2 && m.rw_ok) || (m.flags & PGAS_FLAG_ANCESTOR_GATHER)) return 256;
+    const size_t rows = split_chunk_rows(m, N, n_chains);
+    const size_t pre = 2 * rows * (size_t)n_chains * N * 3 * sizeof(double);
+    const size_t carry = (size_t)n_chains * N * (m.n_x + 2) * sizeof(double);
+    return pre + carry + 1024;
+}
+
+bool pgas_sweep_split_eligible(const SweepArgs& a) {
+    const DevModel& m = a.m;
+    if (!(m.D == 2 && m.rw_ok) || (m.flags & PGAS_FLAG_ANCESTOR_GATHER)) return false;
+    if (!((m.n_x == 2 && m.n_y == 1) || (m.n_x == 2 && m.n_y == 2))) return false;
+    if (a.init_state || a.init_logw || a.dbg || a.row_off != 0 || a.t_begin != 1 || a.t_end != m.T) return false;   // full sweeps only
+    if (a.t_end - a.t_begin < 16 || !a.logw_last) return false;
+    if (getenv("PGAS_SWEEP_FUSED")) return false;                             // developer override
+    return a.ws && a.ws_bytes >= pgas_sweep_split_workspace(m, a.N, a.n_chains);
+}
+
+struct SplitStreams {
+    cudaStream_t aux = nullptr;
+    cudaEvent_t start = nullptr, k1[2] = {nullptr, nullptr}, k2[2] = {nullptr, nullptr};
+    int device = -1;
+};
+static thread_local SplitStreams g_split;
+
+static int split_streams_init() {
+    int dev = 0;
+    PGAS_CUDA(cudaGetDevice(&dev));
+    if (g_split.aux && g_split.device == dev) return 0;
+    g_split = SplitStreams();
+    g_split.device = dev;
+    {   // the state kernel runs AHEAD of the resampling kernel; give the (latency-bound) resampling kernel on the caller's
+        // stream the first pick of freed SM resources by putting the state kernel on the lowest-priority stream
+        int lo = 0, hi = 0;
+        PGAS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PGAS_CUDA(cudaStreamCreateWithPriority(&g_split.aux, cudaStreamNonBlocking, lo));
+    }
+    PGAS_CUDA(cudaEventCreateWithFlags(&g_split.start, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        PGAS_CUDA(cudaEventCreateWithFlags(&g_split.k1[i], cudaEventDisableTiming));
+        PGAS_CUDA(cudaEventCreateWithFlags(&g_split.k2[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+static int launch_state(const StateArgs& s, cudaStream_t st) {
+    const DevModel& m = s.a.m;
+    const size_t smem = sizeof(double) * (((size_t)m.rw_slots + 1) & ~(size_t)1) + sizeof(double) * (2 * m.n_x * m.n_x + 2) + sizeof(int) * RW_MAXBLK + 32;
+    const dim3 grid((unsigned)(s.a.n_chains * s.bpc));
+    if (m.n_y == 1) {
+        PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        csmc_state_kernel<2, 1><<<grid, ST_NT, smem, st>>>(s);
+    } else {
+        PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        csmc_state_kernel<2, 2><<<grid, ST_NT, smem, st>>>(s);
+    }
+    PGAS_KERNEL_CHECK();
+    return 0;
+}
+
+int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
+    if (!pgas_sweep_split_eligible(a)) return pgas_launch_sweep_fused(a, stream);
+    const DevModel& m = a.m;
+    if (int rc = split_streams_init()) return rc;
+    const int rows = split_chunk_rows(m, a.N, a.n_chains);
+    char* base = (char*)(((uintptr_t)a.ws + 255) & ~(uintptr_t)255);
+    const size_t buf = (size_t)rows * a.n_chains * a.N;            // doubles per array per buffer
+    double* pre = (double*)base;
+    double* x_carry = pre + 2 * 3 * buf;
+    double* lw_carry = x_carry + (size_t)a.n_chains * a.N * m.n_x;
+    cudaStream_t s1 = getenv("PGAS_SPLIT_SERIAL") ? stream : g_split.aux;      // developer override: no overlap
+    PGAS_CUDA(cudaEventRecord(g_split.start, stream));
+    PGAS_CUDA(cudaStreamWaitEvent(s1, g_split.start, 0));          // inputs (Theta, Sigma, ref) are ready
+    int c = 0;
+    for (int t0 = a.t_begin; t0 < a.t_end; t0 += rows, ++c) {
+        const int t1 = std::min(t0 + rows, a.t_end), b = c & 1;
+        double* la = pre + (size_t)b * 3 * buf;
+        StateArgs s;
+        s.a = a;
+        s.x_carry = x_carry; s.la = la; s.lr = la + buf; s.ll = la + 2 * buf;
+        s.t0 = t0; s.t1 = t1; s.rows = rows; s.first = (c == 0); s.bpc = (a.N + 2 * ST_NT - 1) / (2 * ST_NT);
+        if (c >= 2) PGAS_CUDA(cudaStreamWaitEvent(s1, g_split.k2[b], 0));      // buffer b was consumed by chunk c-2
+        {   // short-lived state CTAs (sub-chunks) so that resampling CTAs find free slots quickly
+            int sr = 16;
+            if (const char* e = getenv("PGAS_SPLIT_STATE_ROWS")) { const int v = atoi(e); if (v >= 1) sr = v; }
+            for (int ts = t0; ts < t1; ts += sr) {
+                StateArgs q = s;
+                q.t0 = ts; q.t1 = std::min(ts + sr, t1);
+                q.la = s.la + (size_t)(ts - t0) * a.N; q.lr = s.lr + (size_t)(ts - t0) * a.N; q.ll = s.ll + (size_t)(ts - t0) * a.N;
+                q.first = s.first && ts == t0;
+                if (int rc = launch_state(q, s1)) return rc;
+            }
+        }
+        PGAS_CUDA(cudaEventRecord(g_split.k1[b], s1));
+        SweepArgs r = a;
+        r.t_begin = t0; r.t_end = t1;
+        r.pre_la = s.la; r.pre_lr = s.lr; r.pre_ll = s.ll; r.pre_rows = rows; r.pre_off = t0;
+        r.init_logw = (c == 0) ? nullptr : lw_carry;
+        r.logw_last = (t1 == a.t_end) ? a.logw_last : lw_carry;
+        r.ref = nullptr; r.Theta = nullptr; r.Sigma = nullptr; r.state_trace = nullptr;
+        if (const char* e = getenv("PGAS_SPLIT_PRE_C")) {                      // developer override: cluster size of the resampling kernel
+            const int v = atoi(e);
+            if (v >= 1 && v <= 16) { r.C = v; r.P = (a.N + v - 1) / v; }
+        }
+        PGAS_CUDA(cudaStreamWaitEvent(stream, g_split.k1[b], 0));
+        if (int rc = pgas_launch_sweep_pre(r, stream)) return rc;
+        PGAS_CUDA(cudaEventRecord(g_split.k2[b], stream));
+    }
+    return 0;
+}

@@ -234,7 +234,11 @@ static int check_cluster(int C, int N) {
     return 0;
 }
 
-extern "C" size_t pgas_csmc_sweep_workspace_bytes(const pgas_model*, int32_t, int32_t) { return 256; }
+// [logw_last fallback (N * n_chains doubles) | split-form buffers (sweep.cu: pgas_sweep_split_workspace)]
+extern "C" size_t pgas_csmc_sweep_workspace_bytes(const pgas_model* model, int32_t N, int32_t n_chains) {
+    if (!model || N < 1 || n_chains < 1) return 0;
+    return (((size_t)N * n_chains * sizeof(double) + 255) & ~(size_t)255) + pgas_sweep_split_workspace(model->dev, N, n_chains) + 256;
+}
 
 extern "C" int pgas_csmc_sweep_f64(const pgas_model* model, int32_t N, int32_t n_chains, const double* ref_traj, const double* Theta,
                                    const double* Sigma, const pgas_rng* rng, double* state_trace, int32_t* anc_trace,
@@ -257,12 +261,17 @@ extern "C" int pgas_csmc_sweep_f64(const pgas_model* model, int32_t N, int32_t n
     a.ref = ref_traj; a.ref_stride = (long long)m.T * m.n_x; a.Theta = Theta; a.Sigma = Sigma;
     a.state_trace = state_trace; a.anc_trace = anc_trace;
     double* lw = logw_last;
+    const size_t lw_bytes = ((size_t)N * n_chains * sizeof(double) + 255) & ~(size_t)255;
     if (!lw) {
         if (!workspace || workspace_bytes < sizeof(double) * (size_t)N * n_chains)
             PGAS_FAIL(-5, "logw_last is NULL and the workspace is smaller than N*n_chains doubles");
         lw = (double*)workspace;
     }
     a.logw_last = lw;
+    if (workspace && workspace_bytes > lw_bytes) {          // the rest feeds the split form (state kernel ahead of the resampling kernel)
+        a.ws = (char*)workspace + lw_bytes;
+        a.ws_bytes = workspace_bytes - lw_bytes;
+    }
     if (int rc = fill_rng(a, rng)) return rc;
     if (int rc = pgas_launch_sweep(a, st)) return rc;
     if (traj_out || final_idx) {

@@ -23,9 +23,23 @@ struct SweepArgs {
     const double* Z;             // (n_chains, var_rows, N, NX)
     const double* U;             // (n_chains, var_rows, 2)
     long long* dbg;              // optional phase clocks of CTA 0 (8 per step), developer aid
+    // split form (sweep_split.cu): the state recursion does not depend on the resampling in the reference's
+    // semantics (src/PGAS.py:131-133 propagates particle i from particle i), so a separate kernel runs it ahead
+    // and leaves, per step, l_aux = log p(y_t | mu), h = log N(x_ref,t; mu, Sigma) and log p(y_t | x_t) here:
+    const double* pre_la;        // (n_chains, pre_rows, N), row t - pre_off
+    const double* pre_lr;
+    const double* pre_ll;
+    int pre_rows, pre_off;
+    // caller workspace (pgas_csmc_sweep_workspace_bytes); null / too small -> fused kernel only
+    void* ws;
+    size_t ws_bytes;
 };
 
 int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream);
+int pgas_launch_sweep_fused(const SweepArgs& a, cudaStream_t stream);     // one kernel, all phases (sweep.cu)
+int pgas_launch_sweep_pre(const SweepArgs& a, cudaStream_t stream);       // resampling recursion on precomputed log-densities
+bool pgas_sweep_split_eligible(const SweepArgs& a);
+size_t pgas_sweep_split_workspace(const DevModel& m, int N, int n_chains);
 int pgas_choose_cluster(const DevModel& m, int N, int n_chains, int requested);
 size_t pgas_sweep_smem_for(const DevModel& m, int P);
 

@@ -309,13 +309,15 @@ def run_gpu_arm(args):
     lw = torch.empty((count, N), dtype=torch.float64, device="cuda")
     T0, T1, T2, T3 = BI.trajectory_statistics(m, cur)
     A0, S0, _ = BI.mniw_posterior_draw(p0 + T0, p1 + T1, p2 + T2, pg.GP_prior[3] + T3, PG._make_rng(key, first, 999))
+    sw_bytes = int(lib.pgas_csmc_sweep_workspace_bytes(m.handle, N, count))
+    sw_ws = torch.empty((sw_bytes,), dtype=torch.uint8, device="cuda")
     sweep_ms = []
     for r in range(3):
         rng = PG._make_rng(key, first, 1000 + r)
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         L.check(lib.pgas_csmc_sweep_f64(m.handle, N, count, L.ptr(cur), L.ptr(A0), L.ptr(S0), C.byref(rng), L.ptr(st), L.ptr(an),
-                                        L.ptr(lw), C.c_void_p(0), C.c_void_p(0), args.cluster, C.c_void_p(0), 0, L.stream_ptr()))
+                                        L.ptr(lw), C.c_void_p(0), C.c_void_p(0), args.cluster, L.ptr(sw_ws), sw_bytes, L.stream_ptr()))
         a1.record()
         torch.cuda.synchronize()
         sweep_ms.append(a0.elapsed_time(a1))
