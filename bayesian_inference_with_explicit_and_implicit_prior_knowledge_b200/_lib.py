@@ -191,6 +191,12 @@ EXPORTS = {
     "pgas_measure_fp64_peaks": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]),
 }
 
+# developer / measurement exports that are not part of include/pgas_b200.h
+DEBUG_EXPORTS = {
+    "pgas_debug_state_kernel_f64": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Rng),
+                                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
 _lib = None
 
 
@@ -205,6 +211,10 @@ def lib():
         L = C.CDLL(_SO)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(L, name)          # AttributeError if the export is missing
+            fn.restype = res
+            fn.argtypes = args
+        for name, (res, args) in DEBUG_EXPORTS.items():
+            fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
         _lib = L

@@ -1110,3 +1110,45 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
     }
     return 0;
 }
+
+
+// Measurement aid (bench.py roofline): the state kernel ALONE over all T-1 steps on `stream`, launched exactly as
+// pgas_launch_sweep launches it (same sub-chunks, same buffers) but without the resampling kernel.
+extern "C" int pgas_debug_state_kernel_f64(const pgas_model* model, int32_t N, int32_t n_chains, const double* ref, const double* Theta,
+                                           const double* Sigma, const pgas_rng* rng, double* state_trace, void* workspace,
+                                           size_t workspace_bytes, void* stream) {
+    if (!model || !ref || !Theta || !Sigma || !rng || !state_trace || !workspace) PGAS_FAIL(-1, "pgas_debug_state_kernel_f64: null argument");
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = model->dev;
+    const DevModel& m = a.m;
+    a.N = N; a.n_chains = n_chains; a.C = 1; a.P = N;
+    a.t_begin = 1; a.t_end = m.T;
+    a.ref_rows = m.T; a.trace_rows = m.T; a.anc_rows = m.T - 1; a.var_rows = m.T;
+    a.ref = ref; a.ref_stride = (long long)m.T * m.n_x; a.Theta = Theta; a.Sigma = Sigma;
+    a.state_trace = state_trace;
+    a.rng_mode = rng->mode; a.seed = rng->seed; a.chain_base = rng->chain_base; a.iteration = rng->iteration; a.Z = rng->Z; a.U = rng->U;
+    a.logw_last = (double*)workspace;                     // only to pass the eligibility test
+    a.ws = workspace; a.ws_bytes = workspace_bytes;
+    if (!pgas_sweep_split_eligible(a)) PGAS_FAIL(-2, "the split form does not apply to this model / workspace");
+    const int rows = split_chunk_rows(m, N, n_chains);
+    char* base = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    const size_t buf = (size_t)rows * n_chains * N;
+    double* pre = (double*)base;
+    double* x_carry = pre + 2 * 3 * buf;
+    int c = 0;
+    for (int t0 = a.t_begin; t0 < a.t_end; t0 += rows, ++c) {
+        const int t1 = std::min(t0 + rows, a.t_end);
+        double* la = pre + (size_t)(c & 1) * 3 * buf;
+        for (int ts = t0; ts < t1; ts += 16) {
+            StateArgs q;
+            q.a = a;
+            q.x_carry = x_carry;
+            q.t0 = ts; q.t1 = std::min(ts + 16, t1); q.rows = rows;
+            q.la = la + (size_t)(ts - t0) * N; q.lr = la + buf + (size_t)(ts - t0) * N; q.ll = la + 2 * buf + (size_t)(ts - t0) * N;
+            q.first = (c == 0 && ts == t0); q.bpc = (N + 2 * ST_NT - 1) / (2 * ST_NT);
+            if (int rc = launch_state(q, (cudaStream_t)stream)) return rc;
+        }
+    }
+    return 0;
+}

@@ -30,7 +30,8 @@ PKG = "bayesian_inference_with_explicit_and_implicit_prior_knowledge_b200"
 
 N_PART, T_STEPS, M_BASIS, CHAINS_TOTAL = 4096, 2000, 256, 64
 FLOP_PER_PSTEP = 2 * M_BASIS * 2 + M_BASIS * 2          # 2 M n_x + M D  (SURVEY.md 8d), n_x = D = 2
-NCU_DRAM_BYTES_PER_PSTEP = (1.871104e6 + 472.886016e6) / (64 * 4096 * 100)   # profiles/r01_sweep_full_raw.csv
+NCU_DRAM_BYTES_PER_PSTEP = (0.355072e6 + 118.637824e6) / (64 * 4096 * 16)     # profiles/r01_state_kernel_raw.csv (one 16-step launch)
+STATE_BYTES_PER_PSTEP = 8 * 2 + 3 * 8                   # trace row (n_x doubles) + the three log-densities handed to the resampling kernel
 SEED = 12345678                                          # the reference's seed (src/SingleMassOscillator.py:82)
 
 
@@ -322,12 +323,25 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         sweep_ms.append(a0.elapsed_time(a1))
     sweep_avg = float(np.mean(sweep_ms[1:]))
+    # the dominant kernel alone: csmc_state_kernel over all T-1 steps (same launches as inside the sweep, no resampling kernel)
+    state_ms = []
+    for r in range(3):
+        rng = PG._make_rng(key, first, 2000 + r)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        L.check(lib.pgas_debug_state_kernel_f64(m.handle, N, count, L.ptr(cur), L.ptr(A0), L.ptr(S0), C.byref(rng), L.ptr(st), L.ptr(sw_ws),
+                                                sw_bytes, L.stream_ptr()))
+        a1.record()
+        torch.cuda.synchronize()
+        state_ms.append(a0.elapsed_time(a1))
+    state_avg = float(np.mean(state_ms[1:]))
     dfma, dmma = C.c_double(), C.c_double()
     L.check(lib.pgas_measure_fp64_peaks(C.byref(dfma), C.byref(dmma), L.stream_ptr()))
     flops_launch = count * N * (T - 1) * FLOP_PER_PSTEP
-    achieved = flops_launch / (sweep_avg * 1e-3) / 1e12
+    achieved = flops_launch / (state_avg * 1e-3) / 1e12
+    achieved_sweep = flops_launch / (sweep_avg * 1e-3) / 1e12
     peak = max(dfma.value, dmma.value)
-    hbm_bytes = count * N * (T - 1) * (8 * 2 + 4)
+    hbm_bytes = count * N * (T - 1) * STATE_BYTES_PER_PSTEP
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -375,15 +389,19 @@ def run_gpu_arm(args):
                        "cluster_size": args.cluster, "l2": "per-step working set (state + ancestor traces, "
                        f"{count * T * N * 20 / 1e9:.1f} GB on rank 0) exceeds the 126 MB L2", "rng": "Philox-4x32-10 in-kernel"},
             "sweeps_per_s": args.chains * args.steps / (ms * 1e-3),
-            "roofline": {"bound": "tensor", "kernel": "csmc_sweep_kernel (FP64 DMMA m8n8k4 + FP64 FMA)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "tensor", "kernel": "csmc_state_kernel (FP64 FMA row walk; timed alone over all T-1 steps, "
+                         f"{(T - 1 + 15) // 16} launches of <= 16 steps)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_PSTEP * count * N * (T - 1),
-                         "traffic_note": "dram__bytes_read+write of this kernel from the ncu --set full capture in profiles/r01_sweep_full_summary.md "
-                                         "(18.1 B per particle-step measured at T=101, scaled to this launch; algorithmic 20 B)",
-                         "note": f"algorithmic flops = {FLOP_PER_PSTEP} per particle-step (2 M n_x + M D) x {count * N * (T - 1)} particle-steps "
-                                 f"per launch; peak = FP64 measured on this GPU in this run (register-resident DFMA {dfma.value:.1f}, DMMA "
-                                 f"{dmma.value:.1f} TFLOP/s; MEASURED_PEAKS.json has no FP64 figure); sweep launch {sweep_avg:.2f} ms",
-                         "hbm_achieved_gbs": hbm_bytes / (sweep_avg * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
-                         "hbm_frac": hbm_bytes / (sweep_avg * 1e-3) / 1e9 / hbm_peak},
+                         "traffic_note": "dram__bytes_read+write of this kernel from the ncu --set full capture in profiles/r01_state_kernel_summary.md "
+                                         f"(28.4 B per particle-step measured on one 16-step launch, scaled to all launches; algorithmic {STATE_BYTES_PER_PSTEP} B: "
+                                         "part of the log-density rows is still in L2 when the capture ends)",
+                         "note": f"compute bound = FP64 pipe (on B200 the FP64 FMA and FP64 tensor (DMMA) pipes have the same measured rate); algorithmic flops = "
+                                 f"{FLOP_PER_PSTEP} per particle-step (2 M n_x + M D) x {count * N * (T - 1)} particle-steps; peak = FP64 measured on this GPU in this "
+                                 f"run (register-resident DFMA {dfma.value:.1f}, DMMA {dmma.value:.1f} TFLOP/s; MEASURED_PEAKS.json has no FP64 figure); state kernel "
+                                 f"{state_avg:.2f} ms; whole sweep (state kernel overlapped with the resampling kernel) {sweep_avg:.2f} ms",
+                         "sweep_ms": sweep_avg, "sweep_achieved": achieved_sweep, "sweep_frac": achieved_sweep / peak,
+                         "hbm_achieved_gbs": hbm_bytes / (state_avg * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
+                         "hbm_frac": hbm_bytes / (state_avg * 1e-3) / 1e9 / hbm_peak},
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(count * T * 2 * 8),
                     "d2h_bytes_per_step": int(count * T * 2 * 8), "steps": e2e_steps,
                     "api": "PGAS.run_chains(key, host reference trajectories) -> host trajectories (pinned buffers)"},
