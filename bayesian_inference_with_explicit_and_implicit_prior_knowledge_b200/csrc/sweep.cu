@@ -368,6 +368,18 @@ __global__ void __launch_bounds__(NT, (NT == 256 || PRE) ? 2 : 1) csmc_sweep_ker
         if constexpr (PRE) {
             // log-densities were left by the state kernel (sweep_split.cu): l_aux, h; only the weight recursion runs here
             const size_t prow = ((size_t)chain * a.pre_rows + (size_t)(t - a.pre_off)) * N + base;
+            if (t + 1 < a.t_end) {
+                // the rows of step t+1 were written long ago (often evicted to HBM): pull them towards L1 now, a step ahead
+                const size_t nrow = prow + N;
+                for (int q = 0; q < PPT; ++q) {
+                    const int il = q * NT + tid;
+                    if (il < Pc && (il & 15) == 0) {           // one request per 128-byte line
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pre_la + nrow + il));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pre_lr + nrow + il));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pre_ll + nrow + il));
+                    }
+                }
+            }
             for (int qc = 0; qc < PPT; qc += 4) {
                 double lwa[4], lwr[4];
 #pragma unroll
