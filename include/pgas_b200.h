@@ -132,7 +132,11 @@ int pgas_csmc_step_f64(const pgas_model* model, int32_t N, int32_t t, const doub
  *      state_trace (n_chains,T,N,n_x), anc_trace (n_chains,T-1,N) int32, logw_last (n_chains,N),
  *      final_idx (n_chains) int32.
  * state_trace and anc_trace are required (the backward pass reads them); logw_last/final_idx may
- * be NULL.  cluster_size: 0 = choose automatically, else 1,2,4,8,16. */
+ * be NULL.  cluster_size: 0 = choose automatically, else 1,2,4,8,16.
+ * workspace: pgas_csmc_sweep_workspace_bytes bytes enable the split form for two-dimensional bases (a state
+ * kernel running ahead of the resampling kernel on a library-owned low-priority stream, fenced against
+ * `stream` with events); with a NULL / smaller workspace the fused single-kernel form runs.  Both forms
+ * produce the same ancestors and traces. */
 size_t pgas_csmc_sweep_workspace_bytes(const pgas_model* model, int32_t N, int32_t n_chains);
 int pgas_csmc_sweep_f64(const pgas_model* model, int32_t N, int32_t n_chains,
                         const double* ref_traj, const double* Theta, const double* Sigma,
