@@ -144,13 +144,17 @@ class PGAS:
             return A, S
         return A[0].cpu().numpy(), S[0].cpu().numpy()
 
-    def run_chains(self, key, init_ref_state, n_chains=1, chain_base=0, variates=None, want_params=True):
+    def run_chains(self, key, init_ref_state, n_chains=1, chain_base=0, variates=None, want_params=True, iteration=0, K=None):
         """K iterations for n_chains independent chains, entirely stream-ordered on the device
         (pgas_run_chains_f64).  init_ref_state (T,n_x) (shared) or (n_chains,T,n_x).
-        Returns dict(state_trace (n_chains,K,T,n_x), A_trace, S_trace) of CUDA tensors."""
+        Returns dict(state_trace (n_chains,K,T,n_x), A_trace, S_trace) of CUDA tensors.
+
+        Checkpoint / resume: the whole Gibbs state is (reference trajectory, key, iteration index) — the Philox
+        counters carry (chain, iteration, time, particle), nothing else persists.  A run of K iterations equals a
+        run of K1 followed by `run_chains(key, state_trace[:, K1-1], iteration=K1-1, K=K-K1+1)` bit for bit."""
         torch = _lib.require_cuda()
         m = self.cSMC.model
-        K, N = self.N_iterations, self.cSMC.N_samples
+        K, N = (self.N_iterations if K is None else int(K)), self.cSMC.N_samples
         ref = torch.as_tensor(init_ref_state, dtype=torch.float64)
         ref = ref.reshape(-1, m.T, m.n_x)
         if ref.shape[0] == 1 and n_chains > 1:
@@ -163,7 +167,7 @@ class PGAS:
         nbytes = _lib.lib().pgas_run_chains_workspace_bytes(m.handle, N, n_chains)
         ws = torch.empty((nbytes,), dtype=torch.uint8, device="cuda")
         p0, p1, p2 = self._prior()
-        rng = _make_rng(key, chain_base, 0, variates)
+        rng = _make_rng(key, chain_base, iteration, variates)
         _lib.check(_lib.lib().pgas_run_chains_f64(m.handle, N, K, n_chains, _lib.ptr(p0), _lib.ptr(p1), _lib.ptr(p2),
                                                   self.GP_prior[3], _lib.ptr(ref), C.byref(rng), _lib.ptr(out), _lib.ptr(A_tr),
                                                   _lib.ptr(S_tr), self.cSMC.cluster_size, _lib.ptr(ws), nbytes, _lib.stream_ptr()))

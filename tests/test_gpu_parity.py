@@ -289,3 +289,39 @@ def test_split_and_fused_sweeps_agree(built_lib, kind, N, T, chains, cluster):
     for k in ("state_trace", "logw_last", "traj"):
         assert torch.allclose(a[k], b[k], rtol=1e-13, atol=1e-300), k
     assert bool(torch.isfinite(a["state_trace"]).all())
+
+
+def test_run_chains_resume_is_bit_exact(built_lib):
+    """checkpoint / resume (SURVEY.md 8f item 4): the Gibbs state is (reference trajectory, key, iteration index);
+    6 iterations == 4 iterations + a resumed run of 3 starting from trajectory 3"""
+    import torch
+    p = helpers.make_problem("smo", T=40, N=256, seed=8)
+    pg = helpers.product_pgas(p, K=6)
+    key = helpers.pkg("random").key(21)
+    full = pg.run_chains(key, p["ref"], n_chains=2, chain_base=5)
+    first = pg.run_chains(key, p["ref"], n_chains=2, chain_base=5, K=4)
+    rest = pg.run_chains(key, first["state_trace"][:, 3].contiguous(), n_chains=2, chain_base=5, iteration=3, K=3)
+    assert torch.equal(full["state_trace"][:, :4], first["state_trace"])
+    assert torch.equal(full["state_trace"][:, 3:], rest["state_trace"])
+    assert torch.equal(full["A_trace"][:, 3:], rest["A_trace"])
+
+
+def test_split_and_fused_sweeps_agree_at_config5_shape(built_lib):
+    """BASELINE.json configs[4] shape: N=16384 particles, 2-D basis with M=1024 (max lattice index 36), cluster of 16"""
+    import os
+    import torch
+    p = helpers.make_problem("vehicle", T=24, N=16384, M=1024, seed=6)
+    cs = helpers.product_csmc(p, 0)
+    dev = lambda x: torch.as_tensor(np.ascontiguousarray(x)).cuda()
+    ref, Th, Sg = (dev(p[k][None]) for k in ("ref", "Theta", "Sigma"))
+    key = helpers.pkg("random").key(3)
+    os.environ.pop("PGAS_SWEEP_FUSED", None)
+    a = cs.sweep(ref, Th, Sg, key=key)
+    os.environ["PGAS_SWEEP_FUSED"] = "1"
+    try:
+        b = cs.sweep(ref, Th, Sg, key=key)
+    finally:
+        os.environ.pop("PGAS_SWEEP_FUSED", None)
+    assert torch.equal(a["anc_trace"], b["anc_trace"]) and torch.equal(a["idx"], b["idx"])
+    assert torch.allclose(a["state_trace"], b["state_trace"], rtol=1e-12, atol=1e-300)
+    assert bool(torch.isfinite(a["traj"]).all())
