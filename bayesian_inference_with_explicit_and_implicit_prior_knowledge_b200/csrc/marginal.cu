@@ -518,7 +518,8 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             } else {
                 // predictive Student-t from the ancestor's factor (src/Algorithm1.py:249-272)
                 const double* La = wq + L.Lp[g] + (size_t)ac * npk;
-                for (int e = lane; e < npk; e += 32) wc.B[e] = ldcg(La + e);
+#pragma unroll 8
+                for (int e = lane; e < npk; e += 32) wc.B[e] = ldcg(La + e);        // independent L2 gathers in flight
                 __syncwarp();
                 double w[ROWS];
                 warp_fwd_solve<ROWS>(wc.B, wc.phi, M, lane, w);
@@ -545,6 +546,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             double* T1w = wp + L.T1p[g] + (size_t)i * npk;
             const double* T1a = wq + L.T1p[g] + (size_t)ac * npk;
             double* Ag = wc.A[g];
+#pragma unroll 4
             for (int e = lane; e < npk; e += 32) {
                 const unsigned ij = ijt[g][e];
                 double v = wc.phi[ij & 0xffffu] * wc.phi[ij >> 16];
@@ -603,6 +605,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             axi[g] = warp_sum(yv);                                        // prior_mniw_mean . phi_aux
             const double psi = Ag[rowM + M] - yy;
             double* Lw = wp + L.Lp[g] + (size_t)i * npk;
+#pragma unroll 8
             for (int e = lane; e < npk; e += 32) Lw[e] = Ag[e];
             if (lane == 0) wp[L.psi[g] + i] = psi;
             if (MODE == 1) {
@@ -618,6 +621,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                 const double* PR0 = a.tab.PR0[g] + trow * M;
                 const double* T1w = wp + L.T1p[g] + (size_t)i * npk;
                 __syncwarp();
+#pragma unroll 8
                 for (int e = lane; e < npk; e += 32) wc.B[e] = PR1[e] + T1w[e];
                 for (int k = lane; k < M; k += 32) wc.B[rowM + k] = PR0[k] + wp[L.T0[g] + (size_t)i * M + k];
                 if (lane == 0) wc.B[rowM + M] = a.tab.PR2[g][trow] + T2n;
@@ -656,6 +660,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                 else if (e == npk + M) { src = wq + L.T2[g]; stride = 1; }
                 else { src = wq + L.T3[g]; stride = 1; }
                 double acc = 0.0;
+#pragma unroll 8
                 for (int i = 0; i < N; ++i) acc = fma(ldcg(src + (size_t)i * stride), wsm[i], acc);
                 const size_t row = (size_t)chain * T + tp;
                 if (e < npk) {

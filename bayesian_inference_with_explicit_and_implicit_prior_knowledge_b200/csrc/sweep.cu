@@ -165,7 +165,7 @@ __device__ __forceinline__ void load_step_const(const SweepArgs& a, int chain, i
 }
 
 template <int NX, int NY, int D, int NT, bool PRE>
-__global__ void __launch_bounds__(NT, (NT == 256 || PRE) ? 2 : 1) csmc_sweep_kernel(const __grid_constant__ SweepArgs a) {
+__global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csmc_sweep_kernel(const __grid_constant__ SweepArgs a) {
     constexpr int NW = NT / 32;
     const DevModel& m = a.m;
     cg::cluster_group cluster = cg::this_cluster();
@@ -752,9 +752,9 @@ static int launch_variant(const SweepArgs& a, size_t smem, cudaStream_t stream) 
 // resampling recursion on precomputed log-densities (split form); the model dimensions do not matter here
 int pgas_launch_sweep_pre(const SweepArgs& a, cudaStream_t stream) {
     const DevModel& m = a.m;
-    const size_t smem = sweep_smem_bytes(m, m.n_x, a.P, false, 512, true);
+    const size_t smem = sweep_smem_bytes(m, m.n_x, a.P, false, PGAS_PRE_NT, true);
     if (smem > 227 * 1024) PGAS_FAIL(-21, "resampling kernel needs %zu bytes of shared memory per CTA", smem);
-    return launch_variant<2, 1, 2, 512, true>(a, smem, stream);
+    return launch_variant<2, 1, 2, PGAS_PRE_NT, true>(a, smem, stream);
 }
 
 int pgas_launch_sweep_fused(const SweepArgs& a, cudaStream_t stream) {
@@ -855,10 +855,16 @@ struct StateArgs {
     int t0, t1, rows, first, bpc;
 };
 
-constexpr int ST_NT = 256;
+#ifndef PGAS_ST_NT
+#define PGAS_ST_NT 256
+#endif
+#ifndef PGAS_PRE_NT
+#define PGAS_PRE_NT 512
+#endif
+constexpr int ST_NT = PGAS_ST_NT;
 
 template <int NX, int NY>
-__global__ void __launch_bounds__(ST_NT, 2) csmc_state_kernel(const __grid_constant__ StateArgs s) {
+__global__ void __launch_bounds__(ST_NT, 512 / ST_NT) csmc_state_kernel(const __grid_constant__ StateArgs s) {
     constexpr int D = 2;
     const SweepArgs& a = s.a;
     const DevModel& m = a.m;
