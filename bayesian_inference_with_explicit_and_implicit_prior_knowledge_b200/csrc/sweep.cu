@@ -20,6 +20,14 @@
 
 namespace cg = cooperative_groups;
 
+// threads per CTA of the state kernel / the resampling kernel of the split form (compile-time knobs for occupancy experiments)
+#ifndef PGAS_ST_NT
+#define PGAS_ST_NT 256
+#endif
+#ifndef PGAS_PRE_NT
+#define PGAS_PRE_NT 512
+#endif
+
 constexpr int MAXC = 16;         // largest (non-portable) cluster
 
 
@@ -855,12 +863,6 @@ struct StateArgs {
     int t0, t1, rows, first, bpc;
 };
 
-#ifndef PGAS_ST_NT
-#define PGAS_ST_NT 256
-#endif
-#ifndef PGAS_PRE_NT
-#define PGAS_PRE_NT 512
-#endif
 constexpr int ST_NT = PGAS_ST_NT;
 
 template <int NX, int NY>
@@ -1091,9 +1093,18 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
     cudaStream_t s1 = getenv("PGAS_SPLIT_SERIAL") ? stream : g_split.aux;      // developer override: no overlap
     PGAS_CUDA(cudaEventRecord(g_split.start, stream));
     PGAS_CUDA(cudaStreamWaitEvent(s1, g_split.start, 0));          // inputs (Theta, Sigma, ref) are ready
+    // chunk boundaries: a short first chunk (the resampling kernel can start early) and a short last chunk (little
+    // resampling work is left when the state kernel has finished), `rows` in between
+    const int edge = std::min(rows, 16);
     int c = 0;
-    for (int t0 = a.t_begin; t0 < a.t_end; t0 += rows, ++c) {
-        const int t1 = std::min(t0 + rows, a.t_end), b = c & 1;
+    for (int t0 = a.t_begin, t1 = 0; t0 < a.t_end; t0 = t1, ++c) {
+        const int left = a.t_end - t0, b = c & 1;
+        int len;
+        if (left <= edge) len = left;                          // last chunk
+        else if (c == 0) len = edge;                           // first chunk
+        else if (left <= rows + edge) len = left - edge;       // leave exactly `edge` rows for the last chunk
+        else len = rows;
+        t1 = t0 + len;
         double* la = pre + (size_t)b * 3 * buf;
         StateArgs s;
         s.a = a;
