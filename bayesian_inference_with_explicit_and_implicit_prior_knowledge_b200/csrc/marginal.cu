@@ -39,6 +39,19 @@ namespace cg = cooperative_groups;
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
+// Barrier among the CTAs of one chain through a global counter (all CTAs are co-resident: cooperative launch).
+// Same shape as a cooperative-groups grid sync: CTA barrier, one thread publishes (fence + atomic) and spins.
+__device__ __forceinline__ void mg_sw_barrier(unsigned* ctr, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (*((volatile unsigned*)ctr) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void mg_cluster_barrier(bool multi) {
     if (multi) {
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -418,7 +431,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
     const int CS = a.CS, NW = a.NW, N = a.N, T = m.T, G = m.G, nx = m.n_x;
     const int chain = blockIdx.x / CS, rank = blockIdx.x % CS;
     const int WT = CS * NW, wg = rank * NW + warp;
-    const bool multi = CS > 1;
+    const bool multi = CS > 1 && !a.sw_barrier;
     const double lam = a.lambda;
 
     // ---- shared memory carve-up: CTA part, then per-warp parts
@@ -680,11 +693,13 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
     // ------------------------------------------------------------------ t = 0 .. T-1
     const bool want_sst = (MODE == 0) && a.sst[0] != nullptr;
     const int last_owner_rank = ((N - 1) % WT) / NW;
+    int bar_gen = 0;
     const double dN = (double)N;
     for (int t = 0; t < T; ++t) {
         double u_res = 0.0, u_anc = 0.0;
         if (t > 0) {
-            mg_cluster_barrier(multi);
+            if (a.sw_barrier) mg_sw_barrier(a.bar_ctr + chain, (unsigned)CS * (unsigned)(++bar_gen));
+            else mg_cluster_barrier(multi);
             const double* wq = wsc + (size_t)((t - 1) & 1) * L.parity_stride;
             if (want_sst) weighted_trace(t - 1);
             if (a.rng_mode == 1) { u_res = Uc[(size_t)t * 2]; u_anc = Uc[(size_t)t * 2 + 1]; }
@@ -707,7 +722,8 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
         }
     }
     if (want_sst) {
-        mg_cluster_barrier(multi);
+        if (a.sw_barrier) mg_sw_barrier(a.bar_ctr + chain, (unsigned)CS * (unsigned)(++bar_gen));
+        else mg_cluster_barrier(multi);
         weighted_trace(T - 1);
     }
     if (fail && lane == 0) atomicMax(a.status + chain, 1);
@@ -1087,6 +1103,7 @@ extern "C" int pgas_marg_model_destroy(pgas_marg_model* model) {
 
 // ---- workspace: [per-particle ping-pong | reference tables | run traces]
 struct MargHostWs {
+    unsigned* bar;                                 // n_chains software-barrier counters
     double* part;                                  // n_chains * chain_stride
     double *PR0[MG_GP], *PR1[MG_GP], *PR2[MG_GP], *PR3[MG_GP];
     size_t total;
@@ -1097,6 +1114,7 @@ static MargHostWs mg_carve(const MargDev& m, int N, int n_chains, char* base) {
     size_t o = 0;
     auto take = [&](size_t bytes) { char* p = base ? base + o : nullptr; o += (bytes + 255) & ~(size_t)255; return (double*)p; };
     const MargWs L = marg_ws_layout(m, N);
+    w.bar = (unsigned*)take(sizeof(unsigned) * n_chains);
     w.part = take(sizeof(double) * L.chain_stride * n_chains);
     const size_t CT = (size_t)n_chains * m.T;
     for (int g = 0; g < MG_GP; ++g) {
@@ -1143,6 +1161,19 @@ static int mg_launch_variant(const MargArgs& a, size_t smem, cudaStream_t st) {
     auto kern = marg_sweep_kernel<MODE, ROWS>;
     PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (a.CS > 8) PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    if (a.sw_barrier) {
+        int dev = 0, sms = 0, occ = 0;
+        PGAS_CUDA(cudaGetDevice(&dev));
+        PGAS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        PGAS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, a.NW * 32, smem));
+        if ((long long)a.n_chains * a.CS > (long long)sms * occ) return -100;       // not co-resident: caller falls back to clusters
+        MargArgs ac = a;
+        void* params[1] = {(void*)&ac};
+        PGAS_CUDA(cudaMemsetAsync(a.bar_ctr, 0, sizeof(unsigned) * a.n_chains, st));
+        PGAS_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)(a.n_chains * a.CS)), dim3((unsigned)(a.NW * 32)), params, smem, st));
+        PGAS_KERNEL_CHECK();
+        return 0;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(a.n_chains * a.CS));
@@ -1162,7 +1193,7 @@ static int mg_launch_variant(const MargArgs& a, size_t smem, cudaStream_t st) {
 }
 
 // geometry: warps per CTA from the shared-memory budget, cluster size so that every particle has a warp
-static int mg_geometry(MargArgs& a, int requested_cs, size_t* smem_out) {
+static int mg_geometry(MargArgs& a, int requested_cs, size_t* smem_out, bool allow_wide = true) {
     const MargDev& m = a.m;
     a.warp_doubles = mg_warp_doubles(m);
     a.cta_doubles = mg_cta_doubles(m, a.N);
@@ -1170,6 +1201,24 @@ static int mg_geometry(MargArgs& a, int requested_cs, size_t* smem_out) {
     const size_t cta_b = sizeof(double) * a.cta_doubles, warp_b = sizeof(double) * a.warp_doubles;
     if (cta_b + warp_b > budget) PGAS_FAIL(-21, "marginalised filter: N=%d / M too large for the shared-memory carve-up (%zu + %zu bytes)", a.N, cta_b, warp_b);
     int nw = (int)std::min<size_t>(16, (budget - cta_b) / warp_b);
+    a.sw_barrier = 0;
+    if (allow_wide && requested_cs <= 0 && !getenv("PGAS_MARG_CLUSTER")) {
+        // Wide geometry: the step is bound by per-SM instruction issue / latency, not by the barrier, so a chain is
+        // spread over as many SMs as there are (4 warps = 4 particles per CTA, one warp per scheduler); the CTAs of a
+        // chain then synchronise through a global counter, which needs every CTA of the launch to be co-resident.
+        int dev = 0, sms = 0;
+        PGAS_CUDA(cudaGetDevice(&dev));
+        PGAS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int wnw = std::min(nw, 4);
+        const int wcs = std::min(64, (a.N + wnw - 1) / wnw);
+        const size_t wsmem = cta_b + warp_b * wnw;
+        const int per_sm = (int)std::min<size_t>(std::min<size_t>(65536 / (128 * 32 * (size_t)wnw), 16), (228 * 1024) / (wsmem + 1024));
+        if (wcs > 16 && per_sm >= 1 && (long long)a.n_chains * wcs <= (long long)sms * per_sm) {
+            a.sw_barrier = 1; a.NW = wnw; a.CS = wcs;
+            *smem_out = wsmem;
+            return 0;
+        }
+    }
     int cs = requested_cs;
     if (cs <= 0) {
         cs = 1;
@@ -1183,13 +1232,18 @@ static int mg_geometry(MargArgs& a, int requested_cs, size_t* smem_out) {
 }
 
 static int mg_launch_sweep(MargArgs& a, int requested_cs, cudaStream_t st) {
-    size_t smem = 0;
-    if (int rc = mg_geometry(a, requested_cs, &smem)) return rc;
     int mmax = 0;
     for (int g = 0; g < a.m.G; ++g) mmax = std::max(mmax, a.m.gp[g].M);
     const bool small = mmax <= 64;
-    if (a.mode == 0) return small ? mg_launch_variant<0, 2>(a, smem, st) : mg_launch_variant<0, 4>(a, smem, st);
-    return small ? mg_launch_variant<1, 2>(a, smem, st) : mg_launch_variant<1, 4>(a, smem, st);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        size_t smem = 0;
+        if (int rc = mg_geometry(a, requested_cs, &smem, attempt == 0)) return rc;
+        int rc;
+        if (a.mode == 0) rc = small ? mg_launch_variant<0, 2>(a, smem, st) : mg_launch_variant<0, 4>(a, smem, st);
+        else rc = small ? mg_launch_variant<1, 2>(a, smem, st) : mg_launch_variant<1, 4>(a, smem, st);
+        if (rc != -100) return rc;
+    }
+    PGAS_FAIL(-23, "marginalised filter: no launch geometry fits");
 }
 
 static int mg_launch_refstats(const MargDev& m, const double* x, long long x_stride, const double* xi, long long xi_stride,
@@ -1241,7 +1295,7 @@ extern "C" int pgas_marg_filter_f64(const pgas_marg_model* model, int32_t N, int
     memset(&a, 0, sizeof(a));
     a.m = m; a.N = N; a.n_chains = n_chains; a.mode = 0; a.lambda = forgetting_factor;
     a.state_trace = state_trace; a.xi_trace = xi_trace; a.logw_trace = logw_trace; a.anc_trace = anc_trace;
-    a.ws = w.part; a.status = status;
+    a.ws = w.part; a.status = status; a.bar_ctr = w.bar;
     if (sst_trace)
         for (int q = 0; q < 4 * m.G; ++q) {
             if (!sst_trace[q]) PGAS_FAIL(-1, "sst_trace[%d] is null", q);
@@ -1290,7 +1344,7 @@ static int mg_csmc(const pgas_marg_model* model, int N, int n_chains, const doub
     a.ref_xi = ref_xi; a.ref_xi_stride = ref_xi_stride; a.ref_xi_gstride = ref_xi_gstride;
     for (int g = 0; g < m.G; ++g) { a.tab.PR0[g] = w.PR0[g]; a.tab.PR1[g] = w.PR1[g]; a.tab.PR2[g] = w.PR2[g]; a.tab.PR3[g] = w.PR3[g]; }
     a.state_trace = state_trace; a.xi_trace = xi_trace; a.logw_trace = logw_trace; a.anc_trace = anc_trace;
-    a.ws = w.part; a.status = status;
+    a.ws = w.part; a.status = status; a.bar_ctr = w.bar;
     if (int rc = mg_fill_rng(a, rng)) return rc;
     if (int rc = mg_launch_sweep(a, cluster_size, st)) return rc;
     if (traj_x) return mg_launch_pick(m, a, final_idx, traj_x, tx_stride, traj_xi, txi_stride, txi_gstride, st);

@@ -86,7 +86,9 @@ struct MargRefTab {
 
 struct MargArgs {
     MargDev m;
-    int N, n_chains, CS, NW;           // cluster size (CTAs per chain), warps per CTA
+    int N, n_chains, CS, NW;           // CTAs per chain (a hardware cluster, or a cooperative group of CTAs), warps per CTA
+    int sw_barrier;                    // 1: CTAs of a chain synchronise through a global counter (cooperative launch, CS up to 64)
+    unsigned* bar_ctr;                 // (n_chains) counters of the software barrier, zero on entry
     int mode;                          // 0 = Algorithm1 (filter), 1 = Algorithm3 (conditional)
     double lambda;                     // forgetting factor (1 in mode 1)
     size_t warp_doubles, cta_doubles;  // shared-memory carve-up
