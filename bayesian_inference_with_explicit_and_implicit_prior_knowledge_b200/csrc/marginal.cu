@@ -342,6 +342,82 @@ __device__ __forceinline__ void warp_fwd_solve(const double* Lpk, const double* 
     }
 }
 
+// L L^T <- L L^T + sign x x^T for a packed lower factor with TRUE diagonal (n rows), by Givens (sign = +1) or
+// hyperbolic (sign = -1) rotations in the division-free form
+//   rho = L_kk^2 + sign x_k^2,  alpha = L_kk / sqrt(rho),  beta = x_k / sqrt(rho),
+//   L_ik <- alpha L_ik + sign beta x_i,   x_i <- alpha x_i - beta L_ik(old),   L_kk <- sqrt(rho).
+// Lanes own rows (lane + 32 q); x lives in registers.  A non-positive rho (lost definiteness) sets `bad`.
+template <int ROWS>
+__device__ __forceinline__ void warp_rank1(double* Lm, const double* xs, int n, double sign, int lane, int& bad) {
+    double xr[ROWS];
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q) { const int idx = lane + 32 * q; xr[q] = idx < n ? xs[idx] : 0.0; }
+    for (int k = 0; k < n; ++k) {
+        double mine = xr[0];
+#pragma unroll
+        for (int q = 1; q < ROWS; ++q) mine = ((k >> 5) == q) ? xr[q] : mine;
+        const double xk = __shfl_sync(FULL, mine, k & 31);
+        const int dk = tri(k) + k;
+        const double Lkk = Lm[dk];
+        const double rho = fma(sign * xk, xk, Lkk * Lkk);
+        if (!(rho > 0.0)) bad = 1;
+        const double ri = rsqrt(rho);
+        const double alpha = Lkk * ri, beta = xk * ri;
+        __syncwarp();
+        if (lane == 0) Lm[dk] = rho * ri;
+#pragma unroll
+        for (int q = 0; q < ROWS; ++q) {
+            const int idx = lane + 32 * q;
+            if (idx > k && idx < n) {
+                double* p = Lm + tri(idx) + k;
+                const double Lik = *p;
+                *p = fma(sign * beta, xr[q], alpha * Lik);
+                xr[q] = fma(alpha, xr[q], -beta * Lik);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// w = L^-1 b with the inverse diagonal given separately (inv[k] = 1 / L_kk)
+template <int ROWS>
+__device__ __forceinline__ void warp_fwd_solve_inv(const double* Lpk, const double* inv, const double* b, int M, int lane, double (&w)[ROWS]) {
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) { const int idx = lane + 32 * r; w[r] = idx < M ? b[idx] : 0.0; }
+    for (int k = 0; k < M; ++k) {
+        double mine = w[0];
+#pragma unroll
+        for (int r = 1; r < ROWS; ++r) mine = ((k >> 5) == r) ? w[r] : mine;
+        const double wk = __shfl_sync(FULL, mine, k & 31) * inv[k];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int idx = lane + 32 * r;
+            if (idx == k) w[r] = wk;
+            else if (idx > k && idx < M) w[r] = fma(-Lpk[tri(idx) + k], wk, w[r]);
+        }
+    }
+}
+
+// after warp_chol_packed on an augmented matrix with ONE extra row (row M = eta0^T, slot [M][M] = eta2): turn it into the
+// true-diagonal augmented factor (diagonal L_kk, last diagonal sqrt(Psi)); returns log det eta1 and Psi
+__device__ __forceinline__ void finish_aug_factor(double* A, int M, int lane, double& psi) {
+    for (int k = lane; k < M; k += 32) A[tri(k) + k] = 1.0 / A[tri(k) + k];
+    double yy = 0.0;
+    for (int k = lane; k < M; k += 32) { const double y = A[tri(M) + k]; yy = fma(y, y, yy); }
+    yy = warp_sum(yy);
+    psi = A[tri(M) + M] - yy;
+    __syncwarp();
+    if (lane == 0) A[tri(M) + M] = sqrt(psi);
+    __syncwarp();
+}
+
+// log det of the leading M x M block of a true-diagonal factor: 2 sum log L_kk
+__device__ __forceinline__ double factor_logdet(const double* A, int M, int lane) {
+    double s = 0.0;
+    for (int k = lane; k < M; k += 32) s += log(A[tri(k) + k]);
+    return 2.0 * warp_sum(s);
+}
+
 // ---------------------------------------------------------------------------------- CTA-wide softmax / CDF
 // cdf[0..N) <- cumulative sums of softmax(lw) (src/Algorithm3.py:119-121), or — sisr — the table
 // systematic_SISR searches: clip, renormalise (uniform when the sum is not > 0), cumsum, clip to [0,1]
@@ -417,10 +493,15 @@ __device__ __forceinline__ int count_below(const double* cdf, int N, double u) {
 }
 
 // ---------------------------------------------------------------------------------- the persistent kernel
+constexpr int MG_REFRESH = 32;     // Algorithm3: steps between full re-factorisations of the rank-1-updated factors
+
 struct WarpCtx {
     double* A[MG_GP];      // augmented packed matrices (M + 2 rows)
     double* B;             // staging: ancestor's factor / second factorisation (M + 1 rows)
     double* phi;           // basis vector of the new state
+    double* inv;           // inverse diagonal of a factor (Algorithm3)
+    double* zv;            // rank-1 vectors [phi; xi] and [phi_ref; xi_ref] (Algorithm3)
+    double* rv;
 };
 
 template <int MODE, int ROWS>
@@ -451,7 +532,10 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
         for (int g = 0; g < G; ++g) { wc.A[g] = q; q += (tri(m.gp[g].M + 2) + 3) & ~3; mmax = max(mmax, m.gp[g].M); }
         for (int g = G; g < MG_GP; ++g) wc.A[g] = nullptr;
         wc.B = q; q += (tri(mmax + 1) + 3) & ~3;
-        wc.phi = q;
+        wc.phi = q; q += (mmax + 3) & ~3;
+        wc.inv = q; q += (mmax + 3) & ~3;
+        wc.zv = q; q += (mmax + 4) & ~3;
+        wc.rv = q;
     }
     for (int g = 0; g < G; ++g)
         for (int i = tid; i < m.gp[g].M; i += nthr)
@@ -484,6 +568,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
         const int ac = min(max(anc, 0), N - 1);                      // JAX gathers clamp
         const bool pinned = (MODE == 1) && (i == N - 1);
         double x[MG_NX], xi[MG_GP], z[MG_D], T2v[MG_GP], T3v[MG_GP];
+        double ldA[MG_GP], ldB[MG_GP], psA[MG_GP], psB[MG_GP];     // Algorithm3: log det eta1 / Psi of the two factors
         StepVariates sv;
         // ---- new state
         if (t == 0) {
@@ -530,21 +615,42 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                 __syncwarp();
             } else {
                 // predictive Student-t from the ancestor's factor (src/Algorithm1.py:249-272)
-                const double* La = wq + L.Lp[g] + (size_t)ac * npk;
+                double cs = 0.0, ms = 0.0, psia;
+                if constexpr (MODE == 1) {
+                    // Algorithm3: augmented true-diagonal factor of the ancestor -> wc.A[g] (updated in place below)
+                    const int naug = npk + M + 1;
+                    const double* La = wq + L.Lp[g] + (size_t)ac * naug;
+                    double* Ag = wc.A[g];
 #pragma unroll 8
-                for (int e = lane; e < npk; e += 32) wc.B[e] = ldcg(La + e);        // independent L2 gathers in flight
-                __syncwarp();
-                double w[ROWS];
-                warp_fwd_solve<ROWS>(wc.B, wc.phi, M, lane, w);
-                double cs = 0.0, ms = 0.0;
+                    for (int e = lane; e < naug; e += 32) Ag[e] = ldcg(La + e);
+                    __syncwarp();
+                    for (int k = lane; k < M; k += 32) wc.inv[k] = 1.0 / Ag[tri(k) + k];
+                    __syncwarp();
+                    double w[ROWS];
+                    warp_fwd_solve_inv<ROWS>(Ag, wc.inv, wc.phi, M, lane, w);
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                    const int idx = lane + 32 * r;
-                    if (idx < M) { cs = fma(w[r], w[r], cs); ms = fma(ldcg(wq + L.yv[g] + (size_t)ac * M + idx), w[r], ms); }
+                    for (int r = 0; r < ROWS; ++r) {
+                        const int idx = lane + 32 * r;
+                        if (idx < M) { cs = fma(w[r], w[r], cs); ms = fma(Ag[tri(M) + idx], w[r], ms); }
+                    }
+                    const double sp = Ag[tri(M) + M];
+                    psia = sp * sp;
+                } else {
+                    const double* La = wq + L.Lp[g] + (size_t)ac * (npk + M + 1);
+#pragma unroll 8
+                    for (int e = lane; e < npk; e += 32) wc.B[e] = ldcg(La + e);        // independent L2 gathers in flight
+                    __syncwarp();
+                    double w[ROWS];
+                    warp_fwd_solve<ROWS>(wc.B, wc.phi, M, lane, w);
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) {
+                        const int idx = lane + 32 * r;
+                        if (idx < M) { cs = fma(w[r], w[r], cs); ms = fma(ldcg(wq + L.yv[g] + (size_t)ac * M + idx), w[r], ms); }
+                    }
+                    psia = ldcg(wq + L.psi[g] + ac);                      // eta2 - mean eta0
                 }
                 cs = warp_sum(cs) + 1.0;                                  // basis V basis^T + 1
                 ms = warp_sum(ms);                                        // basis mean^T
-                const double psia = ldcg(wq + L.psi[g] + ac);             // eta2 - mean eta0
                 T2a = ldcg(wq + L.T2[g] + ac);
                 T3a = ldcg(wq + L.T3[g] + ac);
                 const double df = (gp.p3 + lam * T3a) + 1.0 - 1.0;        // df + 1 - n_xi (src/BayesianInferrence.py:78)
@@ -559,32 +665,100 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             double* T1w = wp + L.T1p[g] + (size_t)i * npk;
             const double* T1a = wq + L.T1p[g] + (size_t)ac * npk;
             double* Ag = wc.A[g];
-#pragma unroll 4
-            for (int e = lane; e < npk; e += 32) {
-                const unsigned ij = ijt[g][e];
-                double v = wc.phi[ij & 0xffffu] * wc.phi[ij >> 16];
-                if (t > 0) v = fma(lam, ldcg(T1a + e), v);
-                T1w[e] = v;
-                Ag[e] = fma(lam, v, gp.p1[e]);                            // eta1 of the NEXT step: prior + lambda T1
-            }
             const int rowM = tri(M);
-            for (int k = lane; k < M; k += 32) {
-                double v = wc.phi[k] * xiv;
-                if (t > 0) v = fma(lam, ldcg(wq + L.T0[g] + (size_t)ac * M + k), v);
-                wp[L.T0[g] + (size_t)i * M + k] = v;
-                Ag[rowM + k] = fma(lam, v, gp.p0[k]);                     // extra row 1: eta0
-            }
             const double T2n = (t > 0) ? fma(lam, T2a, xiv * xiv) : xiv * xiv;
             const double T3n = (t > 0) ? fma(lam, T3a, 1.0) : 1.0;
             T2v[g] = T2n;
             T3v[g] = T3n;
-            if (lane == 0) {
-                wp[L.T2[g] + i] = T2n;
-                wp[L.T3[g] + i] = T3n;
-                Ag[rowM + M] = fma(lam, T2n, gp.p2);                      // eta2
-                xtrace[((size_t)g * T + t) * N + i] = xiv;
+            if constexpr (MODE == 1) {
+                // Algorithm3 (lambda = 1): the statistics change by the rank-one term [phi; xi][phi; xi]^T and the remaining
+                // reference statistics lose [phi_ref; xi_ref][phi_ref; xi_ref]^T (src/Algorithm3.py:153-174), so both augmented
+                // factors follow by Givens / hyperbolic rotation sweeps, O(M^2), instead of two O(M^3) factorisations.  Every
+                // MG_REFRESH steps (and whenever a downdate loses definiteness) they are rebuilt from the statistics.
+                const size_t trow = (size_t)chain * T + t;
+                const int naug = npk + M + 1;
+#pragma unroll 4
+                for (int e = lane; e < npk; e += 32) {
+                    const unsigned ij = ijt[g][e];
+                    double v = wc.phi[ij & 0xffffu] * wc.phi[ij >> 16];
+                    if (t > 0) v += ldcg(T1a + e);
+                    T1w[e] = v;
+                }
+                for (int k = lane; k < M; k += 32) {
+                    double v = wc.phi[k] * xiv;
+                    if (t > 0) v += ldcg(wq + L.T0[g] + (size_t)ac * M + k);
+                    wp[L.T0[g] + (size_t)i * M + k] = v;
+                    wc.zv[k] = wc.phi[k];
+                    wc.rv[k] = a.tab.RPHI[g][trow * M + k];
+                }
+                if (lane == 0) {
+                    wp[L.T2[g] + i] = T2n;
+                    wp[L.T3[g] + i] = T3n;
+                    wc.zv[M] = xiv;
+                    wc.rv[M] = refxi[(size_t)g * a.ref_xi_gstride + t];
+                    xtrace[((size_t)g * T + t) * N + i] = xiv;
+                }
+                __syncwarp();
+                int bad = 0;
+                const bool refresh = (t % MG_REFRESH) == 0;
+                if (!refresh) {
+                    const double* LBa = wq + L.LB[g] + (size_t)ac * naug;
+#pragma unroll 8
+                    for (int e = lane; e < naug; e += 32) wc.B[e] = ldcg(LBa + e);
+                    __syncwarp();
+                    warp_rank1<ROWS>(Ag, wc.zv, M + 1, 1.0, lane, bad);
+                    warp_rank1<ROWS>(wc.B, wc.zv, M + 1, 1.0, lane, bad);
+                    warp_rank1<ROWS>(wc.B, wc.rv, M + 1, -1.0, lane, bad);
+                    bad = __any_sync(FULL, bad);
+                }
+                if (refresh || bad) {
+                    const double* PR1 = a.tab.PR1[g] + trow * npk;
+                    const double* PR0 = a.tab.PR0[g] + trow * M;
+#pragma unroll 8
+                    for (int e = lane; e < npk; e += 32) { const double v = T1w[e]; Ag[e] = gp.p1[e] + v; wc.B[e] = PR1[e] + v; }
+                    for (int k = lane; k < M; k += 32) {
+                        const double v = wp[L.T0[g] + (size_t)i * M + k];
+                        Ag[rowM + k] = gp.p0[k] + v;
+                        wc.B[rowM + k] = PR0[k] + v;
+                    }
+                    if (lane == 0) { Ag[rowM + M] = gp.p2 + T2n; wc.B[rowM + M] = a.tab.PR2[g][trow] + T2n; }
+                    __syncwarp();
+                    double psi_tmp;
+                    warp_chol_packed(Ag, M, M + 1, lane, fail);
+                    finish_aug_factor(Ag, M, lane, psi_tmp);
+                    warp_chol_packed(wc.B, M, M + 1, lane, fail);
+                    finish_aug_factor(wc.B, M, lane, psi_tmp);
+                }
+                ldA[g] = factor_logdet(Ag, M, lane);
+                ldB[g] = factor_logdet(wc.B, M, lane);
+                { const double sa = Ag[rowM + M], sb = wc.B[rowM + M]; psA[g] = sa * sa; psB[g] = sb * sb; }
+                double* LBw = wp + L.LB[g] + (size_t)i * naug;
+#pragma unroll 8
+                for (int e = lane; e < naug; e += 32) LBw[e] = wc.B[e];
+                __syncwarp();
+            } else {
+#pragma unroll 4
+                for (int e = lane; e < npk; e += 32) {
+                    const unsigned ij = ijt[g][e];
+                    double v = wc.phi[ij & 0xffffu] * wc.phi[ij >> 16];
+                    if (t > 0) v = fma(lam, ldcg(T1a + e), v);
+                    T1w[e] = v;
+                    Ag[e] = fma(lam, v, gp.p1[e]);                            // eta1 of the NEXT step: prior + lambda T1
+                }
+                for (int k = lane; k < M; k += 32) {
+                    double v = wc.phi[k] * xiv;
+                    if (t > 0) v = fma(lam, ldcg(wq + L.T0[g] + (size_t)ac * M + k), v);
+                    wp[L.T0[g] + (size_t)i * M + k] = v;
+                    Ag[rowM + k] = fma(lam, v, gp.p0[k]);                     // extra row 1: eta0
+                }
+                if (lane == 0) {
+                    wp[L.T2[g] + i] = T2n;
+                    wp[L.T3[g] + i] = T3n;
+                    Ag[rowM + M] = fma(lam, T2n, gp.p2);                      // eta2
+                    xtrace[((size_t)g * T + t) * N + i] = xiv;
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
         // ---- weights and traces
         double lw = 0.0;
@@ -604,49 +778,54 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             const int M = gp.M, npk = gp.npk, rowM = tri(M), rowV = tri(M + 1);
             double* Ag = wc.A[g];
             gp_input(m, gp, t + 1, ax, z);
-            basis_eval(gp, z, Ag + rowV, lane);                           // extra row 2: phi(aux state)
-            __syncwarp();
-            const double logdet = warp_chol_packed(Ag, M, M + 2, lane, fail);
-            double yy = 0.0, yv = 0.0;
-            for (int k = lane; k < M; k += 32) {
-                const double y = Ag[rowM + k];
-                yy = fma(y, y, yy);
-                yv = fma(y, Ag[rowV + k], yv);
-                wp[L.yv[g] + (size_t)i * M + k] = y;
-            }
-            yy = warp_sum(yy);
-            axi[g] = warp_sum(yv);                                        // prior_mniw_mean . phi_aux
-            const double psi = Ag[rowM + M] - yy;
-            double* Lw = wp + L.Lp[g] + (size_t)i * npk;
+            if constexpr (MODE == 1) {
+                // Algorithm3: v = L^-1 phi(aux state) by one forward solve on the up-to-date factor; y is its last row
+                const int naug = npk + M + 1;
+                basis_eval(gp, z, wc.phi, lane);
+                for (int k = lane; k < M; k += 32) wc.inv[k] = 1.0 / Ag[tri(k) + k];
+                __syncwarp();
+                double w[ROWS];
+                warp_fwd_solve_inv<ROWS>(Ag, wc.inv, wc.phi, M, lane, w);
+                double yv = 0.0;
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const int idx = lane + 32 * r;
+                    if (idx < M) yv = fma(Ag[rowM + idx], w[r], yv);
+                }
+                axi[g] = warp_sum(yv);                                    // prior_mniw_mean . phi_aux
+                double* Lw = wp + L.Lp[g] + (size_t)i * naug;
 #pragma unroll 8
-            for (int e = lane; e < npk; e += 32) Lw[e] = Ag[e];
-            if (lane == 0) wp[L.psi[g] + i] = psi;
-            if (MODE == 1) {
-                // g_t - g_T (src/Algorithm3.py:92-106); lambda = 1 here
-                const double T3n = T3v[g], T2n = T2v[g];
-                // Only the particle-dependent terms of prior_mniw_log_base_measure are kept: -n m/2 log(2 pi)
-                // cancels between g_t and g_T, and -nu n/2 log 2 - multigammaln(nu/2, n) depend on T3 alone, which
-                // is the same for every particle (T3 = lambda T3[a] + 1 from a common start), so they shift all
-                // ancestor log-weights equally and vanish in the softmax (src/Algorithm3.py:115-118).
-                const double gt = 0.5 * logdet + log(psi) * (0.5 * (gp.p3 + T3n));
+                for (int e = lane; e < naug; e += 32) Lw[e] = Ag[e];
+                // g_t - g_T (src/Algorithm3.py:92-106).  Only the particle-dependent terms of prior_mniw_log_base_measure are
+                // kept: -n m/2 log(2 pi) cancels between g_t and g_T, and -nu n/2 log 2 - multigammaln(nu/2, n) depend on T3
+                // alone, which is the same for every particle, so they shift all ancestor log-weights equally and vanish in the
+                // softmax (src/Algorithm3.py:115-118).
                 const size_t trow = (size_t)chain * T + t;
-                const double* PR1 = a.tab.PR1[g] + trow * npk;
-                const double* PR0 = a.tab.PR0[g] + trow * M;
-                const double* T1w = wp + L.T1p[g] + (size_t)i * npk;
-                __syncwarp();
-#pragma unroll 8
-                for (int e = lane; e < npk; e += 32) wc.B[e] = PR1[e] + T1w[e];
-                for (int k = lane; k < M; k += 32) wc.B[rowM + k] = PR0[k] + wp[L.T0[g] + (size_t)i * M + k];
-                if (lane == 0) wc.B[rowM + M] = a.tab.PR2[g][trow] + T2n;
-                __syncwarp();
-                const double logdet2 = warp_chol_packed(wc.B, M, M + 1, lane, fail);
-                double y2 = 0.0;
-                for (int k = lane; k < M; k += 32) { const double y = wc.B[rowM + k]; y2 = fma(y, y, y2); }
-                const double psi2 = wc.B[rowM + M] - warp_sum(y2);
-                const double gT = 0.5 * logdet2 + log(psi2) * (0.5 * (a.tab.PR3[g][trow] + T3n));
+                const double gt = 0.5 * ldA[g] + log(psA[g]) * (0.5 * (gp.p3 + T3v[g]));
+                const double gT = 0.5 * ldB[g] + log(psB[g]) * (0.5 * (a.tab.PR3[g][trow] + T3v[g]));
                 gdiff += gt - gT;
+                __syncwarp();
+            } else {
+                basis_eval(gp, z, Ag + rowV, lane);                       // extra row 2: phi(aux state)
+                __syncwarp();
+                const double logdet = warp_chol_packed(Ag, M, M + 2, lane, fail);
+                double yy = 0.0, yv = 0.0;
+                for (int k = lane; k < M; k += 32) {
+                    const double y = Ag[rowM + k];
+                    yy = fma(y, y, yy);
+                    yv = fma(y, Ag[rowV + k], yv);
+                    wp[L.yv[g] + (size_t)i * M + k] = y;
+                }
+                yy = warp_sum(yy);
+                axi[g] = warp_sum(yv);                                    // prior_mniw_mean . phi_aux
+                const double psi = Ag[rowM + M] - yy;
+                double* Lw = wp + L.Lp[g] + (size_t)i * (npk + M + 1);
+#pragma unroll 8
+                for (int e = lane; e < npk; e += 32) Lw[e] = Ag[e];
+                if (lane == 0) wp[L.psi[g] + i] = psi;
+                (void)logdet;
+                __syncwarp();
             }
-            __syncwarp();
         }
         const double ell = log_likelihood(m, t + 1, ax, axi);
         const double lwa = ell + lw;
@@ -741,6 +920,7 @@ struct RefStatArgs {
     double* tot_out[4 * MG_GP];        // optional totals out (full matrices)
     long long tot_out_stride[4 * MG_GP];
     double* PR0[MG_GP]; double* PR1[MG_GP]; double* PR2[MG_GP]; double* PR3[MG_GP];   // optional tables
+    double* RPHI[MG_GP];               // optional (n_chains, T, M): basis of the reference trajectory
 };
 
 constexpr int RS_THREADS = 512;
@@ -794,6 +974,8 @@ __global__ void __launch_bounds__(RS_THREADS) marg_refstats_kernel(const __grid_
                 if (lane == 0) xis[s] = xit[t0 + s];
             }
             __syncthreads();
+            if (pass == 1 && a.RPHI[g])
+                for (int e = tid; e < nt * M; e += RS_THREADS) a.RPHI[g][((size_t)chain * T + t0) * M + e] = phis[e];
             for (int s = 0; s < nt; ++s) {
                 const double* ph = phis + s * M;
                 const double xv = xis[s];
@@ -1105,7 +1287,7 @@ extern "C" int pgas_marg_model_destroy(pgas_marg_model* model) {
 struct MargHostWs {
     unsigned* bar;                                 // n_chains software-barrier counters
     double* part;                                  // n_chains * chain_stride
-    double *PR0[MG_GP], *PR1[MG_GP], *PR2[MG_GP], *PR3[MG_GP];
+    double *PR0[MG_GP], *PR1[MG_GP], *PR2[MG_GP], *PR3[MG_GP], *RPHI[MG_GP];
     size_t total;
 };
 
@@ -1123,6 +1305,7 @@ static MargHostWs mg_carve(const MargDev& m, int N, int n_chains, char* base) {
         w.PR1[g] = on ? take(sizeof(double) * CT * m.gp[g].npk) : nullptr;
         w.PR2[g] = on ? take(sizeof(double) * CT) : nullptr;
         w.PR3[g] = on ? take(sizeof(double) * CT) : nullptr;
+        w.RPHI[g] = on ? take(sizeof(double) * CT * m.gp[g].M) : nullptr;
     }
     w.total = o + 256;
     return w;
@@ -1138,7 +1321,7 @@ static size_t mg_warp_doubles(const MargDev& m) {
     int mmax = 0;
     for (int g = 0; g < m.G; ++g) { d += ((m.gp[g].M + 2) * (m.gp[g].M + 3) / 2 + 3) & ~3; mmax = std::max(mmax, m.gp[g].M); }
     d += ((mmax + 1) * (mmax + 2) / 2 + 3) & ~3;
-    d += (mmax + 3) & ~3;
+    d += 2 * ((mmax + 3) & ~3) + 2 * ((mmax + 4) & ~3);
     return d;
 }
 static size_t mg_cta_doubles(const MargDev& m, int N) {
@@ -1234,7 +1417,7 @@ static int mg_geometry(MargArgs& a, int requested_cs, size_t* smem_out, bool all
 static int mg_launch_sweep(MargArgs& a, int requested_cs, cudaStream_t st) {
     int mmax = 0;
     for (int g = 0; g < a.m.G; ++g) mmax = std::max(mmax, a.m.gp[g].M);
-    const bool small = mmax <= 64;
+    const bool small = mmax <= 62;
     for (int attempt = 0; attempt < 2; ++attempt) {
         size_t smem = 0;
         if (int rc = mg_geometry(a, requested_cs, &smem, attempt == 0)) return rc;
@@ -1261,7 +1444,7 @@ static int mg_launch_refstats(const MargDev& m, const double* x, long long x_str
             r.tot_out[4 * g + j] = tot_out ? tot_out[4 * g + j] : nullptr;
             r.tot_out_stride[4 * g + j] = tot_out_stride ? tot_out_stride[4 * g + j] : 0;
         }
-        if (tab) { r.PR0[g] = tab->PR0[g]; r.PR1[g] = tab->PR1[g]; r.PR2[g] = tab->PR2[g]; r.PR3[g] = tab->PR3[g]; }
+        if (tab) { r.PR0[g] = tab->PR0[g]; r.PR1[g] = tab->PR1[g]; r.PR2[g] = tab->PR2[g]; r.PR3[g] = tab->PR3[g]; r.RPHI[g] = tab->RPHI[g]; }
     }
     const size_t smem = sizeof(double) * ((size_t)RS_CHUNK * mmax + RS_CHUNK);
     marg_refstats_kernel<<<dim3(n_chains, m.G), RS_THREADS, smem, st>>>(r);
@@ -1342,7 +1525,7 @@ static int mg_csmc(const pgas_marg_model* model, int N, int n_chains, const doub
     a.m = m; a.N = N; a.n_chains = n_chains; a.mode = 1; a.lambda = 1.0;       // src/Algorithm3.py:34
     a.ref_x = ref_x; a.ref_x_stride = ref_x_stride;
     a.ref_xi = ref_xi; a.ref_xi_stride = ref_xi_stride; a.ref_xi_gstride = ref_xi_gstride;
-    for (int g = 0; g < m.G; ++g) { a.tab.PR0[g] = w.PR0[g]; a.tab.PR1[g] = w.PR1[g]; a.tab.PR2[g] = w.PR2[g]; a.tab.PR3[g] = w.PR3[g]; }
+    for (int g = 0; g < m.G; ++g) { a.tab.PR0[g] = w.PR0[g]; a.tab.PR1[g] = w.PR1[g]; a.tab.PR2[g] = w.PR2[g]; a.tab.PR3[g] = w.PR3[g]; a.tab.RPHI[g] = w.RPHI[g]; }
     a.state_trace = state_trace; a.xi_trace = xi_trace; a.logw_trace = logw_trace; a.anc_trace = anc_trace;
     a.ws = w.part; a.status = status; a.bar_ctr = w.bar;
     if (int rc = mg_fill_rng(a, rng)) return rc;

@@ -47,7 +47,7 @@ struct pgas_marg_model {
 // parities: pass t writes parity t & 1 and gathers, by ancestor, from parity (t - 1) & 1.
 struct MargWs {
     size_t auxx, ellaux, lwaux, lwanc;
-    size_t yv[MG_GP], psi[MG_GP], Lp[MG_GP], T1p[MG_GP], T0[MG_GP], T2[MG_GP], T3[MG_GP];
+    size_t yv[MG_GP], psi[MG_GP], Lp[MG_GP], LB[MG_GP], T1p[MG_GP], T0[MG_GP], T2[MG_GP], T3[MG_GP];
     size_t parity_stride, chain_stride;
 };
 
@@ -64,7 +64,11 @@ __host__ __device__ inline MargWs marg_ws_layout(const MargDev& m, int N) {
         const size_t M = on ? m.gp[g].M : 0, npk = on ? m.gp[g].npk : 0;
         w.yv[g] = take((size_t)N * M);
         w.psi[g] = take(on ? N : 0);
-        w.Lp[g] = take((size_t)N * npk);
+        // Lp: Algorithm1 keeps the M x M factor (inverse diagonal) here; Algorithm3 keeps the AUGMENTED factor of
+        // [[eta1, eta0], [eta0^T, eta2]] (M+1 rows, true diagonal) of prior + statistics, and LB the one of
+        // prior + remaining reference statistics + statistics (rank-1 up/down-dated, marginal.cu)
+        w.Lp[g] = take((size_t)N * (on ? npk + M + 1 : 0));
+        w.LB[g] = take((size_t)N * (on ? npk + M + 1 : 0));
         w.T1p[g] = take((size_t)N * npk);
         w.T0[g] = take((size_t)N * M);
         w.T2[g] = take(on ? N : 0);
@@ -78,6 +82,7 @@ __host__ __device__ inline MargWs marg_ws_layout(const MargDev& m, int N) {
 // prior + remaining reference statistics after step t (src/Algorithm3.py:235-246, :163-174), one row
 // per time step: PR1 packed (T, npk), PR0 (T, M), PR2 (T), PR3 (T); per chain.
 struct MargRefTab {
+    const double* RPHI[MG_GP];         // (T, M) basis of the reference trajectory at every step
     const double* PR0[MG_GP];
     const double* PR1[MG_GP];
     const double* PR2[MG_GP];
