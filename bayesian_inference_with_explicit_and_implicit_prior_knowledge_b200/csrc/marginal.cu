@@ -61,6 +61,13 @@ __device__ __forceinline__ void mg_cluster_barrier(bool multi) {
     }
 }
 
+// asynchronous 16-byte global -> shared copies (L2 only: the sources are rewritten by other SMs every other step)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // GP-input map z = p * link(a . x + b) + q   (pgas_b200.h, group B)
 __device__ __forceinline__ void gp_input(const MargDev& m, const MargGP& gp, int t, const double* x, double* z) {
     for (int d = 0; d < gp.D; ++d) {
@@ -499,6 +506,8 @@ struct WarpCtx {
     double* A[MG_GP];      // augmented packed matrices (M + 2 rows)
     double* B;             // staging: ancestor's factor / second factorisation (M + 1 rows)
     double* phi;           // basis vector of the new state
+    double* Bg[MG_GP];     // Algorithm3: the ancestor's second augmented factor, prefetched per GP
+    double* T1s[MG_GP];    // Algorithm3: the ancestor's packed T1, prefetched per GP
     double* inv;           // inverse diagonal of a factor (Algorithm3)
     double* zv;            // rank-1 vectors [phi; xi] and [phi_ref; xi_ref] (Algorithm3)
     double* rv;
@@ -531,11 +540,17 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
         int mmax = 0;
         for (int g = 0; g < G; ++g) { wc.A[g] = q; q += (tri(m.gp[g].M + 2) + 3) & ~3; mmax = max(mmax, m.gp[g].M); }
         for (int g = G; g < MG_GP; ++g) wc.A[g] = nullptr;
-        wc.B = q; q += (tri(mmax + 1) + 3) & ~3;
+        wc.B = q; q += (MODE == 1) ? 0 : ((tri(mmax + 1) + 3) & ~3);       // Algorithm3 keeps per-GP buffers instead (Bg)
         wc.phi = q; q += (mmax + 3) & ~3;
         wc.inv = q; q += (mmax + 3) & ~3;
         wc.zv = q; q += (mmax + 4) & ~3;
-        wc.rv = q;
+        wc.rv = q; q += (mmax + 4) & ~3;
+        for (int g = 0; g < MG_GP; ++g) { wc.Bg[g] = wc.B; wc.T1s[g] = nullptr; }
+        if (MODE == 1)
+            for (int g = 0; g < G; ++g) {
+                wc.Bg[g] = q; q += (mg_naugp(m.gp[g].M) + 3) & ~3;
+                wc.T1s[g] = q; q += (mg_npkp(m.gp[g].M) + 3) & ~3;
+            }
     }
     for (int g = 0; g < G; ++g)
         for (int i = tid; i < m.gp[g].M; i += nthr)
@@ -567,6 +582,22 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
         const double* wq = wsc + (size_t)(par ^ 1) * L.parity_stride; // gathered by ancestor
         const int ac = min(max(anc, 0), N - 1);                      // JAX gathers clamp
         const bool pinned = (MODE == 1) && (i == N - 1);
+        if constexpr (MODE == 1) {
+            if (t > 0) {
+                // the three per-GP gathers by ancestor (two augmented factors, packed T1: ~21 KB at M = 41) start now and
+                // land in shared memory while the new state, the basis and the variates are computed
+                __syncwarp();
+                for (int g = 0; g < G; ++g) {
+                    const int Mg = m.gp[g].M, na = mg_naugp(Mg), np = mg_npkp(Mg);
+                    const double* s0 = wq + L.Lp[g] + (size_t)ac * na;
+                    const double* s1 = wq + L.LB[g] + (size_t)ac * na;
+                    const double* s2 = wq + L.T1p[g] + (size_t)ac * np;
+                    for (int e = 2 * lane; e < na; e += 64) { cp_async16(wc.A[g] + e, s0 + e); cp_async16(wc.Bg[g] + e, s1 + e); }
+                    for (int e = 2 * lane; e < np; e += 64) cp_async16(wc.T1s[g] + e, s2 + e);
+                }
+                cp_async_commit();
+            }
+        }
         double x[MG_NX], xi[MG_GP], z[MG_D], T2v[MG_GP], T3v[MG_GP];
         double ldA[MG_GP], ldB[MG_GP], psA[MG_GP], psB[MG_GP];     // Algorithm3: log det eta1 / Psi of the two factors
         StepVariates sv;
@@ -618,12 +649,8 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                 double cs = 0.0, ms = 0.0, psia;
                 if constexpr (MODE == 1) {
                     // Algorithm3: augmented true-diagonal factor of the ancestor -> wc.A[g] (updated in place below)
-                    const int naug = npk + M + 1;
-                    const double* La = wq + L.Lp[g] + (size_t)ac * naug;
                     double* Ag = wc.A[g];
-#pragma unroll 8
-                    for (int e = lane; e < naug; e += 32) Ag[e] = ldcg(La + e);
-                    __syncwarp();
+                    if (g == 0) { cp_async_wait_all(); __syncwarp(); }       // prefetched at the top of the pass
                     for (int k = lane; k < M; k += 32) wc.inv[k] = 1.0 / Ag[tri(k) + k];
                     __syncwarp();
                     double w[ROWS];
@@ -636,7 +663,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                     const double sp = Ag[tri(M) + M];
                     psia = sp * sp;
                 } else {
-                    const double* La = wq + L.Lp[g] + (size_t)ac * (npk + M + 1);
+                    const double* La = wq + L.Lp[g] + (size_t)ac * mg_naugp(M);
 #pragma unroll 8
                     for (int e = lane; e < npk; e += 32) wc.B[e] = ldcg(La + e);        // independent L2 gathers in flight
                     __syncwarp();
@@ -662,8 +689,8 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             if (pinned) xiv = refxi[(size_t)g * a.ref_xi_gstride + t];
             xi[g] = xiv;
             // statistics: S_t = lambda S_{t-1}[a] + T(xi, phi)  (src/Algorithm1.py:315-318, :356-375)
-            double* T1w = wp + L.T1p[g] + (size_t)i * npk;
-            const double* T1a = wq + L.T1p[g] + (size_t)ac * npk;
+            double* T1w = wp + L.T1p[g] + (size_t)i * mg_npkp(M);
+            const double* T1a = wq + L.T1p[g] + (size_t)ac * mg_npkp(M);
             double* Ag = wc.A[g];
             const int rowM = tri(M);
             const double T2n = (t > 0) ? fma(lam, T2a, xiv * xiv) : xiv * xiv;
@@ -681,7 +708,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                 for (int e = lane; e < npk; e += 32) {
                     const unsigned ij = ijt[g][e];
                     double v = wc.phi[ij & 0xffffu] * wc.phi[ij >> 16];
-                    if (t > 0) v += ldcg(T1a + e);
+                    if (t > 0) v += wc.T1s[g][e];
                     T1w[e] = v;
                 }
                 for (int k = lane; k < M; k += 32) {
@@ -701,40 +728,37 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                 __syncwarp();
                 int bad = 0;
                 const bool refresh = (t % MG_REFRESH) == 0;
+                double* Bq = wc.Bg[g];
                 if (!refresh) {
-                    const double* LBa = wq + L.LB[g] + (size_t)ac * naug;
-#pragma unroll 8
-                    for (int e = lane; e < naug; e += 32) wc.B[e] = ldcg(LBa + e);
-                    __syncwarp();
                     warp_rank1<ROWS>(Ag, wc.zv, M + 1, 1.0, lane, bad);
-                    warp_rank1<ROWS>(wc.B, wc.zv, M + 1, 1.0, lane, bad);
-                    warp_rank1<ROWS>(wc.B, wc.rv, M + 1, -1.0, lane, bad);
+                    warp_rank1<ROWS>(Bq, wc.zv, M + 1, 1.0, lane, bad);
+                    warp_rank1<ROWS>(Bq, wc.rv, M + 1, -1.0, lane, bad);
                     bad = __any_sync(FULL, bad);
                 }
                 if (refresh || bad) {
                     const double* PR1 = a.tab.PR1[g] + trow * npk;
                     const double* PR0 = a.tab.PR0[g] + trow * M;
 #pragma unroll 8
-                    for (int e = lane; e < npk; e += 32) { const double v = T1w[e]; Ag[e] = gp.p1[e] + v; wc.B[e] = PR1[e] + v; }
+                    for (int e = lane; e < npk; e += 32) { const double v = T1w[e]; Ag[e] = gp.p1[e] + v; Bq[e] = PR1[e] + v; }
                     for (int k = lane; k < M; k += 32) {
                         const double v = wp[L.T0[g] + (size_t)i * M + k];
                         Ag[rowM + k] = gp.p0[k] + v;
-                        wc.B[rowM + k] = PR0[k] + v;
+                        Bq[rowM + k] = PR0[k] + v;
                     }
-                    if (lane == 0) { Ag[rowM + M] = gp.p2 + T2n; wc.B[rowM + M] = a.tab.PR2[g][trow] + T2n; }
+                    if (lane == 0) { Ag[rowM + M] = gp.p2 + T2n; Bq[rowM + M] = a.tab.PR2[g][trow] + T2n; }
                     __syncwarp();
                     double psi_tmp;
                     warp_chol_packed(Ag, M, M + 1, lane, fail);
                     finish_aug_factor(Ag, M, lane, psi_tmp);
-                    warp_chol_packed(wc.B, M, M + 1, lane, fail);
-                    finish_aug_factor(wc.B, M, lane, psi_tmp);
+                    warp_chol_packed(Bq, M, M + 1, lane, fail);
+                    finish_aug_factor(Bq, M, lane, psi_tmp);
                 }
                 ldA[g] = factor_logdet(Ag, M, lane);
-                ldB[g] = factor_logdet(wc.B, M, lane);
-                { const double sa = Ag[rowM + M], sb = wc.B[rowM + M]; psA[g] = sa * sa; psB[g] = sb * sb; }
-                double* LBw = wp + L.LB[g] + (size_t)i * naug;
+                ldB[g] = factor_logdet(Bq, M, lane);
+                { const double sa = Ag[rowM + M], sb = Bq[rowM + M]; psA[g] = sa * sa; psB[g] = sb * sb; }
+                double* LBw = wp + L.LB[g] + (size_t)i * mg_naugp(M);
 #pragma unroll 8
-                for (int e = lane; e < naug; e += 32) LBw[e] = wc.B[e];
+                for (int e = lane; e < naug; e += 32) LBw[e] = Bq[e];
                 __syncwarp();
             } else {
 #pragma unroll 4
@@ -793,7 +817,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                     if (idx < M) yv = fma(Ag[rowM + idx], w[r], yv);
                 }
                 axi[g] = warp_sum(yv);                                    // prior_mniw_mean . phi_aux
-                double* Lw = wp + L.Lp[g] + (size_t)i * naug;
+                double* Lw = wp + L.Lp[g] + (size_t)i * mg_naugp(M);
 #pragma unroll 8
                 for (int e = lane; e < naug; e += 32) Lw[e] = Ag[e];
                 // g_t - g_T (src/Algorithm3.py:92-106).  Only the particle-dependent terms of prior_mniw_log_base_measure are
@@ -819,7 +843,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                 yy = warp_sum(yy);
                 axi[g] = warp_sum(yv);                                    // prior_mniw_mean . phi_aux
                 const double psi = Ag[rowM + M] - yy;
-                double* Lw = wp + L.Lp[g] + (size_t)i * (npk + M + 1);
+                double* Lw = wp + L.Lp[g] + (size_t)i * mg_naugp(M);
 #pragma unroll 8
                 for (int e = lane; e < npk; e += 32) Lw[e] = Ag[e];
                 if (lane == 0) wp[L.psi[g] + i] = psi;
@@ -847,7 +871,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             for (int e = rank * nthr + tid; e < E; e += CS * nthr) {
                 const double* src;
                 size_t stride;
-                if (e < npk) { src = wq + L.T1p[g] + e; stride = npk; }
+                if (e < npk) { src = wq + L.T1p[g] + e; stride = mg_npkp(M); }
                 else if (e < npk + M) { src = wq + L.T0[g] + (e - npk); stride = M; }
                 else if (e == npk + M) { src = wq + L.T2[g]; stride = 1; }
                 else { src = wq + L.T3[g]; stride = 1; }
@@ -1079,7 +1103,7 @@ __global__ void marg_unpack_stats_kernel(const MargDev m, const double* __restri
         if (r < (size_t)M * M) {
             const int rr = (int)(r / M), cc = (int)(r % M);
             const int hi = max(rr, cc), lo = min(rr, cc);
-            T1[ci * M * M + r] = wq[L.T1p[g] + (size_t)i * npk + tri(hi) + lo];
+            T1[ci * M * M + r] = wq[L.T1p[g] + (size_t)i * mg_npkp(M) + tri(hi) + lo];
         } else if (r < (size_t)M * M + M) T0[ci * M + (r - (size_t)M * M)] = wq[L.T0[g] + (size_t)i * M + (r - (size_t)M * M)];
         else if (r == (size_t)M * M + M) T2[ci] = wq[L.T2[g] + i];
         else T3[ci] = wq[L.T3[g] + i];
@@ -1316,12 +1340,14 @@ extern "C" size_t pgas_marg_workspace_bytes(const pgas_marg_model* model, int32_
     return mg_carve(model->dev, N, n_chains, nullptr).total;
 }
 
-static size_t mg_warp_doubles(const MargDev& m) {
+static size_t mg_warp_doubles(const MargDev& m, int mode) {
     size_t d = 0;
     int mmax = 0;
     for (int g = 0; g < m.G; ++g) { d += ((m.gp[g].M + 2) * (m.gp[g].M + 3) / 2 + 3) & ~3; mmax = std::max(mmax, m.gp[g].M); }
-    d += ((mmax + 1) * (mmax + 2) / 2 + 3) & ~3;
+    if (mode != 1) d += ((mmax + 1) * (mmax + 2) / 2 + 3) & ~3;
     d += 2 * ((mmax + 3) & ~3) + 2 * ((mmax + 4) & ~3);
+    if (mode == 1)
+        for (int g = 0; g < m.G; ++g) d += ((mg_naugp(m.gp[g].M) + 3) & ~3) + ((mg_npkp(m.gp[g].M) + 3) & ~3);
     return d;
 }
 static size_t mg_cta_doubles(const MargDev& m, int N) {
@@ -1378,7 +1404,7 @@ static int mg_launch_variant(const MargArgs& a, size_t smem, cudaStream_t st) {
 // geometry: warps per CTA from the shared-memory budget, cluster size so that every particle has a warp
 static int mg_geometry(MargArgs& a, int requested_cs, size_t* smem_out, bool allow_wide = true) {
     const MargDev& m = a.m;
-    a.warp_doubles = mg_warp_doubles(m);
+    a.warp_doubles = mg_warp_doubles(m, a.mode);
     a.cta_doubles = mg_cta_doubles(m, a.N);
     const size_t budget = 225 * 1024;
     const size_t cta_b = sizeof(double) * a.cta_doubles, warp_b = sizeof(double) * a.warp_doubles;
@@ -1393,9 +1419,9 @@ static int mg_geometry(MargArgs& a, int requested_cs, size_t* smem_out, bool all
         PGAS_CUDA(cudaGetDevice(&dev));
         PGAS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const int wnw = std::min(nw, 4);
-        const int wcs = std::min(64, (a.N + wnw - 1) / wnw);
         const size_t wsmem = cta_b + warp_b * wnw;
         const int per_sm = (int)std::min<size_t>(std::min<size_t>(65536 / (128 * 32 * (size_t)wnw), 16), (228 * 1024) / (wsmem + 1024));
+        const int wcs = std::min(std::min(64, (a.N + wnw - 1) / wnw), per_sm >= 1 ? (sms * per_sm) / std::max(a.n_chains, 1) : 0);
         if (wcs > 16 && per_sm >= 1 && (long long)a.n_chains * wcs <= (long long)sms * per_sm) {
             a.sw_barrier = 1; a.NW = wnw; a.CS = wcs;
             *smem_out = wsmem;

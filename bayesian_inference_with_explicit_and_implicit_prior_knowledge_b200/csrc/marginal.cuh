@@ -43,6 +43,10 @@ struct pgas_marg_model {
     size_t arena_bytes;
 };
 
+// per-particle strides (doubles), padded to even so that 16-byte asynchronous copies stay aligned
+__host__ __device__ inline int mg_npkp(int M) { return (M * (M + 1) / 2 + 1) & ~1; }          // packed M x M lower triangle
+__host__ __device__ inline int mg_naugp(int M) { return (M * (M + 1) / 2 + M + 1 + 1) & ~1; }  // augmented (M+1) x (M+1) factor
+
 // Per-chain, per-parity block of the per-particle workspace (element offsets in doubles).  Two
 // parities: pass t writes parity t & 1 and gathers, by ancestor, from parity (t - 1) & 1.
 struct MargWs {
@@ -67,9 +71,9 @@ __host__ __device__ inline MargWs marg_ws_layout(const MargDev& m, int N) {
         // Lp: Algorithm1 keeps the M x M factor (inverse diagonal) here; Algorithm3 keeps the AUGMENTED factor of
         // [[eta1, eta0], [eta0^T, eta2]] (M+1 rows, true diagonal) of prior + statistics, and LB the one of
         // prior + remaining reference statistics + statistics (rank-1 up/down-dated, marginal.cu)
-        w.Lp[g] = take((size_t)N * (on ? npk + M + 1 : 0));
-        w.LB[g] = take((size_t)N * (on ? npk + M + 1 : 0));
-        w.T1p[g] = take((size_t)N * npk);
+        w.Lp[g] = take((size_t)N * (on ? mg_naugp((int)M) : 0));
+        w.LB[g] = take((size_t)N * (on ? mg_naugp((int)M) : 0));
+        w.T1p[g] = take((size_t)N * (on ? mg_npkp((int)M) : 0));
         w.T0[g] = take((size_t)N * M);
         w.T2[g] = take(on ? N : 0);
         w.T3[g] = take(on ? N : 0);
@@ -96,7 +100,7 @@ struct MargArgs {
     unsigned* bar_ctr;                 // (n_chains) counters of the software barrier, zero on entry
     int mode;                          // 0 = Algorithm1 (filter), 1 = Algorithm3 (conditional)
     double lambda;                     // forgetting factor (1 in mode 1)
-    size_t warp_doubles, cta_doubles;  // shared-memory carve-up
+    size_t warp_doubles, cta_doubles;  // shared-memory carve-up (warp_doubles depends on the mode)
     // reference trajectory (mode 1)
     const double* ref_x;  long long ref_x_stride;                       // (n_chains, T, n_x)
     const double* ref_xi; long long ref_xi_stride, ref_xi_gstride;      // xi[c][g][t]
