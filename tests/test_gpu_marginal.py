@@ -196,3 +196,27 @@ def test_shipped_smo_pipeline_recovers_the_spring_damper_force(tmp_path):
     assert back["offline_Sigma_X"].shape == (750, 30, 2) and back["offline_T1"].shape == (30, 41, 41)
     assert back["online_Sigma_F"].shape == (750, 200, 1) and back["basis_plot"].shape == (2500, 41)
     assert np.all(np.isfinite(back["offline_Sigma_X"])) and np.all(np.isfinite(back["online_log_likelihood"]))
+
+
+def test_algorithm3_long_sweep_stays_on_the_oracle():
+    """The rank-one up/down-dated factors (refreshed every 32 steps) must not drift: a 300-step conditional sweep —
+    nine refresh cycles — still reproduces every ancestor index of the re-factorising oracle and its trajectory to 1e-9."""
+    import torch
+    from oracle import marginal as OMg
+    T, N, M = 300, 64, 12
+    prob = HM.make_marg_problem("smo", T=T, N=N, M=M, seed=12)
+    V1 = HM.make_variates(prob, 1.0, seed=41)
+    f = OMg.alg1_run(prob["oracle"], N, 1.0, HM.oracle_variates(V1))
+    ref_x, ref_xi = f["state_trace"][:, 0], [f["int_var_trace"][0][:, 0, 0]]
+    rs = OMg.reference_stats(prob["oracle"], ref_x, ref_xi)
+    V = HM.make_variates(prob, 1.0, seed=42)
+    ref = OMg.alg3_run(prob["oracle"], N, ref_x, ref_xi, rs, HM.oracle_variates(V))
+    A3 = helpers.pkg("Algorithm3").Algorithm3(**prob["prod_kwargs"])
+    f64 = dict(dtype=torch.float64, device="cuda")
+    r = A3.csmc(torch.as_tensor(ref_x[None], **f64), torch.as_tensor(np.stack(ref_xi)[None], **f64), None, variates=HM.device_variates(V))
+    assert int(r["status"][0]) == 0
+    np.testing.assert_array_equal(_np(r["anc_trace"][0]), ref["anc_trace"])
+    assert HM.rel_err(_np(r["state_trace"][0]), ref["state_trace"]) < REL
+    assert HM.rel_err(_np(r["xi_trace"][0, 0]), ref["int_var_trace"][0][..., 0]) < REL
+    assert HM.rel_err(_np(r["logw_trace"][0]), ref["logw_trace"]) < 1e-7       # differences of O(1e3) log-densities
+    assert int(r["idx"][0]) == ref["idx"]
