@@ -386,6 +386,66 @@ __device__ __forceinline__ void warp_rank1(double* Lm, const double* xs, int n, 
     __syncwarp();
 }
 
+// One sweep over the columns that does, in lockstep (four independent dependency chains per column):
+//   A <- chol(A A^T + z z^T)                       (Givens)          statistics gain [phi; xi][phi; xi]^T
+//   B <- chol(B B^T + z z^T - r r^T)               (Givens, hyperbolic)  ... and the reference part loses [phi_ref; xi_ref](.)^T
+//   w <- (new A, leading M x M block)^-1 rhs       (column-oriented forward substitution; 1 / L'_kk is the rsqrt of the rotation)
+// A, B: packed augmented factors with true diagonal, n = M + 1 rows; z, r: n entries; rhs: M entries.
+template <int ROWS>
+__device__ __forceinline__ void warp_fused_update(double* A, double* B, const double* z, const double* r, const double* rhs, int M,
+                                                  int lane, int& bad, double (&w)[ROWS]) {
+    const int n = M + 1;
+    double xa[ROWS], xb[ROWS], xc[ROWS];
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q) {
+        const int idx = lane + 32 * q;
+        xa[q] = xb[q] = idx < n ? z[idx] : 0.0;
+        xc[q] = idx < n ? r[idx] : 0.0;
+        w[q] = idx < M ? rhs[idx] : 0.0;
+    }
+    for (int k = 0; k < n; ++k) {
+        double ma = xa[0], mb = xb[0], mc = xc[0], mw = w[0];
+#pragma unroll
+        for (int q = 1; q < ROWS; ++q) {
+            const bool s = (k >> 5) == q;
+            ma = s ? xa[q] : ma; mb = s ? xb[q] : mb; mc = s ? xc[q] : mc; mw = s ? w[q] : mw;
+        }
+        const int src = k & 31, dk = tri(k) + k;
+        const double ak = __shfl_sync(FULL, ma, src), bk = __shfl_sync(FULL, mb, src), ck = __shfl_sync(FULL, mc, src);
+        const double Akk = A[dk], Bkk = B[dk];
+        const double rhoa = fma(ak, ak, Akk * Akk), rhob = fma(bk, bk, Bkk * Bkk);
+        const double ria = rsqrt(rhoa), rib = rsqrt(rhob);
+        const double Bk1 = rhob * rib;                                        // diagonal of B after the update
+        const double rhoc = fma(-ck, ck, Bk1 * Bk1);
+        if (!(rhoc > 0.0) || !(rhoa > 0.0)) bad = 1;
+        const double ric = rsqrt(rhoc);
+        const double aa = Akk * ria, ba = ak * ria, ab = Bkk * rib, bb = bk * rib, ac = Bk1 * ric, bc = ck * ric;
+        const double wk = __shfl_sync(FULL, mw, src) * ria;                   // forward substitution on the NEW factor
+        __syncwarp();
+        if (lane == 0) { A[dk] = rhoa * ria; B[dk] = rhoc * ric; }
+#pragma unroll
+        for (int q = 0; q < ROWS; ++q) {
+            const int idx = lane + 32 * q;
+            if (idx == k && k < M) w[q] = wk;
+            if (idx > k && idx < n) {
+                double* pa = A + tri(idx) + k;
+                double* pb = B + tri(idx) + k;
+                const double Aik = *pa, Bik = *pb;
+                const double An = fma(ba, xa[q], aa * Aik);
+                xa[q] = fma(aa, xa[q], -ba * Aik);
+                const double B1 = fma(bb, xb[q], ab * Bik);
+                xb[q] = fma(ab, xb[q], -bb * Bik);
+                const double B2 = fma(-bc, xc[q], ac * B1);
+                xc[q] = fma(ac, xc[q], -bc * B1);
+                *pa = An;
+                *pb = B2;
+                if (k < M && idx < M) w[q] = fma(-An, wk, w[q]);
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // w = L^-1 b with the inverse diagonal given separately (inv[k] = 1 / L_kk)
 template <int ROWS>
 __device__ __forceinline__ void warp_fwd_solve_inv(const double* Lpk, const double* inv, const double* b, int M, int lane, double (&w)[ROWS]) {
@@ -600,6 +660,7 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
         }
         double x[MG_NX], xi[MG_GP], z[MG_D], T2v[MG_GP], T3v[MG_GP];
         double ldA[MG_GP], ldB[MG_GP], psA[MG_GP], psB[MG_GP];     // Algorithm3: log det eta1 / Psi of the two factors
+        double T2av[MG_GP], T3av[MG_GP], ax1[MG_NX], axi1[MG_GP];
         StepVariates sv;
         // ---- new state
         if (t == 0) {
@@ -688,6 +749,9 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             }
             if (pinned) xiv = refxi[(size_t)g * a.ref_xi_gstride + t];
             xi[g] = xiv;
+            T2av[g] = T2a;
+            T3av[g] = T3a;
+            if constexpr (MODE == 0) {
             // statistics: S_t = lambda S_{t-1}[a] + T(xi, phi)  (src/Algorithm1.py:315-318, :356-375)
             double* T1w = wp + L.T1p[g] + (size_t)i * mg_npkp(M);
             const double* T1a = wq + L.T1p[g] + (size_t)ac * mg_npkp(M);
@@ -697,70 +761,6 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             const double T3n = (t > 0) ? fma(lam, T3a, 1.0) : 1.0;
             T2v[g] = T2n;
             T3v[g] = T3n;
-            if constexpr (MODE == 1) {
-                // Algorithm3 (lambda = 1): the statistics change by the rank-one term [phi; xi][phi; xi]^T and the remaining
-                // reference statistics lose [phi_ref; xi_ref][phi_ref; xi_ref]^T (src/Algorithm3.py:153-174), so both augmented
-                // factors follow by Givens / hyperbolic rotation sweeps, O(M^2), instead of two O(M^3) factorisations.  Every
-                // MG_REFRESH steps (and whenever a downdate loses definiteness) they are rebuilt from the statistics.
-                const size_t trow = (size_t)chain * T + t;
-                const int naug = npk + M + 1;
-#pragma unroll 4
-                for (int e = lane; e < npk; e += 32) {
-                    const unsigned ij = ijt[g][e];
-                    double v = wc.phi[ij & 0xffffu] * wc.phi[ij >> 16];
-                    if (t > 0) v += wc.T1s[g][e];
-                    T1w[e] = v;
-                }
-                for (int k = lane; k < M; k += 32) {
-                    double v = wc.phi[k] * xiv;
-                    if (t > 0) v += ldcg(wq + L.T0[g] + (size_t)ac * M + k);
-                    wp[L.T0[g] + (size_t)i * M + k] = v;
-                    wc.zv[k] = wc.phi[k];
-                    wc.rv[k] = a.tab.RPHI[g][trow * M + k];
-                }
-                if (lane == 0) {
-                    wp[L.T2[g] + i] = T2n;
-                    wp[L.T3[g] + i] = T3n;
-                    wc.zv[M] = xiv;
-                    wc.rv[M] = refxi[(size_t)g * a.ref_xi_gstride + t];
-                    xtrace[((size_t)g * T + t) * N + i] = xiv;
-                }
-                __syncwarp();
-                int bad = 0;
-                const bool refresh = (t % MG_REFRESH) == 0;
-                double* Bq = wc.Bg[g];
-                if (!refresh) {
-                    warp_rank1<ROWS>(Ag, wc.zv, M + 1, 1.0, lane, bad);
-                    warp_rank1<ROWS>(Bq, wc.zv, M + 1, 1.0, lane, bad);
-                    warp_rank1<ROWS>(Bq, wc.rv, M + 1, -1.0, lane, bad);
-                    bad = __any_sync(FULL, bad);
-                }
-                if (refresh || bad) {
-                    const double* PR1 = a.tab.PR1[g] + trow * npk;
-                    const double* PR0 = a.tab.PR0[g] + trow * M;
-#pragma unroll 8
-                    for (int e = lane; e < npk; e += 32) { const double v = T1w[e]; Ag[e] = gp.p1[e] + v; Bq[e] = PR1[e] + v; }
-                    for (int k = lane; k < M; k += 32) {
-                        const double v = wp[L.T0[g] + (size_t)i * M + k];
-                        Ag[rowM + k] = gp.p0[k] + v;
-                        Bq[rowM + k] = PR0[k] + v;
-                    }
-                    if (lane == 0) { Ag[rowM + M] = gp.p2 + T2n; Bq[rowM + M] = a.tab.PR2[g][trow] + T2n; }
-                    __syncwarp();
-                    double psi_tmp;
-                    warp_chol_packed(Ag, M, M + 1, lane, fail);
-                    finish_aug_factor(Ag, M, lane, psi_tmp);
-                    warp_chol_packed(Bq, M, M + 1, lane, fail);
-                    finish_aug_factor(Bq, M, lane, psi_tmp);
-                }
-                ldA[g] = factor_logdet(Ag, M, lane);
-                ldB[g] = factor_logdet(Bq, M, lane);
-                { const double sa = Ag[rowM + M], sb = Bq[rowM + M]; psA[g] = sa * sa; psB[g] = sb * sb; }
-                double* LBw = wp + L.LB[g] + (size_t)i * mg_naugp(M);
-#pragma unroll 8
-                for (int e = lane; e < naug; e += 32) LBw[e] = Bq[e];
-                __syncwarp();
-            } else {
 #pragma unroll 4
                 for (int e = lane; e < npk; e += 32) {
                     const unsigned ij = ijt[g][e];
@@ -784,6 +784,98 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                 __syncwarp();
             }
         }
+        if constexpr (MODE == 1) {
+            // Algorithm3 (lambda = 1), second pass over the GPs, once every xi is known.  The statistics change by the rank-one
+            // term [phi; xi][phi; xi]^T and the remaining reference statistics lose [phi_ref; xi_ref][phi_ref; xi_ref]^T
+            // (src/Algorithm3.py:153-174), so both augmented factors follow by Givens / hyperbolic rotation sweeps, O(M^2),
+            // instead of two O(M^3) factorisations; the same sweep also solves L'^-1 phi(aux state) for the NEXT step's
+            // auxiliary interface variable.  Every MG_REFRESH steps (and whenever a downdate loses definiteness) the
+            // factors are rebuilt from the statistics.
+            const bool more = t < T - 1;
+            if (more) transition(m, t, x, xi, ax1);
+            for (int g = 0; g < G; ++g) {
+                const MargGP& gp = m.gp[g];
+                const int M = gp.M, npk = gp.npk, rowM = tri(M), naug = npk + M + 1;
+                const size_t trow = (size_t)chain * T + t;
+                const double xiv = xi[g];
+                double* T1w = wp + L.T1p[g] + (size_t)i * mg_npkp(M);
+                double* Ag = wc.A[g];
+                double* Bq = wc.Bg[g];
+                const double T2n = (t > 0) ? T2av[g] + xiv * xiv : xiv * xiv;
+                const double T3n = (t > 0) ? T3av[g] + 1.0 : 1.0;
+                T2v[g] = T2n;
+                T3v[g] = T3n;
+                if (G > 1 || t == 0) { gp_input(m, gp, t, x, z); basis_eval(gp, z, wc.phi, lane); }     // G == 1: still in wc.phi
+                if (more) { gp_input(m, gp, t + 1, ax1, z); basis_eval(gp, z, wc.inv, lane); }           // phi(aux state) -> wc.inv
+                __syncwarp();
+#pragma unroll 4
+                for (int e = lane; e < npk; e += 32) {
+                    const unsigned ij = ijt[g][e];
+                    double v = wc.phi[ij & 0xffffu] * wc.phi[ij >> 16];
+                    if (t > 0) v += wc.T1s[g][e];
+                    T1w[e] = v;
+                }
+                for (int k = lane; k < M; k += 32) {
+                    double v = wc.phi[k] * xiv;
+                    if (t > 0) v += ldcg(wq + L.T0[g] + (size_t)ac * M + k);
+                    wp[L.T0[g] + (size_t)i * M + k] = v;
+                    wc.zv[k] = wc.phi[k];
+                    wc.rv[k] = a.tab.RPHI[g][trow * M + k];
+                    if (!more) wc.inv[k] = 0.0;
+                }
+                if (lane == 0) {
+                    wp[L.T2[g] + i] = T2n;
+                    wp[L.T3[g] + i] = T3n;
+                    wc.zv[M] = xiv;
+                    wc.rv[M] = refxi[(size_t)g * a.ref_xi_gstride + t];
+                    xtrace[((size_t)g * T + t) * N + i] = xiv;
+                }
+                __syncwarp();
+                int bad = 0;
+                const bool refresh = (t % MG_REFRESH) == 0;
+                double w[ROWS];
+                if (!refresh) {
+                    warp_fused_update<ROWS>(Ag, Bq, wc.zv, wc.rv, wc.inv, M, lane, bad, w);
+                    bad = __any_sync(FULL, bad);
+                }
+                if (refresh || bad) {
+                    const double* PR1 = a.tab.PR1[g] + trow * npk;
+                    const double* PR0 = a.tab.PR0[g] + trow * M;
+#pragma unroll 8
+                    for (int e = lane; e < npk; e += 32) { const double v = T1w[e]; Ag[e] = gp.p1[e] + v; Bq[e] = PR1[e] + v; }
+                    for (int k = lane; k < M; k += 32) {
+                        const double v = wp[L.T0[g] + (size_t)i * M + k];
+                        Ag[rowM + k] = gp.p0[k] + v;
+                        Bq[rowM + k] = PR0[k] + v;
+                    }
+                    if (lane == 0) { Ag[rowM + M] = gp.p2 + T2n; Bq[rowM + M] = a.tab.PR2[g][trow] + T2n; }
+                    __syncwarp();
+                    double psi_tmp;
+                    warp_chol_packed(Ag, M, M + 1, lane, fail);
+                    finish_aug_factor(Ag, M, lane, psi_tmp);
+                    warp_chol_packed(Bq, M, M + 1, lane, fail);
+                    finish_aug_factor(Bq, M, lane, psi_tmp);
+                    for (int k = lane; k < M; k += 32) wc.zv[k] = 1.0 / Ag[tri(k) + k];      // zv is free now: inverse diagonal
+                    __syncwarp();
+                    warp_fwd_solve_inv<ROWS>(Ag, wc.zv, wc.inv, M, lane, w);
+                }
+                double yv = 0.0;
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const int idx = lane + 32 * r;
+                    if (idx < M) yv = fma(Ag[rowM + idx], w[r], yv);
+                }
+                axi1[g] = warp_sum(yv);                                   // prior_mniw_mean . phi_aux of the next step
+                ldA[g] = factor_logdet(Ag, M, lane);
+                ldB[g] = factor_logdet(Bq, M, lane);
+                { const double sa = Ag[rowM + M], sb = Bq[rowM + M]; psA[g] = sa * sa; psB[g] = sb * sb; }
+                double* LBw = wp + L.LB[g] + (size_t)i * mg_naugp(M);
+                double* LAw = wp + L.Lp[g] + (size_t)i * mg_naugp(M);
+#pragma unroll 8
+                for (int e = lane; e < naug; e += 32) { LBw[e] = Bq[e]; LAw[e] = Ag[e]; }
+                __syncwarp();
+            }
+        }
         // ---- weights and traces
         double lw = 0.0;
         if (t > 0) lw = log_likelihood(m, t, x, xi) - ldcg(wq + L.ellaux + ac);
@@ -803,32 +895,16 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             double* Ag = wc.A[g];
             gp_input(m, gp, t + 1, ax, z);
             if constexpr (MODE == 1) {
-                // Algorithm3: v = L^-1 phi(aux state) by one forward solve on the up-to-date factor; y is its last row
-                const int naug = npk + M + 1;
-                basis_eval(gp, z, wc.phi, lane);
-                for (int k = lane; k < M; k += 32) wc.inv[k] = 1.0 / Ag[tri(k) + k];
-                __syncwarp();
-                double w[ROWS];
-                warp_fwd_solve_inv<ROWS>(Ag, wc.inv, wc.phi, M, lane, w);
-                double yv = 0.0;
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                    const int idx = lane + 32 * r;
-                    if (idx < M) yv = fma(Ag[rowM + idx], w[r], yv);
-                }
-                axi[g] = warp_sum(yv);                                    // prior_mniw_mean . phi_aux
-                double* Lw = wp + L.Lp[g] + (size_t)i * mg_naugp(M);
-#pragma unroll 8
-                for (int e = lane; e < naug; e += 32) Lw[e] = Ag[e];
-                // g_t - g_T (src/Algorithm3.py:92-106).  Only the particle-dependent terms of prior_mniw_log_base_measure are
-                // kept: -n m/2 log(2 pi) cancels between g_t and g_T, and -nu n/2 log 2 - multigammaln(nu/2, n) depend on T3
-                // alone, which is the same for every particle, so they shift all ancestor log-weights equally and vanish in the
-                // softmax (src/Algorithm3.py:115-118).
+                // Algorithm3: the factors, the auxiliary interface variable and the log-determinants were produced in the second
+                // GP pass above.  g_t - g_T (src/Algorithm3.py:92-106): only the particle-dependent terms of
+                // prior_mniw_log_base_measure are kept — -n m/2 log(2 pi) cancels between g_t and g_T, and -nu n/2 log 2 -
+                // multigammaln(nu/2, n) depend on T3 alone, which is the same for every particle, so they shift all ancestor
+                // log-weights equally and vanish in the softmax (src/Algorithm3.py:115-118).
+                axi[g] = axi1[g];
                 const size_t trow = (size_t)chain * T + t;
                 const double gt = 0.5 * ldA[g] + log(psA[g]) * (0.5 * (gp.p3 + T3v[g]));
                 const double gT = 0.5 * ldB[g] + log(psB[g]) * (0.5 * (a.tab.PR3[g][trow] + T3v[g]));
                 gdiff += gt - gT;
-                __syncwarp();
             } else {
                 basis_eval(gp, z, Ag + rowV, lane);                       // extra row 2: phi(aux state)
                 __syncwarp();
