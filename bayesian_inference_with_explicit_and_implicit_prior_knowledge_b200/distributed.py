@@ -47,3 +47,22 @@ def run_chains_distributed(pgas, key, init_ref_state, n_chains, group=None, want
         res["A_trace"] = gather_chain_outputs(out["A_trace"], n_chains, group)
         res["S_trace"] = gather_chain_outputs(out["S_trace"], n_chains, group)
     return res
+
+
+def run_replicas_distributed(alg2, key, init_ref_state, init_ref_int_var, n_replicas, group=None, K=None):
+    """Monte-Carlo replicates of the marginalised PGAS (Algorithm2): the shipped examples run ONE chain, so the
+    multi-GPU form is `n_replicas` independent chains with global chain ids 0..n_replicas-1 sharded over the ranks
+    ("replicas only"), pooled at the end.  init_ref_state (T,n_x) and init_ref_int_var [G x (T,)] are
+    shared by all replicas.  Returns dict(x_trace (n_replicas,K,T,n_x), xi_trace (n_replicas,G,K,T)) on every rank."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    first, count = shard_chains(n_replicas, rank, world)
+    m = alg2.cSMC.model
+    f64 = dict(dtype=torch.float64, device="cuda")
+    x0 = torch.as_tensor(np.asarray(init_ref_state, dtype=np.float64).reshape(1, m.T, m.n_x), **f64).repeat(max(count, 1), 1, 1)
+    xi0 = torch.as_tensor(np.stack([np.asarray(v, dtype=np.float64).reshape(m.T) for v in init_ref_int_var])[None], **f64).repeat(max(count, 1), 1, 1)
+    out = alg2.run(x0, xi0, key=key, K=K, chain_base=first, want_sst=False)
+    return dict(x_trace=gather_chain_outputs(out["x_trace"][:count], n_replicas, group),
+                xi_trace=gather_chain_outputs(out["xi_trace"][:count], n_replicas, group))

@@ -220,3 +220,17 @@ def test_algorithm3_long_sweep_stays_on_the_oracle():
     assert HM.rel_err(_np(r["xi_trace"][0, 0]), ref["int_var_trace"][0][..., 0]) < REL
     assert HM.rel_err(_np(r["logw_trace"][0]), ref["logw_trace"]) < 1e-7       # differences of O(1e3) log-densities
     assert int(r["idx"][0]) == ref["idx"]
+
+
+def test_replicas_api_single_process():
+    """run_replicas_distributed without a process group = all replicas on this GPU; chain ids define the streams"""
+    A2m, DI = helpers.pkg("Algorithm2"), helpers.pkg("distributed")
+    prob = HM.make_marg_problem("emps", T=14, N=24, M=9, seed=1)
+    A2 = A2m.Algorithm2(N_iterations=3, **prob["prod_kwargs"])
+    key = helpers.pkg("random").key(9)
+    x0 = np.stack([0.1 + 0.001 * np.arange(14), np.zeros(14)], axis=1)
+    r3 = DI.run_replicas_distributed(A2, key, x0, [np.zeros(14)], 3)
+    assert tuple(r3["x_trace"].shape) == (3, 3, 14, 2) and tuple(r3["xi_trace"].shape) == (3, 1, 3, 14)
+    r1 = DI.run_replicas_distributed(A2, key, x0, [np.zeros(14)], 1)
+    np.testing.assert_array_equal(_np(r3["x_trace"][0]), _np(r1["x_trace"][0]))
+    assert not np.array_equal(_np(r3["x_trace"][1, 1:]), _np(r3["x_trace"][0, 1:]))
