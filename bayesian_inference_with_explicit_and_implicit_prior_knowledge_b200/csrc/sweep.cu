@@ -861,6 +861,7 @@ struct StateArgs {
     double* x_carry;             // (n_chains, N, NX): state at step t0-1 on entry (unless first), at t1-1 on exit
     double *la, *lr, *ll;        // (n_chains, rows, N), row t - t0
     int t0, t1, rows, first, bpc;
+    int chain0, nch;             // this launch covers chains chain0 .. chain0 + nch - 1
 };
 
 constexpr int ST_NT = PGAS_ST_NT;
@@ -877,7 +878,7 @@ __global__ void __launch_bounds__(ST_NT, 512 / ST_NT) csmc_state_kernel(const __
     double* slogc = sw + NX * NX;
     int* rwlen = reinterpret_cast<int*>(slogc + 2);
     const int tid = threadIdx.x, N = a.N;
-    const int chain = blockIdx.x / s.bpc, blk = blockIdx.x % s.bpc;
+    const int chain = s.chain0 + blockIdx.x / s.bpc, blk = blockIdx.x % s.bpc;
     {
         const double* Th = a.Theta + (size_t)chain * NX * m.M;
         for (int e = tid; e < m.rw_slots; e += ST_NT) {
@@ -1038,9 +1039,11 @@ bool pgas_sweep_split_eligible(const SweepArgs& a) {
     return a.ws && a.ws_bytes >= pgas_sweep_split_workspace(m, a.N, a.n_chains);
 }
 
+constexpr int SPLIT_GROUPS = 2;      // chain groups of the state kernel: each on its own stream, so that a group's next
+                                     // launch starts as soon as ITS CTAs retire (no wave-quantisation tail across all chains)
 struct SplitStreams {
-    cudaStream_t aux = nullptr;
-    cudaEvent_t start = nullptr, k1[2] = {nullptr, nullptr}, k2[2] = {nullptr, nullptr};
+    cudaStream_t aux = nullptr, auxg[SPLIT_GROUPS] = {nullptr, nullptr};
+    cudaEvent_t start = nullptr, k1[2][SPLIT_GROUPS] = {{nullptr, nullptr}, {nullptr, nullptr}}, k2[2] = {nullptr, nullptr};
     int device = -1;
 };
 static thread_local SplitStreams g_split;
@@ -1055,11 +1058,12 @@ static int split_streams_init() {
         // stream the first pick of freed SM resources by putting the state kernel on the lowest-priority stream
         int lo = 0, hi = 0;
         PGAS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        PGAS_CUDA(cudaStreamCreateWithPriority(&g_split.aux, cudaStreamNonBlocking, lo));
+        for (int g = 0; g < SPLIT_GROUPS; ++g) PGAS_CUDA(cudaStreamCreateWithPriority(&g_split.auxg[g], cudaStreamNonBlocking, lo));
+        g_split.aux = g_split.auxg[0];
     }
     PGAS_CUDA(cudaEventCreateWithFlags(&g_split.start, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
-        PGAS_CUDA(cudaEventCreateWithFlags(&g_split.k1[i], cudaEventDisableTiming));
+        for (int g = 0; g < SPLIT_GROUPS; ++g) PGAS_CUDA(cudaEventCreateWithFlags(&g_split.k1[i][g], cudaEventDisableTiming));
         PGAS_CUDA(cudaEventCreateWithFlags(&g_split.k2[i], cudaEventDisableTiming));
     }
     return 0;
@@ -1068,7 +1072,7 @@ static int split_streams_init() {
 static int launch_state(const StateArgs& s, cudaStream_t st) {
     const DevModel& m = s.a.m;
     const size_t smem = sizeof(double) * (((size_t)m.rw_slots + 1) & ~(size_t)1) + sizeof(double) * (2 * m.n_x * m.n_x + 2) + sizeof(int) * RW_MAXBLK + 32;
-    const dim3 grid((unsigned)(s.a.n_chains * s.bpc));
+    const dim3 grid((unsigned)(s.nch * s.bpc));
     if (m.n_y == 1) {
         PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         csmc_state_kernel<2, 1><<<grid, ST_NT, smem, st>>>(s);
@@ -1090,9 +1094,13 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
     double* pre = (double*)base;
     double* x_carry = pre + 2 * 3 * buf;
     double* lw_carry = x_carry + (size_t)a.n_chains * a.N * m.n_x;
-    cudaStream_t s1 = getenv("PGAS_SPLIT_SERIAL") ? stream : g_split.aux;      // developer override: no overlap
+    const bool serial = getenv("PGAS_SPLIT_SERIAL") != nullptr;                // developer override: no overlap
+    const int ngroups = (!serial && a.n_chains >= 2 * SPLIT_GROUPS && !getenv("PGAS_SPLIT_ONE_GROUP")) ? SPLIT_GROUPS : 1;
+    cudaStream_t sg[SPLIT_GROUPS];
+    for (int g = 0; g < SPLIT_GROUPS; ++g) sg[g] = serial ? stream : g_split.auxg[g];
     PGAS_CUDA(cudaEventRecord(g_split.start, stream));
-    PGAS_CUDA(cudaStreamWaitEvent(s1, g_split.start, 0));          // inputs (Theta, Sigma, ref) are ready
+    for (int g = 0; g < ngroups; ++g)
+        if (!serial) PGAS_CUDA(cudaStreamWaitEvent(sg[g], g_split.start, 0));  // inputs (Theta, Sigma, ref) are ready
     // chunk boundaries: a short first chunk (the resampling kernel can start early) and a short last chunk (little
     // resampling work is left when the state kernel has finished), `rows` in between
     const int edge = std::min(rows, 16);
@@ -1110,7 +1118,8 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
         s.a = a;
         s.x_carry = x_carry; s.la = la; s.lr = la + buf; s.ll = la + 2 * buf;
         s.t0 = t0; s.t1 = t1; s.rows = rows; s.first = (c == 0); s.bpc = (a.N + 2 * ST_NT - 1) / (2 * ST_NT);
-        if (c >= 2) PGAS_CUDA(cudaStreamWaitEvent(s1, g_split.k2[b], 0));      // buffer b was consumed by chunk c-2
+        for (int g = 0; g < ngroups; ++g)
+            if (c >= 2) PGAS_CUDA(cudaStreamWaitEvent(sg[g], g_split.k2[b], 0));   // buffer b was consumed by chunk c-2
         {   // short-lived state CTAs (sub-chunks) so that resampling CTAs find free slots quickly
             int sr = 16;
             if (const char* e = getenv("PGAS_SPLIT_STATE_ROWS")) { const int v = atoi(e); if (v >= 1) sr = v; }
@@ -1119,10 +1128,14 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
                 q.t0 = ts; q.t1 = std::min(ts + sr, t1);
                 q.la = s.la + (size_t)(ts - t0) * a.N; q.lr = s.lr + (size_t)(ts - t0) * a.N; q.ll = s.ll + (size_t)(ts - t0) * a.N;
                 q.first = s.first && ts == t0;
-                if (int rc = launch_state(q, s1)) return rc;
+                for (int g = 0; g < ngroups; ++g) {
+                    q.chain0 = (int)((long long)a.n_chains * g / ngroups);
+                    q.nch = (int)((long long)a.n_chains * (g + 1) / ngroups) - q.chain0;
+                    if (int rc = launch_state(q, sg[g])) return rc;
+                }
             }
         }
-        PGAS_CUDA(cudaEventRecord(g_split.k1[b], s1));
+        for (int g = 0; g < ngroups; ++g) PGAS_CUDA(cudaEventRecord(g_split.k1[b][g], sg[g]));
         SweepArgs r = a;
         r.t_begin = t0; r.t_end = t1;
         r.pre_la = s.la; r.pre_lr = s.lr; r.pre_ll = s.ll; r.pre_rows = rows; r.pre_off = t0;
@@ -1133,7 +1146,7 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
             const int v = atoi(e);
             if (v >= 1 && v <= 16) { r.C = v; r.P = (a.N + v - 1) / v; }
         }
-        PGAS_CUDA(cudaStreamWaitEvent(stream, g_split.k1[b], 0));
+        for (int g = 0; g < ngroups; ++g) PGAS_CUDA(cudaStreamWaitEvent(stream, g_split.k1[b][g], 0));
         if (int rc = pgas_launch_sweep_pre(r, stream)) return rc;
         PGAS_CUDA(cudaEventRecord(g_split.k2[b], stream));
     }
@@ -1176,6 +1189,7 @@ extern "C" int pgas_debug_state_kernel_f64(const pgas_model* model, int32_t N, i
             q.t0 = ts; q.t1 = std::min(ts + 16, t1); q.rows = rows;
             q.la = la + (size_t)(ts - t0) * N; q.lr = la + buf + (size_t)(ts - t0) * N; q.ll = la + 2 * buf + (size_t)(ts - t0) * N;
             q.first = (c == 0 && ts == t0); q.bpc = (N + 2 * ST_NT - 1) / (2 * ST_NT);
+            q.chain0 = 0; q.nch = n_chains;
             if (int rc = launch_state(q, (cudaStream_t)stream)) return rc;
         }
     }
