@@ -15,6 +15,37 @@
 #pragma once
 #include "basis_eval.cuh"
 
+// n last-dimension positions at which the first R rows of the block are active: R Theta' pairs per position
+template <int NX, int PP, int R>
+__device__ __forceinline__ void rw_segment(const double* __restrict__& th, int n, double (&acc)[PP][RW_RB][NX], double (&c)[PP],
+                                           double (&pv)[PP], const double (&b_2c)[PP]) {
+#pragma unroll 2
+    for (int j = 0; j < n; ++j) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            double w[NX];
+            if constexpr (NX == 2) {
+                const double2 v = *reinterpret_cast<const double2*>(th + i * 2);
+                w[0] = v.x; w[1] = v.y;
+            } else {
+#pragma unroll
+                for (int k = 0; k < NX; ++k) w[k] = th[i * NX + k];
+            }
+#pragma unroll
+            for (int p = 0; p < PP; ++p)
+#pragma unroll
+                for (int k = 0; k < NX; ++k) acc[p][i][k] = fma(w[k], c[p], acc[p][i][k]);
+        }
+        th += R * NX;
+#pragma unroll
+        for (int p = 0; p < PP; ++p) {
+            const double n2 = fma(b_2c[p], c[p], -pv[p]);
+            pv[p] = c[p];
+            c[p] = n2;
+        }
+    }
+}
+
 template <int NX, int PP>
 __device__ __forceinline__ void rowwalk_mu(const double* __restrict__ bd, const int* __restrict__ blen, int nblk, int f_start, int f_step,
                                            const double (&t0)[PP], const double (&t1)[PP], double (&mu)[PP][NX]) {
@@ -26,7 +57,7 @@ __device__ __forceinline__ void rowwalk_mu(const double* __restrict__ bd, const 
 #pragma unroll
         for (int k = 0; k < NX; ++k) mu[p][k] = 0.0;
     }
-    const double* th = bd;
+    const double* __restrict__ th = bd;
     for (int b = 0; b < nblk; ++b) {
         double acc[PP][RW_RB][NX];
         double c[PP], pv[PP];
@@ -39,32 +70,12 @@ __device__ __forceinline__ void rowwalk_mu(const double* __restrict__ bd, const 
 #pragma unroll
                 for (int k = 0; k < NX; ++k) acc[p][i][k] = 0.0;
         }
+        // positions with 4, 3, 2, 1 active rows (packed byte counts, common.cuh): only selected lattice entries are walked
         const int L = blen[b];
-#pragma unroll 2
-        for (int j = 0; j < L; ++j) {
-#pragma unroll
-            for (int i = 0; i < RW_RB; ++i) {
-                double w[NX];
-                if constexpr (NX == 2) {
-                    const double2 v = *reinterpret_cast<const double2*>(th + i * 2);
-                    w[0] = v.x; w[1] = v.y;
-                } else {
-#pragma unroll
-                    for (int k = 0; k < NX; ++k) w[k] = th[i * NX + k];
-                }
-#pragma unroll
-                for (int p = 0; p < PP; ++p)
-#pragma unroll
-                    for (int k = 0; k < NX; ++k) acc[p][i][k] = fma(w[k], c[p], acc[p][i][k]);
-            }
-            th += RW_RB * NX;
-#pragma unroll
-            for (int p = 0; p < PP; ++p) {
-                const double n = fma(b_2c[p], c[p], -pv[p]);
-                pv[p] = c[p];
-                c[p] = n;
-            }
-        }
+        rw_segment<NX, PP, 4>(th, L & 255, acc, c, pv, b_2c);
+        rw_segment<NX, PP, 3>(th, (L >> 8) & 255, acc, c, pv, b_2c);
+        rw_segment<NX, PP, 2>(th, (L >> 16) & 255, acc, c, pv, b_2c);
+        rw_segment<NX, PP, 1>(th, (L >> 24) & 255, acc, c, pv, b_2c);
 #pragma unroll
         for (int i = 0; i < RW_RB; ++i)
 #pragma unroll

@@ -37,8 +37,10 @@ constexpr int MAX_LEAD = PGAS_MAX_D - 1;
 // (basis_rowwalk.cuh): first-dimension lattice positions are grouped into blocks of RW_RB; inside a block
 // the last-dimension positions j = 0 .. blen-1 are walked once while RW_RB x n_x accumulators collect
 //   T[i][k] = sum_j Theta'[k, m(i, j)] sin(pi f_j t_last),
-// then mu_k += sin(pi f_i t_first) T[i][k].  Storage order: [block][j][i][k], zero where the lattice
-// search did not select (i, j).
+// then mu_k += sin(pi f_i t_first) T[i][k].  At position j only the first act(j) rows of the block are stored and
+// walked (act = 1 + last row with a selected entry at a position >= j; non-increasing in j), so the padding of the
+// staircase lattice is not computed.  Storage order: [block][j][i < act(j)][k], zero where the lattice search did not
+// select (i, j); rw_blen[block] packs the number of positions with 4, 3, 2, 1 active rows into bytes 0..3.
 constexpr int RW_RB = 4;
 constexpr int RW_MAXBLK = 24;
 
@@ -61,7 +63,7 @@ struct DevModel {
     double R_logc;                                  // -n_y/2 log(2 pi) - sum log diag chol(R)
     double m0[PGAS_MAX_NX], P0c[PGAS_MAX_NX][PGAS_MAX_NX];   // chol(P0) lower
     int rw_ok, rw_nblk, rw_slots;                   // row-walk layout (D == 2): available, blocks, doubles
-    int rw_blen[RW_MAXBLK];                         // last-dimension positions walked per block
+    int rw_blen[RW_MAXBLK];                         // positions with 4 | 3 | 2 | 1 active rows per block (one byte each)
     const int* rw_perm;     // [rw_slots] slot -> m * 4 + k of the Theta entry it holds, or -1 (zero)
     const int* perm;        // [n_packed] fragment slot -> m * 4 + k of the Theta entry it holds, or -1 (zero)
     const int* row_pos;     // [8*NTN / n_x rounded up][MAX_LEAD] leading-dimension positions of each row (0 for padding rows)

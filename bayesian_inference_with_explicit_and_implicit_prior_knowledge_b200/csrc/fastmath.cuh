@@ -11,31 +11,32 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Polynomial coefficients live in the constant bank: ptxas reads two of them with one LDCU.128 and feeds them to DFMA as
+// uniform-register operands, instead of materialising every 64-bit literal with a UMOV pair (two issue slots per
+// coefficient — 10 % of the state kernel's instruction stream, profiles/r01_state_kernel_summary.md).
+static __constant__ double FM_SIN[10] = {-2.2948428997269873e-08, 7.952054001475513e-07, -2.1915353447830217e-05, 0.00046630280576761255,
+                                         -0.0073704309457143504, 0.08214588661112823, -0.5992645293207921, 2.5501640398773455,
+                                         -5.16771278004997, 3.141592653589793};
+static __constant__ double FM_COS[10] = {3.604730797462501e-09, -1.3878952462213771e-07, 4.303069587032947e-06, -0.0001046381049248457,
+                                         0.0019295743094039231, -0.02580689139001406, 0.2353306303588932, -1.3352627688545895,
+                                         4.0587121264167685, -4.934802200544679};
+static __constant__ double FM_EXP[14] = {1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
+                                         2.7557319223985893e-06, 2.48015873015873e-05, 0.0001984126984126984, 0.001388888888888889,
+                                         0.008333333333333333, 0.041666666666666664, 0.16666666666666666, 0.5, 1.0, 1.0};
+static __constant__ double FM_LOG[11] = {1.0 / 23.0, 1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0,
+                                         1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0};
+
 // sin(pi x), cos(pi x): reduce to r = x - n/2, |r| <= 1/4 (exact), Taylor in t = r^2
 __device__ __forceinline__ void sincospi_bf(double x, double& s_out, double& c_out) {
     const double n = rint(x + x);
     const double r = fma(-0.5, n, x);
     const double t = r * r;
-    double ps = -2.2948428997269873e-08;
-    ps = fma(ps, t, 7.952054001475513e-07);
-    ps = fma(ps, t, -2.1915353447830217e-05);
-    ps = fma(ps, t, 0.00046630280576761255);
-    ps = fma(ps, t, -0.0073704309457143504);
-    ps = fma(ps, t, 0.08214588661112823);
-    ps = fma(ps, t, -0.5992645293207921);
-    ps = fma(ps, t, 2.5501640398773455);
-    ps = fma(ps, t, -5.16771278004997);
-    ps = fma(ps, t, 3.141592653589793);
-    double pc = 3.604730797462501e-09;
-    pc = fma(pc, t, -1.3878952462213771e-07);
-    pc = fma(pc, t, 4.303069587032947e-06);
-    pc = fma(pc, t, -0.0001046381049248457);
-    pc = fma(pc, t, 0.0019295743094039231);
-    pc = fma(pc, t, -0.02580689139001406);
-    pc = fma(pc, t, 0.2353306303588932);
-    pc = fma(pc, t, -1.3352627688545895);
-    pc = fma(pc, t, 4.0587121264167685);
-    pc = fma(pc, t, -4.934802200544679);
+    double ps = FM_SIN[0], pc = FM_COS[0];
+#pragma unroll
+    for (int i = 1; i < 10; ++i) {
+        ps = fma(ps, t, FM_SIN[i]);
+        pc = fma(pc, t, FM_COS[i]);
+    }
     const double s = r * ps, c = fma(pc, t, 1.0);
     const int q = (int)__double2ll_rn(n) & 3;
     const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;
@@ -48,20 +49,9 @@ __device__ __forceinline__ double exp_neg_bf(double x) {
     const double n = rint(x * 1.4426950408889634);
     double r = fma(-n, 6.93147180369123816490e-01, x);
     r = fma(-n, 1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;
-    p = fma(p, r, 2.08767569878681e-09);
-    p = fma(p, r, 2.505210838544172e-08);
-    p = fma(p, r, 2.755731922398589e-07);
-    p = fma(p, r, 2.7557319223985893e-06);
-    p = fma(p, r, 2.48015873015873e-05);
-    p = fma(p, r, 0.0001984126984126984);
-    p = fma(p, r, 0.001388888888888889);
-    p = fma(p, r, 0.008333333333333333);
-    p = fma(p, r, 0.041666666666666664);
-    p = fma(p, r, 0.16666666666666666);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    double p = FM_EXP[0];
+#pragma unroll
+    for (int i = 1; i < 14; ++i) p = fma(p, r, FM_EXP[i]);
     const int e = (int)n;
     const double scale = __longlong_as_double((long long)(e + 1023) << 52);
     const double v = p * scale;
@@ -89,17 +79,9 @@ __device__ __forceinline__ double log_unit_bf(double u) {
     double f = num * y;
     f = fma(fma(-den, f, num), y, f);
     const double t = f * f;
-    double p = 1.0 / 23.0;
-    p = fma(p, t, 1.0 / 21.0);
-    p = fma(p, t, 1.0 / 19.0);
-    p = fma(p, t, 1.0 / 17.0);
-    p = fma(p, t, 1.0 / 15.0);
-    p = fma(p, t, 1.0 / 13.0);
-    p = fma(p, t, 1.0 / 11.0);
-    p = fma(p, t, 1.0 / 9.0);
-    p = fma(p, t, 1.0 / 7.0);
-    p = fma(p, t, 1.0 / 5.0);
-    p = fma(p, t, 1.0 / 3.0);
+    double p = FM_LOG[0];
+#pragma unroll
+    for (int i = 1; i < 11; ++i) p = fma(p, t, FM_LOG[i]);
     const double lm = fma(2.0 * f * t, p, 2.0 * f);
     const double de = (double)e;
     return fma(de, 6.93147180369123816490e-01, fma(de, 1.90821492927058770002e-10, lm));

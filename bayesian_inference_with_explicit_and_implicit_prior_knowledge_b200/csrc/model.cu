@@ -178,18 +178,37 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
     dm.rw_ok = 0; dm.rw_nblk = 0; dm.rw_slots = 0;
     if (D == 2 && (dm.npos_d[0] + RW_RB - 1) / RW_RB <= RW_MAXBLK) {
         const int nb = (dm.npos_d[0] + RW_RB - 1) / RW_RB;
+        // per block: act[j] = 1 + (largest row of the block with a selected entry at last-dimension position j' >= j), i.e. how
+        // many leading rows are walked at position j (non-increasing in j); storage [block][j][i < act[j]][k]
         std::vector<int> off(nb + 1, 0);
+        std::vector<std::vector<int>> act(nb), joff(nb);
         for (int b = 0; b < RW_MAXBLK; ++b) dm.rw_blen[b] = 0;
+        int jtop = 0;
+        for (int mI = 0; mI < M; ++mI) jtop = std::max(jtop, pos[(size_t)mI * D + 1] + 1);
+        for (int b = 0; b < nb; ++b) act[b].assign(jtop + 1, 0);
         for (int mI = 0; mI < M; ++mI) {
-            const int b = pos[(size_t)mI * D] / RW_RB;
-            dm.rw_blen[b] = std::max(dm.rw_blen[b], pos[(size_t)mI * D + 1] + 1);
+            const int p0 = pos[(size_t)mI * D], j = pos[(size_t)mI * D + 1];
+            act[p0 / RW_RB][j] = std::max(act[p0 / RW_RB][j], p0 % RW_RB + 1);
         }
-        for (int b = 0; b < nb; ++b) off[b + 1] = off[b] + dm.rw_blen[b] * RW_RB * nx;
+        bool fits = true;
+        for (int b = 0; b < nb; ++b) {
+            for (int j = jtop - 1; j >= 0; --j) act[b][j] = std::max(act[b][j], act[b][j + 1]);
+            int cnt[RW_RB + 1] = {0, 0, 0, 0, 0};
+            joff[b].assign(jtop + 1, 0);
+            for (int j = 0; j < jtop; ++j) {
+                cnt[act[b][j]]++;
+                joff[b][j + 1] = joff[b][j] + act[b][j] * nx;
+            }
+            for (int r = 1; r <= RW_RB; ++r) fits = fits && cnt[r] <= 255;
+            dm.rw_blen[b] = cnt[4] | (cnt[3] << 8) | (cnt[2] << 16) | (cnt[1] << 24);     // walked in this order
+            off[b + 1] = off[b] + joff[b][jtop];
+        }
+        if (!fits) PGAS_FAIL(-20, "basis needs more than 255 lattice positions in its last dimension");
         rw_perm.assign((size_t)off[nb], -1);
         for (int mI = 0; mI < M; ++mI) {
             const int p0 = pos[(size_t)mI * D], j = pos[(size_t)mI * D + 1];
             const int b = p0 / RW_RB, i = p0 % RW_RB;
-            for (int k = 0; k < nx; ++k) rw_perm[(size_t)off[b] + ((size_t)j * RW_RB + i) * nx + k] = mI * 4 + k;
+            for (int k = 0; k < nx; ++k) rw_perm[(size_t)off[b] + joff[b][j] + (size_t)i * nx + k] = mI * 4 + k;
         }
         dm.rw_ok = 1; dm.rw_nblk = nb; dm.rw_slots = off[nb];
     }

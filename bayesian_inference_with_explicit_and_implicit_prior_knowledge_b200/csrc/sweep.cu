@@ -17,6 +17,7 @@
 #include "basis_eval.cuh"
 #include "basis_rowwalk.cuh"
 #include "sweep_args.cuh"
+#include "resample_math.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -31,8 +32,6 @@ namespace cg = cooperative_groups;
 constexpr int MAXC = 16;         // largest (non-portable) cluster
 
 
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 
 // log N(y; H x + h0, R) with e = Rw (y - mean)   (src/StateSpaceModel.py:83-87 semantics, src/EMPS.py:250-252)
 template <int NX, int NY>
@@ -72,57 +71,6 @@ __device__ __forceinline__ double gauss_logpdf_state(const double* __restrict__ 
         q = fma(e, e, q);
     }
     return logc - 0.5 * q;
-}
-
-// value of the resampling CDF at a local inclusive prefix `p` (same expression for the segment
-// boundaries and the interior so they agree bit for bit)
-__device__ __forceinline__ double cdf_value(double p, double f, double g, double rs) {
-    return __dmul_rn(__fma_rn(p, f, g), rs);
-}
-__device__ __forceinline__ double clip01(double v) { return fmin(fmax(v, 0.0), 1.0); }
-
-// U_j = (u + j) / N exactly as src/Filtering.py:28 evaluates it (correctly rounded quotient)
-__device__ __forceinline__ double strat_point(double u, int j, double dN, double rN) {
-    return div_by_count(__dadd_rn(u, (double)j), dN, rN);
-}
-
-// smallest j in [0,N] with U_j > b  (U_j is non-decreasing in j): four candidates around the
-// arithmetic guess are tested in parallel; the loops only run if the guess was off by more
-__device__ __forceinline__ int first_point_above(double b, double u, int N, double dN, double rN) {
-    const double g = floor(fma(b, dN, -u));
-    int j = (g < 1.0) ? 0 : (g > (double)N ? N : (int)g - 1);
-    const bool c0 = strat_point(u, j, dN, rN) > b, c1 = strat_point(u, j + 1, dN, rN) > b;
-    const bool c2 = strat_point(u, j + 2, dN, rN) > b, c3 = strat_point(u, j + 3, dN, rN) > b;
-    j = c0 ? j : (c1 ? j + 1 : (c2 ? j + 2 : (c3 ? j + 3 : j + 4)));
-    j = min(j, N);
-    while (j > 0 && strat_point(u, j - 1, dN, rN) > b) --j;
-    while (j < N && !(strat_point(u, j, dN, rN) > b)) ++j;
-    return j;
-}
-
-// number of elements of the non-decreasing array w that are < x.  w is padded with +inf to a
-// multiple of 256 entries (nblk blocks), so the search is three fixed-radix levels whose loads and
-// compares are all independent: block (<= 16 probes), 16 probes of stride 16, 16 neighbours.
-__device__ __forceinline__ int count_below_padded(const double* __restrict__ w, int nblk, double x) {
-    int base = 0;
-    if (nblk > 1) {
-        int c = 0;
-        for (int b = 0; b < nblk; ++b) c += (w[b * 256 + 255] < x) ? 1 : 0;
-        base = min(c, nblk - 1) * 256;
-    }
-    const double* w1 = w + base;
-    int c1 = 0;
-#pragma unroll
-    for (int g = 0; g < 16; ++g) c1 += (w1[16 * g + 15] < x) ? 1 : 0;
-    c1 = min(c1, 15);
-    const double2* w2 = reinterpret_cast<const double2*>(w1 + 16 * c1);
-    int c2 = 0;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        const double2 v = w2[g];
-        c2 += ((v.x < x) ? 1 : 0) + ((v.y < x) ? 1 : 0);
-    }
-    return base + 16 * c1 + c2;
 }
 
 // per-step constants staged in shared memory (double-buffered by step parity)
@@ -330,7 +278,7 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
         StepConst nxt;                                       // prefetch of step t+1 (thread 0)
         if (tid == 0 && t + 1 < a.t_end) load_step_const(a, chain, t + 1, &nxt);
 
-#define PGAS_TICK(K) do { if (a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 64)) a.dbg[((size_t)(t - a.t_begin) * 2 + (tid ? 1 : 0)) * 8 + (K)] = clock64(); } while (0)
+#define PGAS_TICK(K) do { if (a.dbg && blockIdx.x < 2 && tid == 96) a.dbg[((size_t)(t - a.t_begin) * 2 + blockIdx.x) * 8 + (K)] = clock64(); } while (0)
         PGAS_TICK(0);
         // ---- A: auxiliary mean (DMMA), first-stage log-weights (src/PGAS.py:89-101, :109-117), and the
         //      softmax numerators (:102,:118) with a WARP-local shift: exp(lw - max_warp) and its in-warp
@@ -648,6 +596,7 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
         const bool last_step = (t + 1 == a.t_end);
         if constexpr (PRE) {
             if (C > 1) cluster_wait();
+            PGAS_TICK(7);
             const size_t prow = ((size_t)chain * a.pre_rows + (size_t)(t - a.pre_off)) * N + base;
             for (int q = 0; q < PPT; ++q) {
                 const int il = q * NT + tid;
@@ -1039,6 +988,9 @@ bool pgas_sweep_split_eligible(const SweepArgs& a) {
     return a.ws && a.ws_bytes >= pgas_sweep_split_workspace(m, a.N, a.n_chains);
 }
 
+static long long* g_dbg_split_ticks = nullptr;     // developer aid (tools/ticks_split.py): phase clocks of the resampling kernel
+extern "C" int pgas_debug_set_split_ticks(long long* dev_buf) { g_dbg_split_ticks = dev_buf; return 0; }
+
 constexpr int SPLIT_GROUPS = 2;      // chain groups of the state kernel: each on its own stream, so that a group's next
                                      // launch starts as soon as ITS CTAs retire (no wave-quantisation tail across all chains)
 struct SplitStreams {
@@ -1137,6 +1089,7 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
         }
         for (int g = 0; g < ngroups; ++g) PGAS_CUDA(cudaEventRecord(g_split.k1[b][g], sg[g]));
         SweepArgs r = a;
+        r.dbg = g_dbg_split_ticks;
         r.t_begin = t0; r.t_end = t1;
         r.pre_la = s.la; r.pre_lr = s.lr; r.pre_ll = s.ll; r.pre_rows = rows; r.pre_off = t0;
         r.init_logw = (c == 0) ? nullptr : lw_carry;
@@ -1147,7 +1100,11 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
             if (v >= 1 && v <= 16) { r.C = v; r.P = (a.N + v - 1) / v; }
         }
         for (int g = 0; g < ngroups; ++g) PGAS_CUDA(cudaStreamWaitEvent(stream, g_split.k1[b][g], 0));
-        if (int rc = pgas_launch_sweep_pre(r, stream)) return rc;
+        const int wc = getenv("PGAS_SPLIT_PRE_C") ? 0 : pgas_weights_cluster(a.N);
+        if (wc > 0) {                                                          // dedicated kernel (weights.cu): the chain's CDF fits one CTA
+            r.C = wc; r.P = (a.N + wc - 1) / wc;
+            if (int rc = pgas_launch_weights(r, stream)) return rc;
+        } else if (int rc = pgas_launch_sweep_pre(r, stream)) return rc;
         PGAS_CUDA(cudaEventRecord(g_split.k2[b], stream));
     }
     return 0;

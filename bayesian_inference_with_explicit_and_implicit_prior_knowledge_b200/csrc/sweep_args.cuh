@@ -38,6 +38,8 @@ struct SweepArgs {
 int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream);
 int pgas_launch_sweep_fused(const SweepArgs& a, cudaStream_t stream);     // one kernel, all phases (sweep.cu)
 int pgas_launch_sweep_pre(const SweepArgs& a, cudaStream_t stream);       // resampling recursion on precomputed log-densities
+int pgas_launch_weights(const SweepArgs& a, cudaStream_t stream);         // dedicated resampling kernel of the split form (weights.cu)
+int pgas_weights_cluster(int N);                                           // its cluster size for N particles; 0 = not applicable
 bool pgas_sweep_split_eligible(const SweepArgs& a);
 size_t pgas_sweep_split_workspace(const DevModel& m, int N, int n_chains);
 int pgas_choose_cluster(const DevModel& m, int N, int n_chains, int requested);

@@ -1,0 +1,322 @@
+// weights.cu — the weight recursion of the split sweep (sm_100a): a dedicated resampling kernel.
+//
+// In the reference's semantics (src/PGAS.py:79-153) the states never see an ancestor index, so csmc_state_kernel
+// (sweep.cu) runs ahead and leaves per particle and step  l_aux = log p(y_t | mu),  h = log N(x_ref,t; mu, Sigma)  and
+// ll = log p(y_t | x_t).  What remains sequential in t is
+//   w_aux = softmax(l_aux + logw)                      a    = systematic_SISR(u_res, w_aux)      (:92-106, Filtering.py:6-37)
+//   w_anc = softmax(l_aux + logw + h)                  a_N-1 = searchsorted(cumsum(w_anc), u_anc) (:109-127)
+//   logw' = ll - l_aux[a]                                                                       (:137-147)
+// One cluster of C CTAs owns a chain for all steps of a launch.  Compared with csmc_sweep_kernel<PRE> (the general
+// kernel, still used when a chain's CDF does not fit one CTA's shared memory) this kernel
+//   * gives every thread PPT CONSECUTIVE particles: the log-weights live in registers for the whole launch, the
+//     prefix sums are thread-serial + ONE warp scan per CDF (instead of PPT), a warp is one softmax unit;
+//   * lets EVERY warp fold the NW unit pairs (and then the C CTA pairs) redundantly with the same shuffles, so the
+//     fold needs no second CTA barrier and no warp-0 serial section;
+//   * REPLICATES the finished CDF and l_aux of the whole chain in every CTA of the cluster (DSMEM stores in phase B1):
+//     each CTA then resamples its OWN P points against the full CDF — the work is balanced whatever the weights look
+//     like (with owner-of-segment resampling a CTA holding most of the mass did most of the searches while its peer
+//     waited: 11 k of 33 k cycles per step on skewed weights), the gathered l_aux[a_j] lands in the thread that needs
+//     it, and the step ends without a barrier;
+//   * searches the CDF once per thread and then walks forward: the PPT points of a thread are consecutive.
+// Per step: one CTA barrier, two cluster barriers.
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <stdlib.h>
+#include "sweep_args.cuh"
+#include "resample_math.cuh"
+
+namespace cg = cooperative_groups;
+
+constexpr int WK_NT = 512, WK_PPT = 4, WK_MAXC = 8;
+
+__device__ __forceinline__ void wk_load_step_u(const SweepArgs& a, int chain, int t, double* dst) {
+    if (a.rng_mode == 1) {
+        const double* up = a.U + ((size_t)chain * a.var_rows + (t - a.row_off)) * 2;
+        dst[0] = up[0];
+        dst[1] = up[1];
+    } else {
+        philox_uniform2(a.seed, PURPOSE_STEP_U, a.chain_base + chain, a.iteration, (unsigned)t, 0u, dst[0], dst[1]);
+    }
+}
+
+// PPT consecutive doubles of a row; vectorised when the row offset is 16-byte aligned
+template <int PPT>
+__device__ __forceinline__ void wk_load_row(const double* __restrict__ p, int nvalid, bool vec, double (&out)[PPT]) {
+    if (vec && nvalid == PPT) {
+#pragma unroll
+        for (int u = 0; u < PPT; u += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(p + u);
+            out[u] = v.x;
+            out[u + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) out[u] = (u < nvalid) ? p[u] : 0.0;
+    }
+}
+
+template <int NT, int PPT>
+__global__ void __launch_bounds__(NT, 1024 / NT) csmc_weights_kernel(const __grid_constant__ SweepArgs a) {
+    constexpr int NW = NT / 32;
+    static_assert(NW <= 32 && PPT % 2 == 0, "one fold pass; paired loads");
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = a.C, N = a.N, P = a.P;
+    const int rank = (C > 1) ? (int)cluster.block_rank() : 0;
+    const int chain = blockIdx.x / C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int base = rank * P;
+    const int Pc = max(0, min(P, N - base));
+    const int il0 = tid * PPT;
+    const int nvalid = max(0, min(PPT, Pc - il0));
+    const int c_last = (N - 1) / P;
+    const int nblkN = (N + 255) / 256;
+    const double dN = (double)N, rN = 1.0 / (double)N;
+    const bool vec = ((N & 1) == 0) && ((P & 1) == 0);
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* b1f = reinterpret_cast<double*>(smem_raw);            // CDF of the whole chain, padded with +inf
+    double* lauxf = b1f + (size_t)nblkN * 256 + 8;                // l_aux of the whole chain
+    double* unit = lauxf + (((size_t)N + 1) & ~(size_t)1);        // per warp: (max1, sum1, max2, sum2)
+    double* exch = unit + NW * 4;                                 // per CTA:  (max1, sum1, max2, sum2), all-gathered
+    double* su = exch + WK_MAXC * 4;                              // (u_res, u_anc), double-buffered by step parity
+    int* cnt = reinterpret_cast<int*>(su + 4);                    // particles of CTA `cstar` below u_anc, triple-buffered
+
+    for (int r = tid; r < nblkN * 256 + 8; r += NT) b1f[r] = INFINITY;
+    if (tid == 0) {
+        cnt[0] = cnt[1] = cnt[2] = 0;
+        wk_load_step_u(a, chain, a.t_begin, su + 2 * (a.t_begin & 1));
+    }
+    double logw[PPT];
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) logw[u] = (u < nvalid && a.init_logw) ? a.init_logw[(size_t)chain * N + base + il0 + u] : 0.0;
+    if (C > 1) cluster.sync(); else __syncthreads();
+
+    for (int t = a.t_begin; t < a.t_end; ++t) {
+        if (tid == 0) {
+            if (t + 1 < a.t_end) wk_load_step_u(a, chain, t + 1, su + 2 * ((t + 1) & 1));
+            cnt[(t + 1) % 3] = 0;
+        }
+        // ---- A: first-stage log-weights, softmax numerators with a warp-local shift, prefix sums
+        const size_t prow = ((size_t)chain * a.pre_rows + (size_t)(t - a.pre_off)) * N + base + il0;
+        double la[PPT], lr[PPT];
+        wk_load_row<PPT>(a.pre_la + prow, nvalid, vec, la);
+        wk_load_row<PPT>(a.pre_lr + prow, nvalid, vec, lr);
+        if (t + 1 < a.t_end && nvalid > 0 && (tid & 3) == 0) {    // next step's rows towards L1 (one request per 128-byte line)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pre_la + prow + N));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pre_lr + prow + N));
+        }
+        if (nvalid > 0 && (tid & 3) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pre_ll + prow));
+        double s1[PPT], s2[PPT];
+        double m1t = -INFINITY, m2t = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+            const double lwa = (u < nvalid) ? la[u] + logw[u] : -INFINITY;
+            const double lwr = (u < nvalid) ? lwa + lr[u] : -INFINITY;
+            s1[u] = lwa;
+            s2[u] = lwr;
+            m1t = fmax(m1t, lwa);
+            m2t = fmax(m2t, lwr);
+        }
+        const double m1w = warp_shift_max(m1t), m2w = warp_shift_max(m2t);
+        {
+            double r1 = 0.0, r2 = 0.0;
+#pragma unroll
+            for (int u = 0; u < PPT; ++u) {                        // thread-serial inclusive prefix of the numerators
+                const double e1 = (u < nvalid) ? exp_neg_bf(s1[u] - m1w) : 0.0;
+                const double e2 = (u < nvalid) ? exp_neg_bf(s2[u] - m2w) : 0.0;
+                r1 = __dadd_rn(r1, e1);
+                r2 = __dadd_rn(r2, e2);
+                s1[u] = r1;
+                s2[u] = r2;
+            }
+            const double i1 = warp_scan_incl(r1, lane), i2 = warp_scan_incl(r2, lane);
+            double x1 = __shfl_up_sync(0xffffffffu, i1, 1), x2 = __shfl_up_sync(0xffffffffu, i2, 1);
+            x1 = lane ? x1 : 0.0;
+            x2 = lane ? x2 : 0.0;
+#pragma unroll
+            for (int u = 0; u < PPT; ++u) { s1[u] = __dadd_rn(x1, s1[u]); s2[u] = __dadd_rn(x2, s2[u]); }   // in-warp inclusive prefix
+            if (lane == 31) {
+                const bool any = warp * 32 * PPT < Pc;
+                double* up = unit + warp * 4;
+                up[0] = any ? m1w : -INFINITY; up[1] = any ? i1 : 0.0;
+                up[2] = any ? m2w : -INFINITY; up[3] = any ? i2 : 0.0;
+            }
+        }
+        __syncthreads();
+
+        // ---- X1: every warp folds the NW warp pairs (online-softmax rescaling) — same shuffles, same bits everywhere
+        double fw1, gw1, fw2, gw2;                                 // rescale factor and exclusive offset of this thread's warp
+        double m1c_r, s1c_r, m2c_r, s2c_r;                         // (max, sum) pairs of this CTA
+        {
+            const bool vu = lane < NW;
+            const double mu1 = vu ? unit[lane * 4] : -INFINITY, mu2 = vu ? unit[lane * 4 + 2] : -INFINITY;
+            const double m1c = warp_max(mu1), m2c = warp_max(mu2);
+            const double f1 = (mu1 == -INFINITY) ? 0.0 : exp_neg_bf(mu1 - m1c);
+            const double f2 = (mu2 == -INFINITY) ? 0.0 : exp_neg_bf(mu2 - m2c);
+            const double v1 = vu ? __dmul_rn(unit[lane * 4 + 1], f1) : 0.0, v2 = vu ? __dmul_rn(unit[lane * 4 + 3], f2) : 0.0;
+            const double i1 = warp_scan_incl(v1, lane), i2 = warp_scan_incl(v2, lane);
+            double x1 = __shfl_up_sync(0xffffffffu, i1, 1), x2 = __shfl_up_sync(0xffffffffu, i2, 1);
+            x1 = lane ? x1 : 0.0;
+            x2 = lane ? x2 : 0.0;
+            fw1 = __shfl_sync(0xffffffffu, f1, warp); gw1 = __shfl_sync(0xffffffffu, x1, warp);
+            fw2 = __shfl_sync(0xffffffffu, f2, warp); gw2 = __shfl_sync(0xffffffffu, x2, warp);
+            m1c_r = m1c; m2c_r = m2c;
+            s1c_r = __shfl_sync(0xffffffffu, i1, 31); s2c_r = __shfl_sync(0xffffffffu, i2, 31);
+            if (C > 1) {
+                if (warp == 0 && lane < C) {
+                    double* dst = cluster.map_shared_rank(exch, lane) + rank * 4;
+                    dst[0] = m1c_r; dst[1] = s1c_r; dst[2] = m2c_r; dst[3] = s2c_r;
+                }
+                cluster_arrive();
+                cluster_wait();
+            }
+        }
+        // the C CTA pairs, folded by every warp
+        const double ures = su[2 * (t & 1)], uanc = su[2 * (t & 1) + 1];
+        double myf1, myg1, myf2, myg2, S1, S2;
+        int cstar;
+        {
+            const bool vc = lane < C;
+            const double* ex = exch + lane * 4;                    // single CTA: the pair is already in registers
+            const double mc1 = vc ? (C > 1 ? ex[0] : m1c_r) : -INFINITY, mc2 = vc ? (C > 1 ? ex[2] : m2c_r) : -INFINITY;
+            const double sc1 = vc ? (C > 1 ? ex[1] : s1c_r) : 0.0, sc2 = vc ? (C > 1 ? ex[3] : s2c_r) : 0.0;
+            const double M1 = warp_max(mc1), M2 = warp_max(mc2);
+            const double f1 = (mc1 == -INFINITY) ? 0.0 : exp_neg_bf(mc1 - M1);
+            const double f2 = (mc2 == -INFINITY) ? 0.0 : exp_neg_bf(mc2 - M2);
+            const double v1 = sc1 * f1, v2 = sc2 * f2;
+            const double i1 = warp_scan_incl(v1, lane), i2 = warp_scan_incl(v2, lane);
+            S1 = rcp_bf(__shfl_sync(0xffffffffu, i1, 31));
+            S2 = rcp_bf(__shfl_sync(0xffffffffu, i2, 31));
+            // CTA holding the reference ancestor: number of leading CTAs whose whole CDF segment lies below u_anc
+            cstar = __popc(__ballot_sync(0xffffffffu, lane <= c_last && __dmul_rn(i2, S2) < uanc));
+            double x1 = __shfl_up_sync(0xffffffffu, i1, 1), x2 = __shfl_up_sync(0xffffffffu, i2, 1);
+            x1 = lane ? x1 : 0.0;
+            x2 = lane ? x2 : 0.0;
+            myf1 = __shfl_sync(0xffffffffu, f1, rank); myg1 = __shfl_sync(0xffffffffu, x1, rank);
+            myf2 = __shfl_sync(0xffffffffu, f2, rank); myg2 = __shfl_sync(0xffffffffu, x2, rank);
+        }
+
+        // ---- B1: finished CDF values and l_aux of this CTA's particles -> every CTA of the cluster
+        {
+            int mycnt = 0;
+#pragma unroll
+            for (int u = 0; u < PPT; ++u) {
+                if (u < nvalid) {
+                    // CTA-level inclusive prefix G_warp + s f_warp; W = clip(cumsum(w / sum w), 0, 1)  (src/Filtering.py:23-32)
+                    const double p1 = __dadd_rn(gw1, __dmul_rn(s1[u], fw1));
+                    const double p2 = __dadd_rn(gw2, __dmul_rn(s2[u], fw2));
+                    s1[u] = clip01(cdf_value(p1, myf1, myg1, S1));
+                    // cumsum(softmax(lw_anc)) < u_anc  (src/PGAS.py:118-124), not clipped
+                    if (rank == cstar) mycnt += (cdf_value(p2, myf2, myg2, S2) < uanc) ? 1 : 0;
+                }
+            }
+            for (int c = 0; c < C; ++c) {
+                double* db = (c == rank) ? b1f : cluster.map_shared_rank(b1f, c);
+                double* dl = (c == rank) ? lauxf : cluster.map_shared_rank(lauxf, c);
+                if (vec && nvalid == PPT) {
+#pragma unroll
+                    for (int u = 0; u < PPT; u += 2) {
+                        *reinterpret_cast<double2*>(db + base + il0 + u) = make_double2(s1[u], s1[u + 1]);
+                        *reinterpret_cast<double2*>(dl + base + il0 + u) = make_double2(la[u], la[u + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u)
+                        if (u < nvalid) { db[base + il0 + u] = s1[u]; dl[base + il0 + u] = la[u]; }
+                }
+            }
+            if (rank == cstar) {
+                mycnt = __reduce_add_sync(0xffffffffu, mycnt);
+                if (lane == 0 && mycnt) atomicAdd(&cnt[t % 3], mycnt);
+            }
+        }
+        double ll[PPT];
+        wk_load_row<PPT>(a.pre_ll + prow, nvalid, vec, ll);      // in flight across the barrier
+        if (C > 1) { cluster_arrive(); cluster_wait(); } else __syncthreads();
+
+        // ---- B2 + C: this thread's PPT consecutive points against the full CDF (src/Filtering.py:28-35), the ancestor of
+        //      the conditioned path (src/PGAS.py:118-127), new log-weights (:137-147)
+        if (nvalid > 0) {
+            int anc[PPT];
+            int k = 0;
+#pragma unroll
+            for (int u = 0; u < PPT; ++u) {
+                if (u < nvalid) {
+                    const int j = base + il0 + u;
+                    const double uj = strat_point(ures, j, dN, rN);
+                    if (u == 0) {
+                        k = count_below_padded(b1f, nblkN, uj);
+                    } else {                                       // CDF and points are sorted: walk forward from the previous answer
+                        const int c4 = ((b1f[k] < uj) ? 1 : 0) + ((b1f[k + 1] < uj) ? 1 : 0) + ((b1f[k + 2] < uj) ? 1 : 0) +
+                                       ((b1f[k + 3] < uj) ? 1 : 0);
+                        k = (c4 == 4) ? count_below_padded(b1f, nblkN, uj) : k + c4;
+                    }
+                    int kk = min(k, N - 1), av = kk;
+                    if (j == N - 1) {                              // overwritten by the reference ancestor (:127)
+                        if (cstar > c_last) { av = N; kk = N - 1; }   // cumsum never reached u_anc: searchsorted returns N, gather clamps
+                        else {
+                            const int* cp = (C > 1 && cstar != rank) ? cluster.map_shared_rank(cnt, cstar) : cnt;
+                            const int cv = cp[t % 3];
+                            const int pcs = max(0, min(P, N - cstar * P));
+                            av = cstar * P + cv;
+                            kk = cstar * P + min(cv, pcs - 1);
+                        }
+                    }
+                    anc[u] = av;
+                    logw[u] = ll[u] - lauxf[kk];
+                }
+            }
+            int* anc_row = a.anc_trace + ((size_t)chain * a.anc_rows + (t - 1 - a.row_off + a.anc_shift)) * N + base + il0;
+            if (nvalid == PPT && ((N & 3) == 0) && ((P & 3) == 0) && PPT == 4) {
+                *reinterpret_cast<int4*>(anc_row) = make_int4(anc[0], anc[1], anc[2], anc[3]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < PPT; ++u)
+                    if (u < nvalid) anc_row[u] = anc[u];
+            }
+            if (t + 1 == a.t_end && a.logw_last) {
+#pragma unroll
+                for (int u = 0; u < PPT; ++u)
+                    if (u < nvalid) a.logw_last[(size_t)chain * N + base + il0 + u] = logw[u];
+            }
+        }
+        // no barrier here: the next step's phase A touches registers and `unit` only (its last readers passed the
+        // barrier above); b1f / lauxf are rewritten after the next X1 cluster barrier, when every CTA has left B2
+    }
+    if (C > 1) cluster.sync();                                    // no CTA exits while peers may still read / push into its smem
+}
+
+static size_t weights_smem_bytes(int N) {
+    const size_t nblkN = ((size_t)N + 255) / 256;
+    return (nblkN * 256 + 8 + (((size_t)N + 1) & ~(size_t)1) + (WK_NT / 32) * 4 + WK_MAXC * 4 + 4) * sizeof(double) + 4 * sizeof(int) + 16;
+}
+
+// cluster size of the dedicated kernel for N particles (0: not applicable -> csmc_sweep_kernel<PRE>)
+int pgas_weights_cluster(int N) {
+    if (const char* e = getenv("PGAS_WEIGHTS_KERNEL")) { if (atoi(e) == 0) return 0; }      // developer override
+    if (N < 64 || weights_smem_bytes(N) > 200 * 1024) return 0;
+    int C = 1;
+    while (C * WK_NT * WK_PPT < N) C *= 2;
+    return C <= WK_MAXC ? C : 0;
+}
+
+int pgas_launch_weights(const SweepArgs& a, cudaStream_t stream) {
+    auto kern = csmc_weights_kernel<WK_NT, WK_PPT>;
+    const size_t smem = weights_smem_bytes(a.N);
+    PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(a.C * a.n_chains), 1, 1);
+    cfg.blockDim = dim3(WK_NT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)a.C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PGAS_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    __atomic_add_fetch(&g_pgas_launches, 1, __ATOMIC_RELAXED);
+    return 0;
+}
