@@ -10,15 +10,15 @@
 // kernel, still used when a chain's CDF does not fit one CTA's shared memory) this kernel
 //   * gives every thread PPT CONSECUTIVE particles: the log-weights live in registers for the whole launch, the
 //     prefix sums are thread-serial + ONE warp scan per CDF (instead of PPT), a warp is one softmax unit;
-//   * lets EVERY warp fold the NW unit pairs (and then the C CTA pairs) redundantly with the same shuffles, so the
-//     fold needs no second CTA barrier and no warp-0 serial section;
+//   * all-gathers the warp pairs of the whole cluster (DSMEM) and lets EVERY warp fold them redundantly with the same
+//     shuffles: one fold level, no second barrier, no warp-0 serial section;
 //   * REPLICATES the finished CDF and l_aux of the whole chain in every CTA of the cluster (DSMEM stores in phase B1):
 //     each CTA then resamples its OWN P points against the full CDF — the work is balanced whatever the weights look
 //     like (with owner-of-segment resampling a CTA holding most of the mass did most of the searches while its peer
 //     waited: 11 k of 33 k cycles per step on skewed weights), the gathered l_aux[a_j] lands in the thread that needs
 //     it, and the step ends without a barrier;
 //   * searches the CDF once per thread and then walks forward: the PPT points of a thread are consecutive.
-// Per step: one CTA barrier, two cluster barriers.
+// Per step: two cluster barriers, no CTA barrier.
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <stdlib.h>
@@ -27,7 +27,14 @@
 
 namespace cg = cooperative_groups;
 
-constexpr int WK_NT = 512, WK_PPT = 4, WK_MAXC = 8;
+// threads per CTA and consecutive particles per thread (compile-time knobs for occupancy experiments)
+#ifndef PGAS_WK_NT
+#define PGAS_WK_NT 512
+#endif
+#ifndef PGAS_WK_PPT
+#define PGAS_WK_PPT 4
+#endif
+constexpr int WK_NT = PGAS_WK_NT, WK_PPT = PGAS_WK_PPT, WK_MAXC = 8;
 
 __device__ __forceinline__ void wk_load_step_u(const SweepArgs& a, int chain, int t, double* dst) {
     if (a.rng_mode == 1) {
@@ -56,9 +63,9 @@ __device__ __forceinline__ void wk_load_row(const double* __restrict__ p, int nv
 }
 
 template <int NT, int PPT>
-__global__ void __launch_bounds__(NT, 1024 / NT) csmc_weights_kernel(const __grid_constant__ SweepArgs a) {
+__global__ void __launch_bounds__(NT, 2) csmc_weights_kernel(const __grid_constant__ SweepArgs a) {
     constexpr int NW = NT / 32;
-    static_assert(NW <= 32 && PPT % 2 == 0, "one fold pass; paired loads");
+    static_assert(NW <= 32 && PPT % 2 == 0 && 16 % PPT == 0, "paired loads; whole threads per 128-byte line");
     cg::cluster_group cluster = cg::this_cluster();
     const int C = a.C, N = a.N, P = a.P;
     const int rank = (C > 1) ? (int)cluster.block_rank() : 0;
@@ -68,7 +75,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) csmc_weights_kernel(const __gri
     const int Pc = max(0, min(P, N - base));
     const int il0 = tid * PPT;
     const int nvalid = max(0, min(PPT, Pc - il0));
-    const int c_last = (N - 1) / P;
     const int nblkN = (N + 255) / 256;
     const double dN = (double)N, rN = 1.0 / (double)N;
     const bool vec = ((N & 1) == 0) && ((P & 1) == 0);
@@ -76,10 +82,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) csmc_weights_kernel(const __gri
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* b1f = reinterpret_cast<double*>(smem_raw);            // CDF of the whole chain, padded with +inf
     double* lauxf = b1f + (size_t)nblkN * 256 + 8;                // l_aux of the whole chain
-    double* unit = lauxf + (((size_t)N + 1) & ~(size_t)1);        // per warp: (max1, sum1, max2, sum2)
-    double* exch = unit + NW * 4;                                 // per CTA:  (max1, sum1, max2, sum2), all-gathered
-    double* su = exch + WK_MAXC * 4;                              // (u_res, u_anc), double-buffered by step parity
-    int* cnt = reinterpret_cast<int*>(su + 4);                    // particles of CTA `cstar` below u_anc, triple-buffered
+    double* unit = lauxf + (((size_t)N + 1) & ~(size_t)1);        // per warp of the CLUSTER: (max1, sum1, max2, sum2), all-gathered
+    double* su = unit + WK_MAXC * NW * 4;                              // (u_res, u_anc), double-buffered by step parity
+    int* cnt = reinterpret_cast<int*>(su + 4);                    // particles of this CTA below u_anc, triple-buffered
 
     for (int r = tid; r < nblkN * 256 + 8; r += NT) b1f[r] = INFINITY;
     if (tid == 0) {
@@ -91,7 +96,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) csmc_weights_kernel(const __gri
     for (int u = 0; u < PPT; ++u) logw[u] = (u < nvalid && a.init_logw) ? a.init_logw[(size_t)chain * N + base + il0 + u] : 0.0;
     if (C > 1) cluster.sync(); else __syncthreads();
 
+#define WK_TICK(K) do { if (a.dbg && blockIdx.x < 2 && tid == 96) a.dbg[((size_t)(t - a.t_begin) * 2 + blockIdx.x) * 8 + (K)] = clock64(); } while (0)
     for (int t = a.t_begin; t < a.t_end; ++t) {
+        WK_TICK(0);
         if (tid == 0) {
             if (t + 1 < a.t_end) wk_load_step_u(a, chain, t + 1, su + 2 * ((t + 1) & 1));
             cnt[(t + 1) % 3] = 0;
@@ -101,11 +108,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) csmc_weights_kernel(const __gri
         double la[PPT], lr[PPT];
         wk_load_row<PPT>(a.pre_la + prow, nvalid, vec, la);
         wk_load_row<PPT>(a.pre_lr + prow, nvalid, vec, lr);
-        if (t + 1 < a.t_end && nvalid > 0 && (tid & 3) == 0) {    // next step's rows towards L1 (one request per 128-byte line)
+        if (t + 1 < a.t_end && nvalid > 0 && (tid & (16 / PPT - 1)) == 0) {    // next step's rows towards L1 (one request per 128-byte line)
             asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pre_la + prow + N));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pre_lr + prow + N));
         }
-        if (nvalid > 0 && (tid & 3) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pre_ll + prow));
+        if (nvalid > 0 && (tid & (16 / PPT - 1)) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pre_ll + prow));
         double s1[PPT], s2[PPT];
         double m1t = -INFINITY, m2t = -INFINITY;
 #pragma unroll
@@ -135,79 +142,68 @@ __global__ void __launch_bounds__(NT, 1024 / NT) csmc_weights_kernel(const __gri
             x2 = lane ? x2 : 0.0;
 #pragma unroll
             for (int u = 0; u < PPT; ++u) { s1[u] = __dadd_rn(x1, s1[u]); s2[u] = __dadd_rn(x2, s2[u]); }   // in-warp inclusive prefix
-            if (lane == 31) {
+            if (lane == 31) {                                      // this warp's (max, sum) pairs -> every CTA of the cluster
                 const bool any = warp * 32 * PPT < Pc;
-                double* up = unit + warp * 4;
-                up[0] = any ? m1w : -INFINITY; up[1] = any ? i1 : 0.0;
-                up[2] = any ? m2w : -INFINITY; up[3] = any ? i2 : 0.0;
-            }
-        }
-        __syncthreads();
-
-        // ---- X1: every warp folds the NW warp pairs (online-softmax rescaling) — same shuffles, same bits everywhere
-        double fw1, gw1, fw2, gw2;                                 // rescale factor and exclusive offset of this thread's warp
-        double m1c_r, s1c_r, m2c_r, s2c_r;                         // (max, sum) pairs of this CTA
-        {
-            const bool vu = lane < NW;
-            const double mu1 = vu ? unit[lane * 4] : -INFINITY, mu2 = vu ? unit[lane * 4 + 2] : -INFINITY;
-            const double m1c = warp_max(mu1), m2c = warp_max(mu2);
-            const double f1 = (mu1 == -INFINITY) ? 0.0 : exp_neg_bf(mu1 - m1c);
-            const double f2 = (mu2 == -INFINITY) ? 0.0 : exp_neg_bf(mu2 - m2c);
-            const double v1 = vu ? __dmul_rn(unit[lane * 4 + 1], f1) : 0.0, v2 = vu ? __dmul_rn(unit[lane * 4 + 3], f2) : 0.0;
-            const double i1 = warp_scan_incl(v1, lane), i2 = warp_scan_incl(v2, lane);
-            double x1 = __shfl_up_sync(0xffffffffu, i1, 1), x2 = __shfl_up_sync(0xffffffffu, i2, 1);
-            x1 = lane ? x1 : 0.0;
-            x2 = lane ? x2 : 0.0;
-            fw1 = __shfl_sync(0xffffffffu, f1, warp); gw1 = __shfl_sync(0xffffffffu, x1, warp);
-            fw2 = __shfl_sync(0xffffffffu, f2, warp); gw2 = __shfl_sync(0xffffffffu, x2, warp);
-            m1c_r = m1c; m2c_r = m2c;
-            s1c_r = __shfl_sync(0xffffffffu, i1, 31); s2c_r = __shfl_sync(0xffffffffu, i2, 31);
-            if (C > 1) {
-                if (warp == 0 && lane < C) {
-                    double* dst = cluster.map_shared_rank(exch, lane) + rank * 4;
-                    dst[0] = m1c_r; dst[1] = s1c_r; dst[2] = m2c_r; dst[3] = s2c_r;
+                const double u0 = any ? m1w : -INFINITY, u1 = any ? i1 : 0.0, u2 = any ? m2w : -INFINITY, u3 = any ? i2 : 0.0;
+                for (int c = 0; c < C; ++c) {
+                    double* up = ((c == rank) ? unit : cluster.map_shared_rank(unit, c)) + (rank * NW + warp) * 4;
+                    *reinterpret_cast<double2*>(up) = make_double2(u0, u1);
+                    *reinterpret_cast<double2*>(up + 2) = make_double2(u2, u3);
                 }
-                cluster_arrive();
-                cluster_wait();
             }
         }
-        // the C CTA pairs, folded by every warp
+        WK_TICK(1);
+        if (C > 1) { cluster_arrive(); cluster_wait(); } else __syncthreads();
+        WK_TICK(2);
+
+        // ---- X1: every warp folds the C * NW warp pairs of the chain (online-softmax rescaling) with the same shuffles —
+        //      same bits in every warp of every CTA, no second barrier
         const double ures = su[2 * (t & 1)], uanc = su[2 * (t & 1) + 1];
-        double myf1, myg1, myf2, myg2, S1, S2;
-        int cstar;
+        double fw1 = 0.0, gw1 = 0.0, fw2 = 0.0, gw2 = 0.0;          // rescale factor and exclusive offset of this thread's warp
+        double S1, S2;                                             // reciprocals of the normalisers
         {
-            const bool vc = lane < C;
-            const double* ex = exch + lane * 4;                    // single CTA: the pair is already in registers
-            const double mc1 = vc ? (C > 1 ? ex[0] : m1c_r) : -INFINITY, mc2 = vc ? (C > 1 ? ex[2] : m2c_r) : -INFINITY;
-            const double sc1 = vc ? (C > 1 ? ex[1] : s1c_r) : 0.0, sc2 = vc ? (C > 1 ? ex[3] : s2c_r) : 0.0;
-            const double M1 = warp_max(mc1), M2 = warp_max(mc2);
-            const double f1 = (mc1 == -INFINITY) ? 0.0 : exp_neg_bf(mc1 - M1);
-            const double f2 = (mc2 == -INFINITY) ? 0.0 : exp_neg_bf(mc2 - M2);
-            const double v1 = sc1 * f1, v2 = sc2 * f2;
-            const double i1 = warp_scan_incl(v1, lane), i2 = warp_scan_incl(v2, lane);
-            S1 = rcp_bf(__shfl_sync(0xffffffffu, i1, 31));
-            S2 = rcp_bf(__shfl_sync(0xffffffffu, i2, 31));
-            // CTA holding the reference ancestor: number of leading CTAs whose whole CDF segment lies below u_anc
-            cstar = __popc(__ballot_sync(0xffffffffu, lane <= c_last && __dmul_rn(i2, S2) < uanc));
-            double x1 = __shfl_up_sync(0xffffffffu, i1, 1), x2 = __shfl_up_sync(0xffffffffu, i2, 1);
-            x1 = lane ? x1 : 0.0;
-            x2 = lane ? x2 : 0.0;
-            myf1 = __shfl_sync(0xffffffffu, f1, rank); myg1 = __shfl_sync(0xffffffffu, x1, rank);
-            myf2 = __shfl_sync(0xffffffffu, f2, rank); myg2 = __shfl_sync(0xffffffffu, x2, rank);
+            const int U = C * NW, mine = rank * NW + warp;
+            double m1g = -INFINITY, m2g = -INFINITY;
+            for (int u = lane; u < U; u += 32) { m1g = fmax(m1g, unit[u * 4]); m2g = fmax(m2g, unit[u * 4 + 2]); }
+            m1g = warp_max(m1g);
+            m2g = warp_max(m2g);
+            double c1 = 0.0, c2 = 0.0;
+            for (int u0 = 0; u0 < U; u0 += 32) {
+                const int u = u0 + lane;
+                const bool vu = u < U;
+                const double mu1 = vu ? unit[u * 4] : -INFINITY, mu2 = vu ? unit[u * 4 + 2] : -INFINITY;
+                const double f1 = (mu1 == -INFINITY) ? 0.0 : exp_neg_bf(mu1 - m1g);
+                const double f2 = (mu2 == -INFINITY) ? 0.0 : exp_neg_bf(mu2 - m2g);
+                const double v1 = vu ? __dmul_rn(unit[u * 4 + 1], f1) : 0.0, v2 = vu ? __dmul_rn(unit[u * 4 + 3], f2) : 0.0;
+                const double i1 = warp_scan_incl(v1, lane), i2 = warp_scan_incl(v2, lane);
+                double x1 = __shfl_up_sync(0xffffffffu, i1, 1), x2 = __shfl_up_sync(0xffffffffu, i2, 1);
+                x1 = lane ? __dadd_rn(c1, x1) : c1;
+                x2 = lane ? __dadd_rn(c2, x2) : c2;
+                const int src = (mine - u0) & 31;
+                const double tf1 = __shfl_sync(0xffffffffu, f1, src), tg1 = __shfl_sync(0xffffffffu, x1, src);
+                const double tf2 = __shfl_sync(0xffffffffu, f2, src), tg2 = __shfl_sync(0xffffffffu, x2, src);
+                if (mine >= u0 && mine < u0 + 32) { fw1 = tf1; gw1 = tg1; fw2 = tf2; gw2 = tg2; }
+                c1 = __dadd_rn(c1, __shfl_sync(0xffffffffu, i1, 31));
+                c2 = __dadd_rn(c2, __shfl_sync(0xffffffffu, i2, 31));
+            }
+            S1 = rcp_bf(c1);
+            S2 = rcp_bf(c2);
         }
 
+        WK_TICK(3);
         // ---- B1: finished CDF values and l_aux of this CTA's particles -> every CTA of the cluster
         {
             int mycnt = 0;
 #pragma unroll
             for (int u = 0; u < PPT; ++u) {
                 if (u < nvalid) {
-                    // CTA-level inclusive prefix G_warp + s f_warp; W = clip(cumsum(w / sum w), 0, 1)  (src/Filtering.py:23-32)
+                    // W = clip(cumsum(w / sum w), 0, 1)  (src/Filtering.py:23-32): chain-level inclusive prefix G_warp + s f_warp
                     const double p1 = __dadd_rn(gw1, __dmul_rn(s1[u], fw1));
                     const double p2 = __dadd_rn(gw2, __dmul_rn(s2[u], fw2));
-                    s1[u] = clip01(cdf_value(p1, myf1, myg1, S1));
-                    // cumsum(softmax(lw_anc)) < u_anc  (src/PGAS.py:118-124), not clipped
-                    if (rank == cstar) mycnt += (cdf_value(p2, myf2, myg2, S2) < uanc) ? 1 : 0;
+                    s1[u] = clip01(__dmul_rn(p1, S1));
+                    // cumsum(softmax(lw_anc)) < u_anc  (src/PGAS.py:118-124), not clipped: the counts of all CTAs add up to
+                    // searchsorted's result
+                    mycnt += (__dmul_rn(p2, S2) < uanc) ? 1 : 0;
                 }
             }
             for (int c = 0; c < C; ++c) {
@@ -225,14 +221,14 @@ __global__ void __launch_bounds__(NT, 1024 / NT) csmc_weights_kernel(const __gri
                         if (u < nvalid) { db[base + il0 + u] = s1[u]; dl[base + il0 + u] = la[u]; }
                 }
             }
-            if (rank == cstar) {
-                mycnt = __reduce_add_sync(0xffffffffu, mycnt);
-                if (lane == 0 && mycnt) atomicAdd(&cnt[t % 3], mycnt);
-            }
+            mycnt = __reduce_add_sync(0xffffffffu, mycnt);
+            if (lane == 0 && mycnt) atomicAdd(&cnt[t % 3], mycnt);
         }
         double ll[PPT];
         wk_load_row<PPT>(a.pre_ll + prow, nvalid, vec, ll);      // in flight across the barrier
+        WK_TICK(4);
         if (C > 1) { cluster_arrive(); cluster_wait(); } else __syncthreads();
+        WK_TICK(5);
 
         // ---- B2 + C: this thread's PPT consecutive points against the full CDF (src/Filtering.py:28-35), the ancestor of
         //      the conditioned path (src/PGAS.py:118-127), new log-weights (:137-147)
@@ -253,22 +249,19 @@ __global__ void __launch_bounds__(NT, 1024 / NT) csmc_weights_kernel(const __gri
                     }
                     int kk = min(k, N - 1), av = kk;
                     if (j == N - 1) {                              // overwritten by the reference ancestor (:127)
-                        if (cstar > c_last) { av = N; kk = N - 1; }   // cumsum never reached u_anc: searchsorted returns N, gather clamps
-                        else {
-                            const int* cp = (C > 1 && cstar != rank) ? cluster.map_shared_rank(cnt, cstar) : cnt;
-                            const int cv = cp[t % 3];
-                            const int pcs = max(0, min(P, N - cstar * P));
-                            av = cstar * P + cv;
-                            kk = cstar * P + min(cv, pcs - 1);
-                        }
+                        int cv = 0;
+                        for (int c = 0; c < C; ++c) cv += ((c == rank) ? cnt : cluster.map_shared_rank(cnt, c))[t % 3];
+                        av = cv;                                   // may be N (cumsum never reached u_anc): the gather clamps
+                        kk = min(cv, N - 1);
                     }
                     anc[u] = av;
                     logw[u] = ll[u] - lauxf[kk];
                 }
             }
             int* anc_row = a.anc_trace + ((size_t)chain * a.anc_rows + (t - 1 - a.row_off + a.anc_shift)) * N + base + il0;
-            if (nvalid == PPT && ((N & 3) == 0) && ((P & 3) == 0) && PPT == 4) {
-                *reinterpret_cast<int4*>(anc_row) = make_int4(anc[0], anc[1], anc[2], anc[3]);
+            if (nvalid == PPT && ((N & 3) == 0) && ((P & 3) == 0) && PPT % 4 == 0) {
+#pragma unroll
+                for (int u = 0; u < PPT; u += 4) *reinterpret_cast<int4*>(anc_row + u) = make_int4(anc[u], anc[u + 1], anc[u + 2], anc[u + 3]);
             } else {
 #pragma unroll
                 for (int u = 0; u < PPT; ++u)
@@ -280,6 +273,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) csmc_weights_kernel(const __gri
                     if (u < nvalid) a.logw_last[(size_t)chain * N + base + il0 + u] = logw[u];
             }
         }
+        WK_TICK(6);
         // no barrier here: the next step's phase A touches registers and `unit` only (its last readers passed the
         // barrier above); b1f / lauxf are rewritten after the next X1 cluster barrier, when every CTA has left B2
     }
@@ -288,7 +282,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) csmc_weights_kernel(const __gri
 
 static size_t weights_smem_bytes(int N) {
     const size_t nblkN = ((size_t)N + 255) / 256;
-    return (nblkN * 256 + 8 + (((size_t)N + 1) & ~(size_t)1) + (WK_NT / 32) * 4 + WK_MAXC * 4 + 4) * sizeof(double) + 4 * sizeof(int) + 16;
+    return (nblkN * 256 + 8 + (((size_t)N + 1) & ~(size_t)1) + WK_MAXC * (WK_NT / 32) * 4 + 4) * sizeof(double) + 4 * sizeof(int) + 16;
 }
 
 // cluster size of the dedicated kernel for N particles (0: not applicable -> csmc_sweep_kernel<PRE>)

@@ -114,6 +114,7 @@ def test_step_parity_quirk_flags(built_lib, flags):
 @pytest.mark.parametrize("kind,N,T,cluster", [
     ("smo", 200, 60, 1), ("smo", 512, 40, 4), ("smo", 4096, 12, 16), ("emps", 200, 50, 1), ("toy", 200, 40, 2),
     ("vehicle", 256, 40, 1), ("smo", 200, 60, 0),
+    ("smo", 4096, 12, 0), ("smo", 2501, 16, 0), ("vehicle", 6000, 8, 0),     # split form with the dedicated resampling kernel: clusters of 2 / 2 / 4
 ])
 def test_sweep_parity_injected(built_lib, kind, N, T, cluster):
     p = helpers.make_problem(kind, T=T, N=N, seed=T)
@@ -265,13 +266,19 @@ def test_pgas_reference_call_signature(built_lib):
     assert tr.shape == (14, 2) and np.all(np.isfinite(tr))
 
 
-@pytest.mark.parametrize("kind,N,T,chains,cluster", [("smo", 300, 40, 3, 0), ("vehicle", 700, 50, 2, 2), ("smo", 1100, 150, 2, 4)])
-def test_split_and_fused_sweeps_agree(built_lib, kind, N, T, chains, cluster):
+@pytest.mark.parametrize("kind,N,T,chains,cluster,dedicated", [
+    ("smo", 300, 40, 3, 0, 1), ("vehicle", 700, 50, 2, 2, 1), ("smo", 1100, 150, 2, 4, 1),
+    ("smo", 4096, 70, 2, 0, 1),          # dedicated resampling kernel, cluster of 2 (the bench shape)
+    ("smo", 5001, 20, 1, 0, 1),          # cluster of 4, ragged last CTA, odd N (scalar loads / stores)
+    ("vehicle", 8192, 12, 1, 0, 1),      # cluster of 4, full
+    ("smo", 300, 40, 3, 0, 0), ("smo", 4096, 70, 2, 0, 0)])   # general resampling kernel (csmc_sweep_kernel<PRE>)
+def test_split_and_fused_sweeps_agree(built_lib, kind, N, T, chains, cluster, dedicated, monkeypatch):
     """The split form (state kernel ahead of the resampling kernel, csrc/sweep.cu) and the fused kernel are two schedules
     of the same arithmetic: identical ancestors and traces, for particle counts that are not multiples of the tile sizes,
     several chains, chunk boundaries (T > 64 + 1) and both observation dimensions."""
     import os
     import torch
+    monkeypatch.setenv("PGAS_WEIGHTS_KERNEL", str(dedicated))
     p = helpers.make_problem(kind, T=T, N=N, seed=5)
     cs = helpers.product_csmc(p, cluster)
     dev = lambda x: torch.as_tensor(np.ascontiguousarray(x)).cuda()

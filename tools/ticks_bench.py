@@ -33,11 +33,10 @@ print("ms per iteration", e0.elapsed_time(e1) / n_it)
 lib.pgas_debug_set_split_ticks(None)
 d = dbg.cpu().numpy().reshape(64, 2, 8)
 rows = int((d[:, 0, 0] > 0).sum()); d = d[:rows]
-names = ["A loads+softmax4", "wait sync1", "X1 fold/cluster/fold", "wait sync2", "B1 cdf+count+sync", "B2 resample"]
+names = ["A loads+softmax", "sync1", "X1 folds + cluster barrier", "B1 cdf -> cluster", "barrier 2", "B2 + C"]
 for th in (0, 1):
     seg = np.diff(d[2:, th, :7], axis=1)
     print("cluster rank", th, "cycles/step", np.median(np.diff(d[2:, th, 0])))
     for k, n in enumerate(names):
-        print(f"   {n:22s} {np.median(seg[:, k]):8.0f}")
-    print(f"   {'X2 cluster barrier':22s} {np.median(d[2:, th, 7] - d[2:, th, 6]):8.0f}")
-    print(f"   {'C + loop back':22s} {np.median(d[3:, th, 0] - d[2:-1, th, 7]):8.0f}")
+        print(f"   {n:28s} {np.median(seg[:, k]):8.0f}")
+    print(f"   {'loop back':28s} {np.median(d[3:, th, 0] - d[2:-1, th, 6]):8.0f}")
