@@ -1135,6 +1135,12 @@ extern "C" int pgas_debug_state_kernel_f64(const pgas_model* model, int32_t N, i
     const size_t buf = (size_t)rows * n_chains * N;
     double* pre = (double*)base;
     double* x_carry = pre + 2 * 3 * buf;
+    // the same chain groups on the same low-priority streams as pgas_launch_sweep
+    if (split_streams_init()) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ngroups = (n_chains >= 2 * SPLIT_GROUPS && !getenv("PGAS_SPLIT_ONE_GROUP")) ? SPLIT_GROUPS : 1;
+    PGAS_CUDA(cudaEventRecord(g_split.start, st));
+    for (int g = 0; g < ngroups; ++g) PGAS_CUDA(cudaStreamWaitEvent(g_split.auxg[g], g_split.start, 0));
     int c = 0;
     for (int t0 = a.t_begin; t0 < a.t_end; t0 += rows, ++c) {
         const int t1 = std::min(t0 + rows, a.t_end);
@@ -1146,9 +1152,16 @@ extern "C" int pgas_debug_state_kernel_f64(const pgas_model* model, int32_t N, i
             q.t0 = ts; q.t1 = std::min(ts + 16, t1); q.rows = rows;
             q.la = la + (size_t)(ts - t0) * N; q.lr = la + buf + (size_t)(ts - t0) * N; q.ll = la + 2 * buf + (size_t)(ts - t0) * N;
             q.first = (c == 0 && ts == t0); q.bpc = (N + 2 * ST_NT - 1) / (2 * ST_NT);
-            q.chain0 = 0; q.nch = n_chains;
-            if (int rc = launch_state(q, (cudaStream_t)stream)) return rc;
+            for (int g = 0; g < ngroups; ++g) {
+                q.chain0 = (int)((long long)n_chains * g / ngroups);
+                q.nch = (int)((long long)n_chains * (g + 1) / ngroups) - q.chain0;
+                if (int rc = launch_state(q, g_split.auxg[g])) return rc;
+            }
         }
+    }
+    for (int g = 0; g < ngroups; ++g) {
+        PGAS_CUDA(cudaEventRecord(g_split.k1[0][g], g_split.auxg[g]));
+        PGAS_CUDA(cudaStreamWaitEvent(st, g_split.k1[0][g], 0));
     }
     return 0;
 }

@@ -30,7 +30,7 @@ PKG = "bayesian_inference_with_explicit_and_implicit_prior_knowledge_b200"
 
 N_PART, T_STEPS, M_BASIS, CHAINS_TOTAL = 4096, 2000, 256, 64
 FLOP_PER_PSTEP = 2 * M_BASIS * 2 + M_BASIS * 2          # 2 M n_x + M D  (SURVEY.md 8d), n_x = D = 2
-NCU_DRAM_BYTES_PER_PSTEP = (0.355072e6 + 118.637824e6) / (64 * 4096 * 16)     # profiles/r01_state_kernel_raw.csv (one 16-step launch)
+NCU_DRAM_BYTES_PER_PSTEP = (0.267264e6 + 32.3328e6) / (32 * 4096 * 16)        # profiles/r01_state_kernel_raw.csv (one 16-step launch of one chain group)
 STATE_BYTES_PER_PSTEP = 8 * 2 + 3 * 8                   # trace row (n_x doubles) + the three log-densities handed to the resampling kernel
 SEED = 12345678                                          # the reference's seed (src/SingleMassOscillator.py:82)
 
@@ -390,15 +390,15 @@ def run_gpu_arm(args):
                        f"{count * T * N * 20 / 1e9:.1f} GB on rank 0) exceeds the 126 MB L2", "rng": "Philox-4x32-10 in-kernel"},
             "sweeps_per_s": args.chains * args.steps / (ms * 1e-3),
             "roofline": {"bound": "tensor", "kernel": "csmc_state_kernel (FP64 FMA row walk; timed alone over all T-1 steps, "
-                         f"{(T - 1 + 15) // 16} launches of <= 16 steps)", "achieved": achieved, "peak": peak,
+                         f"{(T - 1 + 15) // 16} launches of <= 16 steps per chain group, two chain groups on two streams exactly as inside the sweep)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_PSTEP * count * N * (T - 1),
                          "traffic_note": "dram__bytes_read+write of this kernel from the ncu --set full capture in profiles/r01_state_kernel_summary.md "
-                                         f"(28.4 B per particle-step measured on one 16-step launch, scaled to all launches; algorithmic {STATE_BYTES_PER_PSTEP} B: "
-                                         "part of the log-density rows is still in L2 when the capture ends)",
+                                         f"({NCU_DRAM_BYTES_PER_PSTEP:.1f} B per particle-step measured on one 16-step launch, scaled to all launches; algorithmic {STATE_BYTES_PER_PSTEP} B: "
+                                         "most of the rows a 16-step launch writes are still in L2 when the capture ends)",
                          "note": f"compute bound = FP64 pipe (on B200 the FP64 FMA and FP64 tensor (DMMA) pipes have the same measured rate); algorithmic flops = "
                                  f"{FLOP_PER_PSTEP} per particle-step (2 M n_x + M D) x {count * N * (T - 1)} particle-steps; peak = FP64 measured on this GPU in this "
                                  f"run (register-resident DFMA {dfma.value:.1f}, DMMA {dmma.value:.1f} TFLOP/s; MEASURED_PEAKS.json has no FP64 figure); state kernel "
-                                 f"{state_avg:.2f} ms; whole sweep (state kernel overlapped with the resampling kernel) {sweep_avg:.2f} ms",
+                                 f"{state_avg:.2f} ms; whole sweep (state kernel overlapped with the resampling kernel csmc_weights_kernel) {sweep_avg:.2f} ms",
                          "sweep_ms": sweep_avg, "sweep_achieved": achieved_sweep, "sweep_frac": achieved_sweep / peak,
                          "hbm_achieved_gbs": hbm_bytes / (state_avg * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
                          "hbm_frac": hbm_bytes / (state_avg * 1e-3) / 1e9 / hbm_peak},
