@@ -70,19 +70,39 @@ __global__ void __launch_bounds__(BT) pick_and_trace_kernel(const double* __rest
         s_idx = idx;
     }
     __syncthreads();
-    // backward walk (dependent loads; the trajectory rows themselves are fetched by all lanes of warp 0)
+    // backward walk: T - 1 DEPENDENT loads a_{t-1} = anc[t-1][a_t], each an HBM miss (~1 us) when walked alone.  Warp 0
+    // walks; the other warps run ahead of it and pull whole ancestor rows (N ints) towards the walker — rows t-L2W..
+    // into L2, rows t-L1W.. into this SM's L1 — so that the dependent load is an L1 / L2 hit.  The trajectory rows
+    // themselves are not on the dependent chain (fetched by the lanes of warp 0 once a_t is known).
+    constexpr int L1W = 8, L2W = 96;                       // look-ahead in rows (L1: 8 x 16 KB at N = 4096)
+    __shared__ volatile int s_t;
+    if (tid == 0) s_t = T - 1;
+    __syncthreads();
+    const int* an = anc_trace + (size_t)chain * (T - 1) * N;
     if (warp == 0) {
         const double* st = state_trace + (size_t)chain * T * N * n;
-        const int* an = anc_trace + (size_t)chain * (T - 1) * N;
         double* tr = traj_out + (size_t)chain * traj_stride;
         int a = min(max(s_idx, 0), N - 1);
         for (int t = T - 1; t >= 0; --t) {
             if (lane < n) tr[(size_t)t * n + lane] = st[((size_t)t * N + a) * n + lane];
             if (t > 0) {
                 int nx = 0;
-                if (lane == 0) nx = an[(size_t)(t - 1) * N + a];
+                if (lane == 0) { nx = an[(size_t)(t - 1) * N + a]; s_t = t - 1; }
                 nx = __shfl_sync(0xffffffffu, nx, 0);
                 a = min(max(nx, 0), N - 1);
+            }
+        }
+    } else {
+        const int lines = (N + 31) / 32;                   // 128-byte lines per ancestor row
+        const bool near = warp < 4;                        // warps 1-3: L1 window, warps 4-7: L2 window
+        const int nth = near ? 96 : BT - 128, me = near ? tid - 32 : tid - 128, win = near ? L1W : L2W;
+        for (int r = T - 2; r >= 0; --r) {
+            while (r < s_t - win) __nanosleep(64);         // stay `win` rows ahead of the walker, not more
+            if (r >= s_t) continue;                        // the walker is already past this row
+            const int* row = an + (size_t)r * N;
+            for (int l = me; l < lines; l += nth) {
+                if (near) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + l * 32));
+                else asm volatile("prefetch.global.L2 [%0];" ::"l"(row + l * 32));
             }
         }
     }
