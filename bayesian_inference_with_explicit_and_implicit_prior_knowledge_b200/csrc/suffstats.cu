@@ -36,8 +36,11 @@ __global__ void __launch_bounds__(SNT) suffstats_kernel(const __grid_constant__ 
     const double* traj = a.traj + (size_t)chain * a.traj_stride;
 
     extern __shared__ __align__(16) double sm[];
-    double* tab = sm;                                   // [D][npos][TK]
-    double* phiI = tab + (size_t)D * npos * TK;         // [TK][ST]
+    // sine table [D][TK][npos | 1]: position fastest, odd row length — the basis products below read it with one bank per
+    // lattice position (lanes of a warp share the time step and differ in the position), the table writes stride an odd length
+    const int nposp = npos | 1;
+    double* tab = sm;
+    double* phiI = tab + (size_t)D * nposp * TK;        // [TK][ST]
     double* phiJ = phiI + TK * ST;                      // [TK][ST]
     double* ych = phiJ + TK * ST;                       // [TK][PGAS_MAX_NX]
     int* posI = reinterpret_cast<int*>(ych + TK * PGAS_MAX_NX);   // [ST][D]
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(SNT) suffstats_kernel(const __grid_constant__ 
         // 1. sine tables of the chunk: thread (tt, d)
         if (tid < TK * D) {
             const int tt = tid % TK, d = tid / TK, t = t0 + tt;
-            double* tb = tab + ((size_t)d * npos) * TK + tt;
+            double* tb = tab + ((size_t)d * TK + tt) * nposp;
             if (t < nsteps) {
                 double x[PGAS_MAX_NX], u[PGAS_MAX_NU], z = 0.0;
                 for (int k = 0; k < nx; ++k) x[k] = traj[(size_t)t * nx + k];
@@ -80,12 +83,12 @@ __global__ void __launch_bounds__(SNT) suffstats_kernel(const __grid_constant__ 
                 double cur, prev, twoc;
                 sine_seed(tn, m.f_start, m.f_step, cur, prev, twoc);
                 for (int p = 0; p < npos; ++p) {
-                    tb[(size_t)p * TK] = cur;
+                    tb[p] = cur;
                     const double n = fma(twoc, cur, -prev);
                     prev = cur; cur = n;
                 }
             } else {
-                for (int p = 0; p < npos; ++p) tb[(size_t)p * TK] = 0.0;
+                for (int p = 0; p < npos; ++p) tb[p] = 0.0;
             }
         }
         if (tid >= SNT - TK) {                      // Y rows of the chunk
@@ -99,8 +102,8 @@ __global__ void __launch_bounds__(SNT) suffstats_kernel(const __grid_constant__ 
             double vi = m.norm, vj = m.norm;
             for (int d = 0; d < D; ++d) {
                 const int pi = posI[mi * PGAS_MAX_D + d], pj = posJ[mi * PGAS_MAX_D + d];
-                vi = (pi >= 0) ? vi * tab[((size_t)d * npos + pi) * TK + tt] : 0.0;
-                vj = (pj >= 0) ? vj * tab[((size_t)d * npos + pj) * TK + tt] : 0.0;
+                vi = (pi >= 0) ? vi * tab[((size_t)d * TK + tt) * nposp + pi] : 0.0;
+                vj = (pj >= 0) ? vj * tab[((size_t)d * TK + tt) * nposp + pj] : 0.0;
             }
             phiI[tt * ST + mi] = vi;
             phiJ[tt * ST + mi] = vj;
@@ -167,7 +170,7 @@ int pgas_launch_suffstats(const DevModel& m, const double* traj, long long traj_
     a.traj = traj; a.traj_stride = traj_stride; a.T0 = T0; a.T1 = T1; a.T2 = T2;
     if (npos > MAXPOS) PGAS_FAIL(-20, "basis uses %d lattice positions per dimension; this build supports <= %d", npos, MAXPOS);
     if (ST * m.n_x > SNT - 16) PGAS_FAIL(-20, "n_x too large for the statistics kernel");
-    const size_t smem = sizeof(double) * ((size_t)m.D * npos * TK + 2 * TK * ST + TK * PGAS_MAX_NX) + sizeof(int) * 2 * ST * PGAS_MAX_D;
+    const size_t smem = sizeof(double) * ((size_t)m.D * (npos | 1) * TK + 2 * TK * ST + TK * PGAS_MAX_NX) + sizeof(int) * 2 * ST * PGAS_MAX_D;
     auto kern = suffstats_kernel;
     PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(a.ntile * (a.ntile + 1) / 2), (unsigned)n_chains, 1);

@@ -73,18 +73,18 @@ __global__ void __launch_bounds__(BT) pick_and_trace_kernel(const double* __rest
     // backward walk: T - 1 DEPENDENT loads a_{t-1} = anc[t-1][a_t], each an HBM miss (~1 us) when walked alone.  Warp 0
     // walks; the other warps run ahead of it and pull whole ancestor rows (N ints) towards the walker — rows t-L2W..
     // into L2, rows t-L1W.. into this SM's L1 — so that the dependent load is an L1 / L2 hit.  The trajectory rows
-    // themselves are not on the dependent chain (fetched by the lanes of warp 0 once a_t is known).
+    // themselves are not on the dependent chain: the walker only records the path a_t; all threads gather the rows afterwards
+    // (a load-then-store inside the walk would stall every hop on an HBM miss).
     constexpr int L1W = 8, L2W = 96;                       // look-ahead in rows (L1: 8 x 16 KB at N = 4096)
     __shared__ volatile int s_t;
     if (tid == 0) s_t = T - 1;
     __syncthreads();
     const int* an = anc_trace + (size_t)chain * (T - 1) * N;
+    extern __shared__ int s_path[];                        // a_t for all t: the state rows are gathered afterwards by all threads
     if (warp == 0) {
-        const double* st = state_trace + (size_t)chain * T * N * n;
-        double* tr = traj_out + (size_t)chain * traj_stride;
         int a = min(max(s_idx, 0), N - 1);
         for (int t = T - 1; t >= 0; --t) {
-            if (lane < n) tr[(size_t)t * n + lane] = st[((size_t)t * N + a) * n + lane];
+            if (lane == 0) s_path[t] = a;
             if (t > 0) {
                 int nx = 0;
                 if (lane == 0) { nx = an[(size_t)(t - 1) * N + a]; s_t = t - 1; }
@@ -105,6 +105,14 @@ __global__ void __launch_bounds__(BT) pick_and_trace_kernel(const double* __rest
                 else asm volatile("prefetch.global.L2 [%0];" ::"l"(row + l * 32));
             }
         }
+    }
+    __syncthreads();
+    // the trajectory rows are independent loads once the path is known (src/Filtering.py:46-53)
+    const double* st = state_trace + (size_t)chain * T * N * n;
+    double* tr = traj_out + (size_t)chain * traj_stride;
+    for (int e = tid; e < T * n; e += BT) {
+        const int t = e / n, k = e - t * n;
+        tr[e] = st[((size_t)t * N + s_path[t]) * n + k];
     }
 }
 
@@ -227,7 +235,9 @@ __global__ void philox_variates_kernel(unsigned long long seed, unsigned chain_b
 int pgas_launch_pick_and_trace(const double* logw_last, const double* state_trace, const int* anc_trace, const int* idx_in,
                                int n_sets, int T, int N, int n, const pgas_rng* rng, int var_rows, int* final_idx, double* traj_out,
                                long long traj_stride, cudaStream_t st) {
-    pick_and_trace_kernel<<<n_sets, BT, 0, st>>>(logw_last, state_trace, anc_trace, idx_in, T, N, n, rng ? rng->mode : 1,
+    if ((size_t)T * sizeof(int) > 200 * 1024) PGAS_FAIL(-20, "trajectory of %d steps is too long for the backward-trace kernel", T);
+    PGAS_CUDA(cudaFuncSetAttribute(pick_and_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T * sizeof(int))));
+    pick_and_trace_kernel<<<n_sets, BT, (size_t)T * sizeof(int), st>>>(logw_last, state_trace, anc_trace, idx_in, T, N, n, rng ? rng->mode : 1,
                                                  rng ? rng->seed : 0ull, rng ? rng->chain_base : 0u, rng ? rng->iteration : 0u,
                                                  rng ? rng->U : nullptr, var_rows, final_idx, traj_out, traj_stride);
     PGAS_KERNEL_CHECK();
