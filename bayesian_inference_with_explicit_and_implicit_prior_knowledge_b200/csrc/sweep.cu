@@ -991,11 +991,14 @@ bool pgas_sweep_split_eligible(const SweepArgs& a) {
 static long long* g_dbg_split_ticks = nullptr;     // developer aid (tools/ticks_split.py): phase clocks of the resampling kernel
 extern "C" int pgas_debug_set_split_ticks(long long* dev_buf) { g_dbg_split_ticks = dev_buf; return 0; }
 
-constexpr int SPLIT_GROUPS = 2;      // chain groups of the state kernel: each on its own stream, so that a group's next
+#ifndef PGAS_SPLIT_GROUPS
+#define PGAS_SPLIT_GROUPS 2
+#endif
+constexpr int SPLIT_GROUPS = PGAS_SPLIT_GROUPS;      // chain groups of the state kernel: each on its own stream, so that a group's next
                                      // launch starts as soon as ITS CTAs retire (no wave-quantisation tail across all chains)
 struct SplitStreams {
-    cudaStream_t aux = nullptr, auxg[SPLIT_GROUPS] = {nullptr, nullptr};
-    cudaEvent_t start = nullptr, k1[2][SPLIT_GROUPS] = {{nullptr, nullptr}, {nullptr, nullptr}}, k2[2] = {nullptr, nullptr};
+    cudaStream_t aux = nullptr, auxg[SPLIT_GROUPS] = {};
+    cudaEvent_t start = nullptr, k1[2][SPLIT_GROUPS] = {}, k2[2] = {nullptr, nullptr};
     int device = -1;
 };
 static thread_local SplitStreams g_split;

@@ -165,8 +165,8 @@ __global__ void __launch_bounds__(NT, 2) csmc_weights_kernel(const __grid_consta
             const int U = C * NW, mine = rank * NW + warp;
             double m1g = -INFINITY, m2g = -INFINITY;
             for (int u = lane; u < U; u += 32) { m1g = fmax(m1g, unit[u * 4]); m2g = fmax(m2g, unit[u * 4 + 2]); }
-            m1g = warp_max(m1g);
-            m2g = warp_max(m2g);
+            m1g = warp_shift_max(m1g);                             // a shift, not the exact maximum: one 32-bit redux each
+            m2g = warp_shift_max(m2g);
             double c1 = 0.0, c2 = 0.0;
             for (int u0 = 0; u0 < U; u0 += 32) {
                 const int u = u0 + lane;
