@@ -332,3 +332,49 @@ def test_split_and_fused_sweeps_agree_at_config5_shape(built_lib):
     assert torch.equal(a["anc_trace"], b["anc_trace"]) and torch.equal(a["idx"], b["idx"])
     assert torch.allclose(a["state_trace"], b["state_trace"], rtol=1e-12, atol=1e-300)
     assert bool(torch.isfinite(a["traj"]).all())
+
+
+@pytest.mark.parametrize("kind,N,T,M,chains", [("smo", 4096, 2000, 256, 2), ("vehicle", 16384, 5000, 1024, 1)])
+def test_full_size_sweep_properties_and_teacher_forced_steps(built_lib, kind, N, T, M, chains):
+    """BASELINE.json configs[3] (N = 4096 particles, T = 2000 steps, M = 256 basis functions) and configs[4] (N = 16384,
+    T = 5000, M = 1024, two observations, slip-angle GP inputs) at FULL size, Philox mode.
+    The oracle's Python loops cannot run 2000 steps of 4096 particles in test time, so the sweep is checked through
+    (a) size-independent properties — ancestors sorted and in range, conditioned particle pinned to the reference,
+    the returned trajectory equals reconstruct_trajectory of the traces — and (b) TEACHER-FORCED oracle steps at
+    sampled depths: the log-weights entering step t are rebuilt from the GPU traces with the oracle's formulas
+    (logw_{t-1} = log p(y_{t-1}|x_{t-1}) - l_aux_{t-1}[a_{t-2}], src/PGAS.py:137-147), then ONE oracle step with the
+    restated Philox variates must reproduce the GPU's ancestors (exactly, CDF ties within 1e-12 excepted) and states
+    (1e-9 relative) at that depth."""
+    import torch
+    from oracle import filtering as OF, pgas as OP, philox as OPH
+    chain_base, it, seed = 5, 3, 0x5EEDBA5E
+    p = helpers.make_problem(kind, T=T, N=N, M=M, seed=12)
+    cs = helpers.product_csmc(p)
+    dev = lambda x: torch.as_tensor(np.ascontiguousarray(x)).cuda()
+    ref, Th, Sg = (dev(np.stack([p[k]] * chains)) for k in ("ref", "Theta", "Sigma"))
+    out = cs.sweep(ref, Th, Sg, key=helpers.pkg("random").key(seed), chain_base=chain_base, iteration=it)
+    st, an = out["state_trace"], out["anc_trace"]
+    assert bool(torch.isfinite(st).all())
+    # (a) properties
+    assert bool((an[:, :, :-1] >= 0).all()) and bool((an[:, :, :-1] <= N - 1).all())
+    assert bool((an[:, :, 1:-1] >= an[:, :, :-2]).all())                     # systematic resampling of sorted points
+    assert bool((an[:, :, -1] >= 0).all()) and bool((an[:, :, -1] <= N).all())   # reference ancestor: unclipped searchsorted
+    assert torch.equal(st[:, :, -1, :], ref)                                 # src/PGAS.py:134,194
+    an_h, st_h = an.cpu().numpy(), st.cpu().numpy()
+    for c in range(chains):
+        want = OF.reconstruct_trajectory(st_h[c], np.clip(an_h[c], 0, N - 1), min(int(out["idx"][c]), N - 1))
+        assert np.array_equal(out["traj"][c].cpu().numpy(), want.reshape(T, -1))
+    # (b) teacher-forced oracle steps at sampled depths
+    model, c = p["omodel"], chains - 1
+    ii = np.arange(N)
+    for t in (2, 3, 417, 1000, T - 1):
+        x2, x1 = st_h[c, t - 2], st_h[c, t - 1]
+        aux_prev = model.basis(x2, model.inputs[t - 1]) @ p["Theta"].T       # mu(x_{t-2}) (src/PGAS.py:45-57)
+        la_prev = model.loglik(model.observations[t - 1], aux_prev, model.inputs[t - 1])
+        a_prev = np.clip(an_h[c, t - 2], 0, N - 1)
+        logw = model.loglik(model.observations[t - 1], x1, model.inputs[t - 1]) - la_prev[a_prev]
+        za, zb = OPH.normal2(seed, OPH.PURPOSE_STATE, chain_base + c, it, np.full(N, t), ii)
+        ua, ub = OPH.uniform2(seed, OPH.PURPOSE_STEP_U, chain_base + c, it, np.array([t]), 0)
+        o = OP.csmc_step(model, t, logw, x1, p["Theta"], p["Sigma"], p["ref"][t], float(ua[0]), float(ub[0]), np.stack([za, zb], axis=1))
+        r = helpers.compare_step(p, o, (o[0], st_h[c, t], an_h[c, t - 1]), float(ua[0]), float(ub[0]))   # log-weights are not traced
+        assert r["ok"], (t, r)
