@@ -107,3 +107,36 @@ def mniw_posterior_draw(eta0, eta1, eta2, eta3, rng, flags=0):
                                              C.byref(rng), int(flags), _lib.ptr(A), _lib.ptr(S), _lib.ptr(status),
                                              _lib.ptr(ws), nbytes, _lib.stream_ptr()))
     return A, S, status
+
+
+def posterior_predictive_batch(eta0, eta1, eta2, eta3, basis=None):
+    """Batched post-processing of traced statistics on the GPU: `jax.vmap(prior_mniw_2naturalPara_inv)`
+    over K statistics sets followed by `prior_mniw_Predictive` on a grid, as the reference's figure scripts do
+    (SingleMassOscillator_Figures.py:58-89, :131-140).  eta0 (K,M,n), eta1 (K,M,M), eta2 (K,n,n), eta3 (K,): natural parameters
+    INCLUDING the prior (array-likes or CUDA tensors); basis (G,M) or None.
+    Returns a dict of CUDA tensors: mean (K,n,M), row_scale (K,n,n), df (K,), status (K,) and, with a grid, pred_mean (K,G,n),
+    pred_col_scale (K,G) = diag(col_scale) of prior_mniw_Predictive, pred_row_scale (K,n,n), pred_df (K,)."""
+    torch = _lib.require_cuda()
+    f64 = dict(dtype=torch.float64, device="cuda")
+    eta0, eta1, eta2 = (torch.as_tensor(np.asarray(t) if not torch.is_tensor(t) else t, **f64).contiguous() for t in (eta0, eta1, eta2))
+    K, M, n = eta0.shape
+    eta3 = torch.as_tensor(np.broadcast_to(np.asarray(eta3.cpu() if torch.is_tensor(eta3) else eta3, dtype=np.float64), (K,)).copy(), **f64)
+    G = 0
+    if basis is not None:
+        basis = torch.as_tensor(np.asarray(basis) if not torch.is_tensor(basis) else basis, **f64).contiguous()
+        G = basis.shape[0]
+    out = dict(mean=torch.empty((K, n, M), **f64), row_scale=torch.empty((K, n, n), **f64), df=torch.empty((K,), **f64),
+               status=torch.zeros((K,), dtype=torch.int32, device="cuda"))
+    pm = torch.empty((K, max(G, 1), n), **f64)
+    pc = torch.empty((K, max(G, 1)), **f64)
+    L = _lib.lib()
+    nbytes = L.pgas_mniw_posterior_batch_workspace_bytes(M, n, K)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device="cuda")
+    _lib.check(L.pgas_mniw_posterior_batch_f64(M, n, K, _lib.ptr(eta0), _lib.ptr(eta1), _lib.ptr(eta2), _lib.ptr(eta3),
+                                               _lib.ptr(basis) if G else None, G, _lib.ptr(out["mean"]), _lib.ptr(out["row_scale"]),
+                                               _lib.ptr(out["df"]), _lib.ptr(pm), _lib.ptr(pc), _lib.ptr(out["status"]), _lib.ptr(ws),
+                                               nbytes, _lib.stream_ptr()))
+    if G:
+        pdf = out["df"] + 1 - n
+        out.update(pred_mean=pm, pred_col_scale=pc, pred_row_scale=out["row_scale"] / pdf[:, None, None], pred_df=pdf)
+    return out

@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libpgas_b200.so")
-_SOURCES = ["model.cu", "sweep.cu", "weights.cu", "sweep_api.cu", "suffstats.cu", "mniw_draw.cu", "chains.cu",
+_SOURCES = ["model.cu", "sweep.cu", "weights.cu", "sweep_api.cu", "suffstats.cu", "mniw_draw.cu", "gp_posterior.cu", "chains.cu",
             "marginal.cu", "microbench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -164,6 +164,10 @@ EXPORTS = {
     "pgas_mniw_draw_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_int32,
                                      C.c_int32, C.POINTER(Rng), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_size_t, C.c_void_p]),
+    "pgas_mniw_posterior_batch_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "pgas_mniw_posterior_batch_f64": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "pgas_run_chains_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
     "pgas_run_chains_f64": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_double, C.c_void_p, C.POINTER(Rng), C.c_void_p,

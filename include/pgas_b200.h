@@ -169,6 +169,23 @@ int pgas_mniw_draw_f64(const double* eta0, const double* eta1, const double* eta
                        int32_t flags, double* A_out, double* S_out, int32_t* status_out,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Post-processing of the traced statistics: what the reference's figure scripts do with
+ * jax.vmap(prior_mniw_2naturalPara_inv) over K iterations (SingleMassOscillator_Figures.py:58-89;
+ * src/BayesianInferrence.py:35-45) followed by a loop of prior_mniw_Predictive on the plot grid (:131-140;
+ * src/BayesianInferrence.py:64-89), batched on the device.
+ *   eta0 (K,M,n), eta1 (K,M,M), eta2 (K,n,n), eta3 (K) device: natural parameters INCLUDING the prior;
+ *   basis (G,M) device: basis functions on the grid (pgas_hgp_eval_f64); G may be 0
+ *   -> mean_out (K,n,M), row_scale_out (K,n,n) = eta2 - mean eta0, df_out (K) = eta3      [2naturalPara_inv]
+ *      pred_mean_out (K,G,n) = basis mean^T, pred_colscale_out (K,G) = diag(basis V basis^T + I)   [Predictive]
+ *   (the predictive row scale / df are row_scale_out / (df_out + 1 - n) and df_out + 1 - n; the full col_cov (M,M) and
+ *   col_scale (G,G) of the reference are not formed).  status_out (K): 0 ok, j>0 = eta1 not positive definite at pivot j. */
+size_t pgas_mniw_posterior_batch_workspace_bytes(int32_t M, int32_t n, int32_t K);
+int pgas_mniw_posterior_batch_f64(int32_t M, int32_t n, int32_t K, const double* eta0, const double* eta1,
+                                  const double* eta2, const double* eta3, const double* basis, int32_t G,
+                                  double* mean_out, double* row_scale_out, double* df_out,
+                                  double* pred_mean_out, double* pred_colscale_out, int32_t* status_out,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* PGAS.__call__ (src/PGAS.py:345-397) for n_chains independent chains, entirely on the device:
  * K iterations of (sweep -> pick -> backward trace -> sufficient statistics -> MNIW draw).
  *   prior eta0 (M,n_x), eta1 (M,M), eta2 (n_x,n_x) device, eta3 host scalar (shared by chains);

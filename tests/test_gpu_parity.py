@@ -378,3 +378,29 @@ def test_full_size_sweep_properties_and_teacher_forced_steps(built_lib, kind, N,
         o = OP.csmc_step(model, t, logw, x1, p["Theta"], p["Sigma"], p["ref"][t], float(ua[0]), float(ub[0]), np.stack([za, zb], axis=1))
         r = helpers.compare_step(p, o, (o[0], st_h[c, t], an_h[c, t - 1]), float(ua[0]), float(ub[0]))   # log-weights are not traced
         assert r["ok"], (t, r)
+
+
+@pytest.mark.parametrize("M,n,K,G", [(41, 1, 6, 70), (64, 2, 3, 300), (9, 1, 17, 5), (256, 2, 2, 33)])
+def test_posterior_predictive_batch_matches_oracle(built_lib, M, n, K, G):
+    """vmap(prior_mniw_2naturalPara_inv) over K statistics sets + prior_mniw_Predictive on a grid
+    (src/BayesianInferrence.py:35-45, :64-89; SingleMassOscillator_Figures.py:58-89, :131-140), batched on the device."""
+    from oracle import mniw as OM
+    rng = np.random.default_rng(M + K)
+    prior = OM.prior_mniw_2naturalPara(np.zeros((n, M)), np.diag(rng.uniform(0.5, 2.0, size=M)), np.eye(n), 3)
+    e0, e1, e2, e3 = [], [], [], []
+    for k in range(K):
+        Phi, Y = rng.normal(size=(40 + 7 * k, M)), rng.normal(size=(40 + 7 * k, n))
+        e0.append(prior[0] + Phi.T @ Y); e1.append(prior[1] + Phi.T @ Phi); e2.append(prior[2] + Y.T @ Y); e3.append(prior[3] + Phi.shape[0])
+    basis = rng.normal(size=(G, M))
+    r = helpers.pkg("BayesianInferrence").posterior_predictive_batch(np.stack(e0), np.stack(e1), np.stack(e2), np.array(e3, dtype=float), basis)
+    assert int(r["status"].abs().sum()) == 0
+    for k in range(K):
+        mean, col_cov, row_scale, df = OM.prior_mniw_2naturalPara_inv(e0[k], e1[k], e2[k], e3[k])
+        assert helpers.rel_err(r["mean"][k].cpu().numpy(), mean) < helpers.REL_TOL
+        assert helpers.rel_err(r["row_scale"][k].cpu().numpy(), row_scale) < helpers.REL_TOL
+        assert float(r["df"][k]) == df
+        pm, pcs, prs, pdf = OM.prior_mniw_Predictive(mean, col_cov, row_scale, df, basis)
+        assert helpers.rel_err(r["pred_mean"][k].cpu().numpy().reshape(np.shape(pm)), pm) < helpers.REL_TOL
+        assert helpers.rel_err(r["pred_col_scale"][k].cpu().numpy(), np.diag(pcs)) < helpers.REL_TOL
+        assert helpers.rel_err(r["pred_row_scale"][k].cpu().numpy(), prs) < helpers.REL_TOL
+        assert float(r["pred_df"][k]) == pdf
