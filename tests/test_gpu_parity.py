@@ -268,9 +268,11 @@ def test_pgas_reference_call_signature(built_lib):
 
 @pytest.mark.parametrize("kind,N,T,chains,cluster,dedicated", [
     ("smo", 300, 40, 3, 0, 1), ("vehicle", 700, 50, 2, 2, 1), ("smo", 1100, 150, 2, 4, 1),
-    ("smo", 4096, 70, 2, 0, 1),          # dedicated resampling kernel, cluster of 2 (the bench shape)
+    ("smo", 4096, 70, 2, 0, 1),          # dedicated resampling kernel, one CTA per chain walking two slices (the bench shape)
     ("smo", 5001, 20, 1, 0, 1),          # cluster of 4, ragged last CTA, odd N (scalar loads / stores)
     ("vehicle", 8192, 12, 1, 0, 1),      # cluster of 4, full
+    ("smo", 300, 40, 3, 0, 2), ("smo", 4096, 70, 2, 0, 2), ("smo", 2500, 30, 1, 0, 2),   # cluster form forced (1 / 2 / 2 CTAs)
+    ("smo", 2049, 30, 2, 0, 1), ("vehicle", 3000, 20, 1, 0, 1),   # one CTA, two slices, ragged second slice
     ("smo", 300, 40, 3, 0, 0), ("smo", 4096, 70, 2, 0, 0)])   # general resampling kernel (csmc_sweep_kernel<PRE>)
 def test_split_and_fused_sweeps_agree(built_lib, kind, N, T, chains, cluster, dedicated, monkeypatch):
     """The split form (state kernel ahead of the resampling kernel, csrc/sweep.cu) and the fused kernel are two schedules
