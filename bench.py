@@ -398,7 +398,7 @@ def run_gpu_arm(args):
                          "note": f"compute bound = FP64 pipe (on B200 the FP64 FMA and FP64 tensor (DMMA) pipes have the same measured rate); algorithmic flops = "
                                  f"{FLOP_PER_PSTEP} per particle-step (2 M n_x + M D) x {count * N * (T - 1)} particle-steps; peak = FP64 measured on this GPU in this "
                                  f"run (register-resident DFMA {dfma.value:.1f}, DMMA {dmma.value:.1f} TFLOP/s; MEASURED_PEAKS.json has no FP64 figure); state kernel "
-                                 f"{state_avg:.2f} ms; whole sweep (state kernel overlapped with the resampling kernel csmc_weights_kernel) {sweep_avg:.2f} ms",
+                                 f"{state_avg:.2f} ms; whole sweep (state kernel overlapped with the resampling kernel csmc_weights1_kernel) {sweep_avg:.2f} ms",
                          "sweep_ms": sweep_avg, "sweep_achieved": achieved_sweep, "sweep_frac": achieved_sweep / peak,
                          "hbm_achieved_gbs": hbm_bytes / (state_avg * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
                          "hbm_frac": hbm_bytes / (state_avg * 1e-3) / 1e9 / hbm_peak},
