@@ -58,3 +58,16 @@ __device__ __forceinline__ int count_below_padded(const double* __restrict__ w, 
     return base + 16 * c1 + c2;
 }
 
+
+// the same count by a branch-free binary search (w sorted, padded with +inf up to n_pad entries): ~13 dependent probes
+// instead of 48 independent ones — a third of the instructions and of the shared-memory traffic.  The resampling kernels of
+// the split sweep share their SMs with the FP64-bound state kernel, where issue slots, not latency, are what a search costs.
+__device__ __forceinline__ int count_below_binary(const double* __restrict__ w, int n_pad, double x) {
+    int base = 0, len = n_pad;
+    while (len > 1) {
+        const int half = len >> 1;
+        base = (w[base + half - 1] < x) ? base + half : base;
+        len -= half;
+    }
+    return base + ((w[base] < x) ? 1 : 0);
+}

@@ -241,11 +241,11 @@ __global__ void __launch_bounds__(NT, 2) csmc_weights_kernel(const __grid_consta
                     const int j = base + il0 + u;
                     const double uj = strat_point(ures, j, dN, rN);
                     if (u == 0) {
-                        k = count_below_padded(b1f, nblkN, uj);
+                        k = count_below_binary(b1f, nblkN * 256, uj);
                     } else {                                       // CDF and points are sorted: walk forward from the previous answer
                         const int c4 = ((b1f[k] < uj) ? 1 : 0) + ((b1f[k + 1] < uj) ? 1 : 0) + ((b1f[k + 2] < uj) ? 1 : 0) +
                                        ((b1f[k + 3] < uj) ? 1 : 0);
-                        k = (c4 == 4) ? count_below_padded(b1f, nblkN, uj) : k + c4;
+                        k = (c4 == 4) ? count_below_binary(b1f, nblkN * 256, uj) : k + c4;
                     }
                     int kk = min(k, N - 1), av = kk;
                     if (j == N - 1) {                              // overwritten by the reference ancestor (:127)
@@ -463,11 +463,11 @@ __global__ void __launch_bounds__(NT, 2) csmc_weights1_kernel(const __grid_const
                         const int j = h * P + il0 + u;
                         const double uj = strat_point(ures, j, dN, rN);
                         if (u == 0) {
-                            k = count_below_padded(b1f, nblkN, uj);
+                            k = count_below_binary(b1f, nblkN * 256, uj);
                         } else {
                             const int c4 = ((b1f[k] < uj) ? 1 : 0) + ((b1f[k + 1] < uj) ? 1 : 0) + ((b1f[k + 2] < uj) ? 1 : 0) +
                                            ((b1f[k + 3] < uj) ? 1 : 0);
-                            k = (c4 == 4) ? count_below_padded(b1f, nblkN, uj) : k + c4;
+                            k = (c4 == 4) ? count_below_binary(b1f, nblkN * 256, uj) : k + c4;
                         }
                         int kk = min(k, N - 1), av = kk;
                         if (j == N - 1) {                          // overwritten by the reference ancestor (src/PGAS.py:127)
