@@ -24,7 +24,7 @@ names = ["A (DMMA+softmax)", "wait sync1", "X1 fold (warp0)", "wait sync2", "B1 
 for th in (0, 1):
     seg = np.diff(d[5:, th, :], axis=1)                    # phases within a step
     nxt = d[6:, th, 0] - d[5:-1, th, 7]
-    print("thread", [0, 64][th], "cycles/step", np.median(d[6:, th, 0] - d[5:-1, th, 0]))
+    print("CTA", th, "(thread 96) cycles/step", np.median(d[6:, th, 0] - d[5:-1, th, 0]))
     for k, n in enumerate(names):
         print(f"   {n:20s} {np.median(seg[:, k]):8.0f}")
     print(f"   {'loop back':20s} {np.median(nxt):8.0f}")

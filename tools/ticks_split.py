@@ -23,7 +23,7 @@ d = d[:rows]
 names = ["A loads+softmax4", "wait sync1", "X1 fold/cluster/fold", "wait sync2", "B1 cdf+count+sync", "B2 resample", "X2+C"]
 for th in (0, 1):
     seg = np.diff(d[2:, th, :7], axis=1)
-    print("thread", [0, 64][th], "cycles/step", np.median(np.diff(d[2:, th, 0])))
+    print("CTA", th, "(thread 96) cycles/step", np.median(np.diff(d[2:, th, 0])))
     for k, n in enumerate(names[:6]):
         print(f"   {n:22s} {np.median(seg[:, k]):8.0f}")
     print(f"   {'X2 cluster barrier':22s} {np.median(d[2:, th, 7] - d[2:, th, 6]):8.0f}")
