@@ -1,5 +1,7 @@
-"""phase clocks of the resampling kernel of the split sweep (developer aid): python tools/ticks_split.py kind N T M chains"""
+"""phase clocks of the GENERAL resampling kernel csmc_sweep_kernel<PRE> of the split sweep (developer aid; the dedicated kernels are
+clocked by tools/ticks_bench.py): python tools/ticks_split.py kind N T M chains"""
 import ctypes as C, sys, os
+os.environ["PGAS_WEIGHTS_KERNEL"] = "0"
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
