@@ -15,11 +15,15 @@
 #pragma once
 #include "basis_eval.cuh"
 
+#ifndef PGAS_RW_UNROLL
+#define PGAS_RW_UNROLL 2        // positions per loop body of the row walk (compile-time knob)
+#endif
 // n last-dimension positions at which the first R rows of the block are active: R Theta' pairs per position
 template <int NX, int PP, int R>
 __device__ __forceinline__ void rw_segment(const double* __restrict__& th, int n, double (&acc)[PP][RW_RB][NX], double (&c)[PP],
                                            double (&pv)[PP], const double (&b_2c)[PP]) {
-#pragma unroll 2
+    constexpr int RW_UNROLL = PGAS_RW_UNROLL;
+#pragma unroll RW_UNROLL
     for (int j = 0; j < n; ++j) {
 #pragma unroll
         for (int i = 0; i < R; ++i) {
