@@ -814,9 +814,13 @@ struct StateArgs {
 };
 
 constexpr int ST_NT = PGAS_ST_NT;
+#ifndef PGAS_ST_PP
+#define PGAS_ST_PP 2
+#endif
+constexpr int ST_PP = PGAS_ST_PP;      // particles per thread of the state kernel (compile-time knob)
 
 template <int NX, int NY>
-__global__ void __launch_bounds__(ST_NT, 512 / ST_NT) csmc_state_kernel(const __grid_constant__ StateArgs s) {
+__global__ void __launch_bounds__(ST_NT, (512 / ST_NT) * (2 / ST_PP)) csmc_state_kernel(const __grid_constant__ StateArgs s) {
     constexpr int D = 2;
     const SweepArgs& a = s.a;
     const DevModel& m = a.m;
@@ -869,12 +873,14 @@ __global__ void __launch_bounds__(ST_NT, 512 / ST_NT) csmc_state_kernel(const __
     MapRegs<NX, D> mapr;
     mapr.init(m);
     const int f_start = m.f_start, f_step = m.f_step, nblk = m.rw_nblk;
-    const int ip[2] = {blk * 2 * ST_NT + tid, blk * 2 * ST_NT + ST_NT + tid};
-    const bool val[2] = {ip[0] < N, ip[1] < N};
-    double x[2][NX];
+    int ip[ST_PP];
+    bool val[ST_PP];
+#pragma unroll
+    for (int p = 0; p < ST_PP; ++p) { ip[p] = blk * ST_PP * ST_NT + p * ST_NT + tid; val[p] = ip[p] < N; }
+    double x[ST_PP][NX];
     const double* refc = a.ref + (size_t)chain * a.ref_stride;
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < ST_PP; ++p) {
         if (s.first) {
             // x_0 ~ N(m0, P0) (src/PGAS.py:167-172), particle N-1 = reference (:194)
             double z[NX];
@@ -917,15 +923,18 @@ __global__ void __launch_bounds__(ST_NT, 512 / ST_NT) csmc_state_kernel(const __
         }
 #pragma unroll
         for (int k = 0; k < NX; ++k) ref[k] = refc[(size_t)t * NX + k];
-        double ta[D], tb[D];
-        mapr.apply(x[0], cz, u, ta);
-        mapr.apply(x[1], cz, u, tb);
-        const double t0v[2] = {ta[0], tb[0]}, t1v[2] = {ta[1], tb[1]};
-        double mu[2][NX];
-        rowwalk_mu<NX, 2>(bd, rwlen, nblk, f_start, f_step, t0v, t1v, mu);
+        double t0v[ST_PP], t1v[ST_PP];
+#pragma unroll
+        for (int p = 0; p < ST_PP; ++p) {
+            double tz[D];
+            mapr.apply(x[p], cz, u, tz);
+            t0v[p] = tz[0]; t1v[p] = tz[1];
+        }
+        double mu[ST_PP][NX];
+        rowwalk_mu<NX, ST_PP>(bd, rwlen, nblk, f_start, f_step, t0v, t1v, mu);
         const size_t prow = ((size_t)chain * s.rows + (size_t)(t - s.t0)) * N;
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
+        for (int p = 0; p < ST_PP; ++p) {
             const int i = min(ip[p], N - 1);
             const double la = gauss_loglik<NX, NY>(m, y, mu[p]);
             const double lr = gauss_logpdf_state<NX>(sw, slogc[0], ref, mu[p]);
@@ -954,7 +963,7 @@ __global__ void __launch_bounds__(ST_NT, 512 / ST_NT) csmc_state_kernel(const __
         }
     }
 #pragma unroll
-    for (int p = 0; p < 2; ++p)
+    for (int p = 0; p < ST_PP; ++p)
         if (val[p]) {
 #pragma unroll
             for (int k = 0; k < NX; ++k) s.x_carry[((size_t)chain * N + ip[p]) * NX + k] = x[p][k];
@@ -1072,7 +1081,7 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
         StateArgs s;
         s.a = a;
         s.x_carry = x_carry; s.la = la; s.lr = la + buf; s.ll = la + 2 * buf;
-        s.t0 = t0; s.t1 = t1; s.rows = rows; s.first = (c == 0); s.bpc = (a.N + 2 * ST_NT - 1) / (2 * ST_NT);
+        s.t0 = t0; s.t1 = t1; s.rows = rows; s.first = (c == 0); s.bpc = (a.N + ST_PP * ST_NT - 1) / (ST_PP * ST_NT);
         for (int g = 0; g < ngroups; ++g)
             if (c >= 2) PGAS_CUDA(cudaStreamWaitEvent(sg[g], g_split.k2[b], 0));   // buffer b was consumed by chunk c-2
         {   // short-lived state CTAs (sub-chunks) so that resampling CTAs find free slots quickly
@@ -1154,7 +1163,7 @@ extern "C" int pgas_debug_state_kernel_f64(const pgas_model* model, int32_t N, i
             q.x_carry = x_carry;
             q.t0 = ts; q.t1 = std::min(ts + 16, t1); q.rows = rows;
             q.la = la + (size_t)(ts - t0) * N; q.lr = la + buf + (size_t)(ts - t0) * N; q.ll = la + 2 * buf + (size_t)(ts - t0) * N;
-            q.first = (c == 0 && ts == t0); q.bpc = (N + 2 * ST_NT - 1) / (2 * ST_NT);
+            q.first = (c == 0 && ts == t0); q.bpc = (N + ST_PP * ST_NT - 1) / (ST_PP * ST_NT);
             for (int g = 0; g < ngroups; ++g) {
                 q.chain0 = (int)((long long)n_chains * g / ngroups);
                 q.nch = (int)((long long)n_chains * (g + 1) / ngroups) - q.chain0;
