@@ -217,3 +217,49 @@ extern "C" int pgas_microbench_f64(double* out5, void* stream) {
     out5[4] = 2.0 * 4.0 * MB_ITERS * 256.0 * g_sms / (ms * 1e-3) / 1e12;
     return 0;
 }
+
+// FP64 pipe concurrency probe: every warp interleaves NF independent DFMA chains with NM independent DMMA fragments.  If the FP64
+// FMA pipe and the FP64 tensor pipe were separate units, the combined rate would exceed either peak.
+template <int NF, int NM>
+__global__ void __launch_bounds__(256) dmix_kernel(double* out, int iters, double a, double b) {
+    double acc[NF > 0 ? NF : 1], c0[NM > 0 ? NM : 1], c1[NM > 0 ? NM : 1];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) acc[i] = (double)(threadIdx.x + i);
+#pragma unroll
+    for (int i = 0; i < NM; ++i) { c0[i] = 0.0; c1[i] = 0.0; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < (NF > NM ? NF : NM); ++i) {
+            if (i < NM)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+            if (i < NF) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(acc[i]) : "d"(a), "d"(b));
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) s += acc[i];
+#pragma unroll
+    for (int i = 0; i < NM; ++i) s += c0[i] + c1[i];
+    if (s == 123.456) out[0] = s;
+}
+
+// out[0..2] = TFLOP/s of (8 DFMA chains), (8 DMMA fragments), (8 + 8 interleaved); out[3] = (8 DFMA + 2 DMMA)
+extern "C" int pgas_microbench_mix_f64(double* out4, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0;
+    PGAS_CUDA(cudaGetDevice(&dev));
+    PGAS_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!g_scratch) PGAS_CUDA(cudaMalloc((void**)&g_scratch, 64 * sizeof(double)));
+    float ms;
+    const double warps = 8.0 * g_sms * 8.0, it = MB_ITERS;
+    if (int rc = time_kernel(st, &ms, [](cudaStream_t s) { dmix_kernel<8, 0><<<g_sms * 8, 256, 0, s>>>(g_scratch, MB_ITERS, 1.0000001, 1e-9); })) return rc;
+    out4[0] = 64.0 * 8 * it * warps / (ms * 1e-3) / 1e12;
+    if (int rc = time_kernel(st, &ms, [](cudaStream_t s) { dmix_kernel<0, 8><<<g_sms * 8, 256, 0, s>>>(g_scratch, MB_ITERS, 1.0000001, 1e-9); })) return rc;
+    out4[1] = 512.0 * 8 * it * warps / (ms * 1e-3) / 1e12;
+    if (int rc = time_kernel(st, &ms, [](cudaStream_t s) { dmix_kernel<8, 8><<<g_sms * 8, 256, 0, s>>>(g_scratch, MB_ITERS, 1.0000001, 1e-9); })) return rc;
+    out4[2] = (512.0 + 64.0) * 8 * it * warps / (ms * 1e-3) / 1e12;
+    if (int rc = time_kernel(st, &ms, [](cudaStream_t s) { dmix_kernel<8, 2><<<g_sms * 8, 256, 0, s>>>(g_scratch, MB_ITERS, 1.0000001, 1e-9); })) return rc;
+    out4[3] = (512.0 * 2 + 64.0 * 8) * it * warps / (ms * 1e-3) / 1e12;
+    return 0;
+}

@@ -15,6 +15,7 @@
 // One CTA per chain; the factor lives in the caller's workspace (L2-resident for M <= ~2000).
 #include "common.cuh"
 #include "sweep_args.cuh"
+#include <algorithm>
 
 constexpr int DT = 256;      // threads
 constexpr int NB = 32;       // panel width
@@ -63,6 +64,10 @@ __device__ double philox_chisquare(unsigned long long seed, unsigned chain, unsi
     }
 }
 
+// BLOCKED = false: everything in one CTA per chain (small M).  BLOCKED = true: the factorisation and the forward solves were done by
+// chol_prep_kernel / chol_panel_kernel / chol_update_kernel (multi-CTA, below) on the augmented matrix; this kernel does the
+// backward solve, Psi, the inverse-Wishart part and A.
+template <bool BLOCKED>
 __global__ void __launch_bounds__(DT) mniw_draw_kernel(const __grid_constant__ DrawArgs a) {
     const int chain = blockIdx.x, tid = threadIdx.x;
     const int M = a.M, nx = a.nx, R2 = 2 * nx;
@@ -70,7 +75,7 @@ __global__ void __launch_bounds__(DT) mniw_draw_kernel(const __grid_constant__ D
     const double* eta0 = a.eta0 + (size_t)chain * a.eta_stride0;
     const double* eta1 = a.eta1 + (size_t)chain * a.eta_stride1;
     const double* eta2 = a.eta2 + (size_t)chain * a.eta_stride2;
-    double* B = a.wsB + (size_t)chain * M * M;
+    double* B = a.wsB + (size_t)chain * (BLOCKED ? (size_t)(M + R2) * M : (size_t)M * M);
     double* F = a.wsF + (size_t)chain * M * R2;
     double* K = a.wsK + (size_t)chain * M * R2;
     double* Aout = a.A + (size_t)chain * nx * M;
@@ -82,8 +87,9 @@ __global__ void __launch_bounds__(DT) mniw_draw_kernel(const __grid_constant__ D
     __shared__ double red[DT / 32][PGAS_MAX_NX * PGAS_MAX_NX];
     __shared__ double Sc[PGAS_MAX_NX][PGAS_MAX_NX];   // S_chol
     __shared__ int s_status;
-    if (tid == 0) s_status = 0;
+    if (tid == 0) s_status = (BLOCKED && a.status) ? a.status[chain] : 0;
 
+    if constexpr (!BLOCKED) {
     // ---- 0. B = J eta1 J (lower part), right-hand sides
     for (size_t e = tid; e < (size_t)M * M; e += DT) {
         const int i = (int)(e / M), j = (int)(e % M);
@@ -220,19 +226,39 @@ __global__ void __launch_bounds__(DT) mniw_draw_kernel(const __grid_constant__ D
         }
         __syncthreads();
     }
+    } else {
+        // the forward solves came out of the augmented factorisation: F[i][c] = Baug[M + c][i]
+        for (int e = tid; e < M * R2; e += DT) {
+            const int i = e % M, c = e / M;
+            F[(size_t)i * R2 + c] = B[(size_t)(M + c) * M + i];
+        }
+        __syncthreads();
+    }
     // ---- 3. backward solve L'^T K = [y | (Nrm part when transposed)]
     const int wk = vt ? R2 : nx;
     for (int e = tid; e < M * nx; e += DT) K[(size_t)(e / nx) * R2 + e % nx] = F[(size_t)(e / nx) * R2 + e % nx];
     __syncthreads();
     for (int kb = ((M - 1) / NB) * NB; kb >= 0; kb -= NB) {
         const int nb = min(NB, M - kb);
-        if (tid < wk) {
-            for (int r = nb - 1; r >= 0; --r) {
-                double v = K[(size_t)(kb + r) * R2 + tid];
-                for (int p = r + 1; p < nb; ++p) v = fma(-B[(size_t)(kb + p) * M + kb + r], xs[p][tid], v);
-                v /= B[(size_t)(kb + r) * M + kb + r];
-                xs[r][tid] = v;
-                K[(size_t)(kb + r) * R2 + tid] = v;
+        for (int e = tid; e < NB * NB; e += DT) {
+            const int r = e / NB, c = e % NB;
+            Dg[r][c] = (r < nb && c <= r) ? B[(size_t)(kb + r) * M + kb + c] : 0.0;
+        }
+        __syncthreads();
+        {   // one warp per right-hand side: lanes split the dot product over the rows below r
+            const int lane = tid & 31, w = tid >> 5;
+            if (w < wk) {
+                for (int r = nb - 1; r >= 0; --r) {
+                    const int p = r + 1 + lane;
+                    double part = (p < nb) ? Dg[p][r] * xs[p][w] : 0.0;
+                    part = warp_sum(part);
+                    if (lane == 0) {
+                        const double v = (K[(size_t)(kb + r) * R2 + w] - part) / Dg[r][r];
+                        xs[r][w] = v;
+                        K[(size_t)(kb + r) * R2 + w] = v;
+                    }
+                    __syncwarp();
+                }
             }
         }
         __syncthreads();
@@ -354,8 +380,175 @@ __global__ void __launch_bounds__(DT) mniw_draw_kernel(const __grid_constant__ D
     }
 }
 
+
+// =================================================================================== multi-CTA blocked factorisation (large M)
+// Right-looking blocked Cholesky of the index-reversed eta1 over ALL SMs, one launch pair per 64-column panel:
+//   chol_panel_kernel   every CTA factorises the 64x64 diagonal block redundantly in shared memory (left-looking, one barrier per
+//                       column) and solves its own 128 rows of the panel, one thread per row with the row in registers;
+//   chol_update_kernel  trailing update B[i,j] -= P_i P_j^T on lower-triangular 64x64 tiles with FP64 DMMA (mma.sync.m8n8k4.f64).
+// The right-hand sides of the forward solves (eta0 and, unless PGAS_FLAG_VCHOL_TRANSPOSE, Nrm) ride along as 2 n_x extra ROWS of the
+// matrix: after the last panel row M + c holds (L'^-1 rhs_c)^T, so no separate forward substitution exists.
+constexpr int CNB = 64;       // panel width = tile edge
+constexpr int CPT = 128;      // threads of the panel / update kernels
+constexpr int LDK = CNB + 4;  // row length of a staged panel tile: == 4 (mod 16) doubles -> fragment loads hit every bank twice
+
+__global__ void __launch_bounds__(256) chol_prep_kernel(const __grid_constant__ DrawArgs a) {
+    const int chain = blockIdx.y, M = a.M, nx = a.nx, R2 = 2 * nx;
+    const bool vt = (a.flags & PGAS_FLAG_VCHOL_TRANSPOSE) != 0;
+    const double* eta0 = a.eta0 + (size_t)chain * a.eta_stride0;
+    const double* eta1 = a.eta1 + (size_t)chain * a.eta_stride1;
+    double* B = a.wsB + (size_t)chain * (M + R2) * M;
+    double* K = a.wsK + (size_t)chain * M * R2;
+    const size_t total = (size_t)(M + R2) * M;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+        const int i = (int)(e / M), j = (int)(e % M);
+        if (i < M) {
+            if (j <= i) B[e] = eta1[(size_t)(M - 1 - i) * M + (M - 1 - j)];
+        } else {
+            const int c = i - M;
+            double v = 0.0;
+            if (c < nx) v = eta0[(size_t)(M - 1 - j) * nx + c];
+            else {
+                const int k = c - nx;
+                double z;
+                if (a.rng_mode == 1) z = a.Nrm[((size_t)chain * nx + k) * M + (M - 1 - j)];
+                else {
+                    const unsigned flat = (unsigned)(k * M + (M - 1 - j));
+                    double za, zb;
+                    philox_normal2(a.seed, PURPOSE_DRAW_N, a.chain_base + chain, a.iteration, 0u, flat >> 1, za, zb);
+                    z = (flat & 1) ? zb : za;
+                }
+                if (vt) K[(size_t)j * R2 + c] = z; else v = z;
+            }
+            B[e] = v;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.status) a.status[chain] = 0;
+}
+
+__global__ void __launch_bounds__(CPT) chol_panel_kernel(const __grid_constant__ DrawArgs a, int kb) {
+    const int chain = blockIdx.y, tid = threadIdx.x, M = a.M, R2 = 2 * a.nx;
+    double* B = a.wsB + (size_t)chain * (M + R2) * M;
+    const int nb = min(CNB, M - kb);
+    __shared__ double Dg[CNB][CNB + 1];
+    __shared__ double rdiag[CNB];
+    for (int e = tid; e < CNB * CNB; e += CPT) {
+        const int r = e / CNB, c = e % CNB;
+        Dg[r][c] = (r < nb && c <= r && c < nb) ? B[(size_t)(kb + r) * M + kb + c] : (r == c ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    // left-looking: at column j thread r >= j forms l_rj = (a_rj - sum_p l_rp l_jp) / l_jj; every thread recomputes the pivot from
+    // row j (the same broadcast loads feed both sums), so one barrier per column suffices.  Diagonal entries are only read at their
+    // own column; the owner keeps its pivot in a register until the loop has ended.
+    double mypiv = 1.0;
+    int bad = 0;
+    for (int j = 0; j < nb; ++j) {
+        const int r = tid;
+        if (r >= j && r < nb) {
+            double s0 = 0.0, s1 = 0.0, d0 = 0.0, d1 = 0.0;
+            int p = 0;
+            for (; p + 1 < j; p += 2) {
+                const double l0 = Dg[j][p], l1 = Dg[j][p + 1];
+                s0 = fma(Dg[r][p], l0, s0); s1 = fma(Dg[r][p + 1], l1, s1);
+                d0 = fma(l0, l0, d0); d1 = fma(l1, l1, d1);
+            }
+            if (p < j) { const double l0 = Dg[j][p]; s0 = fma(Dg[r][p], l0, s0); d0 = fma(l0, l0, d0); }
+            const double d = Dg[j][j] - (d0 + d1);
+            const double piv = sqrt(d);
+            if (r == j) { mypiv = piv; if (!(d > 0.0)) bad = kb + j + 1; }
+            else Dg[r][j] = (Dg[r][j] - (s0 + s1)) / piv;
+        }
+        __syncthreads();
+    }
+    if (tid < nb) Dg[tid][tid] = mypiv;
+    if (tid < CNB) rdiag[tid] = 1.0 / mypiv;
+    if (bad && blockIdx.x == 0 && a.status) atomicCAS(&a.status[chain], 0, bad);     // first non-positive pivot of the chain (panels run in order)
+    __syncthreads();
+    if (blockIdx.x == 0)
+        for (int e = tid; e < nb * nb; e += CPT) {
+            const int r = e / nb, c = e % nb;
+            if (c <= r) B[(size_t)(kb + r) * M + kb + c] = Dg[r][c];
+        }
+    // panel rows below the diagonal block (incl. the right-hand-side rows): X Dg^T = B[i, kb:kb+nb], row i in registers,
+    // right-looking so that the 63 - c updates of a column are independent FMAs
+    const int i = kb + nb + blockIdx.x * CPT + tid;
+    if (i < M + R2) {
+        double x[CNB];
+        double* row = B + (size_t)i * M + kb;
+#pragma unroll
+        for (int c = 0; c < CNB; ++c) x[c] = (c < nb) ? row[c] : 0.0;
+#pragma unroll
+        for (int c = 0; c < CNB; ++c) {
+            const double xc = x[c] * rdiag[c];
+            x[c] = xc;
+#pragma unroll
+            for (int p = c + 1; p < CNB; ++p) x[p] = fma(-xc, Dg[p][c], x[p]);
+        }
+#pragma unroll
+        for (int c = 0; c < CNB; ++c) if (c < nb) row[c] = x[c];
+    }
+}
+
+__global__ void __launch_bounds__(CPT) chol_update_kernel(const __grid_constant__ DrawArgs a, int kb) {
+    const int chain = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, M = a.M, R2 = 2 * a.nx;
+    double* B = a.wsB + (size_t)chain * (M + R2) * M;
+    const int r0 = kb + CNB;                                   // first trailing row / column
+    const int ntc = (M - r0 + CNB - 1) / CNB;                  // column tiles (columns < M)
+    int bi = 0, rem = blockIdx.x;
+    while (rem > bi) { rem -= bi + 1; ++bi; }
+    const int bj = rem;
+    if (bj >= ntc) return;                                     // right-hand-side rows have no columns of their own
+    extern __shared__ __align__(16) double psm[];
+    double* Pi = psm;                                          // [CNB][LDK]: rows of tile bi, panel columns
+    double* Pj = (bi == bj) ? Pi : psm + CNB * LDK;
+    for (int e = tid; e < CNB * (CNB / 2); e += CPT) {
+        const int rr = e / (CNB / 2), c2 = e % (CNB / 2);
+        const int gi = r0 + bi * CNB + rr, gj = r0 + bj * CNB + rr;
+        double2 vi = make_double2(0.0, 0.0), vj = vi;
+        if (gi < M + R2) vi = make_double2(B[(size_t)gi * M + kb + 2 * c2], B[(size_t)gi * M + kb + 2 * c2 + 1]);
+        *reinterpret_cast<double2*>(&Pi[rr * LDK + 2 * c2]) = vi;
+        if (bi != bj) {
+            if (gj < M) vj = make_double2(B[(size_t)gj * M + kb + 2 * c2], B[(size_t)gj * M + kb + 2 * c2 + 1]);
+            *reinterpret_cast<double2*>(&Pj[rr * LDK + 2 * c2]) = vj;
+        }
+    }
+    __syncthreads();
+    const int wi = warp >> 1, wj = warp & 1;
+    double c0[4][4], c1[4][4];
+#pragma unroll
+    for (int fi = 0; fi < 4; ++fi)
+#pragma unroll
+        for (int fj = 0; fj < 4; ++fj) { c0[fi][fj] = 0.0; c1[fi][fj] = 0.0; }
+    const int aoff = (wi * 32 + (lane >> 2)) * LDK + (lane & 3), boff = (wj * 32 + (lane >> 2)) * LDK + (lane & 3);
+#pragma unroll 1
+    for (int kk = 0; kk < CNB; kk += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            af[f] = Pi[aoff + 8 * f * LDK + kk];
+            bf[f] = Pj[boff + 8 * f * LDK + kk];
+        }
+#pragma unroll
+        for (int fi = 0; fi < 4; ++fi)
+#pragma unroll
+            for (int fj = 0; fj < 4; ++fj)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c0[fi][fj]), "+d"(c1[fi][fj]) : "d"(af[fi]), "d"(bf[fj]));
+    }
+#pragma unroll
+    for (int fi = 0; fi < 4; ++fi)
+#pragma unroll
+        for (int fj = 0; fj < 4; ++fj) {
+            const int gi = r0 + bi * CNB + wi * 32 + fi * 8 + (lane >> 2), gj = r0 + bj * CNB + wj * 32 + fj * 8 + 2 * (lane & 3);
+            if (gi < M + R2) {
+                if (gj < M && gj <= gi) B[(size_t)gi * M + gj] -= c0[fi][fj];
+                if (gj + 1 < M && gj + 1 <= gi) B[(size_t)gi * M + gj + 1] -= c1[fi][fj];
+            }
+        }
+}
+
 static size_t draw_ws_per_chain(int M, int nx) {
-    return sizeof(double) * ((size_t)M * M + 2 * (size_t)M * 2 * nx);
+    return sizeof(double) * ((size_t)(M + 2 * nx) * M + 2 * (size_t)M * 2 * nx);     // (augmented) factor + forward / backward solutions
 }
 
 extern "C" size_t pgas_mniw_draw_workspace_bytes(int32_t M, int32_t n_x, int32_t n_chains) {
@@ -383,7 +576,37 @@ int pgas_launch_mniw_draw(const double* eta0, const double* eta1, const double* 
     a.wsB = (double*)w;
     a.wsF = a.wsB + (size_t)n_chains * M * M;
     a.wsK = a.wsF + (size_t)n_chains * M * 2 * nx;
-    mniw_draw_kernel<<<n_chains, DT, 0, st>>>(a);
+    bool blocked = M >= 192;                        // below, one CTA per chain finishes before the launch sequence would
+    if (const char* e = getenv("PGAS_DRAW_BLOCKED")) blocked = atoi(e) != 0;       // developer override
+    if (!blocked) {
+        mniw_draw_kernel<false><<<n_chains, DT, 0, st>>>(a);
+        PGAS_KERNEL_CHECK();
+        return 0;
+    }
+    // augmented matrix (M + 2 n_x rows) in the space of wsB + wsF of the one-CTA form; wsF moves behind it
+    const int R2 = 2 * nx;
+    a.wsF = a.wsB + (size_t)n_chains * (M + R2) * M;
+    a.wsK = a.wsF + (size_t)n_chains * M * R2;
+    {
+        const unsigned gx = (unsigned)std::min<size_t>(((size_t)(M + R2) * M + 2047) / 2048, 1024);
+        chol_prep_kernel<<<dim3(gx, (unsigned)n_chains), 256, 0, st>>>(a);
+        PGAS_KERNEL_CHECK();
+    }
+    const size_t usm = sizeof(double) * 2 * CNB * LDK;
+    PGAS_CUDA(cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usm));
+    for (int kb = 0; kb < M; kb += CNB) {
+        const int nb = std::min(CNB, M - kb);
+        const int below = M + R2 - (kb + nb);
+        chol_panel_kernel<<<dim3((unsigned)((below + CPT - 1) / CPT), (unsigned)n_chains), CPT, 0, st>>>(a, kb);
+        PGAS_KERNEL_CHECK();
+        const int r0 = kb + CNB;
+        if (r0 < M) {
+            const int ntr = (M + R2 - r0 + CNB - 1) / CNB;
+            chol_update_kernel<<<dim3((unsigned)(ntr * (ntr + 1) / 2), (unsigned)n_chains), CPT, usm, st>>>(a, kb);
+            PGAS_KERNEL_CHECK();
+        }
+    }
+    mniw_draw_kernel<true><<<n_chains, DT, 0, st>>>(a);
     PGAS_KERNEL_CHECK();
     return 0;
 }

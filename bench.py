@@ -1,12 +1,13 @@
 #!/usr/bin/env python
-"""bench.py — PGAS particle-steps/s on the BASELINE.json workload "scaled single-mass oscillator":
-N=4096 particles, T=2000 steps, M=256 basis functions (2-D Hilbert GP), 64 independent chains per GPU
-(weak scaling: the path shards over independent chains, every GPU runs the one-GPU workload on its own
-chain ids; chains never communicate, one NCCL all-gather of the per-chain trajectories at the end;
-`--scaling strong` shards 64 chains in total instead).
+"""bench.py — PGAS particle-steps/s on the BASELINE.json workloads
+  --config 4 (default)  "scaled single-mass oscillator": N=4096 particles, T=2000 steps, M=256 basis functions, 64 chains per GPU
+  --config 5            "scaled vehicle model": N=16384, T=5000, M=1024 (2-D tensor-product basis over the slip angles), 16 chains per GPU
+The path shards over independent chains: weak scaling (default) runs the one-GPU workload on every GPU with its own chain
+ids; chains never communicate, one NCCL all-gather of the per-chain trajectories at the end.  Multi-GPU runs add a
+"strong" record: the one-GPU job (64 chains in total, BASELINE.json's named split) sharded over the ranks.
 
-One "step" = one full Gibbs iteration of every chain of the job: conditional-SMC sweep (persistent
-kernel) -> final pick + backward trace -> sufficient statistics -> MNIW posterior draw.
+One "step" = one full Gibbs iteration of every chain of the job: conditional-SMC sweep (state kernel in 16-step launches
+overlapped with the resampling kernel, ~290 launches) -> final pick + backward trace -> sufficient statistics -> MNIW draw.
 
   python bench.py --gpus 1 --steps K --warmup W          # this repo (CUDA, sm_100a)
   python bench.py --impl reference ...                    # CPU restatement of the reference (oracle port:
@@ -28,11 +29,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PKG = "bayesian_inference_with_explicit_and_implicit_prior_knowledge_b200"
 
-N_PART, T_STEPS, M_BASIS, CHAINS_TOTAL = 4096, 2000, 256, 64
-FLOP_PER_PSTEP = 2 * M_BASIS * 2 + M_BASIS * 2          # 2 M n_x + M D  (SURVEY.md 8d), n_x = D = 2
-NCU_DRAM_BYTES_PER_PSTEP = (0.267264e6 + 32.3328e6) / (32 * 4096 * 16)        # profiles/r01_state_kernel_raw.csv (one 16-step launch of one chain group)
-STATE_BYTES_PER_PSTEP = 8 * 2 + 3 * 8                   # trace row (n_x doubles) + the three log-densities handed to the resampling kernel
 SEED = 12345678                                          # the reference's seed (src/SingleMassOscillator.py:82)
+
+# BASELINE.json configs[3] and configs[4].  `chains` = chains per GPU of the bench workload.
+CONFIGS = {
+    4: dict(kind="smo", N=4096, T=2000, M=256, chains=64, n_y=1,
+            name="scaled single-mass oscillator (BASELINE.json configs[3])"),
+    5: dict(kind="vehicle", N=16384, T=5000, M=1024, chains=16, n_y=2,
+            name="scaled vehicle model, 2-D tensor-product basis over the slip angles (BASELINE.json configs[4])"),
+}
+STATE_BYTES_PER_PSTEP = 8 * 2 + 3 * 8                   # trace row (n_x doubles) + the three log-densities handed to the resampling kernel
+
+
+def flop_per_pstep(M):
+    return 2 * M * 2 + M * 2                             # 2 M n_x + M D  (SURVEY.md 8d), n_x = D = 2
 
 
 # ------------------------------------------------------------------------------- workload
@@ -57,11 +67,53 @@ def smo_truth(T, rng):
     return X, Y, F_ext
 
 
-def workload(T=T_STEPS):
+def vehicle_truth(T, rng):
+    """ground-truth single-track vehicle (src/Vehicle.py:17-128, 180-208): x = [yaw rate, lateral velocity],
+    u = [steering angle, 11 m/s], magic-formula tyres, RK4 with dt = 0.02, steering profile of :200-208 stretched to T steps"""
+    m, Izz, lf, lr, g, mux = 1720.0, 1827.5, 1.16, 1.47, 9.81, 0.9
+    mu, B, Cc, E = 0.9, 10.0, 1.9, 0.97
+    dt = 0.02
+    time_ = np.arange(T) * dt
+    t_end = T * dt
+    U = np.zeros((T, 2))
+    U[:, 0] = 10 / 180 * np.pi * np.sin(2 * np.pi * time_ / 5) * np.exp(-0.5 * (time_ - t_end / 2) ** 2 / (t_end / 5) ** 2)
+    U[:, 1] = 11.0
+    Fzf, Fzr = m * g * lr / (lf + lr), m * g * lf / (lf + lr)
+
+    def mu_y(al):
+        ta = np.tan(al)
+        return mu * np.sin(Cc * np.arctan(B * (1 - E) * ta + E * np.arctan(B * ta)))
+
+    def dx(x, u):
+        af = u[0] - np.arctan((x[1] + x[0] * lf) / u[1])
+        ar = -np.arctan((x[1] - x[0] * lr) / u[1])
+        myf, myr = mu_y(af), mu_y(ar)
+        ddpsi = (lf * Fzf * myf * np.cos(u[0]) - lr * Fzr * myr + lf * Fzf * mux * np.sin(u[0])) / Izz
+        ay = (Fzf * myf * np.cos(u[0]) + Fzr * myr + Fzf * mux * np.sin(u[0])) / m - u[1] * x[0]
+        return np.array([ddpsi, ay])
+    X = np.zeros((T, 2))
+    for t in range(1, T):
+        x, u = X[t - 1], U[t - 1]
+        k1 = dx(x, u); k2 = dx(x + dt / 2 * k1, u); k3 = dx(x + dt / 2 * k2, u); k4 = dx(x + dt * k3, u)
+        X[t] = x + dt / 6 * (k1 + 2 * k2 + 2 * k3 + k4) + 1e-4 * rng.normal(size=2)
+    R = np.diag([0.001 / 180 * np.pi, 1e-3])
+    Y = X + rng.normal(size=(T, 2)) * np.sqrt(np.diag(R))
+    return X, Y, U, R
+
+
+def workload(cfg, T=None):
+    """synthetic trajectories + model constants of one BASELINE configuration"""
+    T = T or cfg["T"]
     rng = np.random.default_rng(SEED)
-    X, Y, F = smo_truth(T, rng)
-    return dict(X=X, Y=Y, F=F, domain=np.array([[-7.5, 7.5], [-7.5, 7.5]]), lengthscale=15.0 / M_BASIS, scale=100.0,
-                m0=np.zeros(2), P0=np.diag([1e-4, 1e-4]), R=np.array([[1e-3]]), df=3)
+    M = cfg["M"]
+    if cfg["kind"] == "smo":
+        X, Y, F = smo_truth(max(T, 32), rng)
+        return dict(kind="smo", X=X[:T], Y=Y[:T], U=np.zeros((T, 0)), domain=np.array([[-7.5, 7.5], [-7.5, 7.5]]), lengthscale=15.0 / M,
+                    scale=100.0, hgp_extra=(), m0=np.zeros(2), P0=np.diag([1e-4, 1e-4]), H=np.array([[1.0, 0.0]]), R=np.array([[1e-3]]), df=3)
+    X, Y, U, R = vehicle_truth(max(T, 32), rng)
+    a = 30 / 180 * np.pi
+    return dict(kind="vehicle", X=X[:T], Y=Y[:T], U=U[:T], domain=np.array([[-a, a], [-a, a]]), lengthscale=2 / 180 * np.pi, scale=50.0,
+                hgp_extra=(), m0=np.zeros(2), P0=np.diag([1e-4, 1e-4]), H=np.eye(2), R=R, df=3, slip=(1.16, 1.47))
 
 
 # ------------------------------------------------------------------------------- clocks
@@ -104,66 +156,74 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- CPU baseline
-def _oracle_model(w, T):
+def _oracle_model(cfg, w, T):
     from oracle import basis as OB, mniw as OM, pgas as OP
-    hgp, sd = OB.generate_Hilbert_BasisFunction(M_BASIS, w["domain"], w["lengthscale"], w["scale"])
-    model = OP.ThetaModel(w["Y"][:T], np.zeros((T, 0)), w["m0"], w["P0"], OP.affine_hgp_basis(hgp, np.eye(2), np.zeros(2)),
-                          OP.gaussian_loglik([[1.0, 0.0]], [0.0], w["R"]))
-    prior = OM.prior_mniw_2naturalPara(np.zeros((2, M_BASIS)), np.diag(sd), np.eye(2), w["df"])
+    M = cfg["M"]
+    hgp, sd = OB.generate_Hilbert_BasisFunction(M, w["domain"], w["lengthscale"], w["scale"])
+    if w["kind"] == "vehicle":
+        basis = OP.vehicle_slip_basis(hgp, *w["slip"])
+    else:
+        basis = OP.affine_hgp_basis(hgp, np.eye(2), np.zeros(2))
+    model = OP.ThetaModel(w["Y"][:T], w["U"][:T], w["m0"], w["P0"], basis, OP.gaussian_loglik(w["H"], np.zeros(w["H"].shape[0]), w["R"]))
+    prior = OM.prior_mniw_2naturalPara(np.zeros((2, M)), np.diag(sd), np.eye(2), w["df"])
     return model, prior
 
 
 def _cpu_chain_sample(args):
     """one bounded sample of the workload on one core: a sweep of `T` steps at full N and M (the sweep is
     exactly linear in T) + statistics + draw, with the NumPy restatement of the reference"""
-    T, seed = args
+    config, T, seed = args
     from threadpoolctl import threadpool_limits
     from oracle import pgas as OP
-    w = workload(max(T, 32))
-    model, prior = _oracle_model(w, T)
+    cfg = CONFIGS[config]
+    N, M = cfg["N"], cfg["M"]
+    w = workload(cfg, max(T, 32))
+    model, prior = _oracle_model(cfg, w, T)
     rng = np.random.default_rng(seed)
     df = prior[3] + T - 1
-    A, S, _ = OP.sample_params(model, prior, w["X"][:T], rng.chisquare(df - np.arange(2)), rng.normal(size=(2, 2)), rng.normal(size=(2, M_BASIS)))
-    Z, U = rng.normal(size=(T, N_PART, 2)), rng.uniform(size=(T, 2))
+    A, S, _ = OP.sample_params(model, prior, w["X"][:T], rng.chisquare(df - np.arange(2)), rng.normal(size=(2, 2)), rng.normal(size=(2, M)))
+    Z, U = rng.normal(size=(T, N, 2)), rng.uniform(size=(T, 2))
     with threadpool_limits(limits=1):
         t0 = time.perf_counter()
-        sw = OP.csmc_sweep(model, N_PART, w["X"][:T], A, S, Z, U)
-        OP.sample_params(model, prior, sw["traj"], rng.chisquare(df - np.arange(2)), rng.normal(size=(2, 2)), rng.normal(size=(2, M_BASIS)))
+        sw = OP.csmc_sweep(model, N, w["X"][:T], A, S, Z, U)
+        OP.sample_params(model, prior, sw["traj"], rng.chisquare(df - np.arange(2)), rng.normal(size=(2, 2)), rng.normal(size=(2, M)))
         dt = time.perf_counter() - t0
-    return N_PART * (T - 1), dt
+    return N * (T - 1), dt
 
 
-def cpu_baseline_single(T_sample=41):
-    _cpu_chain_sample((9, 0))                              # warm-up (imports, page-in)
-    ps, dt = _cpu_chain_sample((T_sample, 1))
+def cpu_baseline_single(config):
+    cfg = CONFIGS[config]
+    T_sample = 41 if config == 4 else 9
+    _cpu_chain_sample((config, 5, 0))                      # warm-up (imports, page-in)
+    ps, dt = _cpu_chain_sample((config, T_sample, 1))
     return {"value": ps / dt, "unit": "particle-steps/s", "cores": 1, "kind": "port",
-            "sample": f"1 chain, N={N_PART}, M={M_BASIS}, {T_sample - 1} of {T_STEPS - 1} steps (sweep is linear in T), NumPy restatement "
+            "sample": f"1 chain, N={cfg['N']}, M={cfg['M']}, {T_sample - 1} of {cfg['T'] - 1} steps (sweep is linear in T), NumPy restatement "
                       f"of the reference (oracle/pgas.py), single thread; jax/equinox not installable offline"}
 
 
 def run_reference_arm(args):
     """the reference's CPU implementation of the path = the oracle port on all host cores, one chain per core"""
     import multiprocessing as mp
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
-    T_sample = 21
+    T_sample = 21 if args.config == 4 else 6
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         for _ in range(max(args.warmup, 1) if args.warmup else 0):
-            pool.map(_cpu_chain_sample, [(9, 100 + c) for c in range(cores)])
+            pool.map(_cpu_chain_sample, [(args.config, 5, 100 + c) for c in range(cores)])
         times, psteps = [], 0
         for k in range(args.steps):
-            res = pool.map(_cpu_chain_sample, [(T_sample, 1000 * k + c) for c in range(cores)])
+            res = pool.map(_cpu_chain_sample, [(args.config, T_sample, 1000 * k + c) for c in range(cores)])
             times.append(max(r[1] for r in res))              # slowest chain of the step (setup excluded)
             psteps += sum(r[0] for r in res)
     total = sum(times)
     value = psteps / total
-    sample = (f"{cores} chains in parallel (one per host core), N={N_PART}, M={M_BASIS}, {T_sample - 1} of {T_STEPS - 1} steps per chain "
+    sample = (f"{cores} chains in parallel (one per host core), N={cfg['N']}, M={cfg['M']}, {T_sample - 1} of {cfg['T'] - 1} steps per chain "
               f"per step, NumPy restatement of the reference (oracle/); jax 0.4.38 / equinox 0.12.2 not installable offline")
     line = {"impl": "reference", "metric": "pgas_particle_steps_per_s", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "scaled single-mass oscillator: N=4096, T=2000, M=256, 64 chains per GPU (BASELINE.json configs[3])",
-                       "sample": sample},
+            "config": {"workload": f"{cfg['name']}: N={cfg['N']}, T={cfg['T']}, M={cfg['M']}, {cfg['chains']} chains per GPU", "sample": sample},
             "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -222,6 +282,40 @@ def marginalised_leg(key_mod):
 
 
 # ------------------------------------------------------------------------------- GPU arm
+def ncu_traffic(kernel_regex):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel, from the committed `ncu --set full`
+    raw page of this round (profiles/r02_*_raw.csv); None when no capture is committed.  The capture is named in the result."""
+    import csv
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_*_raw.csv"))):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units = rows[0], rows[1]
+            ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            for r in rows[2:]:
+                if re.search(kernel_regex, r[ik]):
+                    best = {"bytes_per_launch": float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0),
+                            "capture": os.path.relpath(path, ROOT)}
+        except Exception:
+            continue
+    return best
+
+
+def cuda_time(torch, fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(); fn(); a1.record()
+        torch.cuda.synchronize()
+        ts.append(a0.elapsed_time(a1))
+    return float(np.mean(ts))
+
+
 def run_gpu_arm(args):
     import importlib
     import torch
@@ -244,124 +338,142 @@ def run_gpu_arm(args):
     BF, MD, PG, DI, BI = (importlib.import_module(PKG + "." + n) for n in ("BasisFunctions", "models", "PGAS", "distributed", "BayesianInferrence"))
     RND = importlib.import_module(PKG + ".random")
 
-    w = workload()
-    T = args.T
-    hgp, sd = BF.generate_Hilbert_BasisFunction(M_BASIS, w["domain"], w["lengthscale"], w["scale"])
-    prior = BI.prior_mniw_2naturalPara(np.zeros((2, M_BASIS)), np.diag(sd), np.eye(2), w["df"])
-    if args.scaling == "weak":
-        args.chains = args.chains * world                    # per-GPU work fixed: 64 chains on every rank
-    first, count = DI.shard_chains(args.chains, rank, world)
-    K = args.steps + args.warmup + 1                         # iteration 0 is the initial draw
-    del K
-    pg = PG.PGAS(N_samples=args.particles, N_iterations=2, observations=w["Y"][:T], inputs=np.zeros((T, 0)), init_state_mean=w["m0"],
-                 init_state_cov=w["P0"], likelihood_fcn=MD.gaussian_likelihood(lambda x: x[0], w["R"]), GP_prior=prior,
-                 basis_fcn=lambda state, inp: hgp(state), cluster_size=args.cluster)
+    cfg = CONFIGS[args.config]
+    M = cfg["M"]
+    T = args.T or cfg["T"]
+    N = args.particles or cfg["N"]
+    chains_per_gpu = args.chains or cfg["chains"]
+    w = workload(cfg, T)
+    hgp, sd = BF.generate_Hilbert_BasisFunction(M, w["domain"], w["lengthscale"], w["scale"])
+    prior = BI.prior_mniw_2naturalPara(np.zeros((2, M)), np.diag(sd), np.eye(2), w["df"])
+    if w["kind"] == "vehicle":
+        basis_fcn = MD.VehicleSlipBasis(hgp, *w["slip"])
+        lik = MD.GaussianLikelihood(w["H"], np.zeros(2), w["R"])
+    else:
+        basis_fcn = lambda state, inp: hgp(state)                   # noqa: E731
+        lik = MD.gaussian_likelihood(lambda x: x[0], w["R"])
+
+    def make_pgas():
+        return PG.PGAS(N_samples=N, N_iterations=2, observations=w["Y"], inputs=w["U"], init_state_mean=w["m0"], init_state_cov=w["P0"],
+                       likelihood_fcn=lik, GP_prior=prior, basis_fcn=basis_fcn, cluster_size=args.cluster)
+    pg = make_pgas()
     m = pg.cSMC.model
     key = RND.key(SEED)
-    N = args.particles
-
-    # ---- device-resident leg: K iterations, timed per iteration with CUDA events on the launching stream
-    ref = torch.as_tensor(np.broadcast_to(w["X"][:T], (count, T, 2)).copy()).cuda()
-    nbytes = lib.pgas_run_chains_workspace_bytes(m.handle, N, count)
-    ws = torch.empty((nbytes,), dtype=torch.uint8, device="cuda")
     p0, p1, p2 = pg._prior()
 
-    def run_iterations(k_first, n_it, ref_t, out_t):
-        """iterations k_first .. k_first+n_it-1 continuing from ref_t; out_t (count, n_it+1, T, 2), row 0 = ref_t"""
-        rng = PG._make_rng(key, first, k_first)
-        L.check(lib.pgas_run_chains_f64(m.handle, N, n_it + 1, count, L.ptr(p0), L.ptr(p1), L.ptr(p2), pg.GP_prior[3], L.ptr(ref_t),
-                                        C.byref(rng), L.ptr(out_t), C.c_void_p(0), C.c_void_p(0), args.cluster, L.ptr(ws), nbytes,
-                                        L.stream_ptr()))
-
-    # sweep-kernel-only timing for the roofline (same launches as inside the loop)
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    W = args.warmup
-    out_w = torch.empty((count, W + 1, T, 2), dtype=torch.float64, device="cuda")
-    out_t = torch.empty((count, args.steps + 1, T, 2), dtype=torch.float64, device="cuda")
-    run_iterations(0, W, ref, out_w)                          # warm-up: W full iterations
-    cur = out_w[:, W].contiguous()
-    sync_all()
-    launches0 = lib.pgas_launch_count()
-    with ClockSampler(local) as clk:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        run_iterations(W, args.steps, cur, out_t)             # EXACTLY `steps` Gibbs iterations of every chain of this rank
-        cur = out_t[:, args.steps].contiguous()
-        gathered = DI.gather_chain_outputs(cur, args.chains)  # the only collective: final gather of the trajectories
-        e1.record()
-        sync_all()
-        ms = e0.elapsed_time(e1)
-    launches = lib.pgas_launch_count() - launches0
-    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms = float(t_ms[0])
-    psteps_job = args.chains * N * (T - 1) * args.steps
-    value = psteps_job / (ms * 1e-3)
+    def timed_job(chains_total, steps, warmup):
+        """`steps` Gibbs iterations of every chain of the job after `warmup` untimed ones; device-resident inputs; CUDA events on the
+        launching stream, max over ranks; the only collective is the final gather of the trajectories"""
+        first, count = DI.shard_chains(chains_total, rank, world)
+        cnt = max(count, 1)
+        ref = torch.as_tensor(np.broadcast_to(w["X"], (cnt, T, 2)).copy()).cuda()
+        nbytes = lib.pgas_run_chains_workspace_bytes(m.handle, N, cnt)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device="cuda")
 
-    # ---- sweep kernel alone (the dominant kernel), CUDA events, for the roofline
-    st = torch.empty((count, T, N, 2), dtype=torch.float64, device="cuda")
-    an = torch.empty((count, T - 1, N), dtype=torch.int32, device="cuda")
-    lw = torch.empty((count, N), dtype=torch.float64, device="cuda")
+        def run_iterations(k_first, n_it, ref_t, out_t):
+            rng = PG._make_rng(key, first, k_first)
+            L.check(lib.pgas_run_chains_f64(m.handle, N, n_it + 1, cnt, L.ptr(p0), L.ptr(p1), L.ptr(p2), pg.GP_prior[3], L.ptr(ref_t),
+                                            C.byref(rng), L.ptr(out_t), C.c_void_p(0), C.c_void_p(0), args.cluster, L.ptr(ws), nbytes,
+                                            L.stream_ptr()))
+        out_w = torch.empty((cnt, warmup + 1, T, 2), dtype=torch.float64, device="cuda")
+        out_t = torch.empty((cnt, steps + 1, T, 2), dtype=torch.float64, device="cuda")
+        run_iterations(0, warmup, ref, out_w)
+        cur = out_w[:, warmup].contiguous()
+        sync_all()
+        l0 = lib.pgas_launch_count()
+        with ClockSampler(local) as clk:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run_iterations(warmup, steps, cur, out_t)         # EXACTLY `steps` Gibbs iterations of every chain of this rank
+            cur = out_t[:, steps].contiguous()
+            DI.gather_chain_outputs(cur[:count], chains_total)
+            e1.record()
+            sync_all()
+            ms = e0.elapsed_time(e1)
+        launches = lib.pgas_launch_count() - l0
+        t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        ms = float(t_ms[0])
+        del ws, out_w, out_t, ref
+        return dict(ms=ms, value=chains_total * N * (T - 1) * steps / (ms * 1e-3), launches=int(launches), clocks=clk.summary(),
+                    first=first, count=count, cur=cur, chains_total=chains_total)
+
+    chains_total = chains_per_gpu * world if args.scaling == "weak" else chains_per_gpu
+    job = timed_job(chains_total, args.steps, args.warmup)
+    ms, value, first, count, cur = job["ms"], job["value"], job["first"], job["count"], job["cur"]
+    # the named split of BASELINE.json (configs[3]: 64 chains sharded over the GPUs of the box) beside the weak-scaling headline
+    strong = None
+    if world > 1 and args.scaling == "weak" and not args.no_strong:
+        sj = timed_job(chains_per_gpu, args.steps, args.warmup)
+        strong = {"chains_total": chains_per_gpu, "chains_per_gpu": chains_per_gpu / world, "value": sj["value"], "unit": "particle-steps/s",
+                  "ms_per_step": sj["ms"] / args.steps, "note": "strong scaling: the one-GPU job (same chain ids, same results) sharded over the ranks"}
+
+    # ---- the kernels of one iteration alone (CUDA events), for the rooflines
+    cnt = max(count, 1)
+    st = torch.empty((cnt, T, N, 2), dtype=torch.float64, device="cuda")
+    an = torch.empty((cnt, T - 1, N), dtype=torch.int32, device="cuda")
+    lw = torch.empty((cnt, N), dtype=torch.float64, device="cuda")
     T0, T1, T2, T3 = BI.trajectory_statistics(m, cur)
-    A0, S0, _ = BI.mniw_posterior_draw(p0 + T0, p1 + T1, p2 + T2, pg.GP_prior[3] + T3, PG._make_rng(key, first, 999))
-    sw_bytes = int(lib.pgas_csmc_sweep_workspace_bytes(m.handle, N, count))
+    e0_, e1_, e2_ = (p0 + T0).contiguous(), (p1 + T1).contiguous(), (p2 + T2).contiguous()
+    A0, S0, _ = BI.mniw_posterior_draw(e0_, e1_, e2_, pg.GP_prior[3] + T3, PG._make_rng(key, first, 999))
+    sw_bytes = int(lib.pgas_csmc_sweep_workspace_bytes(m.handle, N, cnt))
     sw_ws = torch.empty((sw_bytes,), dtype=torch.uint8, device="cuda")
-    sweep_ms = []
-    for r in range(3):
-        rng = PG._make_rng(key, first, 1000 + r)
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        L.check(lib.pgas_csmc_sweep_f64(m.handle, N, count, L.ptr(cur), L.ptr(A0), L.ptr(S0), C.byref(rng), L.ptr(st), L.ptr(an),
+    it = [1000]
+
+    def sweep_once():
+        it[0] += 1
+        rng = PG._make_rng(key, first, it[0])
+        L.check(lib.pgas_csmc_sweep_f64(m.handle, N, cnt, L.ptr(cur), L.ptr(A0), L.ptr(S0), C.byref(rng), L.ptr(st), L.ptr(an),
                                         L.ptr(lw), C.c_void_p(0), C.c_void_p(0), args.cluster, L.ptr(sw_ws), sw_bytes, L.stream_ptr()))
-        a1.record()
-        torch.cuda.synchronize()
-        sweep_ms.append(a0.elapsed_time(a1))
-    sweep_avg = float(np.mean(sweep_ms[1:]))
-    # the dominant kernel alone: csmc_state_kernel over all T-1 steps (same launches as inside the sweep, no resampling kernel)
-    state_ms = []
-    for r in range(3):
-        rng = PG._make_rng(key, first, 2000 + r)
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        L.check(lib.pgas_debug_state_kernel_f64(m.handle, N, count, L.ptr(cur), L.ptr(A0), L.ptr(S0), C.byref(rng), L.ptr(st), L.ptr(sw_ws),
+
+    def state_once():
+        it[0] += 1
+        rng = PG._make_rng(key, first, it[0])
+        L.check(lib.pgas_debug_state_kernel_f64(m.handle, N, cnt, L.ptr(cur), L.ptr(A0), L.ptr(S0), C.byref(rng), L.ptr(st), L.ptr(sw_ws),
                                                 sw_bytes, L.stream_ptr()))
-        a1.record()
-        torch.cuda.synchronize()
-        state_ms.append(a0.elapsed_time(a1))
-    state_avg = float(np.mean(state_ms[1:]))
+    sweep_avg = cuda_time(torch, sweep_once, 2)
+    state_avg = cuda_time(torch, state_once, 2)
+    suff_avg = cuda_time(torch, lambda: BI.trajectory_statistics(m, cur), 5)
+    draw_avg = cuda_time(torch, lambda: BI.mniw_posterior_draw(e0_, e1_, e2_, pg.GP_prior[3] + T3, PG._make_rng(key, first, 998)), 5)
     dfma, dmma = C.c_double(), C.c_double()
     L.check(lib.pgas_measure_fp64_peaks(C.byref(dfma), C.byref(dmma), L.stream_ptr()))
-    flops_launch = count * N * (T - 1) * FLOP_PER_PSTEP
-    achieved = flops_launch / (state_avg * 1e-3) / 1e12
-    achieved_sweep = flops_launch / (sweep_avg * 1e-3) / 1e12
+    FLOP = flop_per_pstep(M)
+    psteps_rank = cnt * N * (T - 1)
+    flops_sweep = psteps_rank * FLOP
+    achieved = flops_sweep / (state_avg * 1e-3) / 1e12
+    achieved_sweep = flops_sweep / (sweep_avg * 1e-3) / 1e12
     peak = max(dfma.value, dmma.value)
-    hbm_bytes = count * N * (T - 1) * STATE_BYTES_PER_PSTEP
+    n_state_launches = ((T - 1 + 15) // 16) * (2 if cnt >= 4 else 1)
+    hbm_bytes = psteps_rank * STATE_BYTES_PER_PSTEP
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_src = "measured (MEASURED_PEAKS.json)"
     except Exception:
-        pass
+        hbm_src = "fallback (B200_PROFILING.md)"
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    flops_suff = cnt * ((T - 1) * M * (M + 1) + 2 * (T - 1) * M * 2)
+    flops_draw = cnt * (M ** 3 / 3.0 + 3 * 2 * M * M)          # what this implementation performs: one factorisation + three triangular solves with n_x columns
+    tr_state, tr_suff, tr_draw = ncu_traffic(r"csmc_state_kernel"), ncu_traffic(r"suffstats_kernel"), ncu_traffic(r"chol_update_kernel")
 
     # ---- end-to-end leg: the public API with HOST buffers (pinned), H2D of the reference trajectories and D2H of the
     #      new trajectories inside the timed region, every step
-    pg2 = PG.PGAS(N_samples=N, N_iterations=2, observations=w["Y"][:T], inputs=np.zeros((T, 0)), init_state_mean=w["m0"],
-                  init_state_cov=w["P0"], likelihood_fcn=MD.gaussian_likelihood(lambda x: x[0], w["R"]), GP_prior=prior,
-                  basis_fcn=lambda state, inp: hgp(state), cluster_size=args.cluster)
+    pg2 = make_pgas()
     pg2.cSMC._model = m
-    host_ref = torch.as_tensor(np.broadcast_to(w["X"][:T], (count, T, 2)).copy()).pin_memory()
-    host_out = torch.empty((count, T, 2), dtype=torch.float64).pin_memory()
+    host_ref = torch.as_tensor(np.broadcast_to(w["X"], (cnt, T, 2)).copy()).pin_memory()
+    host_out = torch.empty((cnt, T, 2), dtype=torch.float64).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
 
     def e2e_step(k):
         dref = host_ref.cuda(non_blocking=True)
-        res = pg2.run_chains(RND.key(SEED + k), dref, n_chains=count, chain_base=first, want_params=False)
+        res = pg2.run_chains(RND.key(SEED + k), dref, n_chains=cnt, chain_base=first, want_params=False)
         host_out.copy_(res["state_trace"][:, 1], non_blocking=True)
         torch.cuda.synchronize()
         host_ref.copy_(host_out)
@@ -375,41 +487,54 @@ def run_gpu_arm(args):
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = args.chains * N * (T - 1) * e2e_steps / float(t_e[0])
+    e2e_value = chains_total * N * (T - 1) * e2e_steps / float(t_e[0])
 
     if rank == 0:
-        cpu = cpu_baseline_single() if (world == 1 and not args.no_cpu_baseline) else None
+        cpu = cpu_baseline_single(args.config) if (world == 1 and not args.no_cpu_baseline) else None
+        pk = f"FP64 peak measured on this GPU in this run (register-resident DFMA {dfma.value:.1f}, DMMA {dmma.value:.1f} TFLOP/s; MEASURED_PEAKS.json has no FP64 figure)"
         line = {
             "metric": "pgas_particle_steps_per_s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"scaled single-mass oscillator (BASELINE.json configs[3]): N={N} particles, T={T} steps, M={M_BASIS} basis "
-                                   f"functions (2-D Hilbert GP), {args.chains} independent chains in total, {count} on rank 0 ({args.scaling} scaling)",
+            "config": {"workload": f"{cfg['name']}: N={N} particles, T={T} steps, M={M} basis functions (2-D Hilbert GP), {chains_total} independent "
+                                   f"chains in total, {count} on rank 0 ({args.scaling} scaling)",
                        "step": "one Gibbs iteration of every chain: cSMC sweep + pick/backward trace + sufficient statistics + MNIW draw",
                        "cluster_size": args.cluster, "l2": "per-step working set (state + ancestor traces, "
-                       f"{count * T * N * 20 / 1e9:.1f} GB on rank 0) exceeds the 126 MB L2", "rng": "Philox-4x32-10 in-kernel"},
-            "sweeps_per_s": args.chains * args.steps / (ms * 1e-3),
-            "roofline": {"bound": "tensor", "kernel": "csmc_state_kernel (FP64 FMA row walk; timed alone over all T-1 steps, "
-                         f"{(T - 1 + 15) // 16} launches of <= 16 steps per chain group, two chain groups on two streams exactly as inside the sweep)", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_PSTEP * count * N * (T - 1),
-                         "traffic_note": "dram__bytes_read+write of this kernel from the ncu --set full capture in profiles/r01_state_kernel_summary.md "
-                                         f"({NCU_DRAM_BYTES_PER_PSTEP:.1f} B per particle-step measured on one 16-step launch, scaled to all launches; algorithmic {STATE_BYTES_PER_PSTEP} B: "
-                                         "most of the rows a 16-step launch writes are still in L2 when the capture ends)",
-                         "note": f"compute bound = FP64 pipe (on B200 the FP64 FMA and FP64 tensor (DMMA) pipes have the same measured rate); algorithmic flops = "
-                                 f"{FLOP_PER_PSTEP} per particle-step (2 M n_x + M D) x {count * N * (T - 1)} particle-steps; peak = FP64 measured on this GPU in this "
-                                 f"run (register-resident DFMA {dfma.value:.1f}, DMMA {dmma.value:.1f} TFLOP/s; MEASURED_PEAKS.json has no FP64 figure); state kernel "
-                                 f"{state_avg:.2f} ms; whole sweep (state kernel overlapped with the resampling kernel csmc_weights1_kernel) {sweep_avg:.2f} ms",
+                       f"{cnt * T * N * 20 / 1e9:.1f} GB on rank 0) exceeds the 126 MB L2", "rng": "Philox-4x32-10 in-kernel"},
+            "sweeps_per_s": chains_total * args.steps / (ms * 1e-3),
+            "roofline": {"bound": "fp64", "kernel": "csmc_state_kernel (FP64 FMA row walk; timed alone over all T-1 steps, launched exactly as inside the sweep)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "launches": n_state_launches, "flop_per_launch": flops_sweep / n_state_launches, "avg_launch_ms": state_avg / n_state_launches,
+                         "traffic": tr_state["bytes_per_launch"] if tr_state else None,
+                         "traffic_capture": tr_state["capture"] if tr_state else None,
+                         "algorithmic_bytes_per_launch": hbm_bytes / n_state_launches,
+                         "note": f"the bound is the FP64 pipe, not HBM and not the bf16 tensor pipe (tcgen05 has no f64 kind; on B200 FP64 FMA and FP64 DMMA share "
+                                 f"one pipe: interleaved they reach the single-pipe rate, profiles/r02_microbench.md); algorithmic flops = {FLOP} per "
+                                 f"particle-step (2 M n_x + M D) x {psteps_rank} particle-steps; peak = {pk}; state kernel {state_avg:.2f} ms; whole sweep "
+                                 f"(state kernel overlapped with the resampling kernel) {sweep_avg:.2f} ms",
                          "sweep_ms": sweep_avg, "sweep_achieved": achieved_sweep, "sweep_frac": achieved_sweep / peak,
-                         "hbm_achieved_gbs": hbm_bytes / (state_avg * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
+                         "hbm_achieved_gbs": hbm_bytes / (state_avg * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
                          "hbm_frac": hbm_bytes / (state_avg * 1e-3) / 1e9 / hbm_peak},
-            "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(count * T * 2 * 8),
-                    "d2h_bytes_per_step": int(count * T * 2 * 8), "steps": e2e_steps,
+            "roofline_kernels": {
+                "sweep": {"bound": "fp64", "ms": sweep_avg, "achieved": achieved_sweep, "peak": peak, "unit": "TFLOP/s", "frac": achieved_sweep / peak},
+                "suffstats": {"bound": "fp64", "kernel": "suffstats_kernel (SYRK over time, mma.sync.m8n8k4.f64)", "ms": suff_avg,
+                              "achieved": flops_suff / (suff_avg * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                              "frac": flops_suff / (suff_avg * 1e-3) / 1e12 / peak, "flops": flops_suff,
+                              "traffic": tr_suff["bytes_per_launch"] if tr_suff else None, "traffic_capture": tr_suff["capture"] if tr_suff else None},
+                "mniw_draw": {"bound": "fp64 (latency-limited panels)", "kernel": "chol_prep/panel/update kernels + mniw_draw_kernel (one factorisation, M^3/3)",
+                              "ms": draw_avg, "achieved": flops_draw / (draw_avg * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                              "frac": flops_draw / (draw_avg * 1e-3) / 1e12 / peak, "flops": flops_draw,
+                              "traffic": tr_draw["bytes_per_launch"] if tr_draw else None, "traffic_capture": tr_draw["capture"] if tr_draw else None}},
+            "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(cnt * T * 2 * 8),
+                    "d2h_bytes_per_step": int(cnt * T * 2 * 8), "steps": e2e_steps,
                     "api": "PGAS.run_chains(key, host reference trajectories) -> host trajectories (pinned buffers)"},
-            "gpu_launches": int(launches), "clocks": clk.summary(),
+            "gpu_launches": job["launches"], "clocks": job["clocks"],
         }
+        if strong is not None:
+            line["strong"] = strong
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if world == 1 and not args.no_marginalised:
+        if world == 1 and args.config == 4 and not args.no_marginalised:
             line["marginalised"] = marginalised_leg(RND)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -423,11 +548,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chains", type=int, default=CHAINS_TOTAL, help="chains per GPU (weak scaling) or in total (strong)")
+    ap.add_argument("--config", type=int, default=4, choices=[4, 5], help="BASELINE.json configuration (1-based): 4 = scaled oscillator, 5 = scaled vehicle")
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (weak scaling) or in total (strong); default: the configuration's")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-strong", action="store_true", help="multi-GPU runs: skip the additional strong-scaling leg")
     ap.add_argument("--no-marginalised", action="store_true", help="skip the marginalised-path (Algorithm2/3) leg")
-    ap.add_argument("--particles", type=int, default=N_PART)
-    ap.add_argument("--T", type=int, default=T_STEPS)
+    ap.add_argument("--particles", type=int, default=0)
+    ap.add_argument("--T", type=int, default=0)
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

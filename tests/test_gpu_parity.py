@@ -168,11 +168,24 @@ def test_chain_ids_give_identical_results_regardless_of_batching(built_lib):
 
 # ----------------------------------------------------------------------------- A13 statistics + draw
 @pytest.mark.parametrize("kind,M,T", [("smo", 41, 80), ("smo", 100, 300), ("smo", 256, 120), ("emps", 64, 60),
-                                      ("emps", 200, 90), ("toy", 40, 40), ("vehicle", 36, 100)])
+                                      ("emps", 200, 90), ("toy", 40, 40), ("vehicle", 36, 100),
+                                      # configuration-scale bases: EMPS PGAS baseline (3-D, M = 729, configs[2]), configs[3] (M = 256)
+                                      # at its full T, configs[4] (vehicle lattice, M = 1024)
+                                      ("emps", 729, 400), ("smo", 256, 2000), ("vehicle", 1024, 700), ("smo", 1024, 300)])
 def test_suffstats_and_draw_parity(built_lib, kind, M, T):
     p = helpers.make_problem(kind, T=T, N=32, M=M, seed=M)
     r = helpers.run_draw_parity(p)
     assert r["ok"], str(r)
+
+
+@pytest.mark.parametrize("kind,M,T,flags", [("smo", 100, 150, 0), ("smo", 130, 90, 4), ("emps", 200, 90, 0), ("smo", 41, 60, 0)])
+def test_blocked_and_one_cta_factorisations_agree(built_lib, monkeypatch, kind, M, T, flags):
+    """the multi-CTA blocked Cholesky (default for M >= 192) and the one-CTA form give the same draw; both against the oracle"""
+    p = helpers.make_problem(kind, T=T, N=32, M=M, seed=M + 1, flags=flags)
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PGAS_DRAW_BLOCKED", mode)
+        r = helpers.run_draw_parity(p)
+        assert r["ok"], (mode, str(r))
 
 
 def test_draw_transpose_flag(built_lib):
@@ -205,6 +218,13 @@ def test_draw_rejects_indefinite_eta1(built_lib):
     A, S, status = BI.mniw_posterior_draw(torch.zeros((1, M, nx), dtype=torch.float64, device="cuda"), e1,
                                           torch.eye(nx, dtype=torch.float64, device="cuda")[None].clone(), 10.0, rng)
     assert int(status[0]) == M - 7          # pivot position in the reversed factorisation order (1-based)
+    # the multi-CTA blocked factorisation reports the same position
+    M = 200
+    e1 = torch.eye(M, dtype=torch.float64, device="cuda")[None].repeat(2, 1, 1)
+    e1[1, 150, 150] = -1.0
+    A, S, status = BI.mniw_posterior_draw(torch.zeros((2, M, nx), dtype=torch.float64, device="cuda"), e1,
+                                          torch.eye(nx, dtype=torch.float64, device="cuda")[None].repeat(2, 1, 1), 10.0, rng)
+    assert int(status[0]) == 0 and int(status[1]) == M - 150
 
 
 # ----------------------------------------------------------------------------- A14 full Gibbs loop

@@ -27,6 +27,11 @@ lib.pgas_microbench_f64.argtypes = [C.POINTER(C.c_double), C.c_void_p]
 arr = (C.c_double * 8)()
 L.check(lib.pgas_microbench_f64(arr, L.stream_ptr()))
 out["dfma_latency_cyc"], out["dfma_issue_cyc"], out["cluster16_barrier_cyc"], out["cluster8_barrier_cyc"], out["dfma_2w_ilp4_tflops"], out["dmma_latency_cyc"], out["dmma_1w_ilp5_cyc"], out["dmma_16w_ilp5_cyc"] = list(arr)
+lib.pgas_microbench_mix_f64.restype = C.c_int
+lib.pgas_microbench_mix_f64.argtypes = [C.POINTER(C.c_double), C.c_void_p]
+arr4 = (C.c_double * 4)()
+L.check(lib.pgas_microbench_mix_f64(arr4, L.stream_ptr()))
+out["mix_dfma8_tflops"], out["mix_dmma8_tflops"], out["mix_dfma8_dmma8_tflops"], out["mix_dfma8_dmma2_tflops"] = list(arr4)
 print(json.dumps(out), flush=True)
 if len(sys.argv) > 1: sys.exit(0)
 
