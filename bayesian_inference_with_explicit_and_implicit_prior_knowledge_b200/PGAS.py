@@ -61,7 +61,9 @@ class condSequentialMonteCarlo:
     # ---- batched device API -------------------------------------------------------------
     def sweep(self, ref, Theta, Sigma, key=None, variates=None, chain_base=0, iteration=0, want_traces=True):
         """n_chains sweeps.  ref (n_chains,T,n_x), Theta (n_chains,n_x,M), Sigma (n_chains,n_x,n_x) CUDA
-        float64 tensors.  Returns dict(traj, state_trace, anc_trace, logw_last, idx) of CUDA tensors."""
+        float64 tensors.  Returns dict(traj, state_trace, anc_trace, logw_last, idx) of CUDA tensors.
+        anc_trace[..., N-1] is the reference particle's ancestor as src/PGAS.py:122-127 stores it (unclipped: it is N when
+        rounding leaves cumsum(w)[-1] below u_anc); clamp to N-1 before indexing with it (Filtering.reconstruct_trajectory does)."""
         torch = _lib.require_cuda()
         m = self.model
         ref = ref.reshape(-1, m.T, m.n_x).contiguous()

@@ -37,6 +37,13 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _header_abi_version():
+    import re
+    with open(os.path.join(_HERE, "..", "include", "pgas_b200.h")) as f:
+        m = re.search(r"#define\s+PGAS_ABI_VERSION\s+(\d+)", f.read())
+    return int(m.group(1)) if m else None
+
+
 def build(force=False, verbose=False):
     """Compile csrc/*.cu for sm_100a and link libpgas_b200.so in-tree (nvcc cross-compiles
     without a GPU)."""
@@ -145,6 +152,7 @@ EXPORTS = {
     # name: (restype, argtypes)
     "pgas_last_error": (C.c_char_p, []),
     "pgas_version": (C.c_int, []),
+    "pgas_abi_version": (C.c_int, []),
     "pgas_device_count": (C.c_int, []),
     "pgas_launch_count": (C.c_longlong, []),
     "pgas_model_create": (C.c_int, [C.POINTER(ModelParams), C.POINTER(C.c_void_p)]),
@@ -212,7 +220,19 @@ def lib():
             raise RuntimeError(
                 f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU fallback for the PGAS hot path)")
+        if _stale():
+            import warnings
+            warnings.warn(f"{_SO} is older than csrc/ or include/pgas_b200.h: run __graft_entry__.build() to rebuild", RuntimeWarning)
         L = C.CDLL(_SO)
+        want = _header_abi_version()
+        try:
+            L.pgas_abi_version.restype = C.c_int
+            got = L.pgas_abi_version()
+        except AttributeError:
+            got = None
+        if got != want:
+            raise RuntimeError(f"{_SO} was built against ABI {got}, include/pgas_b200.h declares {want}: rebuild with "
+                               "__graft_entry__.build() (ctypes layouts and the binary must come from the same header)")
         for name, (res, args) in EXPORTS.items():
             fn = getattr(L, name)          # AttributeError if the export is missing
             fn.restype = res

@@ -5,6 +5,7 @@
 // with no host synchronisation inside the loop.  Chains never communicate; the multi-GPU layer
 // (Python, torch.distributed) shards chain ids across ranks and gathers the traces at the end.
 #include "sweep_args.cuh"
+#include <algorithm>
 
 __global__ void add_prior_kernel(const double* __restrict__ p0, const double* __restrict__ p1, const double* __restrict__ p2,
                                  const double* __restrict__ T0, const double* __restrict__ T1, const double* __restrict__ T2, int M,
@@ -58,6 +59,24 @@ extern "C" size_t pgas_run_chains_workspace_bytes(const pgas_model* model, int32
     return carve(model->dev, N, n_chains, nullptr).total;
 }
 
+// dst[c * dstride + e] = src[c * sstride + e], e < len, c < rows
+__global__ void __launch_bounds__(256) strided_rows_copy_kernel(double* __restrict__ dst, long long dstride, const double* __restrict__ src,
+                                                                long long sstride, size_t len, int rows) {
+    const size_t total = len * (size_t)rows;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+        const size_t c = e / len, i = e % len;
+        dst[c * dstride + i] = src[c * sstride + i];
+    }
+}
+static int strided_rows_copy(double* dst, long long dstride, const double* src, long long sstride, size_t len, int rows, cudaStream_t st) {
+    const size_t total = len * (size_t)rows;
+    if (!total) return 0;
+    const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 8);
+    strided_rows_copy_kernel<<<grid, 256, 0, st>>>(dst, dstride, src, sstride, len, rows);
+    PGAS_KERNEL_CHECK();
+    return 0;
+}
+
 extern "C" int pgas_run_chains_f64(const pgas_model* model, int32_t N, int32_t K, int32_t n_chains, const double* eta0,
                                    const double* eta1, const double* eta2, double eta3, const double* init_ref, const pgas_rng* rng,
                                    double* state_trace_out, double* A_trace_out, double* S_trace_out, int32_t cluster_size,
@@ -75,9 +94,11 @@ extern "C" int pgas_run_chains_f64(const pgas_model* model, int32_t N, int32_t K
     if (rng->mode == 1 && (!rng->chi2 || !rng->G || !rng->Nrm || (K > 1 && (!rng->Z || !rng->U))))
         PGAS_FAIL(-1, "injected rng mode needs Z, U, chi2, G and Nrm");
 
-    PGAS_CUDA(cudaMemcpy2DAsync(state_trace_out, sizeof(double) * tstride, init_ref, sizeof(double) * T * nx, sizeof(double) * T * nx,
-                                n_chains, cudaMemcpyDeviceToDevice, st));
+    // per-chain blocks into the (n_chains, K, ...) traces: one strided copy kernel (a pitched cudaMemcpy2D rejects destination
+    // pitches above cudaDevAttrMaxPitch, i.e. long runs with K T n_x > ~2.7e8)
+    if (int rc = strided_rows_copy(state_trace_out, tstride, init_ref, (long long)(T * nx), T * nx, n_chains, st)) return rc;
     const int C = pgas_choose_cluster(m, N, n_chains, cluster_size);
+    if (C < 1 || C > 16) PGAS_FAIL(-2, "cluster_size must be 0 (auto) or 1..16 (got %d -> %d)", cluster_size, C);
     for (int k = 0; k < K; ++k) {
         pgas_rng r = *rng;
         r.iteration = rng->iteration + (unsigned)k;
@@ -114,11 +135,9 @@ extern "C" int pgas_run_chains_f64(const pgas_model* model, int32_t N, int32_t K
                                            w.S, w.status, w.draw, w.draw_bytes, st))
             return rc;
         if (A_trace_out)
-            PGAS_CUDA(cudaMemcpy2DAsync(A_trace_out + (size_t)k * nx * M, sizeof(double) * K * nx * M, w.A, sizeof(double) * nx * M,
-                                        sizeof(double) * nx * M, n_chains, cudaMemcpyDeviceToDevice, st));
+            if (int rc = strided_rows_copy(A_trace_out + (size_t)k * nx * M, (long long)(K * nx * M), w.A, (long long)(nx * M), nx * M, n_chains, st)) return rc;
         if (S_trace_out)
-            PGAS_CUDA(cudaMemcpy2DAsync(S_trace_out + (size_t)k * nx * nx, sizeof(double) * K * nx * nx, w.S, sizeof(double) * nx * nx,
-                                        sizeof(double) * nx * nx, n_chains, cudaMemcpyDeviceToDevice, st));
+            if (int rc = strided_rows_copy(S_trace_out + (size_t)k * nx * nx, (long long)(K * nx * nx), w.S, (long long)(nx * nx), nx * nx, n_chains, st)) return rc;
     }
     return 0;
 }

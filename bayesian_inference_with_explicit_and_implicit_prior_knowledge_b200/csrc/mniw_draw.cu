@@ -245,23 +245,22 @@ __global__ void __launch_bounds__(DT) mniw_draw_kernel(const __grid_constant__ D
             Dg[r][c] = (r < nb && c <= r) ? B[(size_t)(kb + r) * M + kb + c] : 0.0;
         }
         __syncthreads();
-        {   // one warp per right-hand side: lanes split the dot product over the rows below r
+        for (int e = tid; e < nb * wk; e += DT) xs[e / wk][e % wk] = K[(size_t)(kb + e / wk) * R2 + e % wk];
+        __syncthreads();
+        {   // one warp per right-hand side, block and right-hand sides in shared memory: lanes split the dot product over the rows below r
             const int lane = tid & 31, w = tid >> 5;
             if (w < wk) {
                 for (int r = nb - 1; r >= 0; --r) {
                     const int p = r + 1 + lane;
                     double part = (p < nb) ? Dg[p][r] * xs[p][w] : 0.0;
                     part = warp_sum(part);
-                    if (lane == 0) {
-                        const double v = (K[(size_t)(kb + r) * R2 + w] - part) / Dg[r][r];
-                        xs[r][w] = v;
-                        K[(size_t)(kb + r) * R2 + w] = v;
-                    }
+                    if (lane == 0) xs[r][w] = (xs[r][w] - part) / Dg[r][r];
                     __syncwarp();
                 }
             }
         }
         __syncthreads();
+        for (int e = tid; e < nb * wk; e += DT) K[(size_t)(kb + e / wk) * R2 + e % wk] = xs[e / wk][e % wk];
         for (int j = tid; j < kb; j += DT) {
             double acc[2 * PGAS_MAX_NX];
 #pragma unroll
@@ -426,64 +425,94 @@ __global__ void __launch_bounds__(256) chol_prep_kernel(const __grid_constant__ 
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.status) a.status[chain] = 0;
 }
 
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 __global__ void __launch_bounds__(CPT) chol_panel_kernel(const __grid_constant__ DrawArgs a, int kb) {
     const int chain = blockIdx.y, tid = threadIdx.x, M = a.M, R2 = 2 * a.nx;
     double* B = a.wsB + (size_t)chain * (M + R2) * M;
     const int nb = min(CNB, M - kb);
-    __shared__ double Dg[CNB][CNB + 1];
-    __shared__ double rdiag[CNB];
+    constexpr int LDT = CNB + 2;                       // even row length: 16-byte aligned rows for the paired broadcast loads
+    __shared__ __align__(16) double LT[CNB * LDT];     // staging of the block, then the TRANSPOSED factor: LT[c][p] = L[p][c]
+    __shared__ __align__(16) double colbuf[2][CNB];    // column j of the factor, double-buffered by parity
+    __shared__ double rdiag[CNB], pdiag[CNB];
     for (int e = tid; e < CNB * CNB; e += CPT) {
         const int r = e / CNB, c = e % CNB;
-        Dg[r][c] = (r < nb && c <= r && c < nb) ? B[(size_t)(kb + r) * M + kb + c] : (r == c ? 1.0 : 0.0);
+        LT[r * LDT + c] = (r < nb && c <= r) ? B[(size_t)(kb + r) * M + kb + c] : (r == c ? 1.0 : 0.0);
     }
-    __syncthreads();
-    // left-looking: at column j thread r >= j forms l_rj = (a_rj - sum_p l_rp l_jp) / l_jj; every thread recomputes the pivot from
-    // row j (the same broadcast loads feed both sums), so one barrier per column suffices.  Diagonal entries are only read at their
-    // own column; the owner keeps its pivot in a register until the loop has ended.
-    double mypiv = 1.0;
-    int bad = 0;
-    for (int j = 0; j < nb; ++j) {
-        const int r = tid;
-        if (r >= j && r < nb) {
-            double s0 = 0.0, s1 = 0.0, d0 = 0.0, d1 = 0.0;
-            int p = 0;
-            for (; p + 1 < j; p += 2) {
-                const double l0 = Dg[j][p], l1 = Dg[j][p + 1];
-                s0 = fma(Dg[r][p], l0, s0); s1 = fma(Dg[r][p + 1], l1, s1);
-                d0 = fma(l0, l0, d0); d1 = fma(l1, l1, d1);
-            }
-            if (p < j) { const double l0 = Dg[j][p]; s0 = fma(Dg[r][p], l0, s0); d0 = fma(l0, l0, d0); }
-            const double d = Dg[j][j] - (d0 + d1);
-            const double piv = sqrt(d);
-            if (r == j) { mypiv = piv; if (!(d > 0.0)) bad = kb + j + 1; }
-            else Dg[r][j] = (Dg[r][j] - (s0 + s1)) / piv;
-        }
-        __syncthreads();
-    }
-    if (tid < nb) Dg[tid][tid] = mypiv;
-    if (tid < CNB) rdiag[tid] = 1.0 / mypiv;
-    if (bad && blockIdx.x == 0 && a.status) atomicCAS(&a.status[chain], 0, bad);     // first non-positive pivot of the chain (panels run in order)
-    __syncthreads();
-    if (blockIdx.x == 0)
-        for (int e = tid; e < nb * nb; e += CPT) {
-            const int r = e / nb, c = e % nb;
-            if (c <= r) B[(size_t)(kb + r) * M + kb + c] = Dg[r][c];
-        }
-    // panel rows below the diagonal block (incl. the right-hand-side rows): X Dg^T = B[i, kb:kb+nb], row i in registers,
-    // right-looking so that the 63 - c updates of a column are independent FMAs
+    // this thread's panel row (below the diagonal block, incl. the right-hand-side rows) travels while the block is factorised
     const int i = kb + nb + blockIdx.x * CPT + tid;
+    double x[CNB];
     if (i < M + R2) {
-        double x[CNB];
-        double* row = B + (size_t)i * M + kb;
+        const double* row = B + (size_t)i * M + kb;
 #pragma unroll
         for (int c = 0; c < CNB; ++c) x[c] = (c < nb) ? row[c] : 0.0;
+    }
+    __syncthreads();
+    // ---- the diagonal block, redundantly in every CTA: right-looking, row r in the registers of thread r (threads 0..63), one column per
+    //      iteration: [A] l_rj = a_rj / l_jj into colbuf, barrier, [B] a_rc -= l_rj l_cj for j < c <= r (paired broadcast loads of the
+    //      column), and the owner of row j + 1 publishes the next pivot, barrier.  Two named barriers of 64 threads per column.
+    if (tid < CNB) {
+        const int r = tid;
+        double ar[CNB];
+#pragma unroll
+        for (int c = 0; c < CNB; ++c) ar[c] = LT[r * LDT + c];
+        int bad = 0;
+        if (r == 0) {
+            const double d = ar[0];
+            if (!(d > 0.0)) bad = kb + 1;
+            const double ri = rsqrt(d);
+            rdiag[0] = ri; pdiag[0] = d * ri;
+        }
+        bar_sync_named(1, CNB);
+#pragma unroll
+        for (int j = 0; j < CNB; ++j) {
+            double* cb = colbuf[j & 1];
+            const double l = (r > j) ? ar[j] * rdiag[j] : 0.0;
+            ar[j] = (r == j) ? pdiag[j] : l;
+            cb[r] = l;
+            bar_sync_named(1, CNB);
+            if (r > j) {
+#pragma unroll
+                for (int c = (j + 1) & ~1; c < CNB; c += 2) {
+                    const double2 lc = *reinterpret_cast<const double2*>(cb + c);
+                    if (c > j) ar[c] = fma(-l, lc.x, ar[c]);
+                    ar[c + 1] = fma(-l, lc.y, ar[c + 1]);
+                }
+            }
+            if (j + 1 < CNB && r == j + 1) {
+                const double d = ar[j + 1];
+                if (!(d > 0.0) && !bad && j + 1 < nb) bad = kb + j + 2;
+                const double ri = rsqrt(d);
+                rdiag[j + 1] = ri; pdiag[j + 1] = d * ri;
+            }
+            bar_sync_named(1, CNB);
+        }
+        if (bad && blockIdx.x == 0 && a.status) atomicCAS(&a.status[chain], 0, bad);     // first non-positive pivot of the chain (panels run in order; one owner per column)
+        // transposed factor for the panel solve; CTA 0 also writes the block back
+#pragma unroll
+        for (int c = 0; c < CNB; ++c) LT[c * LDT + r] = (c <= r) ? ar[c] : 0.0;
+        if (blockIdx.x == 0 && r < nb) {
+            double* row = B + (size_t)(kb + r) * M + kb;
+#pragma unroll
+            for (int c = 0; c < CNB; ++c) if (c <= r) row[c] = ar[c];
+        }
+    }
+    __syncthreads();
+    // ---- panel rows: X L^T = B[i, kb:kb+nb], row i in registers, right-looking: the updates of a column are independent FMAs fed by
+    //      paired broadcast loads of the transposed factor
+    if (i < M + R2) {
 #pragma unroll
         for (int c = 0; c < CNB; ++c) {
             const double xc = x[c] * rdiag[c];
             x[c] = xc;
 #pragma unroll
-            for (int p = c + 1; p < CNB; ++p) x[p] = fma(-xc, Dg[p][c], x[p]);
+            for (int p = (c + 1) & ~1; p < CNB; p += 2) {
+                const double2 lp = *reinterpret_cast<const double2*>(&LT[c * LDT + p]);
+                if (p > c) x[p] = fma(-xc, lp.x, x[p]);
+                x[p + 1] = fma(-xc, lp.y, x[p + 1]);
+            }
         }
+        double* row = B + (size_t)i * M + kb;
 #pragma unroll
         for (int c = 0; c < CNB; ++c) if (c < nb) row[c] = x[c];
     }

@@ -24,7 +24,8 @@ long long g_pgas_launches = 0;
 
 extern "C" const char* pgas_last_error(void) { return g_err; }
 extern "C" long long pgas_launch_count(void) { return __atomic_load_n(&g_pgas_launches, __ATOMIC_RELAXED); }
-extern "C" int pgas_version(void) { return 100; }
+extern "C" int pgas_version(void) { return 200; }
+extern "C" int pgas_abi_version(void) { return PGAS_ABI_VERSION; }
 extern "C" int pgas_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

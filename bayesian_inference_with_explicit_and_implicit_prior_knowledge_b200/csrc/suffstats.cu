@@ -31,6 +31,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+template <int D>
 __global__ void __launch_bounds__(SNT, 5) suffstats_kernel(const __grid_constant__ SuffArgs a) {
     const DevModel& m = a.m;
     // tile pair (I >= J) from the linear block index
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(SNT, 5) suffstats_kernel(const __grid_constant
     const int J = rem;
     const int chain = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nx = m.n_x, D = m.D, M = m.M, npos = a.npos, TK = a.TK;
+    const int nx = m.n_x, M = m.M, npos = a.npos, TK = a.TK;
     const double* traj = a.traj + (size_t)chain * a.traj_stride;
 
     extern __shared__ __align__(16) double sm[];
@@ -50,16 +51,22 @@ __global__ void __launch_bounds__(SNT, 5) suffstats_kernel(const __grid_constant
     double* phiI = tab + (size_t)D * nposp * TK;        // [TK][LDP]
     double* phiJ = phiI + TK * LDP;                     // [TK][LDP] (aliases phiI on diagonal tiles)
     double* ych = phiJ + TK * LDP;                      // [TK][PGAS_MAX_NX]
-    int* posI = reinterpret_cast<int*>(ych + TK * PGAS_MAX_NX);   // [ST][D]
-    int* posJ = posI + ST * PGAS_MAX_D;
     const bool diag = (I == J);
     if (diag) phiJ = phiI;
 
-    for (int e = tid; e < ST * D; e += SNT) {
-        const int mi = e / D, d = e % D;
+    // every thread evaluates ONE basis column of each tile block (mi = tid % 64) at every second time step of a chunk: its lattice
+    // positions are loop-invariant registers, a basis value costs D shared loads and D multiplies
+    const int mi = tid & (ST - 1), tt0 = tid >> 6;
+    int pI[D], pJ[D];
+    bool vI, vJ;
+    {
         const int gi = I * ST + mi, gj = J * ST + mi;
-        posI[mi * PGAS_MAX_D + d] = (gi < M) ? (m.freq[(size_t)gi * D + d] - m.f_start) / m.f_step : -1;
-        posJ[mi * PGAS_MAX_D + d] = (gj < M) ? (m.freq[(size_t)gj * D + d] - m.f_start) / m.f_step : -1;
+        vI = gi < M; vJ = gj < M;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            pI[d] = vI ? (m.freq[(size_t)gi * D + d] - m.f_start) / m.f_step : 0;
+            pJ[d] = vJ ? (m.freq[(size_t)gj * D + d] - m.f_start) / m.f_step : 0;
+        }
     }
     // accumulator fragments: quadrant rows wi*32 + 8 fi + lane/4, columns wj*32 + 8 fj + 2 (lane%4) + {0,1}
     const int wi = warp >> 1, wj = warp & 1;
@@ -113,20 +120,20 @@ __global__ void __launch_bounds__(SNT, 5) suffstats_kernel(const __grid_constant
         }
         __syncthreads();
         // 2. basis values of the two tile blocks (one on diagonal tiles)
-        for (int e = tid; e < TK * ST; e += SNT) {
-            const int mi = e % ST, tt = e / ST;
-            double vi = m.norm, vj = m.norm;
-            for (int d = 0; d < D; ++d) {
-                const int pi = posI[mi * PGAS_MAX_D + d];
-                vi = (pi >= 0) ? vi * tab[((size_t)d * TK + tt) * nposp + pi] : 0.0;
-            }
-            phiI[tt * LDP + mi] = vi;
-            if (!diag) {
-                for (int d = 0; d < D; ++d) {
-                    const int pj = posJ[mi * PGAS_MAX_D + d];
-                    vj = (pj >= 0) ? vj * tab[((size_t)d * TK + tt) * nposp + pj] : 0.0;
+        {
+            const double* tb = tab + (size_t)tt0 * nposp;
+            const int dstride = TK * nposp;
+            for (int tt = tt0; tt < TK; tt += 2, tb += 2 * nposp) {
+                double vi = vI ? m.norm : 0.0;
+#pragma unroll
+                for (int d = 0; d < D; ++d) vi *= tb[d * dstride + pI[d]];
+                phiI[tt * LDP + mi] = vi;
+                if (!diag) {
+                    double vj = vJ ? m.norm : 0.0;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) vj *= tb[d * dstride + pJ[d]];
+                    phiJ[tt * LDP + mi] = vj;
                 }
-                phiJ[tt * LDP + mi] = vj;
             }
         }
         __syncthreads();
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(SNT, 5) suffstats_kernel(const __grid_constant
 }
 
 static size_t suff_smem(int D, int npos, int TK) {
-    return sizeof(double) * ((size_t)D * (npos | 1) * TK + 2 * (size_t)TK * LDP + (size_t)TK * PGAS_MAX_NX) + sizeof(int) * 2 * ST * PGAS_MAX_D;
+    return sizeof(double) * ((size_t)D * (npos | 1) * TK + 2 * (size_t)TK * LDP + (size_t)TK * PGAS_MAX_NX);
 }
 
 int pgas_launch_suffstats(const DevModel& m, const double* traj, long long traj_stride, int n_chains, double* T0, double* T1,
@@ -211,7 +218,7 @@ int pgas_launch_suffstats(const DevModel& m, const double* traj, long long traj_
     while (TK > 8 && suff_smem(m.D, npos, TK) > 45 * 1024) TK -= 4;
     a.TK = TK;
     const size_t smem = suff_smem(m.D, npos, TK);
-    auto kern = suffstats_kernel;
+    auto kern = (m.D == 1) ? suffstats_kernel<1> : (m.D == 2) ? suffstats_kernel<2> : suffstats_kernel<3>;
     PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(a.ntile * (a.ntile + 1) / 2), (unsigned)n_chains, 1);
     kern<<<grid, SNT, smem, st>>>(a);

@@ -125,12 +125,15 @@ __global__ void __launch_bounds__(NT, 2) csmc_weights_kernel(const __grid_consta
             m2t = fmax(m2t, lwr);
         }
         const double m1w = warp_shift_max(m1t), m2w = warp_shift_max(m2t);
+        // a warp whose log-weights are all -inf is an empty unit (numerators 0, not exp(-inf + inf) = NaN): jax.nn.softmax gives
+        // such entries weight 0 as long as the chain has one finite entry
+        const double sh1 = (m1w == -INFINITY) ? 0.0 : m1w, sh2 = (m2w == -INFINITY) ? 0.0 : m2w;
         {
             double r1 = 0.0, r2 = 0.0;
 #pragma unroll
             for (int u = 0; u < PPT; ++u) {                        // thread-serial inclusive prefix of the numerators
-                const double e1 = (u < nvalid) ? exp_neg_bf(s1[u] - m1w) : 0.0;
-                const double e2 = (u < nvalid) ? exp_neg_bf(s2[u] - m2w) : 0.0;
+                const double e1 = (u < nvalid) ? exp_neg_bf(s1[u] - sh1) : 0.0;
+                const double e2 = (u < nvalid) ? exp_neg_bf(s2[u] - sh2) : 0.0;
                 r1 = __dadd_rn(r1, e1);
                 r2 = __dadd_rn(r2, e2);
                 s1[u] = r1;
@@ -161,6 +164,8 @@ __global__ void __launch_bounds__(NT, 2) csmc_weights_kernel(const __grid_consta
         const double ures = su[2 * (t & 1)], uanc = su[2 * (t & 1) + 1];
         double fw1 = 0.0, gw1 = 0.0, fw2 = 0.0, gw2 = 0.0;          // rescale factor and exclusive offset of this thread's warp
         double S1, S2;                                             // reciprocals of the normalisers
+        bool uni;                                                  // sum of the numerators not > 0 (all -inf, or a NaN): systematic_SISR
+                                                                   // falls back to uniform weights (src/Filtering.py:24-25)
         {
             const int U = C * NW, mine = rank * NW + warp;
             double m1g = -INFINITY, m2g = -INFINITY;
@@ -188,6 +193,7 @@ __global__ void __launch_bounds__(NT, 2) csmc_weights_kernel(const __grid_consta
             }
             S1 = rcp_bf(c1);
             S2 = rcp_bf(c2);
+            uni = !(c1 > 0.0);
         }
 
         WK_TICK(3);
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(NT, 2) csmc_weights_kernel(const __grid_consta
                     // W = clip(cumsum(w / sum w), 0, 1)  (src/Filtering.py:23-32): chain-level inclusive prefix G_warp + s f_warp
                     const double p1 = __dadd_rn(gw1, __dmul_rn(s1[u], fw1));
                     const double p2 = __dadd_rn(gw2, __dmul_rn(s2[u], fw2));
-                    s1[u] = clip01(__dmul_rn(p1, S1));
+                    s1[u] = uni ? div_by_count((double)(base + il0 + u + 1), dN, rN) : clip01(__dmul_rn(p1, S1));
                     // cumsum(softmax(lw_anc)) < u_anc  (src/PGAS.py:118-124), not clipped: the counts of all CTAs add up to
                     // searchsorted's result
                     mycnt += (__dmul_rn(p2, S2) < uanc) ? 1 : 0;
@@ -359,11 +365,12 @@ __global__ void __launch_bounds__(NT, 2) csmc_weights1_kernel(const __grid_const
                 m2t = fmax(m2t, lwr);
             }
             const double m1w = warp_shift_max(m1t), m2w = warp_shift_max(m2t);
+            const double sh1 = (m1w == -INFINITY) ? 0.0 : m1w, sh2 = (m2w == -INFINITY) ? 0.0 : m2w;     // all -inf: an empty unit, not NaN
             double r1 = 0.0, r2 = 0.0;
 #pragma unroll
             for (int u = 0; u < PPT; ++u) {
-                const double e1 = (u < nv) ? exp_neg_bf(s1[u] - m1w) : 0.0;
-                const double e2 = (u < nv) ? exp_neg_bf(s2[u] - m2w) : 0.0;
+                const double e1 = (u < nv) ? exp_neg_bf(s1[u] - sh1) : 0.0;
+                const double e2 = (u < nv) ? exp_neg_bf(s2[u] - sh2) : 0.0;
                 r1 = __dadd_rn(r1, e1);
                 r2 = __dadd_rn(r2, e2);
                 s1[u] = r1;
@@ -395,6 +402,7 @@ __global__ void __launch_bounds__(NT, 2) csmc_weights1_kernel(const __grid_const
         // ---- X1: every warp folds the H * NW (slice, warp) pairs
         const double ures = su[2 * (t & 1)], uanc = su[2 * (t & 1) + 1];
         double fw1[H], gw1[H], fw2[H], gw2[H], S1, S2;
+        bool uni;                                                 // sum not > 0 (all -inf, or a NaN) -> uniform weights (src/Filtering.py:24-25)
         {
             const bool vu = lane < U;
             const double mu1 = vu ? unit[lane * 4] : -INFINITY, mu2 = vu ? unit[lane * 4 + 2] : -INFINITY;
@@ -412,8 +420,10 @@ __global__ void __launch_bounds__(NT, 2) csmc_weights1_kernel(const __grid_const
                 fw1[h] = __shfl_sync(0xffffffffu, f1, src); gw1[h] = __shfl_sync(0xffffffffu, x1, src);
                 fw2[h] = __shfl_sync(0xffffffffu, f2, src); gw2[h] = __shfl_sync(0xffffffffu, x2, src);
             }
-            S1 = rcp_bf(__shfl_sync(0xffffffffu, i1, 31));
+            const double c1 = __shfl_sync(0xffffffffu, i1, 31);
+            S1 = rcp_bf(c1);
             S2 = rcp_bf(__shfl_sync(0xffffffffu, i2, 31));
+            uni = !(c1 > 0.0);
         }
         WK_TICK(3);
         // ---- B1: finished CDF values; particles below u_anc
@@ -429,6 +439,10 @@ __global__ void __launch_bounds__(NT, 2) csmc_weights1_kernel(const __grid_const
                         const double2 a2 = *reinterpret_cast<const double2*>(s2s + (size_t)h * P + il0 + u);
                         w[u] = clip01(__dmul_rn(__dadd_rn(gw1[h], __dmul_rn(a1.x, fw1[h])), S1));
                         w[u + 1] = clip01(__dmul_rn(__dadd_rn(gw1[h], __dmul_rn(a1.y, fw1[h])), S1));
+                        if (uni) {
+                            w[u] = div_by_count((double)(h * P + il0 + u + 1), dN, rN);
+                            w[u + 1] = div_by_count((double)(h * P + il0 + u + 2), dN, rN);
+                        }
                         mycnt += (__dmul_rn(__dadd_rn(gw2[h], __dmul_rn(a2.x, fw2[h])), S2) < uanc) ? 1 : 0;
                         mycnt += (__dmul_rn(__dadd_rn(gw2[h], __dmul_rn(a2.y, fw2[h])), S2) < uanc) ? 1 : 0;
                         *reinterpret_cast<double2*>(b1f + (size_t)h * P + il0 + u) = make_double2(w[u], w[u + 1]);
@@ -436,7 +450,7 @@ __global__ void __launch_bounds__(NT, 2) csmc_weights1_kernel(const __grid_const
                 } else {
                     for (int u = 0; u < nvalid[h]; ++u) {
                         const size_t e = (size_t)h * P + il0 + u;
-                        b1f[e] = clip01(__dmul_rn(__dadd_rn(gw1[h], __dmul_rn(s1s[e], fw1[h])), S1));
+                        b1f[e] = uni ? div_by_count((double)(e + 1), dN, rN) : clip01(__dmul_rn(__dadd_rn(gw1[h], __dmul_rn(s1s[e], fw1[h])), S1));
                         mycnt += (__dmul_rn(__dadd_rn(gw2[h], __dmul_rn(s2s[e], fw2[h])), S2) < uanc) ? 1 : 0;
                     }
                 }

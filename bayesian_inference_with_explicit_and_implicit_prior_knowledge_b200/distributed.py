@@ -40,8 +40,18 @@ def run_chains_distributed(pgas, key, init_ref_state, n_chains, group=None, want
     first, count = shard_chains(n_chains, rank, world)
     ref = np.asarray(init_ref_state, dtype=np.float64)
     if ref.ndim == 3:
+        if ref.shape[0] != n_chains:
+            raise ValueError(f"init_ref_state holds {ref.shape[0]} trajectories for {n_chains} chains")
         ref = ref[first:first + count]
-    out = pgas.run_chains(key, ref, n_chains=count, chain_base=first, want_params=want_params)
+    if count > 0:
+        out = pgas.run_chains(key, ref, n_chains=count, chain_base=first, want_params=want_params)
+    else:
+        # more ranks than chains: this rank owns none.  It still takes part in the gathers, with zero-length blocks of the
+        # right trailing shape (running a dummy chain would reuse another rank's chain id).
+        import torch
+        m, K = pgas.cSMC.model, pgas.N_iterations
+        z = lambda *shape: torch.zeros((0,) + shape, dtype=torch.float64, device="cuda")   # noqa: E731
+        out = dict(state_trace=z(K, m.T, m.n_x), A_trace=z(K, m.n_x, m.M), S_trace=z(K, m.n_x, m.n_x))
     res = dict(state_trace=gather_chain_outputs(out["state_trace"], n_chains, group))
     if want_params:
         res["A_trace"] = gather_chain_outputs(out["A_trace"], n_chains, group)

@@ -92,6 +92,10 @@ typedef struct pgas_rng {
 
 const char* pgas_last_error(void);
 int pgas_version(void);
+/* PGAS_ABI_VERSION of the header the library was compiled against: a binding compares it with its own copy of
+ * the header before the first call (struct layouts and argument orders are only meaningful when they agree). */
+#define PGAS_ABI_VERSION 201
+int pgas_abi_version(void);
 int pgas_device_count(void);
 /* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */
 long long pgas_launch_count(void);
@@ -115,24 +119,28 @@ int pgas_hgp_eval_f64(const pgas_model* model, const double* states, const doubl
 
 /* condSequentialMonteCarlo.step (src/PGAS.py:79-153), one step for testing/teacher forcing:
  * logw (N), state (N,n_x), Theta (n_x,M), Sigma (n_x,n_x), ref_t (n_x), u2 = {u_res,u_anc} (2),
- * z (N,n_x) -> logw_out (N), state_out (N,n_x), anc_out (N) int32.  Runs the sweep kernel for a
- * single time step `t` (same code path as pgas_csmc_sweep_f64). */
+ * z (N,n_x) -> logw_out (N), state_out (N,n_x), anc_out (N) int32.  Runs the fused sweep kernel for a
+ * single time step `t`.  anc_out[N-1] is the reference particle's ancestor exactly as src/PGAS.py:122-127
+ * stores it: unclipped, i.e. N when rounding leaves cumsum(w)[-1] below u_anc (JAX's gather at :146 clamps;
+ * NumPy indexing would not) - clamp to N-1 before indexing with it on the host. */
 int pgas_csmc_step_f64(const pgas_model* model, int32_t N, int32_t t, const double* logw,
                        const double* state, const double* Theta, const double* Sigma,
                        const double* ref_t, const double* u2, const double* z,
                        double* logw_out, double* state_out, int32_t* anc_out,
                        int32_t cluster_size, void* stream);
 
-/* condSequentialMonteCarlo.__call__ (src/PGAS.py:176-228) for n_chains independent chains: the
- * persistent sweep kernel (one CTA or one thread-block cluster per chain, particles resident in
- * shared memory for all T steps), the final categorical pick (:224-225) and
- * reconstruct_trajectory (src/Filtering.py:40-55).
+/* condSequentialMonteCarlo.__call__ (src/PGAS.py:176-228) for n_chains independent chains: the sweep
+ * (split form: csmc_state_kernel in launches of <= 16 steps running ahead of a resampling kernel that
+ * keeps the chain's log-weights in registers and its CDF in shared memory, about 290 launches per sweep
+ * at T = 2000; or the fused single kernel with the particle set resident in shared memory / DSMEM),
+ * the final categorical pick (:224-225) and reconstruct_trajectory (src/Filtering.py:40-55).
  *   ref_traj (n_chains,T,n_x), Theta (n_chains,n_x,M), Sigma (n_chains,n_x,n_x)
  *   -> traj_out (n_chains,T,n_x); optional (may be NULL... see below) traces:
  *      state_trace (n_chains,T,N,n_x), anc_trace (n_chains,T-1,N) int32, logw_last (n_chains,N),
  *      final_idx (n_chains) int32.
  * state_trace and anc_trace are required (the backward pass reads them); logw_last/final_idx may
- * be NULL.  cluster_size: 0 = choose automatically, else 1,2,4,8,16.
+ * be NULL.  anc_trace[.., N-1] (reference particle) is unclipped as in the reference and may equal N
+ * (see pgas_csmc_step_f64); every device consumer clamps.  cluster_size: 0 = choose automatically, else 1,2,4,8,16.
  * workspace: pgas_csmc_sweep_workspace_bytes bytes enable the split form for two-dimensional bases (a state
  * kernel running ahead of the resampling kernel on a library-owned low-priority stream, fenced against
  * `stream` with events); with a NULL / smaller workspace the fused single-kernel form runs.  Both forms

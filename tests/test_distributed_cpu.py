@@ -32,7 +32,7 @@ def _worker(rank, world, port, n_chains, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_chains", [8, 5, 2])
+@pytest.mark.parametrize("n_chains", [8, 5, 2, 1])      # 1: the second rank owns no chain (zero-length block in the gather)
 def test_shard_and_gather_world2(n_chains):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
