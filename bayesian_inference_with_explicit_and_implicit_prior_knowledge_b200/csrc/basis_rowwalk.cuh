@@ -18,29 +18,39 @@
 #ifndef PGAS_RW_UNROLL
 #define PGAS_RW_UNROLL 2        // positions per loop body of the row walk (compile-time knob)
 #endif
-// n last-dimension positions at which the first R rows of the block are active: R Theta' pairs per position
+// One Theta' pair = the n_x coefficients of one (row, position): a 16-byte broadcast LDS.128 for n_x = 2.
+template <int NX>
+__device__ __forceinline__ void rw_load(const double* __restrict__ p, double (&w)[NX]) {
+    if constexpr (NX == 2) {
+        const double2 v = *reinterpret_cast<const double2*>(p);
+        w[0] = v.x; w[1] = v.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < NX; ++k) w[k] = p[k];
+    }
+}
+
+// n last-dimension positions at which the first R rows of the block are active: R Theta' pairs per position.
+// The pairs travel through a register ring `w`: on entry w[i] holds the pair th[i] (i < R); a pair is re-loaded for the NEXT
+// position right after its DFMAs, i.e. (R-1) pairs = 4 (R-1) PP DFMAs ahead of its use, so that the ~25-cycle LDS latency is
+// covered inside ONE warp (ptxas left one pair of look-ahead: a warp walking alone reached a quarter of the pipe rate,
+// profiles/r02_state_kernel_summary.md).  On exit w[i] holds the pair at the new th[i] for i < R, which is what the next
+// segment (R - 1 rows) expects; the over-read past the last block touches the bytes that follow Theta' in shared memory.
 template <int NX, int PP, int R>
 __device__ __forceinline__ void rw_segment(const double* __restrict__& th, int n, double (&acc)[PP][RW_RB][NX], double (&c)[PP],
-                                           double (&pv)[PP], const double (&b_2c)[PP]) {
+                                           double (&pv)[PP], const double (&b_2c)[PP], double (&w)[RW_RB][NX]) {
     constexpr int RW_UNROLL = PGAS_RW_UNROLL;
 #pragma unroll RW_UNROLL
     for (int j = 0; j < n; ++j) {
+        th += R * NX;
 #pragma unroll
         for (int i = 0; i < R; ++i) {
-            double w[NX];
-            if constexpr (NX == 2) {
-                const double2 v = *reinterpret_cast<const double2*>(th + i * 2);
-                w[0] = v.x; w[1] = v.y;
-            } else {
-#pragma unroll
-                for (int k = 0; k < NX; ++k) w[k] = th[i * NX + k];
-            }
 #pragma unroll
             for (int p = 0; p < PP; ++p)
 #pragma unroll
-                for (int k = 0; k < NX; ++k) acc[p][i][k] = fma(w[k], c[p], acc[p][i][k]);
+                for (int k = 0; k < NX; ++k) acc[p][i][k] = fma(w[i][k], c[p], acc[p][i][k]);
+            rw_load<NX>(th + i * NX, w[i]);
         }
-        th += R * NX;
 #pragma unroll
         for (int p = 0; p < PP; ++p) {
             const double n2 = fma(b_2c[p], c[p], -pv[p]);
@@ -54,6 +64,10 @@ template <int NX, int PP>
 __device__ __forceinline__ void rowwalk_mu(const double* __restrict__ bd, const int* __restrict__ blen, int nblk, int f_start, int f_step,
                                            const double (&t0)[PP], const double (&t1)[PP], double (&mu)[PP][NX]) {
     double a_cur[PP], a_prev[PP], a_2c[PP], b_cur[PP], b_prev[PP], b_2c[PP];
+    const double* __restrict__ th = bd;
+    double w[RW_RB][NX];
+#pragma unroll
+    for (int i = 0; i < RW_RB; ++i) rw_load<NX>(th + i * NX, w[i]);
 #pragma unroll
     for (int p = 0; p < PP; ++p) {
         sine_seed(t0[p], f_start, f_step, a_cur[p], a_prev[p], a_2c[p]);
@@ -61,7 +75,6 @@ __device__ __forceinline__ void rowwalk_mu(const double* __restrict__ bd, const 
 #pragma unroll
         for (int k = 0; k < NX; ++k) mu[p][k] = 0.0;
     }
-    const double* __restrict__ th = bd;
     for (int b = 0; b < nblk; ++b) {
         double acc[PP][RW_RB][NX];
         double c[PP], pv[PP];
@@ -76,10 +89,14 @@ __device__ __forceinline__ void rowwalk_mu(const double* __restrict__ bd, const 
         }
         // positions with 4, 3, 2, 1 active rows (packed byte counts, common.cuh): only selected lattice entries are walked
         const int L = blen[b];
-        rw_segment<NX, PP, 4>(th, L & 255, acc, c, pv, b_2c);
-        rw_segment<NX, PP, 3>(th, (L >> 8) & 255, acc, c, pv, b_2c);
-        rw_segment<NX, PP, 2>(th, (L >> 16) & 255, acc, c, pv, b_2c);
-        rw_segment<NX, PP, 1>(th, (L >> 24) & 255, acc, c, pv, b_2c);
+        rw_segment<NX, PP, 4>(th, L & 255, acc, c, pv, b_2c, w);
+        rw_segment<NX, PP, 3>(th, (L >> 8) & 255, acc, c, pv, b_2c, w);
+        rw_segment<NX, PP, 2>(th, (L >> 16) & 255, acc, c, pv, b_2c, w);
+        rw_segment<NX, PP, 1>(th, (L >> 24) & 255, acc, c, pv, b_2c, w);
+        // the next block starts with all RW_RB rows: pairs 1.. of its first position (pair 0 is in the ring already) are
+        // requested before this block's accumulators are folded
+#pragma unroll
+        for (int i = 1; i < RW_RB; ++i) rw_load<NX>(th + i * NX, w[i]);
 #pragma unroll
         for (int i = 0; i < RW_RB; ++i)
 #pragma unroll

@@ -118,7 +118,7 @@ __device__ __forceinline__ void philox_normal2(uint64_t seed, uint32_t purpose, 
                                                uint32_t t, uint32_t i, double& za, double& zb) {
     double ua, ub;
     philox_uniform2(seed, purpose, chain, iter, t, i, ua, ub);
-    const double r = sqrt_bf(fmax(-2.0 * log_unit_bf(ua + (1.0 / 9007199254740992.0)), 1e-300));
+    const double r = sqrt_bf(fmax(-2.0 * log_unit_bf(ua + (1.0 / 9007199254740992.0)), 1e-30));
     double s, c;
     sincospi_bf(2.0 * ub, s, c);
     za = r * c;

@@ -58,9 +58,12 @@ __device__ __forceinline__ double exp_neg_bf(double x) {
     return (x < -708.0) ? 0.0 : v;        // valid for x <= ~+700 as well (the shift may undershoot the max slightly)
 }
 
-// 1/d for normal positive d: float seed + two Newton steps (~1 ulp)
+// 1/d for normal positive d: float seed + two Newton steps (~1 ulp).  The seed is the bare MUFU.RCP: __frcp_rn carries a
+// slow-path CALL that splits the caller's basic block, which stops ptxas from interleaving independent evaluations.
 __device__ __forceinline__ double rcp_bf(double d) {
-    double y = (double)__frcp_rn((float)d);
+    float y0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"((float)d));
+    double y = (double)y0;
     y = y * fma(-d, y, 2.0);
     y = y * fma(-d, y, 2.0);
     return fma(y, fma(-d, y, 1.0), y);
@@ -89,7 +92,9 @@ __device__ __forceinline__ double log_unit_bf(double u) {
 
 // sqrt(a), a > 0 normal: float rsqrt seed + Newton (~1 ulp)
 __device__ __forceinline__ double sqrt_bf(double a) {
-    double y = (double)rsqrtf((float)a);
+    float y0;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"((float)a));
+    double y = (double)y0;
     y = y * fma(-0.5 * a, y * y, 1.5);
     y = y * fma(-0.5 * a, y * y, 1.5);
     double s = a * y;

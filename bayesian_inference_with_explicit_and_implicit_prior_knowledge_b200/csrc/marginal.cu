@@ -198,7 +198,7 @@ __device__ __forceinline__ StepVariates philox_step_variates(unsigned long long 
     uint32_t o[4];
     philox4x32_10(i, c1, iter, (purpose << 24) | (chain & 0xFFFFFFu), (uint32_t)seed, (uint32_t)(seed >> 32), o);
     const double ua = u53(o[0], o[1]), ub = u53(o[2], o[3]);
-    const double r = sqrt_bf(fmax(-2.0 * log_unit_bf(ua + (1.0 / 9007199254740992.0)), 1e-300));
+    const double r = sqrt_bf(fmax(-2.0 * log_unit_bf(ua + (1.0 / 9007199254740992.0)), 1e-30));
     double sn, cs;
     sincospi_bf(2.0 * ub, sn, cs);
     const double za = r * cs, zb = r * sn;

@@ -819,7 +819,9 @@ constexpr int ST_NT = PGAS_ST_NT;
 #endif
 constexpr int ST_PP = PGAS_ST_PP;      // particles per thread of the state kernel (compile-time knob)
 
-template <int NX, int NY>
+// INJ: injected variates (tests) instead of the in-kernel Philox stream — a template parameter so that the noise of a thread's
+// particles sits in ONE basic block (no run-time branch per draw) and ptxas interleaves their Philox / Box-Muller chains
+template <int NX, int NY, bool INJ>
 __global__ void __launch_bounds__(ST_NT, (512 / ST_NT) * (2 / ST_PP)) csmc_state_kernel(const __grid_constant__ StateArgs s) {
     constexpr int D = 2;
     const SweepArgs& a = s.a;
@@ -923,6 +925,29 @@ __global__ void __launch_bounds__(ST_NT, (512 / ST_NT) * (2 / ST_PP)) csmc_state
         }
 #pragma unroll
         for (int k = 0; k < NX; ++k) ref[k] = refc[(size_t)t * NX + k];
+        // the noise of step t does not depend on the state: drawn first, both particles' Philox / Box-Muller chains in one
+        // straight-line block next to the sine seeds of the row walk (independent dependent-FP64 chains for the scheduler)
+        double z[ST_PP][NX];
+        if constexpr (INJ) {
+#pragma unroll
+            for (int p = 0; p < ST_PP; ++p) {
+                const double* zp = a.Z + (((size_t)chain * a.var_rows + (t - a.row_off)) * N + min(ip[p], N - 1)) * NX;
+#pragma unroll
+                for (int k = 0; k < NX; ++k) z[p][k] = zp[k];
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < ST_PP; ++p) {
+#pragma unroll
+                for (int k = 0; k < NX; k += 2) {
+                    double za, zb;
+                    philox_normal2(a.seed, PURPOSE_STATE, a.chain_base + chain, a.iteration, (unsigned)t | ((unsigned)(k >> 1) << 28),
+                                   (unsigned)min(ip[p], N - 1), za, zb);
+                    z[p][k] = za;
+                    if (k + 1 < NX) z[p][k + 1] = zb;
+                }
+            }
+        }
         double t0v[ST_PP], t1v[ST_PP];
 #pragma unroll
         for (int p = 0; p < ST_PP; ++p) {
@@ -933,32 +958,34 @@ __global__ void __launch_bounds__(ST_NT, (512 / ST_NT) * (2 / ST_PP)) csmc_state
         double mu[ST_PP][NX];
         rowwalk_mu<NX, ST_PP>(bd, rwlen, nblk, f_start, f_step, t0v, t1v, mu);
         const size_t prow = ((size_t)chain * s.rows + (size_t)(t - s.t0)) * N;
+        // log-densities and the new state of all particles of the thread, branch-free; the stores follow
+        double la[ST_PP], lr[ST_PP], ll[ST_PP];
 #pragma unroll
         for (int p = 0; p < ST_PP; ++p) {
-            const int i = min(ip[p], N - 1);
-            const double la = gauss_loglik<NX, NY>(m, y, mu[p]);
-            const double lr = gauss_logpdf_state<NX>(sw, slogc[0], ref, mu[p]);
-            double z[NX];
-            draw_normals<NX>(a, chain, t, i, z);
+            la[p] = gauss_loglik<NX, NY>(m, y, mu[p]);
+            lr[p] = gauss_logpdf_state<NX>(sw, slogc[0], ref, mu[p]);
+            const bool is_ref = ip[p] == N - 1;
 #pragma unroll
             for (int r = 0; r < NX; ++r) {
                 double v = mu[p][r];
 #pragma unroll
-                for (int c = 0; c <= r; ++c) v = fma(chol[r * NX + c], z[c], v);
-                x[p][r] = v;
+                for (int c = 0; c <= r; ++c) v = fma(chol[r * NX + c], z[p][c], v);
+                x[p][r] = is_ref ? ref[r] : v;                              // src/PGAS.py:134
             }
-            if (ip[p] == N - 1) {
+            ll[p] = gauss_loglik<NX, NY>(m, y, x[p]);
+        }
 #pragma unroll
-                for (int k = 0; k < NX; ++k) x[p][k] = ref[k];                 // src/PGAS.py:134
-            }
-            const double ll = gauss_loglik<NX, NY>(m, y, x[p]);
+        for (int p = 0; p < ST_PP; ++p) {
             if (val[p]) {
                 double* out = a.state_trace + (((size_t)chain * a.trace_rows + t) * N + ip[p]) * NX;
+                if constexpr (NX == 2) *reinterpret_cast<double2*>(out) = make_double2(x[p][0], x[p][1]);
+                else {
 #pragma unroll
-                for (int k = 0; k < NX; ++k) out[k] = x[p][k];
-                s.la[prow + ip[p]] = la;
-                s.lr[prow + ip[p]] = lr;
-                s.ll[prow + ip[p]] = ll;
+                    for (int k = 0; k < NX; ++k) out[k] = x[p][k];
+                }
+                s.la[prow + ip[p]] = la[p];
+                s.lr[prow + ip[p]] = lr[p];
+                s.ll[prow + ip[p]] = ll[p];
             }
         }
     }
@@ -1037,13 +1064,13 @@ static int launch_state(const StateArgs& s, cudaStream_t st) {
     const DevModel& m = s.a.m;
     const size_t smem = sizeof(double) * (((size_t)m.rw_slots + 1) & ~(size_t)1) + sizeof(double) * (2 * m.n_x * m.n_x + 2) + sizeof(int) * RW_MAXBLK + 32;
     const dim3 grid((unsigned)(s.nch * s.bpc));
-    if (m.n_y == 1) {
-        PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        csmc_state_kernel<2, 1><<<grid, ST_NT, smem, st>>>(s);
-    } else {
-        PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        csmc_state_kernel<2, 2><<<grid, ST_NT, smem, st>>>(s);
-    }
+    const bool inj = s.a.rng_mode == 1;
+#define PGAS_ST_LAUNCH(NYv, INJv) do { \
+        PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, NYv, INJv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        csmc_state_kernel<2, NYv, INJv><<<grid, ST_NT, smem, st>>>(s); } while (0)
+    if (m.n_y == 1) { if (inj) PGAS_ST_LAUNCH(1, true); else PGAS_ST_LAUNCH(1, false); }
+    else { if (inj) PGAS_ST_LAUNCH(2, true); else PGAS_ST_LAUNCH(2, false); }
+#undef PGAS_ST_LAUNCH
     PGAS_KERNEL_CHECK();
     return 0;
 }
