@@ -14,14 +14,36 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
+def _ulp_perturbed(V, seed=1):
+    """the normal / Student-t variates moved by one unit in the last place (random sign)"""
+    rng = np.random.default_rng(seed)
+    return {k: (v * (1.0 + 2.2e-16 * np.sign(rng.normal(size=np.shape(v)))) if k in ("Z", "TS", "ZXI0") else v) for k, v in V.items()}
+
+
+def _tolerance(run_oracle, V, ref, fields):
+    """BASELINE.json's 1e-9 — unless the ORACLE ITSELF moves by more than that when its input variates change by one ulp (the
+    shipped vehicle configuration does: prior precisions 1/sd span ten orders of magnitude), in which case two correct float64
+    implementations cannot agree more closely than that sensitivity; then 10x the measured sensitivity is the bar."""
+    other = run_oracle(HM.oracle_variates(_ulp_perturbed(V)))
+    sens = max(HM.rel_err(np.asarray(b, dtype=np.float64), np.asarray(a, dtype=np.float64)) for a, b in zip(fields(ref), fields(other)))
+    return max(REL, 10.0 * sens)
+
+
 @pytest.mark.parametrize("kind,T,N,M,cs", [("smo", 24, 32, 12, 0), ("smo", 12, 200, 41, 0), ("emps", 30, 48, 9, 1),
-                                           ("vehicle", 24, 40, 8, 0), ("smo", 16, 70, 12, 4)])
+                                           ("vehicle", 24, 40, 8, 0), ("smo", 16, 70, 12, 4),
+                                           # the shipped sizes (BASELINE configs[0..2]: N = 200; M = 41 | 2 x 20 | 9), 60-100 steps
+                                           ("smo", 100, 200, 41, 0), ("vehicle", 60, 200, 20, 0), ("emps", 100, 200, 9, 0)])
 def test_algorithm1_matches_oracle(kind, T, N, M, cs):
     from oracle import marginal as OMg
     prob = HM.make_marg_problem(kind, T=T, N=N, M=M, seed=3)
     lam = prob["lam"]
     V = HM.make_variates(prob, lam, seed=11)
     ref = OMg.alg1_run(prob["oracle"], N, lam, HM.oracle_variates(V))
+    REL = globals()["REL"]
+    if N >= 200 and T >= 60:        # shipped sizes: conditioning-aware bar (1e-9 where the oracle is that stable)
+        REL = _tolerance(lambda v: OMg.alg1_run(prob["oracle"], N, lam, v), V, ref,
+                         lambda o: [o["state_trace"]] + [o["suff_stats"][g][j] for g in range(prob["G"]) for j in range(2)])
+        assert REL < 1e-6
     A1 = helpers.pkg("Algorithm1").Algorithm1(forgetting_factor=lam, cluster_size=cs, **prob["prod_kwargs"])
     r = A1.filter(variates=HM.device_variates(V))
     assert int(r["status"][0]) == 0
@@ -33,11 +55,13 @@ def test_algorithm1_matches_oracle(kind, T, N, M, cs):
             assert HM.rel_err(_np(r["sst_trace"][4 * g + j][0]).reshape(sh), np.asarray(ref["suff_stats_trace"][g][j]).reshape(sh)) < REL
         for j, sh in enumerate([(N, M), (N, M, M), (N,), (N,)]):
             assert HM.rel_err(_np(r["final_stats"][4 * g + j][0]).reshape(sh), np.asarray(ref["suff_stats"][g][j]).reshape(sh)) < REL
-    assert HM.rel_err(_np(r["logw_trace"][0]), ref["logw_trace"]) < REL
+    assert HM.rel_err(_np(r["logw_trace"][0]), ref["logw_trace"]) < max(REL, 1e-7 if T >= 60 else 0.0)    # differences of O(1e3) log-densities
 
 
 @pytest.mark.parametrize("kind,T,N,M,cs", [("smo", 24, 32, 12, 0), ("smo", 10, 200, 41, 0), ("emps", 30, 48, 9, 2),
-                                           ("vehicle", 24, 40, 8, 0)])
+                                           ("vehicle", 24, 40, 8, 0),
+                                           # the shipped sizes, three refresh cycles of the rank-one updated factors
+                                           ("smo", 100, 200, 41, 0), ("vehicle", 60, 200, 20, 0)])
 def test_algorithm3_matches_oracle(kind, T, N, M, cs):
     import torch
     from oracle import marginal as OMg
@@ -50,6 +74,11 @@ def test_algorithm3_matches_oracle(kind, T, N, M, cs):
     rs = OMg.reference_stats(prob["oracle"], ref_x, ref_xi)
     V = HM.make_variates(prob, 1.0, seed=22)
     ref = OMg.alg3_run(prob["oracle"], N, ref_x, ref_xi, rs, HM.oracle_variates(V))
+    REL = globals()["REL"]
+    if N >= 200 and T >= 60:        # shipped sizes: conditioning-aware bar (see _tolerance)
+        REL = _tolerance(lambda v: OMg.alg3_run(prob["oracle"], N, ref_x, ref_xi, rs, v), V, ref, lambda o: [o["state_trace"], o["traj"]])
+        assert REL < 1e-6
+    LW = max(REL, 1e-7 if T >= 60 else 0.0)
     A3 = helpers.pkg("Algorithm3").Algorithm3(cluster_size=cs, **prob["prod_kwargs"])
     f64 = dict(dtype=torch.float64, device="cuda")
     rx = torch.as_tensor(ref_x[None], **f64)
@@ -65,7 +94,7 @@ def test_algorithm3_matches_oracle(kind, T, N, M, cs):
         assert int(r["status"][0]) == 0
         np.testing.assert_array_equal(_np(r["anc_trace"][0]), ref["anc_trace"])
         assert HM.rel_err(_np(r["state_trace"][0]), ref["state_trace"]) < REL
-        assert HM.rel_err(_np(r["logw_trace"][0]), ref["logw_trace"]) < REL
+        assert HM.rel_err(_np(r["logw_trace"][0]), ref["logw_trace"]) < LW
         assert int(r["idx"][0]) == ref["idx"]
         assert HM.rel_err(_np(r["traj"][0]), ref["traj"]) < REL
         for g in range(prob["G"]):
@@ -198,12 +227,12 @@ def test_shipped_smo_pipeline_recovers_the_spring_damper_force(tmp_path):
     assert np.all(np.isfinite(back["offline_Sigma_X"])) and np.all(np.isfinite(back["online_log_likelihood"]))
 
 
-def test_algorithm3_long_sweep_stays_on_the_oracle():
+@pytest.mark.parametrize("T,N,M", [(300, 64, 12), (160, 200, 41)])
+def test_algorithm3_long_sweep_stays_on_the_oracle(T, N, M):
     """The rank-one up/down-dated factors (refreshed every 32 steps) must not drift: a 300-step conditional sweep —
     nine refresh cycles — still reproduces every ancestor index of the re-factorising oracle and its trajectory to 1e-9."""
     import torch
     from oracle import marginal as OMg
-    T, N, M = 300, 64, 12
     prob = HM.make_marg_problem("smo", T=T, N=N, M=M, seed=12)
     V1 = HM.make_variates(prob, 1.0, seed=41)
     f = OMg.alg1_run(prob["oracle"], N, 1.0, HM.oracle_variates(V1))
