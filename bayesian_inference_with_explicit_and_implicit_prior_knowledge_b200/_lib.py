@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libpgas_b200.so")
-_SOURCES = ["model.cu", "sweep.cu", "weights.cu", "sweep_api.cu", "suffstats.cu", "mniw_draw.cu", "gp_posterior.cu", "chains.cu",
+_SOURCES = ["model.cu", "sweep.cu", "weights.cu", "weights_lat.cu", "sweep_api.cu", "suffstats.cu", "mniw_draw.cu", "gp_posterior.cu", "chains.cu",
             "marginal.cu", "microbench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

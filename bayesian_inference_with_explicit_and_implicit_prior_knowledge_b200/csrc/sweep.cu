@@ -813,16 +813,19 @@ struct StateArgs {
     int chain0, nch;             // this launch covers chains chain0 .. chain0 + nch - 1
 };
 
-constexpr int ST_NT = PGAS_ST_NT;
 #ifndef PGAS_ST_PP
 #define PGAS_ST_PP 2
 #endif
-constexpr int ST_PP = PGAS_ST_PP;      // particles per thread of the state kernel (compile-time knob)
+constexpr int ST_NT_BIG = PGAS_ST_NT, ST_PP_BIG = PGAS_ST_PP;      // geometry of the state kernel when the launch fills the GPU
+constexpr int ST_NT_SMALL = 64, ST_PP_SMALL = 1;                   // ... and when it does not
 
 // INJ: injected variates (tests) instead of the in-kernel Philox stream — a template parameter so that the noise of a thread's
 // particles sits in ONE basic block (no run-time branch per draw) and ptxas interleaves their Philox / Box-Muller chains
-template <int NX, int NY, bool INJ>
-__global__ void __launch_bounds__(ST_NT, (512 / ST_NT) * (2 / ST_PP)) csmc_state_kernel(const __grid_constant__ StateArgs s) {
+// ST_NT threads per CTA, ST_PP particles per thread: <256, 2> when the chains of a launch fill the GPU (two particles share every
+// Theta' pair: half the shared-memory traffic per DFMA, 128 registers, two CTAs per SM); <64, 1> when they do not (few chains:
+// four times as many, smaller CTAs spread over all SMs, and a step's dependent chain per thread is half as long).
+template <int NX, int NY, bool INJ, int ST_NT, int ST_PP>
+__global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_state_kernel(const __grid_constant__ StateArgs s) {
     constexpr int D = 2;
     const SweepArgs& a = s.a;
     const DevModel& m = a.m;
@@ -1030,6 +1033,9 @@ extern "C" int pgas_debug_set_split_ticks(long long* dev_buf) { g_dbg_split_tick
 #ifndef PGAS_SPLIT_GROUPS
 #define PGAS_SPLIT_GROUPS 2
 #endif
+#ifndef PGAS_LAT_MAX_CHAINS
+#define PGAS_LAT_MAX_CHAINS 16      // up to this many chains per launch the latency form of the resampling kernel is the default
+#endif
 constexpr int SPLIT_GROUPS = PGAS_SPLIT_GROUPS;      // chain groups of the state kernel: each on its own stream, so that a group's next
                                      // launch starts as soon as ITS CTAs retire (no wave-quantisation tail across all chains)
 struct SplitStreams {
@@ -1060,16 +1066,27 @@ static int split_streams_init() {
     return 0;
 }
 
-static int launch_state(const StateArgs& s, cudaStream_t st) {
+static int launch_state(const StateArgs& s_in, cudaStream_t st) {
+    StateArgs s = s_in;
     const DevModel& m = s.a.m;
     const size_t smem = sizeof(double) * (((size_t)m.rw_slots + 1) & ~(size_t)1) + sizeof(double) * (2 * m.n_x * m.n_x + 2) + sizeof(int) * RW_MAXBLK + 32;
-    const dim3 grid((unsigned)(s.nch * s.bpc));
     const bool inj = s.a.rng_mode == 1;
-#define PGAS_ST_LAUNCH(NYv, INJv) do { \
-        PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, NYv, INJv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        csmc_state_kernel<2, NYv, INJv><<<grid, ST_NT, smem, st>>>(s); } while (0)
-    if (m.n_y == 1) { if (inj) PGAS_ST_LAUNCH(1, true); else PGAS_ST_LAUNCH(1, false); }
-    else { if (inj) PGAS_ST_LAUNCH(2, true); else PGAS_ST_LAUNCH(2, false); }
+    // geometry: big CTAs unless they would leave SMs idle (fewer than ~1.5 CTAs per SM slot pair); PGAS_STATE_SMALL=0|1 forces one
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int bpc_big = (s.a.N + ST_PP_BIG * ST_NT_BIG - 1) / (ST_PP_BIG * ST_NT_BIG);
+    bool small = s.a.n_chains * bpc_big < (3 * sms) / 2;                       // judged on the whole sweep, not on one chain group
+    if (const char* e = getenv("PGAS_STATE_SMALL")) small = atoi(e) != 0;     // developer override
+    const int per = small ? ST_PP_SMALL * ST_NT_SMALL : ST_PP_BIG * ST_NT_BIG;
+    s.bpc = (s.a.N + per - 1) / per;
+    const dim3 grid((unsigned)(s.nch * s.bpc));
+#define PGAS_ST_LAUNCH(NYv, INJv, NTv, PPv) do { \
+        PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, NYv, INJv, NTv, PPv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        csmc_state_kernel<2, NYv, INJv, NTv, PPv><<<grid, NTv, smem, st>>>(s); } while (0)
+#define PGAS_ST_GEOM(NYv, INJv) do { if (small) PGAS_ST_LAUNCH(NYv, INJv, ST_NT_SMALL, ST_PP_SMALL); else PGAS_ST_LAUNCH(NYv, INJv, ST_NT_BIG, ST_PP_BIG); } while (0)
+    if (m.n_y == 1) { if (inj) PGAS_ST_GEOM(1, true); else PGAS_ST_GEOM(1, false); }
+    else { if (inj) PGAS_ST_GEOM(2, true); else PGAS_ST_GEOM(2, false); }
+#undef PGAS_ST_GEOM
 #undef PGAS_ST_LAUNCH
     PGAS_KERNEL_CHECK();
     return 0;
@@ -1108,7 +1125,7 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
         StateArgs s;
         s.a = a;
         s.x_carry = x_carry; s.la = la; s.lr = la + buf; s.ll = la + 2 * buf;
-        s.t0 = t0; s.t1 = t1; s.rows = rows; s.first = (c == 0); s.bpc = (a.N + ST_PP * ST_NT - 1) / (ST_PP * ST_NT);
+        s.t0 = t0; s.t1 = t1; s.rows = rows; s.first = (c == 0); s.bpc = 0;     // set by launch_state
         for (int g = 0; g < ngroups; ++g)
             if (c >= 2) PGAS_CUDA(cudaStreamWaitEvent(sg[g], g_split.k2[b], 0));   // buffer b was consumed by chunk c-2
         {   // short-lived state CTAs (sub-chunks) so that resampling CTAs find free slots quickly
@@ -1140,7 +1157,16 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
         }
         for (int g = 0; g < ngroups; ++g) PGAS_CUDA(cudaStreamWaitEvent(stream, g_split.k1[b][g], 0));
         const int wc = getenv("PGAS_SPLIT_PRE_C") ? 0 : pgas_weights_cluster(a.N);
-        if (wc > 0) {                                                          // dedicated kernel (weights.cu): the chain's CDF fits one CTA
+        // few chains: the per-step latency of the recursion bounds the sweep -> latency form (weights_lat.cu); many chains: the
+        // FP64 pipe does, and one CTA per chain (weights.cu) leaves the most room for the state kernel.  PGAS_WEIGHTS_KERNEL=3 / 1
+        // force one or the other (developer override).
+        const char* wk_env = getenv("PGAS_WEIGHTS_KERNEL");
+        const int lc = getenv("PGAS_SPLIT_PRE_C") ? 0 : pgas_weights_lat_cluster(a.N);
+        const bool use_lat = lc > 0 && (wk_env ? atoi(wk_env) == 3 : a.n_chains <= PGAS_LAT_MAX_CHAINS);
+        if (use_lat) {
+            r.C = lc; r.P = (a.N + lc - 1) / lc;
+            if (int rc = pgas_launch_weights_lat(r, stream)) return rc;
+        } else if (wc > 0) {                                                          // dedicated kernel (weights.cu): the chain's CDF fits one CTA
             r.C = wc; r.P = (a.N + wc - 1) / wc;
             if (int rc = pgas_launch_weights(r, stream)) return rc;
         } else if (int rc = pgas_launch_sweep_pre(r, stream)) return rc;
@@ -1190,7 +1216,7 @@ extern "C" int pgas_debug_state_kernel_f64(const pgas_model* model, int32_t N, i
             q.x_carry = x_carry;
             q.t0 = ts; q.t1 = std::min(ts + 16, t1); q.rows = rows;
             q.la = la + (size_t)(ts - t0) * N; q.lr = la + buf + (size_t)(ts - t0) * N; q.ll = la + 2 * buf + (size_t)(ts - t0) * N;
-            q.first = (c == 0 && ts == t0); q.bpc = (N + ST_PP * ST_NT - 1) / (ST_PP * ST_NT);
+            q.first = (c == 0 && ts == t0); q.bpc = 0;
             for (int g = 0; g < ngroups; ++g) {
                 q.chain0 = (int)((long long)n_chains * g / ngroups);
                 q.nch = (int)((long long)n_chains * (g + 1) / ngroups) - q.chain0;

@@ -40,6 +40,8 @@ int pgas_launch_sweep_fused(const SweepArgs& a, cudaStream_t stream);     // one
 int pgas_launch_sweep_pre(const SweepArgs& a, cudaStream_t stream);       // resampling recursion on precomputed log-densities
 int pgas_launch_weights(const SweepArgs& a, cudaStream_t stream);         // dedicated resampling kernel of the split form (weights.cu)
 int pgas_weights_cluster(int N);                                           // its cluster size for N particles; 0 = not applicable
+int pgas_launch_weights_lat(const SweepArgs& a, cudaStream_t stream);     // latency form: cluster per chain, st.async + mbarrier hand-offs (weights_lat.cu)
+int pgas_weights_lat_cluster(int N);                                       // its cluster size for N particles; 0 = not applicable
 bool pgas_sweep_split_eligible(const SweepArgs& a);
 size_t pgas_sweep_split_workspace(const DevModel& m, int N, int n_chains);
 int pgas_choose_cluster(const DevModel& m, int N, int n_chains, int requested);

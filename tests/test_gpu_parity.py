@@ -293,7 +293,10 @@ def test_pgas_reference_call_signature(built_lib):
     ("vehicle", 8192, 12, 1, 0, 1),      # cluster of 4, full
     ("smo", 300, 40, 3, 0, 2), ("smo", 4096, 70, 2, 0, 2), ("smo", 2500, 30, 1, 0, 2),   # cluster form forced (1 / 2 / 2 CTAs)
     ("smo", 2049, 30, 2, 0, 1), ("vehicle", 3000, 20, 1, 0, 1),   # one CTA, two slices, ragged second slice
-    ("smo", 300, 40, 3, 0, 0), ("smo", 4096, 70, 2, 0, 0)])   # general resampling kernel (csmc_sweep_kernel<PRE>)
+    ("smo", 300, 40, 3, 0, 0), ("smo", 4096, 70, 2, 0, 0),    # general resampling kernel (csmc_sweep_kernel<PRE>)
+    # latency form (weights_lat.cu: offspring scatter, st.async + mbarrier hand-offs): clusters of 1 / 8 / 10 (ragged, odd N) / 16 / 5 / 2
+    ("smo", 300, 40, 3, 0, 3), ("smo", 4096, 150, 2, 0, 3), ("smo", 5001, 20, 1, 0, 3), ("vehicle", 8192, 12, 1, 0, 3),
+    ("smo", 2049, 30, 2, 0, 3), ("vehicle", 700, 50, 2, 2, 3)])
 def test_split_and_fused_sweeps_agree(built_lib, kind, N, T, chains, cluster, dedicated, monkeypatch):
     """The split form (state kernel ahead of the resampling kernel, csrc/sweep.cu) and the fused kernel are two schedules
     of the same arithmetic: identical ancestors and traces, for particle counts that are not multiples of the tile sizes,
@@ -301,6 +304,8 @@ def test_split_and_fused_sweeps_agree(built_lib, kind, N, T, chains, cluster, de
     import os
     import torch
     monkeypatch.setenv("PGAS_WEIGHTS_KERNEL", str(dedicated))
+    if dedicated != 3:          # state kernel: the fill-the-GPU geometry <256, 2>; the latency-form cases run the few-chains one <64, 1>
+        monkeypatch.setenv("PGAS_STATE_SMALL", "0")
     p = helpers.make_problem(kind, T=T, N=N, seed=5)
     cs = helpers.product_csmc(p, cluster)
     dev = lambda x: torch.as_tensor(np.ascontiguousarray(x)).cuda()
