@@ -13,6 +13,7 @@
 //   C  x_t^i = mu + chol(Sigma) z,  logw_t^i = log p(y_t|x_t^i) - l_aux[a_i],  trace row written
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <vector>
 #include <stdlib.h>
 #include "basis_eval.cuh"
 #include "basis_rowwalk.cuh"
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
     StepConst* sc = reinterpret_cast<StepConst*>(sp);  sp += 2 * ((sizeof(StepConst) + 7) / 8);
     int* ip = reinterpret_cast<int*>(sp);
     int* rowpos = ip;           ip += ((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD;
-    int* cnt = ip;              ip += 2;
+    int* cnt = ip;              ip += 4;
     int* ntc_s = ip;            ip += 18;                      // per column block: position steps with non-zero tiles (basis_eval.cuh: kcb)
     int* rwlen = ip;            ip += RW_MAXBLK;               // row-walk block lengths
 
@@ -293,8 +294,9 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const bool v = (qc + u) * NT + tid < Pc && qc + u < PPT;
-                e1[u] = v ? exp_neg_bf(lwa[u] - m1w[u]) : 0.0;
-                e2[u] = v ? exp_neg_bf(lwr[u] - m2w[u]) : 0.0;
+                // a warp whose log-weights are all -inf is an empty unit (numerators 0, not exp(-inf + inf) = NaN)
+                e1[u] = v ? exp_neg_bf(lwa[u] - (m1w[u] == -INFINITY ? 0.0 : m1w[u])) : 0.0;
+                e2[u] = v ? exp_neg_bf(lwr[u] - (m2w[u] == -INFINITY ? 0.0 : m2w[u])) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) { s1[u] = e1[u]; s2[u] = e2[u]; }
@@ -434,8 +436,8 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
                 PGAS_FTICK(20);
                 const double m1w = warp_shift_max(lwa), m2w = warp_shift_max(lwr);
                 PGAS_FTICK(21);
-                const double e1 = (il < Pc) ? exp_neg_bf(lwa - m1w) : 0.0;
-                const double e2 = (il < Pc) ? exp_neg_bf(lwr - m2w) : 0.0;
+                const double e1 = (il < Pc) ? exp_neg_bf(lwa - (m1w == -INFINITY ? 0.0 : m1w)) : 0.0;
+                const double e2 = (il < Pc) ? exp_neg_bf(lwr - (m2w == -INFINITY ? 0.0 : m2w)) : 0.0;
                 PGAS_FTICK(22);
                 const double s1 = warp_scan_incl(e1, lane), s2 = warp_scan_incl(e2, lane);
                 PGAS_FTICK(23);
@@ -514,12 +516,14 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
                 gsum[(lane + 1) * 2] = i1;
                 gsum[(lane + 1) * 2 + 1] = i2;
             }
+            const int uni_flag = !(__shfl_sync(0xffffffffu, i1, 31) > 0.0) ? 1 : 0;    // all -inf, or a NaN: uniform weights (src/Filtering.py:24-25)
             if (lane == 0) {
                 gsum[0] = 0.0;
                 gsum[1] = 0.0;
                 fx[2 * MAXC] = r1;
                 fx[2 * MAXC + 1] = r2;
                 cnt[1] = __popc(below);
+                cnt[2] = uni_flag;
             }
         }
         PGAS_TICK(3);
@@ -530,6 +534,7 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
         const double myf1 = fx[rank * 2], myf2 = fx[rank * 2 + 1];
         const double S1 = fx[2 * MAXC], S2 = fx[2 * MAXC + 1];      // reciprocals of the normalisers
         const int cstar = cnt[1];
+        const bool uni = cnt[2] != 0;
         int mycnt = 0;
         for (int q = 0; q < PPT; ++q) {
             const int il = q * NT + tid;
@@ -539,7 +544,7 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
                 const double p1 = __dadd_rn(fp[1], __dmul_rn(b1[il], fp[0]));
                 const double p2 = __dadd_rn(fp[3], __dmul_rn(b2[il], fp[2]));
                 // W = clip(cumsum(w / sum w), 0, 1)  (src/Filtering.py:23-32)
-                b1[il] = clip01(cdf_value(p1, myf1, myg1, S1));
+                b1[il] = uni ? div_by_count((double)(base + il + 1), dN, rN) : clip01(cdf_value(p1, myf1, myg1, S1));
                 // cumsum(softmax(lw_anc)) < u_anc  (src/PGAS.py:118-124), not clipped
                 if (rank == cstar) mycnt += (cdf_value(p2, myf2, myg2, S2) < k_t.uanc) ? 1 : 0;
             }
@@ -553,7 +558,8 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
         PGAS_TICK(5);
         // ---- B2: systematic resampling (src/Filtering.py:28-35) by the owner of the CDF segment
         {
-            const double blo = clip01(__dmul_rn(myg1, S1)), bhi = clip01(__dmul_rn(g1hi, S1));
+            const double blo = uni ? div_by_count((double)min(base, N), dN, rN) : clip01(__dmul_rn(myg1, S1));
+            const double bhi = uni ? div_by_count((double)min(base + P, N), dN, rN) : clip01(__dmul_rn(g1hi, S1));
             const int jlo = (rank == 0) ? 0 : first_point_above(blo, k_t.ures, N, dN, rN);
             int jhi = (rank == c_last) ? N : first_point_above(bhi, k_t.ures, N, dN, rN);
             if (rank > c_last) jhi = jlo;                     // empty CTA
@@ -667,7 +673,7 @@ static size_t sweep_smem_bytes(const DevModel& m, int NX, int P, bool gather, in
     size_t d = (pre ? 0 : (rw ? (size_t)((m.rw_slots + 1) & ~1) : (size_t)m.n_packed + (size_t)m.NTNP * 32 + (size_t)NW * sine_tile_doubles(m)) + (size_t)NX * P * 2) + (size_t)P * 4 + (size_t)((P + 255) / 256) * 256 +
                ((gather && !pre) ? (size_t)NX * P : 0) + MAXC * 4 + 2 * (MAXC + 1) + 2 * MAXC + 2 + (size_t)((P + NT - 1) / NT) * NW * 8 + 2 * NX * NX + 2 +
                2 * ((sizeof(StepConst) + 7) / 8);
-    return d * 8 + (size_t)(((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD + 2 + 18 + RW_MAXBLK) * 4 + 32;
+    return d * 8 + (size_t)(((8 * m.NTNP + NX - 1) / NX + 1) * MAX_LEAD + 4 + 18 + RW_MAXBLK) * 4 + 32;
 }
 
 // threads per CTA: 512 (16 warps hide the dependent-FP64 latency best) when the per-warp sine tiles
@@ -1034,7 +1040,7 @@ extern "C" int pgas_debug_set_split_ticks(long long* dev_buf) { g_dbg_split_tick
 #define PGAS_SPLIT_GROUPS 2
 #endif
 #ifndef PGAS_LAT_MAX_CHAINS
-#define PGAS_LAT_MAX_CHAINS 16      // up to this many chains per launch the latency form of the resampling kernel is the default
+#define PGAS_LAT_MAX_CHAINS 32      // up to this many chains per launch the latency form of the resampling kernel is the default (A/B on B200: profiles/r02_strong_scaling.md)
 #endif
 constexpr int SPLIT_GROUPS = PGAS_SPLIT_GROUPS;      // chain groups of the state kernel: each on its own stream, so that a group's next
                                      // launch starts as soon as ITS CTAs retire (no wave-quantisation tail across all chains)
@@ -1107,6 +1113,10 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
     cudaStream_t sg[SPLIT_GROUPS];
     for (int g = 0; g < SPLIT_GROUPS; ++g) sg[g] = serial ? stream : g_split.auxg[g];
     PGAS_CUDA(cudaEventRecord(g_split.start, stream));
+    const bool timeline = getenv("PGAS_SPLIT_TIMELINE") != nullptr;
+    std::vector<cudaEvent_t> tl_state, tl_w;
+    cudaEvent_t tl_start = nullptr;
+    if (timeline) { cudaEventCreate(&tl_start); cudaEventRecord(tl_start, stream); }
     for (int g = 0; g < ngroups; ++g)
         if (!serial) PGAS_CUDA(cudaStreamWaitEvent(sg[g], g_split.start, 0));  // inputs (Theta, Sigma, ref) are ready
     // chunk boundaries: a short first chunk (the resampling kernel can start early) and a short last chunk (little
@@ -1144,6 +1154,9 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
             }
         }
         for (int g = 0; g < ngroups; ++g) PGAS_CUDA(cudaEventRecord(g_split.k1[b][g], sg[g]));
+        if (timeline) {                                                       // developer aid: PGAS_SPLIT_TIMELINE=1
+            cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sg[0]); tl_state.push_back(e);
+        }
         SweepArgs r = a;
         r.dbg = g_dbg_split_ticks;
         r.t_begin = t0; r.t_end = t1;
@@ -1171,6 +1184,19 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
             if (int rc = pgas_launch_weights(r, stream)) return rc;
         } else if (int rc = pgas_launch_sweep_pre(r, stream)) return rc;
         PGAS_CUDA(cudaEventRecord(g_split.k2[b], stream));
+        if (timeline) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream); tl_w.push_back(e); }
+    }
+    if (timeline) {
+        cudaStreamSynchronize(stream);
+        fprintf(stderr, "chunk: state group 0 done / resampling done [ms since sweep start]\n");
+        for (size_t i = 0; i < tl_w.size(); ++i) {
+            float ts = 0, tw = 0;
+            cudaEventElapsedTime(&ts, tl_start, tl_state[i]);
+            cudaEventElapsedTime(&tw, tl_start, tl_w[i]);
+            fprintf(stderr, "  %2zu  %8.3f  %8.3f\n", i, ts, tw);
+            cudaEventDestroy(tl_state[i]); cudaEventDestroy(tl_w[i]);
+        }
+        cudaEventDestroy(tl_start);
     }
     return 0;
 }

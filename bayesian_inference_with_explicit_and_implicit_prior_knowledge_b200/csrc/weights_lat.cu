@@ -71,13 +71,13 @@ __device__ __noinline__ int wl_points_exact(double W, double u, int N, double dN
 
 // number of stratified points U_j = (u + j) / N, j in [0, N), that are <= W  (U_j evaluated as src/Filtering.py:28 does):
 // the arithmetic guess and whether W N - u lies within 1e-9 of a point (then the caller decides with the exact quotient)
-__device__ __forceinline__ int wl_points_guess(double W, double u, double dN, bool& near) {
-    const double t = fma(W, dN, -u);
-    const double fl = floor(t);
-    const double fr = t - fl;
-    near = !(fr >= 1e-9 && fr <= 1.0 - 1e-9);
-    return (int)fmin(fmax(fl + 1.0, 0.0), dN);
+__device__ __forceinline__ int wl_points_guess(double W, double u, double dN, int N, bool& near) {
+    const double t = fma(W, dN, -u);                                        // W in [0, 1]: t in [-1, N]
+    near = fabs(t - rint(t)) < 1e-9;
+    return min(max(__double2int_rd(t) + 1, 0), N);
 }
+// min(v, 1) for a non-negative, non-NaN v (the CDF values: sums of non-negative numerators times a positive reciprocal)
+__device__ __forceinline__ double wl_min1(double v) { return v > 1.0 ? 1.0 : v; }
 
 __device__ __forceinline__ double wl_scan_max_incl(double v, int lane) {
 #pragma unroll
@@ -104,7 +104,7 @@ __device__ __forceinline__ void wl_exp_parts(double x, double& p, int& n) {
     double q = FM_EXP[0];
 #pragma unroll
     for (int i = 1; i < 14; ++i) q = fma(q, r, FM_EXP[i]);
-    p = (dead || isnan_) ? 0.0 : q;
+    p = dead ? 0.0 : q;                                                     // `dead` is true for NaN as well
     n = isnan_ ? WL_KNAN : (dead ? WL_KNONE : (int)nd);
 }
 // 2^d for d < 1024 (exactly 0 at and below the bottom of the normal range): an exact scale factor, three integer instructions
@@ -303,8 +303,8 @@ __global__ void __launch_bounds__(NT) csmc_weights_lat_kernel(const __grid_const
             nan2 = KK2 >= WL_KNAN;
             sc1 = wl_pow2(kw1 - KK1); sc2 = wl_pow2(kw2 - KK2);             // exact powers of two
             of1 = __dmul_rn((double)(my1 + (qw1 >> sh1)), unitq); of2 = __dmul_rn((double)(my2 + (qw2 >> sh2)), unitq);
-            lo1 = clip01(__dmul_rn(of1, S1));
-            hi1 = clip01(__dmul_rn(__dmul_rn((double)(my1 + (qn1 >> sh1)), unitq), S1));
+            lo1 = wl_min1(__dmul_rn(of1, S1));
+            hi1 = wl_min1(__dmul_rn(__dmul_rn((double)(my1 + (qn1 >> sh1)), unitq), S1));
             lo2 = __dmul_rn(of2, S2);
         }
 
@@ -316,14 +316,14 @@ __global__ void __launch_bounds__(NT) csmc_weights_lat_kernel(const __grid_const
             bool below[PPT];
 #pragma unroll
             for (int u = 0; u < PPT; ++u) {
-                W[u] = uni ? div_by_count((double)(g0 + u + 1), dN, rN) : clip01(__dmul_rn(__dadd_rn(of1, __dmul_rn(sc1, s1[u])), S1));
+                W[u] = uni ? div_by_count((double)(g0 + u + 1), dN, rN) : wl_min1(__dmul_rn(__dadd_rn(of1, __dmul_rn(sc1, s1[u])), S1));
                 below[u] = (u < nvalid) && !nan2 && (__dmul_rn(__dadd_rn(of2, __dmul_rn(sc2, s2[u])), S2) < uanc);
             }
             bool n_lo, n_hi, n_w[PPT];
-            int c_lo = wl_points_guess(lo1, ures, dN, n_lo), c_hi = wl_points_guess(hi1, ures, dN, n_hi);
+            int c_lo = wl_points_guess(lo1, ures, dN, N, n_lo), c_hi = wl_points_guess(hi1, ures, dN, N, n_hi);
             int cend[PPT];
 #pragma unroll
-            for (int u = 0; u < PPT; ++u) cend[u] = wl_points_guess(W[u], ures, dN, n_w[u]);
+            for (int u = 0; u < PPT; ++u) cend[u] = wl_points_guess(W[u], ures, dN, N, n_w[u]);
             bool any_near = n_lo || n_hi;
 #pragma unroll
             for (int u = 0; u < PPT; ++u) any_near = any_near || n_w[u];
@@ -472,7 +472,8 @@ int pgas_launch_weights_lat(const SweepArgs& a, cudaStream_t stream) {
     auto kern = a.C <= 1 ? csmc_weights_lat_kernel<WL_NT, WL_PPT, 1> : a.C <= 2 ? csmc_weights_lat_kernel<WL_NT, WL_PPT, 2>
               : a.C <= 4 ? csmc_weights_lat_kernel<WL_NT, WL_PPT, 4> : a.C <= 8 ? csmc_weights_lat_kernel<WL_NT, WL_PPT, 8>
                                                                                  : csmc_weights_lat_kernel<WL_NT, WL_PPT, 16>;
-    const size_t smem = weights_lat_smem(a.C);
+    size_t smem = weights_lat_smem(a.C);
+    if (const char* e = getenv("PGAS_WL_SMEM_KB")) smem = std::max(smem, (size_t)atoi(e) * 1024);   // developer knob: a large request keeps other CTAs off the SM
     PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (a.C > 8) PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};

@@ -325,6 +325,35 @@ def test_split_and_fused_sweeps_agree(built_lib, kind, N, T, chains, cluster, de
     assert bool(torch.isfinite(a["state_trace"]).all())
 
 
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3])
+def test_sweep_with_dead_and_degenerate_weights(built_lib, kernel, monkeypatch):
+    """Weights that vanish for whole warps and a step whose weights are all -inf, in every resampling kernel of the split sweep
+    (0 general, 1 one CTA per chain, 2 cluster form, 3 latency form): jax.nn.softmax gives -inf entries weight 0, and
+    systematic_SISR falls back to uniform weights when the sum is not > 0 (src/Filtering.py:24-25) — after which every
+    log-weight is NaN and every later step is uniform too.  Ancestors must equal the oracle's exactly."""
+    import warnings
+    import torch
+    from oracle import pgas as OP
+    monkeypatch.setenv("PGAS_WEIGHTS_KERNEL", str(kernel))
+    p = helpers.make_problem("smo", T=24, N=1024, seed=9)
+    p["obs"] = np.array(p["obs"], dtype=np.float64, copy=True)
+    p["obs"][17] = 1.0e200                                  # log p(y_17 | .) = -inf for every particle (the squared residual overflows)
+    p["omodel"].observations = p["obs"]
+    Z, U = helpers.sweep_variates(p, 4)
+    Z[5, 128:384] = 1.0e3                                   # 256 consecutive particles thrown far off: log-weights ~ -5e8 -> weight 0
+    cs = helpers.product_csmc(p)
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    g = cs.sweep(dev(p["ref"]), dev(p["Theta"]), dev(p["Sigma"]), variates=dict(Z=dev(Z[None]), U=dev(U[None])))
+    with warnings.catch_warnings(), np.errstate(all="ignore"):
+        warnings.simplefilter("ignore")
+        o = OP.csmc_sweep(p["omodel"], p["N"], p["ref"], p["Theta"], p["Sigma"], Z, U, keep_weights=True, **helpers.oracle_flags(p))
+    an_g, an_o = g["anc_trace"][0].cpu().numpy(), np.asarray(o["anc_trace"])
+    for t in range(1, p["T"]):
+        assert np.array_equal(an_g[t - 1], an_o[t - 1]), (kernel, t, int((an_g[t - 1] != an_o[t - 1]).sum()))
+    assert np.array_equal(an_o[17 - 1][:-1], np.arange(p["N"] - 1))          # the degenerate step resampled uniformly
+    assert helpers.rel_err(g["state_trace"][0].cpu().numpy(), o["state_trace"]) < helpers.REL_TOL
+
+
 def test_run_chains_resume_is_bit_exact(built_lib):
     """checkpoint / resume (SURVEY.md 8f item 4): the Gibbs state is (reference trajectory, key, iteration index);
     6 iterations == 4 iterations + a resumed run of 3 starting from trajectory 3"""
