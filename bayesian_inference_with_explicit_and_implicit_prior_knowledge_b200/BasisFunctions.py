@@ -74,6 +74,8 @@ class HilbertBasis:
     def __call__(self, x):
         if isinstance(x, _tracing.Expr):                 # marginalised filters (Algorithm1/2/3): per-step tracer
             return _tracing.BasisCall(self, x)
+        if isinstance(x, _models.Sym):                   # non-affine GP-input map: expression program (model plug-in)
+            return _models.ProgramBasis(self, x)
         if isinstance(x, _models.Affine):
             if len(x) != self.D:
                 raise ValueError(f"basis expects {self.D} inputs, traced value has {len(x)}")

@@ -20,7 +20,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 PGAS_MAX_NX, PGAS_MAX_NY, PGAS_MAX_NU, PGAS_MAX_D, PGAS_MAX_GP = 4, 2, 4, 3, 2
 LINK_IDENTITY, LINK_ATAN, LINK_TANH = 0, 1, 2
-MAP_AFFINE, MAP_VEHICLE_SLIP = 0, 1
+MAP_AFFINE, MAP_VEHICLE_SLIP, MAP_PROGRAM = 0, 1, 2
+PGAS_MAX_PROG, PGAS_PROG_STACK = 64, 8
+OPS = dict(PUSH_X=1, PUSH_U=2, PUSH_C=3, ADD=4, SUB=5, MUL=6, DIV=7, NEG=8, SIN=9, COS=10, TAN=11, TANH=12, ATAN=13, EXP=14, LOG=15,
+           SQRT=16, ABS=17, POW=18, ATAN2=19)
 FLAG_ANCESTOR_GATHER, FLAG_INPUT_PREV, FLAG_VCHOL_TRANSPOSE = 1, 2, 4
 
 
@@ -92,6 +95,7 @@ class ModelParams(C.Structure):
         ("Az", (C.c_double * (PGAS_MAX_NX + PGAS_MAX_NU)) * PGAS_MAX_D),
         ("bz", C.c_double * PGAS_MAX_D),
         ("slip_lf", C.c_double), ("slip_lr", C.c_double),
+        ("prog_len", C.c_int32), ("prog_op", C.c_int32 * PGAS_MAX_PROG), ("prog_const", C.c_double * PGAS_MAX_PROG),
         ("H", (C.c_double * PGAS_MAX_NX) * PGAS_MAX_NY),
         ("h0", C.c_double * PGAS_MAX_NY),
         ("R", (C.c_double * PGAS_MAX_NY) * PGAS_MAX_NY),

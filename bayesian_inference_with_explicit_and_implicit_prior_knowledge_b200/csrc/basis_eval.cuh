@@ -206,14 +206,83 @@ __device__ __forceinline__ void eval_mu_warp(const EvalCtx<D>& cx, const double*
     }
 }
 
+// ---------------------------------------------------------------------------------- expression programs (model plug-in)
+// The GP-input map of a user callable outside the affine / slip-angle families, traced on the host into a postfix program
+// (include/pgas_b200.h: PGAS_MAP_PROGRAM; models.py: Sym).  Interpreted per particle: the program is the same for every
+// thread (uniform control flow), the operand stack lives in local memory.  Kept out of line so that the compiled-in families
+// do not pay registers for it.
+static __device__ __noinline__ void pgas_map_program(const DevModel* m, const double* x, const double* u, double* z) {
+    double st[PGAS_PROG_STACK];
+    int sp = 0;
+    const int n = m->prog_len;
+    for (int pc = 0; pc < n; ++pc) {
+        const int ins = m->prog_op[pc], op = ins & 0xff, arg = ins >> 8;
+        if (op <= PGAS_OP_PUSH_C) {
+            st[sp & (PGAS_PROG_STACK - 1)] = (op == PGAS_OP_PUSH_X) ? x[arg] : (op == PGAS_OP_PUSH_U) ? u[arg] : m->prog_const[arg];
+            ++sp;
+        } else if (op <= PGAS_OP_DIV || op >= PGAS_OP_POW) {
+            const double b = st[(--sp) & (PGAS_PROG_STACK - 1)], a = st[(sp - 1) & (PGAS_PROG_STACK - 1)];
+            double r;
+            switch (op) {
+                case PGAS_OP_ADD: r = a + b; break;
+                case PGAS_OP_SUB: r = a - b; break;
+                case PGAS_OP_MUL: r = a * b; break;
+                case PGAS_OP_DIV: r = a / b; break;
+                case PGAS_OP_POW: r = pow(a, b); break;
+                default: r = atan2(a, b); break;
+            }
+            st[(sp - 1) & (PGAS_PROG_STACK - 1)] = r;
+        } else {
+            const double a = st[(sp - 1) & (PGAS_PROG_STACK - 1)];
+            double r;
+            switch (op) {
+                case PGAS_OP_NEG: r = -a; break;
+                case PGAS_OP_SIN: r = sin(a); break;
+                case PGAS_OP_COS: r = cos(a); break;
+                case PGAS_OP_TAN: r = tan(a); break;
+                case PGAS_OP_TANH: r = tanh(a); break;
+                case PGAS_OP_ATAN: r = atan(a); break;
+                case PGAS_OP_EXP: r = exp(a); break;
+                case PGAS_OP_LOG: r = log(a); break;
+                case PGAS_OP_SQRT: r = sqrt(a); break;
+                default: r = fabs(a); break;
+            }
+            st[(sp - 1) & (PGAS_PROG_STACK - 1)] = r;
+        }
+    }
+    for (int d = 0; d < m->D; ++d) z[d] = st[d];
+}
+
+// GP-input map z = g(state, input) of any family on zero-padded arrays x[PGAS_MAX_NX], u[PGAS_MAX_NU] -> z[PGAS_MAX_D]
+// (src/PGAS.py:52-54: basis_fcn(state, inputs[t])); used where the map is not on a hot path (statistics, basis evaluation)
+__device__ __forceinline__ void gp_map_any(const DevModel& m, const double* x, const double* u, double* z) {
+    if (m.map_kind == PGAS_MAP_PROGRAM) {
+        pgas_map_program(&m, x, u, z);
+    } else if (m.map_kind == PGAS_MAP_VEHICLE_SLIP) {
+        // src/Vehicle.py:50-57: alpha_f = delta - atan((v_y + psi_dot l_f)/v_x), alpha_r = -atan((v_y - psi_dot l_r)/v_x)
+        z[0] = u[0] - atan((x[1] + x[0] * m.slip_lf) / u[1]);
+        z[1] = -atan((x[1] - x[0] * m.slip_lr) / u[1]);
+        z[2] = 0.0;
+    } else {
+        for (int d = 0; d < m.D; ++d) {
+            double acc = m.bz[d];
+            for (int k = 0; k < m.n_x; ++k) acc = fma(m.Az[d][k], x[k], acc);
+            for (int k = 0; k < m.n_u; ++k) acc = fma(m.Az[d][m.n_x + k], u[k], acc);
+            z[d] = acc;
+        }
+    }
+}
+
+
 // GP-input map with the model constants hoisted into registers once per kernel (kernel-parameter reads
 // with run-time indices cost ~100 cycles each on the critical path of every step)
 template <int NX, int D>
 struct MapRegs {
     double A[D][NX], off[D], sc[D], lf, lr;
     int kind;
+    const DevModel* mp;
     __device__ __forceinline__ void init(const DevModel& m) {
-        kind = m.map_kind; lf = m.slip_lf; lr = m.slip_lr;
+        kind = m.map_kind; lf = m.slip_lf; lr = m.slip_lr; mp = &m;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             off[d] = m.L[d] - m.center[d];
@@ -225,7 +294,16 @@ struct MapRegs {
     // cz[d] = bz[d] + sum_k Az[d][n_x+k] u[k] is the per-step constant part (StepConst)
     __device__ __forceinline__ void apply(const double x[NX], const double* __restrict__ cz, const double* __restrict__ u, double tz[D]) const {
         double z[D];
-        if (kind == PGAS_MAP_VEHICLE_SLIP) {
+        if (kind == PGAS_MAP_PROGRAM) {                     // model plug-in: temporaries keep the address-taking out of the other paths
+            double xl[PGAS_MAX_NX], ul[PGAS_MAX_NU], zl[PGAS_MAX_D];
+#pragma unroll
+            for (int k = 0; k < PGAS_MAX_NX; ++k) xl[k] = (k < NX) ? x[k < NX ? k : 0] : 0.0;
+#pragma unroll
+            for (int k = 0; k < PGAS_MAX_NU; ++k) ul[k] = u[k];
+            pgas_map_program(mp, xl, ul, zl);
+#pragma unroll
+            for (int d = 0; d < D; ++d) z[d] = zl[d];
+        } else if (kind == PGAS_MAP_VEHICLE_SLIP) {
             const double x0 = x[0], x1 = x[NX > 1 ? 1 : 0];
             z[0] = u[0] - atan((x1 + x0 * lf) / u[1]);
             if constexpr (D >= 2) z[1] = -atan((x1 - x0 * lr) / u[1]);
@@ -248,7 +326,16 @@ struct MapRegs {
 template <int NX, int D>
 __device__ __forceinline__ void gp_input(const DevModel& m, const double x[NX], const double* __restrict__ u, double tz[D]) {
     double z[D];
-    if (m.map_kind == PGAS_MAP_VEHICLE_SLIP) {
+    if (m.map_kind == PGAS_MAP_PROGRAM) {
+        double xl[PGAS_MAX_NX], ul[PGAS_MAX_NU], zl[PGAS_MAX_D];
+#pragma unroll
+        for (int k = 0; k < PGAS_MAX_NX; ++k) xl[k] = (k < NX) ? x[k < NX ? k : 0] : 0.0;
+#pragma unroll
+        for (int k = 0; k < PGAS_MAX_NU; ++k) ul[k] = (k < m.n_u) ? u[k] : 0.0;
+        pgas_map_program(&m, xl, ul, zl);
+#pragma unroll
+        for (int d = 0; d < D; ++d) z[d] = zl[d];
+    } else if (m.map_kind == PGAS_MAP_VEHICLE_SLIP) {
         // src/Vehicle.py:50-57: alpha_f = delta - atan((v_y + psi_dot l_f)/v_x), alpha_r = -atan((v_y - psi_dot l_r)/v_x)
         const double x0 = x[0], x1 = (NX > 1) ? x[NX > 1 ? 1 : 0] : 0.0;
         const double af = u[0] - atan((x1 + x0 * m.slip_lf) / u[1]);

@@ -62,7 +62,24 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
     if (p->idx_step < 1 || p->idx_start < 1) PGAS_FAIL(-2, "idx_start and idx_step must be >= 1");
     if (p->map_kind == PGAS_MAP_VEHICLE_SLIP && (p->n_x < 2 || p->n_u < 2))
         PGAS_FAIL(-2, "vehicle slip map needs n_x >= 2 and n_u >= 2");
-    if (p->map_kind != PGAS_MAP_AFFINE && p->map_kind != PGAS_MAP_VEHICLE_SLIP) PGAS_FAIL(-2, "unknown map_kind %d", p->map_kind);
+    if (p->map_kind != PGAS_MAP_AFFINE && p->map_kind != PGAS_MAP_VEHICLE_SLIP && p->map_kind != PGAS_MAP_PROGRAM)
+        PGAS_FAIL(-2, "unknown map_kind %d", p->map_kind);
+    if (p->map_kind == PGAS_MAP_PROGRAM) {
+        // validate the expression program: known opcodes, operands in range, stack within bounds, exactly D results
+        if (p->prog_len < 1 || p->prog_len > PGAS_MAX_PROG) PGAS_FAIL(-2, "expression program of %d instructions (1..%d)", p->prog_len, PGAS_MAX_PROG);
+        int sp = 0;
+        for (int i = 0; i < p->prog_len; ++i) {
+            const int op = p->prog_op[i] & 0xff, arg = p->prog_op[i] >> 8;
+            if (op == PGAS_OP_PUSH_X) { if (arg < 0 || arg >= p->n_x) PGAS_FAIL(-2, "program instruction %d: state component %d", i, arg); ++sp; }
+            else if (op == PGAS_OP_PUSH_U) { if (arg < 0 || arg >= p->n_u) PGAS_FAIL(-2, "program instruction %d: input component %d", i, arg); ++sp; }
+            else if (op == PGAS_OP_PUSH_C) { if (arg < 0 || arg >= PGAS_MAX_PROG) PGAS_FAIL(-2, "program instruction %d: constant %d", i, arg); ++sp; }
+            else if ((op >= PGAS_OP_ADD && op <= PGAS_OP_DIV) || op == PGAS_OP_POW || op == PGAS_OP_ATAN2) { if (sp < 2) PGAS_FAIL(-2, "program instruction %d: stack underflow", i); --sp; }
+            else if (op >= PGAS_OP_NEG && op <= PGAS_OP_ABS) { if (sp < 1) PGAS_FAIL(-2, "program instruction %d: stack underflow", i); }
+            else PGAS_FAIL(-2, "program instruction %d: unknown opcode %d", i, op);
+            if (sp > PGAS_PROG_STACK) PGAS_FAIL(-2, "program instruction %d: more than %d operands on the stack", i, PGAS_PROG_STACK);
+        }
+        if (sp != p->D) PGAS_FAIL(-2, "expression program leaves %d values, the basis has D = %d inputs", sp, p->D);
+    }
 
     const int D = p->D, M = p->M;
     DevModel dm;
@@ -83,6 +100,8 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
         for (int k = 0; k < p->n_x + p->n_u; ++k) dm.Az[d][k] = p->Az[d][k];
     }
     dm.slip_lf = p->slip_lf; dm.slip_lr = p->slip_lr;
+    dm.prog_len = (p->map_kind == PGAS_MAP_PROGRAM) ? p->prog_len : 0;
+    for (int i = 0; i < dm.prog_len; ++i) { dm.prog_op[i] = p->prog_op[i]; dm.prog_const[i] = p->prog_const[i]; }
     for (int r = 0; r < p->n_y; ++r) {
         dm.h0[r] = p->h0[r];
         for (int k = 0; k < p->n_x; ++k) dm.H[r][k] = p->H[r][k];

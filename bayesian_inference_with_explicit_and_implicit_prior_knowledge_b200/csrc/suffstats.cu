@@ -93,14 +93,16 @@ __global__ void __launch_bounds__(SNT, 5) suffstats_kernel(const __grid_constant
                 for (int k = 0; k < PGAS_MAX_NX; ++k) x[k] = (k < nx) ? traj[(size_t)t * nx + k] : 0.0;
 #pragma unroll
                 for (int k = 0; k < PGAS_MAX_NU; ++k) u[k] = (k < m.n_u) ? m.inputs[(size_t)t * m.n_u + k] : 0.0;   // x_t pairs with u_t (src/PGAS.py:294-296)
-                if (m.map_kind == PGAS_MAP_VEHICLE_SLIP) {
-                    z = (d == 0) ? u[0] - atan((x[1] + x[0] * m.slip_lf) / u[1]) : -atan((x[1] - x[0] * m.slip_lr) / u[1]);
-                } else {
+                if (m.map_kind == PGAS_MAP_AFFINE) {
                     z = m.bz[d];
 #pragma unroll
                     for (int k = 0; k < PGAS_MAX_NX; ++k) z = (k < nx) ? fma(m.Az[d][k], x[k], z) : z;
 #pragma unroll
                     for (int k = 0; k < PGAS_MAX_NU; ++k) z = (k < m.n_u) ? fma(m.Az[d][nx + k], u[k], z) : z;
+                } else {                                   // slip angles / expression program: all components, this item keeps one
+                    double zz[PGAS_MAX_D];
+                    gp_map_any(m, x, u, zz);
+                    z = zz[d];
                 }
                 const double tn = (z - m.center[d] + m.L[d]) * m.inv2L[d];
                 double cur, prev, twoc;

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(BT) resample_kernel(const double* __restrict__
 
 // ------------------------------------------------------------------ basis evaluation
 // phi (n, M) in the reference's basis order, using the same sine recurrences as the sweep.
-__global__ void __launch_bounds__(128) hgp_eval_kernel(const DevModel m, const double* __restrict__ states, const double* __restrict__ inputs,
+__global__ void __launch_bounds__(128) hgp_eval_kernel(const __grid_constant__ DevModel m, const double* __restrict__ states, const double* __restrict__ inputs,
                                                        int input_stride, int n, int npos, double* __restrict__ phi) {
     // one warp per sample: lanes build the per-dimension sine tables in shared memory, then
     // stride over the M basis functions.
@@ -175,18 +175,9 @@ __global__ void __launch_bounds__(128) hgp_eval_kernel(const DevModel m, const d
         double x[PGAS_MAX_NX], u[PGAS_MAX_NU], z[PGAS_MAX_D];
         for (int k = 0; k < m.n_x; ++k) x[k] = states[(size_t)smp * m.n_x + k];
         for (int k = 0; k < m.n_u; ++k) u[k] = inputs[(size_t)smp * input_stride + k];
-        if (m.map_kind == PGAS_MAP_VEHICLE_SLIP) {
-            z[0] = u[0] - atan((x[1] + x[0] * m.slip_lf) / u[1]);
-            z[1] = -atan((x[1] - x[0] * m.slip_lr) / u[1]);
-            z[2] = 0.0;
-        } else {
-            for (int d = 0; d < m.D; ++d) {
-                double acc = m.bz[d];
-                for (int k = 0; k < m.n_x; ++k) acc = fma(m.Az[d][k], x[k], acc);
-                for (int k = 0; k < m.n_u; ++k) acc = fma(m.Az[d][m.n_x + k], u[k], acc);
-                z[d] = acc;
-            }
-        }
+        for (int k = m.n_x; k < PGAS_MAX_NX; ++k) x[k] = 0.0;
+        for (int k = m.n_u; k < PGAS_MAX_NU; ++k) u[k] = 0.0;
+        gp_map_any(m, x, u, z);
         __syncwarp();
         if (lane < m.D) {
             const int d = lane;

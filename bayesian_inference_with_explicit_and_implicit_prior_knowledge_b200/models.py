@@ -11,7 +11,11 @@ affine values and reduced to a parameter block of a compiled-in family:
   likelihood_fcn -> Gaussian log-density of obs around an affine map of the state
                     (src/EMPS.py:250-252, src/Toy_Example.py:142-144).
 
-A callable outside these families raises at construction time; nothing falls back to the host.
+A `basis_fcn` whose GP-input map is not affine (np.sin(state[0]), products of state components, ...) is traced a second
+time with symbolic EXPRESSIONS (`Sym`) and shipped to the kernels as a postfix program they interpret per particle
+(include/pgas_b200.h: PGAS_MAP_PROGRAM) — the model plug-in of SURVEY.md 8f item 2: arithmetic, powers and the elementary
+functions of numpy, no data-dependent Python control flow.  Anything else raises at construction time; nothing falls back to
+the host.
 """
 import ctypes as C
 
@@ -105,10 +109,164 @@ class Affine:
         raise TypeError(f"numpy.{func.__name__} of a state-dependent value is not supported by the model tracer")
 
 
+# ----------------------------------------------------------------------------- expression tracer (model plug-in)
+_UNARY = {np.negative: "NEG", np.sin: "SIN", np.cos: "COS", np.tan: "TAN", np.tanh: "TANH", np.arctan: "ATAN", np.exp: "EXP",
+          np.log: "LOG", np.sqrt: "SQRT", np.abs: "ABS", np.absolute: "ABS", np.fabs: "ABS"}
+_BINARY = {np.add: "ADD", np.subtract: "SUB", np.multiply: "MUL", np.divide: "DIV", np.true_divide: "DIV", np.power: "POW",
+           np.arctan2: "ATAN2"}
+
+
+class Sym:
+    """Symbolic vector of expression trees over (state, input).  A node is ("x", k) | ("u", k) | ("c", value) |
+    (opcode name, child[, child])."""
+    __array_priority__ = 1000
+
+    def __init__(self, nodes, scalar=False):
+        self.nodes, self.scalar = list(nodes), scalar
+
+    @property
+    def shape(self):
+        return () if self.scalar else (len(self.nodes),)
+
+    def __len__(self):
+        return len(self.nodes)
+
+    def __getitem__(self, idx):
+        if isinstance(idx, (int, np.integer)):
+            return Sym([self.nodes[idx]], scalar=True)
+        return Sym(list(np.asarray(self.nodes, dtype=object)[idx]) if not isinstance(idx, slice) else self.nodes[idx])
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self.nodes)))
+
+    @staticmethod
+    def _lift(o, n):
+        if isinstance(o, Sym):
+            nodes = o.nodes
+        elif isinstance(o, Affine):
+            raise TypeError("mixing affine and expression tracers")
+        else:
+            nodes = [("c", float(v)) for v in np.ravel(np.asarray(o, dtype=np.float64))]
+        if len(nodes) == n:
+            return nodes
+        if len(nodes) == 1:
+            return nodes * n
+        raise TypeError(f"shape mismatch: {len(nodes)} vs {n}")
+
+    def _binary(self, name, o, swap=False):
+        n = max(len(self), len(o) if isinstance(o, Sym) else np.size(o))
+        a, b = self._lift(self, n), self._lift(o, n)
+        if swap:
+            a, b = b, a
+        out = []
+        for x, y in zip(a, b):
+            if x[0] == "c" and y[0] == "c":                          # constant folding
+                fold = {"ADD": np.add, "SUB": np.subtract, "MUL": np.multiply, "DIV": np.divide, "POW": np.power, "ATAN2": np.arctan2}[name]
+                out.append(("c", float(fold(x[1], y[1]))))
+            else:
+                out.append((name, x, y))
+        return Sym(out, self.scalar and (o.scalar if isinstance(o, Sym) else np.ndim(o) == 0))
+
+    def _unary(self, name):
+        return Sym([(name, x) for x in self.nodes], self.scalar)
+
+    def __add__(self, o): return self._binary("ADD", o)
+    def __radd__(self, o): return self._binary("ADD", o, swap=True)
+    def __sub__(self, o): return self._binary("SUB", o)
+    def __rsub__(self, o): return self._binary("SUB", o, swap=True)
+    def __mul__(self, o): return self._binary("MUL", o)
+    def __rmul__(self, o): return self._binary("MUL", o, swap=True)
+    def __truediv__(self, o): return self._binary("DIV", o)
+    def __rtruediv__(self, o): return self._binary("DIV", o, swap=True)
+    def __pow__(self, o): return self._binary("POW", o)
+    def __rpow__(self, o): return self._binary("POW", o, swap=True)
+    def __neg__(self): return self._unary("NEG")
+    def __pos__(self): return self
+    def __abs__(self): return self._unary("ABS")
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kw):
+        if method != "__call__":
+            return NotImplemented
+        if ufunc in _UNARY:
+            return inputs[0]._unary(_UNARY[ufunc])
+        if ufunc is np.square:
+            return inputs[0]._binary("MUL", inputs[0])
+        if ufunc in _BINARY:
+            a, b = inputs
+            return a._binary(_BINARY[ufunc], b) if isinstance(a, Sym) else b._binary(_BINARY[ufunc], a, swap=True)
+        raise TypeError(f"numpy.{ufunc.__name__} of a state-dependent value is not in the expression-program instruction set "
+                        "(arithmetic, power, sin cos tan tanh arctan arctan2 exp log sqrt abs)")
+
+    def __array_function__(self, func, types, args, kwargs):
+        if func in (np.hstack, np.concatenate):
+            nodes = []
+            for part in args[0]:
+                nodes += part.nodes if isinstance(part, Sym) else [("c", float(v)) for v in np.ravel(part)]
+            return Sym(nodes)
+        if func in (np.atleast_1d, np.ravel, np.asarray, np.squeeze):
+            return Sym(self.nodes, scalar=(func is np.squeeze and len(self) == 1))
+        raise TypeError(f"numpy.{func.__name__} of a state-dependent value is not supported by the model tracer")
+
+
+def compile_program(sym):
+    """Postfix program (ops, consts) of a Sym vector; after the last instruction the stack holds the components in order."""
+    ops, consts = [], []
+
+    def depth_of(node):
+        if node[0] in ("x", "u", "c"):
+            return 1
+        ds = [depth_of(c) for c in node[1:]]
+        return ds[0] if len(ds) == 1 else max(ds[0], ds[1] + 1)
+
+    def emit(node):
+        kind = node[0]
+        if kind == "x":
+            ops.append(_lib.OPS["PUSH_X"] | (node[1] << 8))
+        elif kind == "u":
+            ops.append(_lib.OPS["PUSH_U"] | (node[1] << 8))
+        elif kind == "c":
+            if node[1] not in consts:
+                consts.append(node[1])
+            ops.append(_lib.OPS["PUSH_C"] | (consts.index(node[1]) << 8))
+        else:
+            for child in node[1:]:
+                emit(child)
+            ops.append(_lib.OPS[kind])
+    for i, node in enumerate(sym.nodes):
+        if i + depth_of(node) > _lib.PGAS_PROG_STACK:
+            raise TypeError(f"GP-input expression {i} needs more than {_lib.PGAS_PROG_STACK} operands on the stack")
+        emit(node)
+    if len(ops) > _lib.PGAS_MAX_PROG or len(consts) > _lib.PGAS_MAX_PROG:
+        raise TypeError(f"GP-input map compiles to {len(ops)} instructions / {len(consts)} constants (limit {_lib.PGAS_MAX_PROG})")
+    return ops, consts
+
+
+def run_program(ops, consts, x, u):
+    """Host mirror of the device interpreter (csrc/basis_eval.cuh: pgas_map_program), for tests and debugging."""
+    names = {v: k for k, v in _lib.OPS.items()}
+    una = {"NEG": np.negative, "SIN": np.sin, "COS": np.cos, "TAN": np.tan, "TANH": np.tanh, "ATAN": np.arctan, "EXP": np.exp, "LOG": np.log,
+           "SQRT": np.sqrt, "ABS": np.abs}
+    bina = {"ADD": np.add, "SUB": np.subtract, "MUL": np.multiply, "DIV": np.divide, "POW": np.power, "ATAN2": np.arctan2}
+    st = []
+    for ins in ops:
+        name, arg = names[ins & 0xFF], ins >> 8
+        if name == "PUSH_X":
+            st.append(float(x[arg]))
+        elif name == "PUSH_U":
+            st.append(float(u[arg]))
+        elif name == "PUSH_C":
+            st.append(consts[arg])
+        elif name in bina:
+            b = st.pop(); a = st.pop(); st.append(float(bina[name](a, b)))
+        else:
+            st.append(float(una[name](st.pop())))
+    return np.array(st)
+
+
 def hstack(parts):
     """stand-in for jnp.hstack usable on traced values"""
-    if any(isinstance(p, Affine) for p in parts):
-        ref = next(p for p in parts if isinstance(p, Affine))
+    if any(isinstance(p, (Affine, Sym)) for p in parts):
+        ref = next(p for p in parts if isinstance(p, (Affine, Sym)))
         return ref.__array_function__(np.hstack, (), (parts,), {})
     return np.hstack(parts)
 
@@ -144,9 +302,25 @@ class VehicleSlipBasis:
         return self.hgp.M
 
 
+class ProgramBasis:
+    """basis over a GP-input map given as an expression program (model plug-in)."""
+
+    def __init__(self, hgp, sym):
+        if len(sym) != hgp.D:
+            raise ValueError(f"basis expects {hgp.D} inputs, traced value has {len(sym)}")
+        self.hgp, self.sym = hgp, sym
+        self.ops, self.consts = compile_program(sym)
+        self.map_kind = _lib.MAP_PROGRAM
+        self.slip = (0.0, 0.0)
+        self.Az, self.bz = np.zeros((hgp.D, _lib.PGAS_MAX_NX + _lib.PGAS_MAX_NU)), np.zeros(hgp.D)
+
+    def __len__(self):
+        return self.hgp.M
+
+
 def trace_basis(basis_fcn, n_x, n_u):
     """Reduce `basis_fcn(state, input)` to a descriptor (BasisExpr / VehicleSlipBasis)."""
-    if isinstance(basis_fcn, (BasisExpr, VehicleSlipBasis)):
+    if isinstance(basis_fcn, (BasisExpr, VehicleSlipBasis, ProgramBasis)):
         return basis_fcn
     from .BasisFunctions import HilbertBasis
     if isinstance(basis_fcn, HilbertBasis):
@@ -156,10 +330,16 @@ def trace_basis(basis_fcn, n_x, n_u):
     s, u = _tracers(n_x, n_u)
     try:
         out = basis_fcn(s, u if n_u > 0 else np.zeros(0))
-    except TypeError as e:
-        raise TypeError("basis_fcn is outside the compiled-in model families (Hilbert-space GP basis of an "
-                        f"affine map of state/input, or models.VehicleSlipBasis): {e}") from e
-    if not isinstance(out, (BasisExpr, VehicleSlipBasis)):
+    except TypeError:
+        # not affine: trace again with symbolic expressions -> expression program interpreted by the kernels (model plug-in)
+        xs = Sym([("x", k) for k in range(n_x)])
+        us = Sym([("u", k) for k in range(n_u)]) if n_u > 0 else np.zeros(0)
+        try:
+            out = basis_fcn(xs, us)
+        except TypeError as e:
+            raise TypeError("basis_fcn is outside the supported model families (Hilbert-space GP basis of an affine map, of the "
+                            f"vehicle slip angles, or of an expression of numpy arithmetic / elementary functions): {e}") from e
+    if not isinstance(out, (BasisExpr, VehicleSlipBasis, ProgramBasis)):
         raise TypeError("basis_fcn must return the value of a generate_Hilbert_BasisFunction basis")
     return out
 
@@ -257,6 +437,12 @@ class DeviceModel:
                 p.Az[d][k] = self.basis.Az[d, k] if k < self.basis.Az.shape[1] else 0.0
         p.map_kind = self.basis.map_kind
         p.slip_lf, p.slip_lr = self.basis.slip
+        if isinstance(self.basis, ProgramBasis):
+            p.prog_len = len(self.basis.ops)
+            for i, ins in enumerate(self.basis.ops):
+                p.prog_op[i] = ins
+            for i, c in enumerate(self.basis.consts):
+                p.prog_const[i] = c
         for r in range(self.n_y):
             p.h0[r] = self.likelihood.h0[r]
             for k in range(self.n_x):

@@ -8,6 +8,7 @@ ids; chains never communicate, one NCCL all-gather of the per-chain trajectories
 
 One "step" = one full Gibbs iteration of every chain of the job: conditional-SMC sweep (state kernel in 16-step launches
 overlapped with the resampling kernel, ~290 launches) -> final pick + backward trace -> sufficient statistics -> MNIW draw.
+One-GPU runs add "split_8gpu_share": one eighth of the chains on this GPU = the per-rank work of the named 8-GPU split.
 
   python bench.py --gpus 1 --steps K --warmup W          # this repo (CUDA, sm_100a)
   python bench.py --impl reference ...                    # CPU restatement of the reference (oracle port:
@@ -415,6 +416,17 @@ def run_gpu_arm(args):
         strong = {"chains_total": chains_per_gpu, "chains_per_gpu": chains_per_gpu / world, "value": sj["value"], "unit": "particle-steps/s",
                   "ms_per_step": sj["ms"] / args.steps, "note": "strong scaling: the one-GPU job (same chain ids, same results) sharded over the ranks"}
 
+    # one GPU: this GPU's SHARE of the named 8-GPU split (configs[3]: 64 chains over 8 GPUs = 8 chains per GPU; chains never
+    # communicate, so the share runs here exactly as it would on rank r of 8) -> projected strong-scaling efficiency
+    share = None
+    if world == 1 and args.scaling == "weak" and not args.no_strong and chains_per_gpu >= 8:
+        sj = timed_job(chains_per_gpu // 8, args.steps, args.warmup)
+        share = {"chains_on_this_gpu": chains_per_gpu // 8, "ms_per_step": sj["ms"] / args.steps, "value": sj["value"], "unit": "particle-steps/s",
+                 "projected_value_8_gpus": 8 * sj["value"],
+                 "projected_strong_scaling_efficiency_8_gpus": (ms / args.steps / 8) / (sj["ms"] / args.steps),
+                 "note": f"one eighth of the one-GPU job ({chains_per_gpu // 8} of {chains_per_gpu} chains) on one GPU: what each rank of the named "
+                         "8-GPU split executes (no data-path collective); efficiency = (one-GPU time / 8) / this time"}
+
     # ---- the kernels of one iteration alone (CUDA events), for the rooflines
     cnt = max(count, 1)
     st = torch.empty((cnt, T, N, 2), dtype=torch.float64, device="cuda")
@@ -532,6 +544,8 @@ def run_gpu_arm(args):
         }
         if strong is not None:
             line["strong"] = strong
+        if share is not None:
+            line["split_8gpu_share"] = share
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if world == 1 and args.config == 4 and not args.no_marginalised:

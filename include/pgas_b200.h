@@ -33,7 +33,22 @@ extern "C" {
 
 /* GP-input map g: (state, input) -> z in R^D fed to the Hilbert basis. */
 enum { PGAS_MAP_AFFINE = 0,      /* z = Az [state; input] + bz  (src/EMPS.py:110-113, src/Toy_Example.py:146) */
-       PGAS_MAP_VEHICLE_SLIP = 1 /* z = (alpha_f, alpha_r) of src/Vehicle.py:50-57, input = [delta, v_x]     */ };
+       PGAS_MAP_VEHICLE_SLIP = 1,/* z = (alpha_f, alpha_r) of src/Vehicle.py:50-57, input = [delta, v_x]     */
+       PGAS_MAP_PROGRAM = 2      /* z = an expression program over (state, input): the model plug-in */ };
+
+/* Expression programs: the reference hands an arbitrary Python callable basis_fcn(state, input) to the sampler
+ * (src/PGAS.py:24-43, src/StateSpaceModel.py:19-30) and lets JAX trace it.  Here the host traces the callable's GP-input map
+ * symbolically (models.py: Sym) into a postfix program that every kernel evaluating the map interprets per particle — uniform
+ * control flow, no run-time compiler in the loop.  prog_op[i] = opcode | (argument << 8); after the last instruction the
+ * stack holds z_0 .. z_{D-1}. */
+#define PGAS_MAX_PROG 64
+#define PGAS_PROG_STACK 8
+enum { PGAS_OP_PUSH_X = 1,   /* argument: state component          */
+       PGAS_OP_PUSH_U = 2,   /* argument: input component          */
+       PGAS_OP_PUSH_C = 3,   /* argument: index into prog_const    */
+       PGAS_OP_ADD = 4, PGAS_OP_SUB = 5, PGAS_OP_MUL = 6, PGAS_OP_DIV = 7, PGAS_OP_NEG = 8,
+       PGAS_OP_SIN = 9, PGAS_OP_COS = 10, PGAS_OP_TAN = 11, PGAS_OP_TANH = 12, PGAS_OP_ATAN = 13, PGAS_OP_EXP = 14,
+       PGAS_OP_LOG = 15, PGAS_OP_SQRT = 16, PGAS_OP_ABS = 17, PGAS_OP_POW = 18, PGAS_OP_ATAN2 = 19 };
 
 /* reference quirks; the default 0 reproduces the reference bit for bit */
 enum { PGAS_FLAG_ANCESTOR_GATHER = 1, /* propagate x_t^i from x_{t-1}^{a_i} instead of x_{t-1}^i (src/PGAS.py:131-133) */
@@ -58,6 +73,9 @@ typedef struct pgas_model_params {
     double Az[PGAS_MAX_D][PGAS_MAX_NX + PGAS_MAX_NU];
     double bz[PGAS_MAX_D];
     double slip_lf, slip_lr;
+    int32_t prog_len;             /* PGAS_MAP_PROGRAM: number of instructions (<= PGAS_MAX_PROG) */
+    int32_t prog_op[PGAS_MAX_PROG];
+    double prog_const[PGAS_MAX_PROG];
     /* Gaussian likelihood N(y; H x + h0, R) */
     double H[PGAS_MAX_NY][PGAS_MAX_NX];
     double h0[PGAS_MAX_NY];
@@ -94,7 +112,7 @@ const char* pgas_last_error(void);
 int pgas_version(void);
 /* PGAS_ABI_VERSION of the header the library was compiled against: a binding compares it with its own copy of
  * the header before the first call (struct layouts and argument orders are only meaningful when they agree). */
-#define PGAS_ABI_VERSION 201
+#define PGAS_ABI_VERSION 202
 int pgas_abi_version(void);
 int pgas_device_count(void);
 /* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */

@@ -84,6 +84,18 @@ def make_problem(kind, T=30, N=64, M=None, seed=0, flags=0):
         inputs = np.stack([10 / 180 * np.pi * np.sin(2 * np.pi * tt / 5), 11.0 + 0 * tt], axis=1)
         ref = np.stack([0.2 * np.sin(tt), 0.5 * np.cos(tt)], axis=1)
         df = 3
+    elif kind == "plugin":
+        # a GP-input map outside the compiled-in families (model plug-in): sines, tanh, a rational term
+        M = M or 41
+        dom = np.array([[-7.5, 7.5], [-7.5, 7.5]])
+        args = (M, dom, 15.0 / M, 100.0)
+        n_x, n_u = 2, 1
+        A, b = None, None
+        H, h0, R = np.array([[1.0, 0.0]]), np.zeros(1), np.array([[1e-3]])
+        m0, P0 = np.zeros(2), np.diag([1e-2, 1e-2])
+        inputs = 0.5 * rng.normal(size=(T, 1))
+        ref = np.cumsum(0.05 * rng.normal(size=(T, 2)), axis=0)
+        df = 3
     else:
         raise ValueError(kind)
     hgp, sd = OB.generate_Hilbert_BasisFunction(*args)
@@ -91,6 +103,11 @@ def make_problem(kind, T=30, N=64, M=None, seed=0, flags=0):
     obs = ref @ H.T + h0 + rng.normal(size=(T, H.shape[0])) * np.sqrt(np.diag(R))
     if kind == "vehicle":
         obasis = OP.vehicle_slip_basis(hgp, 1.16, 1.47)
+    elif kind == "plugin":
+        def obasis(states, inp):                 # the user callable evaluated directly with numpy, particle by column
+            st = np.atleast_2d(states)
+            z = plugin_map([st[:, 0], st[:, 1]], [np.full(st.shape[0], float(np.ravel(inp)[0]))])
+            return hgp.batch(np.stack(z, axis=1))
     else:
         obasis = OP.affine_hgp_basis(hgp, A, b)
     Sg = rng.normal(size=(n_x, n_x))
@@ -113,11 +130,26 @@ def make_problem(kind, T=30, N=64, M=None, seed=0, flags=0):
     return p
 
 
+def plugin_map(state, inp):
+    """GP-input map of the "plugin" problems, written the way a user writes a basis_fcn: plain numpy on state / input components"""
+    z0 = 2.0 * np.sin(state[0]) + 0.3 * state[1] + 0.5 * inp[0]
+    z1 = 3.0 * np.tanh(state[1]) - state[0] ** 2 / (1.0 + np.abs(state[0]))
+    return [z0, z1]
+
+
+def _product_basis(hgp, p, MD):
+    if p["kind"] == "vehicle":
+        return MD.VehicleSlipBasis(hgp, 1.16, 1.47)
+    if p["kind"] == "plugin":
+        return lambda state, inp: hgp(MD.hstack(plugin_map(state, inp)))
+    return _BasisThunk(hgp, p, MD)
+
+
 def product_csmc(p, cluster_size=0):
     """condSequentialMonteCarlo of the product for problem p."""
     BF, MD, PG = pkg("BasisFunctions"), pkg("models"), pkg("PGAS")
     hgp, _ = BF.generate_Hilbert_BasisFunction(*p["hgp_args"])
-    basis = MD.VehicleSlipBasis(hgp, 1.16, 1.47) if p["kind"] == "vehicle" else _BasisThunk(hgp, p, MD)
+    basis = _product_basis(hgp, p, MD)
     lik = MD.GaussianLikelihood(p["H"], p["h0"], p["R"])
     return PG.condSequentialMonteCarlo(N_samples=p["N"], observations=p["obs"], inputs=p["inputs"],
                                        init_state_mean=p["m0"], init_state_cov=p["P0"], likelihood_fcn=lik,
@@ -143,7 +175,7 @@ class _BasisThunk:
 def product_pgas(p, K, cluster_size=0):
     BF, MD, PG = pkg("BasisFunctions"), pkg("models"), pkg("PGAS")
     hgp, _ = BF.generate_Hilbert_BasisFunction(*p["hgp_args"])
-    basis = MD.VehicleSlipBasis(hgp, 1.16, 1.47) if p["kind"] == "vehicle" else _BasisThunk(hgp, p, MD)
+    basis = _product_basis(hgp, p, MD)
     lik = MD.GaussianLikelihood(p["H"], p["h0"], p["R"])
     return PG.PGAS(N_samples=p["N"], N_iterations=K, observations=p["obs"], inputs=p["inputs"], init_state_mean=p["m0"],
                    init_state_cov=p["P0"], likelihood_fcn=lik, GP_prior=p["prior"], basis_fcn=basis, flags=p["flags"],

@@ -76,8 +76,10 @@ def test_model_tracer_affine_families():
     assert np.allclose(e.Az, [[0, 1, 0]])
     e = MD.trace_basis(lambda s, u: hgp1(2.0 * s[0] - 0.5 + u[0] * 0.1), 2, 1)
     assert np.allclose(e.Az, [[2, 0, 0.1]]) and np.allclose(e.bz, [-0.5])
+    e = MD.trace_basis(lambda s, u: hgp1(np.sin(s[0])), 2, 1)        # not affine: expression program (model plug-in), no longer an error
+    assert isinstance(e, MD.ProgramBasis) and e.ops == [MD._lib.OPS["PUSH_X"], MD._lib.OPS["SIN"]]
     with pytest.raises(TypeError):
-        MD.trace_basis(lambda s, u: hgp1(np.sin(s[0])), 2, 1)
+        MD.trace_basis(lambda s, u: hgp1(np.floor(s[0])), 2, 1)      # outside the instruction set
     with pytest.raises(TypeError):
         MD.trace_basis(lambda s, u: s[0], 2, 1)
     lik = MD.resolve_likelihood(MD.gaussian_likelihood(lambda x: x[0], np.eye(1) * 1e-4), 2)       # src/EMPS.py:250-252
@@ -119,3 +121,28 @@ def test_natural_parameter_host_conversions_match_oracle():
         assert np.allclose(a, b, rtol=1e-12)
     T = (eta[0], eta[1], eta[2] + np.eye(n), 7.0)
     assert abs(BI.prior_mniw_log_base_measure(*T) - OM.prior_mniw_log_base_measure(*T)) < 1e-9
+
+
+def test_expression_tracer_compiles_a_non_affine_basis_fcn():
+    """model plug-in: a basis_fcn that is not affine is traced into a postfix program; the host mirror of
+    the device interpreter reproduces the callable; affine callables keep the compiled-in family"""
+    import helpers
+    MD = helpers.pkg("models")
+    L = helpers.pkg("_lib")
+
+    class FakeBasis:                                   # stands in for HilbertBasis.__call__ without a device
+        D, M = 2, 7
+
+        def __call__(self, x):
+            return MD.ProgramBasis(self, x) if isinstance(x, MD.Sym) else MD.BasisExpr(self, x.A, x.b)
+    hgp = FakeBasis()
+    b = MD.trace_basis(lambda s, u: hgp(MD.hstack(helpers.plugin_map(s, u))), 2, 1)
+    assert isinstance(b, MD.ProgramBasis) and b.map_kind == L.MAP_PROGRAM and len(b.ops) <= L.PGAS_MAX_PROG
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        x, u = rng.normal(size=2) * 3, rng.normal(size=1)
+        assert np.allclose(MD.run_program(b.ops, b.consts, x, u), np.array(helpers.plugin_map(x, u)), rtol=1e-14, atol=1e-14)
+    a = MD.trace_basis(lambda s, u: hgp(MD.hstack([s[0] * 2.0 + u[0], s[1] - 1.0])), 2, 1)
+    assert isinstance(a, MD.BasisExpr) and a.map_kind == L.MAP_AFFINE
+    with pytest.raises(TypeError):
+        MD.trace_basis(lambda s, u: hgp(np.floor(s)), 2, 1)       # not in the instruction set: raises, no host fallback

@@ -115,6 +115,8 @@ def test_step_parity_quirk_flags(built_lib, flags):
     ("smo", 200, 60, 1), ("smo", 512, 40, 4), ("smo", 4096, 12, 16), ("emps", 200, 50, 1), ("toy", 200, 40, 2),
     ("vehicle", 256, 40, 1), ("smo", 200, 60, 0),
     ("smo", 4096, 12, 0), ("smo", 2501, 16, 0), ("vehicle", 6000, 8, 0),     # split form with the dedicated resampling kernel: clusters of 2 / 2 / 4
+    # model plug-in: a GP-input map of sines / tanh / a rational term, traced into an expression program (split form; fused kernel)
+    ("plugin", 512, 40, 0), ("plugin", 200, 30, 1), ("plugin", 4096, 12, 0),
 ])
 def test_sweep_parity_injected(built_lib, kind, N, T, cluster):
     p = helpers.make_problem(kind, T=T, N=N, seed=T)
@@ -168,7 +170,7 @@ def test_chain_ids_give_identical_results_regardless_of_batching(built_lib):
 
 # ----------------------------------------------------------------------------- A13 statistics + draw
 @pytest.mark.parametrize("kind,M,T", [("smo", 41, 80), ("smo", 100, 300), ("smo", 256, 120), ("emps", 64, 60),
-                                      ("emps", 200, 90), ("toy", 40, 40), ("vehicle", 36, 100),
+                                      ("emps", 200, 90), ("toy", 40, 40), ("vehicle", 36, 100), ("plugin", 64, 120),
                                       # configuration-scale bases: EMPS PGAS baseline (3-D, M = 729, configs[2]), configs[3] (M = 256)
                                       # at its full T, configs[4] (vehicle lattice, M = 1024)
                                       ("emps", 729, 400), ("smo", 256, 2000), ("vehicle", 1024, 700), ("smo", 1024, 300)])
@@ -228,7 +230,7 @@ def test_draw_rejects_indefinite_eta1(built_lib):
 
 
 # ----------------------------------------------------------------------------- A14 full Gibbs loop
-@pytest.mark.parametrize("kind,cluster", [("smo", 1), ("smo", 2), ("toy", 1)])
+@pytest.mark.parametrize("kind,cluster", [("smo", 1), ("smo", 2), ("toy", 1), ("plugin", 0)])
 def test_run_chains_matches_oracle(built_lib, kind, cluster):
     from oracle import pgas as OP
     import torch
