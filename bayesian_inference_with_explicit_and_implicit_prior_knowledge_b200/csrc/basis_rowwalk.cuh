@@ -1,4 +1,4 @@
-// basis_rowwalk.cuh — mu = Theta phi(z) for TWO-dimensional Hilbert bases, one particle per thread, on the
+// basis_rowwalk.cuh — mu = Theta phi(z) for two- and three-dimensional Hilbert bases, one or two particles per thread, on the
 // FP64 FMA pipe.
 //
 // Replaces vmap(basis_fcn) + einsum("kj,ij->ik") (reference src/BasisFunctions.py:77-80, src/PGAS.py:52-55,
@@ -60,21 +60,13 @@ __device__ __forceinline__ void rw_segment(const double* __restrict__& th, int n
     }
 }
 
+// One SLICE of the walk: nblk blocks of RW_RB rows x positions, mu += sum_i a_i (sum_j Theta'[.., i, j] b_j) with the row sines a
+// and the position sines b given by their recurrence seeds.  `w` is the Theta' register ring (rw_segment), `th` the read pointer.
 template <int NX, int PP>
-__device__ __forceinline__ void rowwalk_mu(const double* __restrict__ bd, const int* __restrict__ blen, int nblk, int f_start, int f_step,
-                                           const double (&t0)[PP], const double (&t1)[PP], double (&mu)[PP][NX]) {
-    double a_cur[PP], a_prev[PP], a_2c[PP], b_cur[PP], b_prev[PP], b_2c[PP];
-    const double* __restrict__ th = bd;
-    double w[RW_RB][NX];
-#pragma unroll
-    for (int i = 0; i < RW_RB; ++i) rw_load<NX>(th + i * NX, w[i]);
-#pragma unroll
-    for (int p = 0; p < PP; ++p) {
-        sine_seed(t0[p], f_start, f_step, a_cur[p], a_prev[p], a_2c[p]);
-        sine_seed(t1[p], f_start, f_step, b_cur[p], b_prev[p], b_2c[p]);
-#pragma unroll
-        for (int k = 0; k < NX; ++k) mu[p][k] = 0.0;
-    }
+__device__ __forceinline__ void rowwalk_slice(const double* __restrict__& th, const int* __restrict__ blen, int nblk, double (&w)[RW_RB][NX],
+                                              double (&a_cur)[PP], double (&a_prev)[PP], const double (&a_2c)[PP],
+                                              const double (&b_cur)[PP], const double (&b_prev)[PP], const double (&b_2c)[PP],
+                                              double (&mu)[PP][NX]) {
     for (int b = 0; b < nblk; ++b) {
         double acc[PP][RW_RB][NX];
         double c[PP], pv[PP];
@@ -107,5 +99,53 @@ __device__ __forceinline__ void rowwalk_mu(const double* __restrict__ bd, const 
                 a_prev[p] = a_cur[p];
                 a_cur[p] = n;
             }
+    }
+}
+
+// D = 2: one slice (rows = first dimension, positions = second).  D = 3: one slice per first-dimension position i0,
+//   mu_k = sum_i0 s0_i0 * [ sum_i1 s1_i1 ( sum_j Theta'[k, m(i0,i1,j)] s2_j ) ],
+// rows = second dimension (its recurrence restarts in every slice), positions = third; slice_nblk[i0] blocks per slice.
+template <int NX, int PP, int D>
+__device__ __forceinline__ void rowwalk_mu(const double* __restrict__ bd, const int* __restrict__ blen, const int* __restrict__ slice_nblk,
+                                           int nslice, int f_start, int f_step, const double (&tz)[PP][D], double (&mu)[PP][NX]) {
+    double a_cur[PP], a_prev[PP], a_2c[PP], b_cur[PP], b_prev[PP], b_2c[PP];
+    const double* __restrict__ th = bd;
+    double w[RW_RB][NX];
+#pragma unroll
+    for (int i = 0; i < RW_RB; ++i) rw_load<NX>(th + i * NX, w[i]);
+#pragma unroll
+    for (int p = 0; p < PP; ++p) {
+        sine_seed(tz[p][D - 2], f_start, f_step, a_cur[p], a_prev[p], a_2c[p]);
+        sine_seed(tz[p][D - 1], f_start, f_step, b_cur[p], b_prev[p], b_2c[p]);
+#pragma unroll
+        for (int k = 0; k < NX; ++k) mu[p][k] = 0.0;
+    }
+    if constexpr (D == 2) {
+        rowwalk_slice<NX, PP>(th, blen, slice_nblk[0], w, a_cur, a_prev, a_2c, b_cur, b_prev, b_2c, mu);
+    } else {
+        double s_cur[PP], s_prev[PP], s_2c[PP];
+#pragma unroll
+        for (int p = 0; p < PP; ++p) sine_seed(tz[p][0], f_start, f_step, s_cur[p], s_prev[p], s_2c[p]);
+        int boff = 0;
+        for (int sl = 0; sl < nslice; ++sl) {
+            double ac[PP], ap[PP], part[PP][NX];
+#pragma unroll
+            for (int p = 0; p < PP; ++p) {
+                ac[p] = a_cur[p]; ap[p] = a_prev[p];
+#pragma unroll
+                for (int k = 0; k < NX; ++k) part[p][k] = 0.0;
+            }
+            const int nb = slice_nblk[sl];
+            rowwalk_slice<NX, PP>(th, blen + boff, nb, w, ac, ap, a_2c, b_cur, b_prev, b_2c, part);
+            boff += nb;
+#pragma unroll
+            for (int p = 0; p < PP; ++p) {
+#pragma unroll
+                for (int k = 0; k < NX; ++k) mu[p][k] = fma(s_cur[p], part[p][k], mu[p][k]);
+                const double n = fma(s_2c[p], s_cur[p], -s_prev[p]);
+                s_prev[p] = s_cur[p];
+                s_cur[p] = n;
+            }
+        }
     }
 }

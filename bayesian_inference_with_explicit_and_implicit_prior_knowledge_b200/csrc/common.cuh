@@ -42,7 +42,8 @@ constexpr int MAX_LEAD = PGAS_MAX_D - 1;
 // staircase lattice is not computed.  Storage order: [block][j][i < act(j)][k], zero where the lattice search did not
 // select (i, j); rw_blen[block] packs the number of positions with 4, 3, 2, 1 active rows into bytes 0..3.
 constexpr int RW_RB = 4;
-constexpr int RW_MAXBLK = 24;
+constexpr int RW_MAXBLK = 64;
+constexpr int RW_MAXSLICE = 16;      // three-dimensional bases: first-dimension positions (one slice of blocks each)
 
 struct DevModel {
     int n_x, n_y, n_u, D, M, T;
@@ -66,6 +67,7 @@ struct DevModel {
     double m0[PGAS_MAX_NX], P0c[PGAS_MAX_NX][PGAS_MAX_NX];   // chol(P0) lower
     int rw_ok, rw_nblk, rw_slots;                   // row-walk layout (D == 2): available, blocks, doubles
     int rw_blen[RW_MAXBLK];                         // positions with 4 | 3 | 2 | 1 active rows per block (one byte each)
+    int rw_nslice, rw_slice_nblk[RW_MAXSLICE];      // D = 3: blocks per first-dimension position (D = 2: one slice holding all blocks)
     const int* rw_perm;     // [rw_slots] slot -> m * 4 + k of the Theta entry it holds, or -1 (zero)
     const int* perm;        // [n_packed] fragment slot -> m * 4 + k of the Theta entry it holds, or -1 (zero)
     const int* row_pos;     // [8*NTN / n_x rounded up][MAX_LEAD] leading-dimension positions of each row (0 for padding rows)

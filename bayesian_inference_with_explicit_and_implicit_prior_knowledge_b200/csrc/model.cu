@@ -193,44 +193,65 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
     for (int r = 0; r < dm.R; ++r)
         for (int d = 0; d < D - 1; ++d) row_pos[(size_t)rank[r] * MAX_LEAD + d] = row_lead[r][d];
 
-    // ---- row-walk layout (two-dimensional bases): [block][j][i][k] --------------------------
+    // ---- row-walk layout (two- and three-dimensional bases): [slice][block][j][i][k] ----------------------
+    // rows = positions of dimension D-2 in blocks of RW_RB, walked positions j = dimension D-1; D = 3: one slice of blocks per
+    // position of dimension 0 (D = 2: a single slice)
     std::vector<int> rw_perm;
-    dm.rw_ok = 0; dm.rw_nblk = 0; dm.rw_slots = 0;
-    if (D == 2 && (dm.npos_d[0] + RW_RB - 1) / RW_RB <= RW_MAXBLK) {
-        const int nb = (dm.npos_d[0] + RW_RB - 1) / RW_RB;
-        // per block: act[j] = 1 + (largest row of the block with a selected entry at last-dimension position j' >= j), i.e. how
-        // many leading rows are walked at position j (non-increasing in j); storage [block][j][i < act[j]][k]
-        std::vector<int> off(nb + 1, 0);
-        std::vector<std::vector<int>> act(nb), joff(nb);
-        for (int b = 0; b < RW_MAXBLK; ++b) dm.rw_blen[b] = 0;
+    dm.rw_ok = 0; dm.rw_nblk = 0; dm.rw_slots = 0; dm.rw_nslice = 0;
+    for (int b = 0; b < RW_MAXBLK; ++b) dm.rw_blen[b] = 0;
+    for (int sl = 0; sl < RW_MAXSLICE; ++sl) dm.rw_slice_nblk[sl] = 0;
+    if (D == 2 || D == 3) {
+        const int dr = D - 2, dj = D - 1;                                    // row / walked dimension
+        const int nslice = (D == 3) ? dm.npos_d[0] : 1;
+        const int nb_per = (dm.npos_d[dr] + RW_RB - 1) / RW_RB;              // upper bound of blocks per slice
+        bool fits = nslice <= RW_MAXSLICE;
         int jtop = 0;
-        for (int mI = 0; mI < M; ++mI) jtop = std::max(jtop, pos[(size_t)mI * D + 1] + 1);
-        for (int b = 0; b < nb; ++b) act[b].assign(jtop + 1, 0);
+        for (int mI = 0; mI < M; ++mI) jtop = std::max(jtop, pos[(size_t)mI * D + dj] + 1);
+        // act[slice][block][j] = 1 + (largest row of the block with a selected entry at walked position j' >= j)
+        std::vector<std::vector<std::vector<int>>> act(nslice, std::vector<std::vector<int>>(nb_per, std::vector<int>(jtop + 1, 0)));
         for (int mI = 0; mI < M; ++mI) {
-            const int p0 = pos[(size_t)mI * D], j = pos[(size_t)mI * D + 1];
-            act[p0 / RW_RB][j] = std::max(act[p0 / RW_RB][j], p0 % RW_RB + 1);
+            const int sl = (D == 3) ? pos[(size_t)mI * D] : 0, r = pos[(size_t)mI * D + dr], j = pos[(size_t)mI * D + dj];
+            act[sl][r / RW_RB][j] = std::max(act[sl][r / RW_RB][j], r % RW_RB + 1);
         }
-        bool fits = true;
-        for (int b = 0; b < nb; ++b) {
-            for (int j = jtop - 1; j >= 0; --j) act[b][j] = std::max(act[b][j], act[b][j + 1]);
-            int cnt[RW_RB + 1] = {0, 0, 0, 0, 0};
-            joff[b].assign(jtop + 1, 0);
-            for (int j = 0; j < jtop; ++j) {
-                cnt[act[b][j]]++;
-                joff[b][j + 1] = joff[b][j] + act[b][j] * nx;
+        // blocks in walk order (slice-major; empty trailing blocks of a slice are dropped), their offsets and per-position offsets
+        std::vector<int> blk_off, blk_slice, blk_index;
+        std::vector<std::vector<int>> joff;
+        int total = 0, nblk = 0;
+        for (int sl = 0; sl < nslice && fits; ++sl) {
+            int used = 0;
+            for (int b = 0; b < nb_per; ++b) {
+                for (int j = jtop - 1; j >= 0; --j) act[sl][b][j] = std::max(act[sl][b][j], act[sl][b][j + 1]);
+                if (act[sl][b][0] > 0) used = b + 1;
             }
-            for (int r = 1; r <= RW_RB; ++r) fits = fits && cnt[r] <= 255;
-            dm.rw_blen[b] = cnt[4] | (cnt[3] << 8) | (cnt[2] << 16) | (cnt[1] << 24);     // walked in this order
-            off[b + 1] = off[b] + joff[b][jtop];
+            dm.rw_slice_nblk[sl] = used;
+            for (int b = 0; b < used; ++b) {
+                if (nblk >= RW_MAXBLK) { fits = false; break; }
+                int cnt[RW_RB + 1] = {0, 0, 0, 0, 0};
+                std::vector<int> jo(jtop + 1, 0);
+                for (int j = 0; j < jtop; ++j) {
+                    cnt[act[sl][b][j]]++;
+                    jo[j + 1] = jo[j] + act[sl][b][j] * nx;
+                }
+                for (int r = 1; r <= RW_RB; ++r) fits = fits && cnt[r] <= 255;
+                dm.rw_blen[nblk] = cnt[4] | (cnt[3] << 8) | (cnt[2] << 16) | (cnt[1] << 24);     // walked in this order
+                blk_off.push_back(total); blk_slice.push_back(sl); blk_index.push_back(b);
+                joff.push_back(jo);
+                total += jo[jtop];
+                ++nblk;
+            }
         }
-        if (!fits) PGAS_FAIL(-20, "basis needs more than 255 lattice positions in its last dimension");
-        rw_perm.assign((size_t)off[nb], -1);
-        for (int mI = 0; mI < M; ++mI) {
-            const int p0 = pos[(size_t)mI * D], j = pos[(size_t)mI * D + 1];
-            const int b = p0 / RW_RB, i = p0 % RW_RB;
-            for (int k = 0; k < nx; ++k) rw_perm[(size_t)off[b] + joff[b][j] + (size_t)i * nx + k] = mI * 4 + k;
+        if (fits && nblk > 0) {
+            // block id of (slice, block-in-slice)
+            std::vector<std::vector<int>> bid(nslice, std::vector<int>(nb_per, -1));
+            for (int q = 0; q < nblk; ++q) bid[blk_slice[q]][blk_index[q]] = q;
+            rw_perm.assign((size_t)total, -1);
+            for (int mI = 0; mI < M; ++mI) {
+                const int sl = (D == 3) ? pos[(size_t)mI * D] : 0, r = pos[(size_t)mI * D + dr], j = pos[(size_t)mI * D + dj];
+                const int q = bid[sl][r / RW_RB], i = r % RW_RB;
+                for (int k = 0; k < nx; ++k) rw_perm[(size_t)blk_off[q] + joff[q][j] + (size_t)i * nx + k] = mI * 4 + k;
+            }
+            dm.rw_ok = 1; dm.rw_nblk = nblk; dm.rw_slots = total; dm.rw_nslice = nslice;
         }
-        dm.rw_ok = 1; dm.rw_nblk = nb; dm.rw_slots = off[nb];
     }
 
     // ---- one device arena ---------------------------------------------------------------

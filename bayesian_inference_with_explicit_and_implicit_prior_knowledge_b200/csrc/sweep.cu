@@ -1,13 +1,20 @@
-// sweep.cu — persistent conditional-SMC sweep with ancestor sampling (sm_100a).
+// sweep.cu — conditional-SMC sweep with ancestor sampling (sm_100a): the two schedules of condSequentialMonteCarlo.step / __call__
+// (reference src/PGAS.py:79-153, :176-228) and their launcher.
 //
-// Replaces condSequentialMonteCarlo.step / __call__ (reference src/PGAS.py:79-153, :176-228):
-// one CTA — or one thread-block cluster of C CTAs for large N — owns one chain for ALL T steps.
-// The particle set (state, log-weight, auxiliary mean, CDF) lives in shared memory / DSMEM; per
-// step the only HBM traffic is the trace (state row + ancestor row).  Each step, in one pass:
-//   A  mu_i = Theta phi(x_{t-1}^i, u_t)  (basis_eval.cuh), l_aux, h;  CTA max + exp + CTA scan
+// SPLIT FORM (default for two-dimensional bases; second half of this file): in the reference's semantics the states never see an
+// ancestor index, so csmc_state_kernel propagates all particles ahead in launches of <= 16 steps (no synchronisation; particles in
+// registers; traces and three log-densities per particle-step to HBM) while a resampling kernel runs the weight recursion
+// chunk-wise behind it on a second stream: weights_lat.cu (cluster per chain, up to 32 chains per launch), weights.cu (one CTA per
+// chain, many chains) or csmc_sweep_kernel<PRE> below (chains whose CDF does not fit one CTA).  About 290 launches per sweep at
+// T = 2000.
+//
+// FUSED FORM (csmc_sweep_kernel<PRE = false>; textbook ancestor gather, D != 2, single steps, no workspace): one CTA — or one
+// thread-block cluster of C CTAs — owns one chain for all T steps of a launch; the particle set (state, log-weight, auxiliary mean,
+// CDF) lives in shared memory / DSMEM and the only HBM traffic is the trace.  Each step, in one pass:
+//   A  mu_i = Theta phi(x_{t-1}^i, u_t)  (basis_eval.cuh), l_aux, h;  warp-local softmax shift + exp + scans
 //   X1 per-CTA (max, sum) pairs all-gathered through DSMEM  -> cluster barrier #1
 //   B  global log-sum-exp / CDF offsets; systematic resampling by the owner of the CDF segment
-//      (binary search in local shared memory), ancestor sampling of the reference particle;
+//      (search in local shared memory), ancestor sampling of the reference particle;
 //      l_aux[a_j] (and mu[a_j] in gather mode) pushed to the owner of j through DSMEM
 //   X2 cluster barrier #2 — its latency is covered by the noise draw and the new state
 //   C  x_t^i = mu + chol(Sigma) z,  logw_t^i = log p(y_t|x_t^i) - l_aux[a_i],  trace row written
@@ -386,9 +393,9 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
                                 }
                                 mapr.apply(xa, k_t.cz, k_t.u, ta);
                                 mapr.apply(xb, k_t.cz, k_t.u, tb);
-                                const double t0[2] = {ta[0], tb[0]}, t1[2] = {ta[1], tb[1]};
+                                const double tzz[2][2] = {{ta[0], ta[1]}, {tb[0], tb[1]}};
                                 double mu2[2][NX];
-                                rowwalk_mu<NX, 2>(bfrag, rwlen, nblk_rw, ecx.f_start, ecx.f_step, t0, t1, mu2);
+                                rowwalk_mu<NX, 2, 2>(bfrag, rwlen, &nblk_rw, 1, ecx.f_start, ecx.f_step, tzz, mu2);
                                 if (ila < Pc) weights(ila, mu2[0], lwa[2 * h], lwr[2 * h]);
                                 if (ilb < Pc) weights(ilb, mu2[1], lwa[2 * h + 1], lwr[2 * h + 1]);
                             } else {
@@ -396,9 +403,9 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
 #pragma unroll
                                 for (int k = 0; k < NX; ++k) xa[k] = (ila < Pc) ? xs[(size_t)k * P + ila] : 0.0;
                                 mapr.apply(xa, k_t.cz, k_t.u, ta);
-                                const double t0[1] = {ta[0]}, t1[1] = {ta[1]};
+                                const double tzz[1][2] = {{ta[0], ta[1]}};
                                 double mu1[1][NX];
-                                rowwalk_mu<NX, 1>(bfrag, rwlen, nblk_rw, ecx.f_start, ecx.f_step, t0, t1, mu1);
+                                rowwalk_mu<NX, 1, 2>(bfrag, rwlen, &nblk_rw, 1, ecx.f_start, ecx.f_step, tzz, mu1);
                                 if (ila < Pc) weights(ila, mu1[0], lwa[2 * h], lwr[2 * h]);
                             }
                         }
@@ -830,9 +837,9 @@ constexpr int ST_NT_SMALL = 64, ST_PP_SMALL = 1;                   // ... and wh
 // ST_NT threads per CTA, ST_PP particles per thread: <256, 2> when the chains of a launch fill the GPU (two particles share every
 // Theta' pair: half the shared-memory traffic per DFMA, 128 registers, two CTAs per SM); <64, 1> when they do not (few chains:
 // four times as many, smaller CTAs spread over all SMs, and a step's dependent chain per thread is half as long).
-template <int NX, int NY, bool INJ, int ST_NT, int ST_PP>
+// D: dimension of the Hilbert basis (2, or 3: one more level of the row walk — the EMPS baseline of src/EMPS.py:101-123).
+template <int NX, int NY, bool INJ, int ST_NT, int ST_PP, int D = 2>
 __global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_state_kernel(const __grid_constant__ StateArgs s) {
-    constexpr int D = 2;
     const SweepArgs& a = s.a;
     const DevModel& m = a.m;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -883,7 +890,7 @@ __global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_stat
     __syncthreads();
     MapRegs<NX, D> mapr;
     mapr.init(m);
-    const int f_start = m.f_start, f_step = m.f_step, nblk = m.rw_nblk;
+    const int f_start = m.f_start, f_step = m.f_step;
     int ip[ST_PP];
     bool val[ST_PP];
 #pragma unroll
@@ -957,15 +964,11 @@ __global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_stat
                 }
             }
         }
-        double t0v[ST_PP], t1v[ST_PP];
+        double tzv[ST_PP][D];
 #pragma unroll
-        for (int p = 0; p < ST_PP; ++p) {
-            double tz[D];
-            mapr.apply(x[p], cz, u, tz);
-            t0v[p] = tz[0]; t1v[p] = tz[1];
-        }
+        for (int p = 0; p < ST_PP; ++p) mapr.apply(x[p], cz, u, tzv[p]);
         double mu[ST_PP][NX];
-        rowwalk_mu<NX, ST_PP>(bd, rwlen, nblk, f_start, f_step, t0v, t1v, mu);
+        rowwalk_mu<NX, ST_PP, D>(bd, rwlen, m.rw_slice_nblk, m.rw_nslice, f_start, f_step, tzv, mu);
         const size_t prow = ((size_t)chain * s.rows + (size_t)(t - s.t0)) * N;
         // log-densities and the new state of all particles of the thread, branch-free; the stores follow
         double la[ST_PP], lr[ST_PP], ll[ST_PP];
@@ -1016,7 +1019,7 @@ static int split_chunk_rows(const DevModel& m, int N, int n_chains) {
 }
 
 size_t pgas_sweep_split_workspace(const DevModel& m, int N, int n_chains) {
-    if (!(m.D == 2 && m.rw_ok) || (m.flags & PGAS_FLAG_ANCESTOR_GATHER)) return 256;
+    if (!((m.D == 2 || m.D == 3) && m.rw_ok) || (m.flags & PGAS_FLAG_ANCESTOR_GATHER)) return 256;
     const size_t rows = split_chunk_rows(m, N, n_chains);
     const size_t pre = 2 * rows * (size_t)n_chains * N * 3 * sizeof(double);
     const size_t carry = (size_t)n_chains * N * (m.n_x + 2) * sizeof(double);
@@ -1025,8 +1028,8 @@ size_t pgas_sweep_split_workspace(const DevModel& m, int N, int n_chains) {
 
 bool pgas_sweep_split_eligible(const SweepArgs& a) {
     const DevModel& m = a.m;
-    if (!(m.D == 2 && m.rw_ok) || (m.flags & PGAS_FLAG_ANCESTOR_GATHER)) return false;
-    if (!((m.n_x == 2 && m.n_y == 1) || (m.n_x == 2 && m.n_y == 2))) return false;
+    if (!((m.D == 2 || m.D == 3) && m.rw_ok) || (m.flags & PGAS_FLAG_ANCESTOR_GATHER)) return false;
+    if (!((m.n_x == 2 && m.n_y == 1) || (m.n_x == 2 && m.n_y == 2 && m.D == 2))) return false;
     if (a.init_state || a.init_logw || a.dbg || a.row_off != 0 || a.t_begin != 1 || a.t_end != m.T) return false;   // full sweeps only
     if (a.t_end - a.t_begin < 16 || !a.logw_last) return false;
     if (getenv("PGAS_SWEEP_FUSED")) return false;                             // developer override
@@ -1086,12 +1089,13 @@ static int launch_state(const StateArgs& s_in, cudaStream_t st) {
     const int per = small ? ST_PP_SMALL * ST_NT_SMALL : ST_PP_BIG * ST_NT_BIG;
     s.bpc = (s.a.N + per - 1) / per;
     const dim3 grid((unsigned)(s.nch * s.bpc));
-#define PGAS_ST_LAUNCH(NYv, INJv, NTv, PPv) do { \
-        PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, NYv, INJv, NTv, PPv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        csmc_state_kernel<2, NYv, INJv, NTv, PPv><<<grid, NTv, smem, st>>>(s); } while (0)
-#define PGAS_ST_GEOM(NYv, INJv) do { if (small) PGAS_ST_LAUNCH(NYv, INJv, ST_NT_SMALL, ST_PP_SMALL); else PGAS_ST_LAUNCH(NYv, INJv, ST_NT_BIG, ST_PP_BIG); } while (0)
-    if (m.n_y == 1) { if (inj) PGAS_ST_GEOM(1, true); else PGAS_ST_GEOM(1, false); }
-    else { if (inj) PGAS_ST_GEOM(2, true); else PGAS_ST_GEOM(2, false); }
+#define PGAS_ST_LAUNCH(NYv, INJv, NTv, PPv, Dv) do { \
+        PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, NYv, INJv, NTv, PPv, Dv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        csmc_state_kernel<2, NYv, INJv, NTv, PPv, Dv><<<grid, NTv, smem, st>>>(s); } while (0)
+#define PGAS_ST_GEOM(NYv, INJv, Dv) do { if (small) PGAS_ST_LAUNCH(NYv, INJv, ST_NT_SMALL, ST_PP_SMALL, Dv); else PGAS_ST_LAUNCH(NYv, INJv, ST_NT_BIG, ST_PP_BIG, Dv); } while (0)
+    if (m.D == 3) { if (inj) PGAS_ST_GEOM(1, true, 3); else PGAS_ST_GEOM(1, false, 3); }
+    else if (m.n_y == 1) { if (inj) PGAS_ST_GEOM(1, true, 2); else PGAS_ST_GEOM(1, false, 2); }
+    else { if (inj) PGAS_ST_GEOM(2, true, 2); else PGAS_ST_GEOM(2, false, 2); }
 #undef PGAS_ST_GEOM
 #undef PGAS_ST_LAUNCH
     PGAS_KERNEL_CHECK();

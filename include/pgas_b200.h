@@ -147,11 +147,13 @@ int pgas_csmc_step_f64(const pgas_model* model, int32_t N, int32_t t, const doub
                        double* logw_out, double* state_out, int32_t* anc_out,
                        int32_t cluster_size, void* stream);
 
-/* condSequentialMonteCarlo.__call__ (src/PGAS.py:176-228) for n_chains independent chains: the sweep
- * (split form: csmc_state_kernel in launches of <= 16 steps running ahead of a resampling kernel that
- * keeps the chain's log-weights in registers and its CDF in shared memory, about 290 launches per sweep
- * at T = 2000; or the fused single kernel with the particle set resident in shared memory / DSMEM),
- * the final categorical pick (:224-225) and reconstruct_trajectory (src/Filtering.py:40-55).
+/* condSequentialMonteCarlo.__call__ (src/PGAS.py:176-228) for n_chains independent chains: the sweep, the final categorical
+ * pick (:224-225) and reconstruct_trajectory (src/Filtering.py:40-55).  The sweep runs in one of two schedules of the same
+ * arithmetic.  Split form (two-dimensional bases, reference semantics, workspace given): csmc_state_kernel in launches of <= 16
+ * steps runs ahead and writes traces plus three log-densities per particle-step to HBM; a resampling kernel (cluster per chain
+ * with st.async / mbarrier hand-offs up to 32 chains, one CTA per chain beyond) runs the weight recursion chunk-wise behind it —
+ * about 290 launches per sweep at T = 2000, nothing resident across the whole sweep.  Fused form (otherwise): one kernel per
+ * launch range with the particle set in shared memory / DSMEM.
  *   ref_traj (n_chains,T,n_x), Theta (n_chains,n_x,M), Sigma (n_chains,n_x,n_x)
  *   -> traj_out (n_chains,T,n_x); optional (may be NULL... see below) traces:
  *      state_trace (n_chains,T,N,n_x), anc_trace (n_chains,T-1,N) int32, logw_last (n_chains,N),
