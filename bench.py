@@ -283,25 +283,26 @@ def marginalised_leg(key_mod):
 
 
 # ------------------------------------------------------------------------------- GPU arm
-def ncu_traffic(kernel_regex):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel, from the committed `ncu --set full`
-    raw page of this round (profiles/r02_*_raw.csv); None when no capture is committed.  The capture is named in the result."""
+def ncu_traffic(kernel_regex, capture):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel, from the committed `ncu --set full` raw page of this
+    round (profiles/<capture>); None when the capture does not hold that kernel.  Several matching launches: the largest.  The
+    capture is named in the result — the number is an ncu measurement of the same kernel at the same launch geometry, not of this run."""
     import csv
-    import glob
     import re
+    path = os.path.join(ROOT, "profiles", capture)
     best = None
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_*_raw.csv"))):
-        try:
-            rows = list(csv.reader(open(path)))
-            hdr, units = rows[0], rows[1]
-            ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            for r in rows[2:]:
-                if re.search(kernel_regex, r[ik]):
-                    best = {"bytes_per_launch": float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0),
-                            "capture": os.path.relpath(path, ROOT)}
-        except Exception:
-            continue
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if re.search(kernel_regex, r[ik]):
+                b = float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
+                if best is None or b > best["bytes_per_launch"]:
+                    best = {"bytes_per_launch": b, "capture": "profiles/" + capture, "kernel": r[ik][:80]}
+    except Exception:
+        return None
     return best
 
 
@@ -473,7 +474,11 @@ def run_gpu_arm(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     flops_suff = cnt * ((T - 1) * M * (M + 1) + 2 * (T - 1) * M * 2)
     flops_draw = cnt * (M ** 3 / 3.0 + 3 * 2 * M * M)          # what this implementation performs: one factorisation + three triangular solves with n_x columns
-    tr_state, tr_suff, tr_draw = ncu_traffic(r"csmc_state_kernel"), ncu_traffic(r"suffstats_kernel"), ncu_traffic(r"chol_update_kernel")
+    # ncu captures of the same kernels at the same launch geometry (the state kernel's: one 16-step launch of one chain group of
+    # configs[3]; the draw's and the statistics': configs[4], 16 chains) — null for a configuration that was not captured
+    tr_state = ncu_traffic(rf"csmc_state_kernel<2, {cfg['n_y']}, 0, 256, 2", "r02_state_kernel_raw.csv") if cnt * ((N + 511) // 512) >= 222 else None
+    tr_suff = ncu_traffic(r"suffstats_kernel", "r02_suffstats_kernel_raw.csv") if args.config == 5 else None
+    tr_draw = ncu_traffic(r"chol_update_kernel", "r02_tail_kernels_raw.csv") if args.config == 5 else None
 
     # ---- end-to-end leg: the public API with HOST buffers (pinned), H2D of the reference trajectories and D2H of the
     #      new trajectories inside the timed region, every step
