@@ -15,6 +15,9 @@
 #pragma once
 #include "basis_eval.cuh"
 
+#ifndef PGAS_RW_SHORT_ROLLED
+#define PGAS_RW_SHORT_ROLLED 0  // 1: do not unroll the short staircase segments (compile-time knob)
+#endif
 #ifndef PGAS_RW_UNROLL
 #define PGAS_RW_UNROLL 2        // positions per loop body of the row walk (compile-time knob)
 #endif
@@ -39,7 +42,7 @@ __device__ __forceinline__ void rw_load(const double* __restrict__ p, double (&w
 template <int NX, int PP, int R>
 __device__ __forceinline__ void rw_segment(const double* __restrict__& th, int n, double (&acc)[PP][RW_RB][NX], double (&c)[PP],
                                            double (&pv)[PP], const double (&b_2c)[PP], double (&w)[RW_RB][NX]) {
-    constexpr int RW_UNROLL = PGAS_RW_UNROLL;
+    constexpr int RW_UNROLL = (R == RW_RB || !PGAS_RW_SHORT_ROLLED) ? PGAS_RW_UNROLL : 1;    // the staircase segments (R < 4) are 1-3 positions long
 #pragma unroll RW_UNROLL
     for (int j = 0; j < n; ++j) {
         th += R * NX;
