@@ -91,7 +91,7 @@ __device__ __forceinline__ double wl_scan_max_incl(double v, int lane) {
 
 constexpr int WL_KNONE = -(1 << 29);    // exponent of an empty unit (all weights zero)
 constexpr int WL_KNAN = 1 << 29;        // exponent code of a unit that saw a NaN log-weight: wins every maximum, the step falls back to uniform weights
-constexpr int WL_QBITS = 48;            // fixed-point fraction bits of the unit sums (values < 2^7 per warp, < 2^14 per chain of 16 CTAs: no overflow in 63 bits)
+constexpr int WL_QBITS2 = 48, WL_QBITS4 = 46;            // fixed-point fraction bits of the unit sums (values < 2^8 per warp of 128 particles, < 2^16 per chain of 16 CTAs x 16 warps: no overflow in 63 bits)
 
 // exp(x) = p * 2^n with |log p| <= ln2 / 2; x = -inf (or below -1e9) -> (0, WL_KNONE); NaN -> (0, WL_KNAN)
 __device__ __forceinline__ void wl_exp_parts(double x, double& p, int& n) {
@@ -120,8 +120,8 @@ __device__ __forceinline__ long long wl_scan3(long long v, int lane, int levels)
 // CT: compile-time bound of the cluster size (1 | 2 | 4 | 8 | 16; records of CTAs c >= C stay empty), so that both folds unroll
 template <int NT, int PPT, int CT>
 __global__ void __launch_bounds__(NT) csmc_weights_lat_kernel(const __grid_constant__ SweepArgs a) {
-    constexpr int NW = NT / 32, P = NT * PPT;
-    static_assert(PPT == 1 || PPT == 2, "one or two consecutive particles per thread");
+    constexpr int NW = NT / 32, P = NT * PPT, WL_QBITS = PPT <= 2 ? WL_QBITS2 : WL_QBITS4;
+    static_assert(PPT == 1 || PPT == 2 || PPT == 4, "one, two or four consecutive particles per thread");
     const int C = a.C, N = a.N;
     uint32_t rank_u;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank_u));
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(NT) csmc_weights_lat_kernel(const __grid_const
     const int U = C * NW, mine = rank * NW + warp;
     const int first_of_unit = g0 - lane * PPT;                               // global index of the warp's first particle
     const double dN = (double)N, rN = 1.0 / (double)N;
-    const bool vec = PPT == 2 && (N & 1) == 0;
+    const bool vec = PPT >= 2 && (N & 1) == 0;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* wrec = reinterpret_cast<double*>(smem_raw);                      // [2][NW][4]: (sum1, sum2, k1, k2) of every warp of this CTA
@@ -178,9 +178,12 @@ __global__ void __launch_bounds__(NT) csmc_weights_lat_kernel(const __grid_const
     const double *pla = a.pre_la + prow0, *plr = a.pre_lr + prow0, *pll = a.pre_ll + prow0;
     auto load_rows = [&](double (&la)[PPT], double (&lr)[PPT], double (&ll)[PPT]) {
         if (vec && nvalid == PPT) {
-            const double2 x = *reinterpret_cast<const double2*>(pla), y = *reinterpret_cast<const double2*>(plr),
-                          z = *reinterpret_cast<const double2*>(pll);
-            la[0] = x.x; la[PPT - 1] = x.y; lr[0] = y.x; lr[PPT - 1] = y.y; ll[0] = z.x; ll[PPT - 1] = z.y;
+#pragma unroll
+            for (int u = 0; u + 1 < PPT; u += 2) {
+                const double2 x = *reinterpret_cast<const double2*>(pla + u), y = *reinterpret_cast<const double2*>(plr + u),
+                              z = *reinterpret_cast<const double2*>(pll + u);
+                la[u] = x.x; la[u + 1] = x.y; lr[u] = y.x; lr[u + 1] = y.y; ll[u] = z.x; ll[u + 1] = z.y;
+            }
         } else {
 #pragma unroll
             for (int u = 0; u < PPT; ++u) {
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(NT) csmc_weights_lat_kernel(const __grid_const
         const double ures = su[2 * par], uanc = su[2 * par + 1];
 
         // ---- X1: fold of this CTA's NW warp records.  The warp sums are rescaled to the CTA's largest exponent (exact) and turned
-        //      into 64-bit FIXED-POINT numbers (2^-48 of the largest unit: 2e-13 of the CDF, far below the 1e-12 tie tolerance):
+        //      into 64-bit FIXED-POINT numbers (2^-48 of the largest unit, 2^-46 at four particles per thread: below 1e-12 of the CDF, far below the 1e-12 tie tolerance):
         //      integer sums are associative, so the shuffle scan below gives every warp of the chain bit-identical, monotone
         //      unit boundaries whatever the order of the additions.  Lane w < NW of every warp handles record w.
         long long qw1, qn1, qw2, qn2;                                       // this warp's start / end offset inside the CTA (CTA scale)
@@ -338,7 +341,8 @@ __global__ void __launch_bounds__(NT) csmc_weights_lat_kernel(const __grid_const
             c_hi = (end_of_unit >= N) ? N : c_hi;                           // the last particle takes what is left (Filtering.py:35)
             if (first_of_unit >= N) c_lo = N;
             c_hi = max(c_hi, c_lo);
-            if (PPT == 2) cend[PPT - 1] = max(cend[PPT - 1], cend[0]);
+#pragma unroll
+            for (int u = 1; u < PPT; ++u) cend[u] = max(cend[u], cend[u - 1]);
             // monotone inside the warp (running maximum over the lanes — only if some lane is out of order, which takes a rounding
             // glitch of the scan), clamped between the warp's boundaries; the warp's last particle ends at the upper boundary
             int rm = cend[PPT - 1];
@@ -456,23 +460,27 @@ __global__ void __launch_bounds__(NT) csmc_weights_lat_kernel(const __grid_const
     cluster_wait();
 }
 
-static size_t weights_lat_smem(int C) {
-    const size_t NW = WL_NT / 32, U = (size_t)C * NW, P = (size_t)WL_NT * WL_PPT;
+static size_t weights_lat_smem(int C, int ppt) {
+    const size_t NW = WL_NT / 32, U = (size_t)C * NW, P = (size_t)WL_NT * ppt;
     return (2 * NW * 4 + 2 * WL_MAXC * 4 + 2 * P + 2 * U * 2 + 4) * sizeof(double) + 4 * sizeof(unsigned long long) + 16;
 }
 
+// particles per thread: 2 while a cluster of <= 16 CTAs of 256 threads covers the chain (N <= 8192), else 4 (N <= 16384)
+static int weights_lat_ppt(int N) { return (N + WL_NT * WL_PPT - 1) / (WL_NT * WL_PPT) <= WL_MAXC ? WL_PPT : 2 * WL_PPT; }
+
 // cluster size of the latency form for N particles (0: not applicable)
 int pgas_weights_lat_cluster(int N) {
-    const int P = WL_NT * WL_PPT;
+    const int P = WL_NT * weights_lat_ppt(N);
     const int C = (N + P - 1) / P;
     return (N >= 64 && C <= WL_MAXC) ? C : 0;
 }
 
-int pgas_launch_weights_lat(const SweepArgs& a, cudaStream_t stream) {
-    auto kern = a.C <= 1 ? csmc_weights_lat_kernel<WL_NT, WL_PPT, 1> : a.C <= 2 ? csmc_weights_lat_kernel<WL_NT, WL_PPT, 2>
-              : a.C <= 4 ? csmc_weights_lat_kernel<WL_NT, WL_PPT, 4> : a.C <= 8 ? csmc_weights_lat_kernel<WL_NT, WL_PPT, 8>
-                                                                                 : csmc_weights_lat_kernel<WL_NT, WL_PPT, 16>;
-    size_t smem = weights_lat_smem(a.C);
+template <int PPT>
+static int weights_lat_launch(const SweepArgs& a, cudaStream_t stream) {
+    auto kern = a.C <= 1 ? csmc_weights_lat_kernel<WL_NT, PPT, 1> : a.C <= 2 ? csmc_weights_lat_kernel<WL_NT, PPT, 2>
+              : a.C <= 4 ? csmc_weights_lat_kernel<WL_NT, PPT, 4> : a.C <= 8 ? csmc_weights_lat_kernel<WL_NT, PPT, 8>
+                                                                                 : csmc_weights_lat_kernel<WL_NT, PPT, 16>;
+    size_t smem = weights_lat_smem(a.C, PPT);
     if (const char* e = getenv("PGAS_WL_SMEM_KB")) smem = std::max(smem, (size_t)atoi(e) * 1024);   // developer knob: a large request keeps other CTAs off the SM
     PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (a.C > 8) PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -491,4 +499,8 @@ int pgas_launch_weights_lat(const SweepArgs& a, cudaStream_t stream) {
     PGAS_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     __atomic_add_fetch(&g_pgas_launches, 1, __ATOMIC_RELAXED);
     return 0;
+}
+
+int pgas_launch_weights_lat(const SweepArgs& a, cudaStream_t stream) {
+    return weights_lat_ppt(a.N) == WL_PPT ? weights_lat_launch<WL_PPT>(a, stream) : weights_lat_launch<2 * WL_PPT>(a, stream);
 }

@@ -300,7 +300,9 @@ def test_pgas_reference_call_signature(built_lib):
     ("smo", 300, 40, 3, 0, 3), ("smo", 4096, 150, 2, 0, 3), ("smo", 5001, 20, 1, 0, 3), ("vehicle", 8192, 12, 1, 0, 3),
     ("smo", 2049, 30, 2, 0, 3), ("vehicle", 700, 50, 2, 2, 3),
     # three-dimensional basis (EMPS baseline shape, src/EMPS.py:101-123): the row walk with one more level, both geometries
-    ("emps", 200, 80, 1, 0, 3), ("emps", 1500, 40, 3, 0, 1), ("emps", 700, 30, 2, 0, 0)])
+    ("emps", 200, 80, 1, 0, 3), ("emps", 1500, 40, 3, 0, 1), ("emps", 700, 30, 2, 0, 0),
+    # latency form with four particles per thread (N > 8192): clusters of 10 (ragged) and 16
+    ("smo", 10001, 12, 1, 0, 3), ("vehicle", 16384, 10, 2, 0, 3)])
 def test_split_and_fused_sweeps_agree(built_lib, kind, N, T, chains, cluster, dedicated, monkeypatch):
     """The split form (state kernel ahead of the resampling kernel, csrc/sweep.cu) and the fused kernel are two schedules
     of the same arithmetic: identical ancestors and traces, for particle counts that are not multiples of the tile sizes,
