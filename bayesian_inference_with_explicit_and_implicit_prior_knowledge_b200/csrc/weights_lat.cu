@@ -120,8 +120,8 @@ __device__ __forceinline__ long long wl_scan3(long long v, int lane, int levels)
 // CT: compile-time bound of the cluster size (1 | 2 | 4 | 8 | 16; records of CTAs c >= C stay empty), so that both folds unroll
 template <int NT, int PPT, int CT>
 __global__ void __launch_bounds__(NT) csmc_weights_lat_kernel(const __grid_constant__ SweepArgs a) {
-    constexpr int NW = NT / 32, P = NT * PPT, WL_QBITS = PPT <= 2 ? WL_QBITS2 : WL_QBITS4;
-    static_assert(PPT == 1 || PPT == 2 || PPT == 4, "one, two or four consecutive particles per thread");
+    constexpr int NW = NT / 32, P = NT * PPT, WL_QBITS = (PPT * NT <= 512) ? WL_QBITS2 : WL_QBITS4 - (PPT * NT > 1024 ? 2 : 0);
+    static_assert(PPT == 1 || PPT == 2 || PPT == 4 || PPT == 8, "1, 2, 4 or 8 consecutive particles per thread");
     const int C = a.C, N = a.N;
     uint32_t rank_u;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank_u));
