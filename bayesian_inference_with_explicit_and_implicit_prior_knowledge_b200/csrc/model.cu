@@ -254,12 +254,42 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
         }
     }
 
+    // ---- DMMA layout (two-dimensional bases, n_x = 2; basis_mma.cuh): per block of RW_RB rows and k-step s the 32 A-fragment
+    //      entries of mma.sync.m8n8k4: lane -> row = lane / 4 = 2 * i_local + k, column = lane % 4 -> walked position 4 s + lane % 4
+    std::vector<int> mma_perm;
+    dm.mma_ok = 0; dm.mma_nblk = 0; dm.mma_slots = 0;
+    for (int b = 0; b < RW_MAXBLK; ++b) dm.mma_ks[b] = 0;
+    if (D == 2 && nx == 2) {
+        const int nb = (dm.npos_d[0] + RW_RB - 1) / RW_RB;
+        if (nb <= RW_MAXBLK) {
+            std::vector<int> Lb(nb, 0), off(nb + 1, 0);
+            for (int mI = 0; mI < M; ++mI) Lb[pos[(size_t)mI * D] / RW_RB] = std::max(Lb[pos[(size_t)mI * D] / RW_RB], pos[(size_t)mI * D + 1] + 1);
+            bool fits = true;
+            for (int b = 0; b < nb; ++b) {
+                const int ks = (Lb[b] + 3) / 4;
+                fits = fits && ks <= 255;
+                dm.mma_ks[b] = (unsigned char)ks;
+                off[b + 1] = off[b] + ks * 32;
+            }
+            if (fits) {
+                mma_perm.assign((size_t)off[nb], -1);
+                for (int mI = 0; mI < M; ++mI) {
+                    const int i = pos[(size_t)mI * D], j = pos[(size_t)mI * D + 1];
+                    const int b = i / RW_RB, il = i % RW_RB, sk = j / 4, c = j % 4;
+                    for (int k = 0; k < nx; ++k) mma_perm[(size_t)off[b] + sk * 32 + (2 * il + k) * 4 + c] = mI * 4 + k;
+                }
+                dm.mma_ok = 1; dm.mma_nblk = nb; dm.mma_slots = off[nb];
+            }
+        }
+    }
+
     // ---- one device arena ---------------------------------------------------------------
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_rows = al(sizeof(int) * row_pos.size()), b_perm = al(sizeof(int) * dm.n_packed), b_freq = al(sizeof(int) * M * D);
     const size_t b_obs = al(sizeof(double) * (size_t)p->T * p->n_y), b_in = al(sizeof(double) * (size_t)p->T * std::max(p->n_u, 1));
     const size_t b_rw = al(sizeof(int) * std::max<size_t>(rw_perm.size(), 1));
-    const size_t total = b_rows + b_perm + b_freq + b_obs + b_in + b_rw;
+    const size_t b_mma = al(sizeof(int) * std::max<size_t>(mma_perm.size(), 1));
+    const size_t total = b_rows + b_perm + b_freq + b_obs + b_in + b_rw + b_mma;
     char* arena = nullptr;
     PGAS_CUDA(cudaMalloc((void**)&arena, total));
     size_t o = 0;
@@ -275,6 +305,7 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
     dm.obs = (const double*)up(p->observations, sizeof(double) * (size_t)p->T * p->n_y, b_obs);
     dm.inputs = (const double*)up(p->inputs, p->n_u ? sizeof(double) * (size_t)p->T * p->n_u : 0, b_in);
     dm.rw_perm = (const int*)up(rw_perm.data(), sizeof(int) * rw_perm.size(), b_rw);
+    dm.mma_perm = (const int*)up(mma_perm.data(), sizeof(int) * mma_perm.size(), b_mma);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { cudaFree(arena); PGAS_FAIL((int)e, "model upload failed: %s", cudaGetErrorString(e)); }
 

@@ -24,6 +24,7 @@
 #include <stdlib.h>
 #include "basis_eval.cuh"
 #include "basis_rowwalk.cuh"
+#include "basis_mma.cuh"
 #include "sweep_args.cuh"
 #include "resample_math.cuh"
 
@@ -838,25 +839,30 @@ constexpr int ST_NT_SMALL = 64, ST_PP_SMALL = 1;                   // ... and wh
 // Theta' pair: half the shared-memory traffic per DFMA, 128 registers, two CTAs per SM); <64, 1> when they do not (few chains:
 // four times as many, smaller CTAs spread over all SMs, and a step's dependent chain per thread is half as long).
 // D: dimension of the Hilbert basis (2, or 3: one more level of the row walk — the EMPS baseline of src/EMPS.py:101-123).
-template <int NX, int NY, bool INJ, int ST_NT, int ST_PP, int D = 2>
+// MMA: the contraction on DMMA tiles (basis_mma.cuh) instead of the FMA row walk; needs ST_PP == 2, D == 2, NX == 2.
+template <int NX, int NY, bool INJ, int ST_NT, int ST_PP, int D = 2, bool MMA = false>
 __global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_state_kernel(const __grid_constant__ StateArgs s) {
+    static_assert(!MMA || (ST_PP == 2 && D == 2 && NX == 2), "DMMA form: two particles per thread, two-dimensional basis, n_x = 2");
     const SweepArgs& a = s.a;
     const DevModel& m = a.m;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* bd = reinterpret_cast<double*>(smem_raw);
-    double* chol = bd + ((m.rw_slots + 1) & ~1);
+    const int n_theta = MMA ? m.mma_slots : m.rw_slots;
+    double* chol = bd + ((n_theta + 1) & ~1);
     double* sw = chol + NX * NX;
     double* slogc = sw + NX * NX;
     int* rwlen = reinterpret_cast<int*>(slogc + 2);
+    double* mma_w = reinterpret_cast<double*>(rwlen + RW_MAXBLK) + (size_t)(threadIdx.x >> 5) * MMA_WARP_DOUBLES;   // DMMA form: per-warp seeds + tile buffer
     const int tid = threadIdx.x, N = a.N;
     const int chain = s.chain0 + blockIdx.x / s.bpc, blk = blockIdx.x % s.bpc;
     {
         const double* Th = a.Theta + (size_t)chain * NX * m.M;
-        for (int e = tid; e < m.rw_slots; e += ST_NT) {
-            const int q = m.rw_perm[e];
+        const int* perm = MMA ? m.mma_perm : m.rw_perm;
+        for (int e = tid; e < n_theta; e += ST_NT) {
+            const int q = perm[e];
             bd[e] = (q >= 0) ? m.norm * Th[(size_t)(q & 3) * m.M + (q >> 2)] : 0.0;
         }
-        if (tid < RW_MAXBLK) rwlen[tid] = m.rw_blen[tid];
+        if (tid < RW_MAXBLK) rwlen[tid] = MMA ? (int)m.mma_ks[tid] : m.rw_blen[tid];
         if (tid == 0) {
             const double* S = a.Sigma + (size_t)chain * NX * NX;
             double Lc[NX][NX], Li[NX][NX], logdet = 0.0;
@@ -894,7 +900,11 @@ __global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_stat
     int ip[ST_PP];
     bool val[ST_PP];
 #pragma unroll
-    for (int p = 0; p < ST_PP; ++p) { ip[p] = blk * ST_PP * ST_NT + p * ST_NT + tid; val[p] = ip[p] < N; }
+    for (int p = 0; p < ST_PP; ++p) {
+        // DMMA form: a warp owns 64 consecutive particles, lane l the particles l and 32 + l of them
+        ip[p] = MMA ? blk * ST_PP * ST_NT + (tid >> 5) * 64 + p * 32 + (tid & 31) : blk * ST_PP * ST_NT + p * ST_NT + tid;
+        val[p] = ip[p] < N;
+    }
     double x[ST_PP][NX];
     const double* refc = a.ref + (size_t)chain * a.ref_stride;
 #pragma unroll
@@ -968,7 +978,8 @@ __global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_stat
 #pragma unroll
         for (int p = 0; p < ST_PP; ++p) mapr.apply(x[p], cz, u, tzv[p]);
         double mu[ST_PP][NX];
-        rowwalk_mu<NX, ST_PP, D>(bd, rwlen, m.rw_slice_nblk, m.rw_nslice, f_start, f_step, tzv, mu);
+        if constexpr (MMA) mma_mu<NX>(bd, m.mma_ks, m.mma_nblk, mma_w, tid & 31, f_start, f_step, tzv, mu);
+        else rowwalk_mu<NX, ST_PP, D>(bd, rwlen, m.rw_slice_nblk, m.rw_nslice, f_start, f_step, tzv, mu);
         const size_t prow = ((size_t)chain * s.rows + (size_t)(t - s.t0)) * N;
         // log-densities and the new state of all particles of the thread, branch-free; the stores follow
         double la[ST_PP], lr[ST_PP], ll[ST_PP];
@@ -1042,6 +1053,9 @@ extern "C" int pgas_debug_set_split_ticks(long long* dev_buf) { g_dbg_split_tick
 #ifndef PGAS_SPLIT_GROUPS
 #define PGAS_SPLIT_GROUPS 2
 #endif
+#ifndef PGAS_STATE_MMA_DEFAULT
+#define PGAS_STATE_MMA_DEFAULT 0    // 1: the DMMA form of the contraction is the default in the big geometry
+#endif
 #ifndef PGAS_LAT_MAX_CHAINS
 #define PGAS_LAT_MAX_CHAINS 32      // up to this many chains per launch the latency form of the resampling kernel is the default (A/B on B200: profiles/r02_strong_scaling.md)
 #endif
@@ -1078,7 +1092,6 @@ static int split_streams_init() {
 static int launch_state(const StateArgs& s_in, cudaStream_t st) {
     StateArgs s = s_in;
     const DevModel& m = s.a.m;
-    const size_t smem = sizeof(double) * (((size_t)m.rw_slots + 1) & ~(size_t)1) + sizeof(double) * (2 * m.n_x * m.n_x + 2) + sizeof(int) * RW_MAXBLK + 32;
     const bool inj = s.a.rng_mode == 1;
     // geometry: big CTAs unless they would leave SMs idle (fewer than ~1.5 CTAs per SM slot pair); PGAS_STATE_SMALL=0|1 forces one
     int sms = 148;
@@ -1086,13 +1099,20 @@ static int launch_state(const StateArgs& s_in, cudaStream_t st) {
     const int bpc_big = (s.a.N + ST_PP_BIG * ST_NT_BIG - 1) / (ST_PP_BIG * ST_NT_BIG);
     bool small = s.a.n_chains * bpc_big < (3 * sms) / 2;                       // judged on the whole sweep, not on one chain group
     if (const char* e = getenv("PGAS_STATE_SMALL")) small = atoi(e) != 0;     // developer override
+    // contraction on DMMA tiles (basis_mma.cuh) in the big geometry of two-dimensional bases; PGAS_STATE_MMA=0|1 forces
+    bool mma = !small && m.D == 2 && m.mma_ok && ST_PP_BIG == 2 && PGAS_STATE_MMA_DEFAULT;
+    if (const char* e = getenv("PGAS_STATE_MMA")) mma = atoi(e) != 0 && !small && m.D == 2 && m.mma_ok && ST_PP_BIG == 2;
+    const int n_theta = mma ? m.mma_slots : m.rw_slots;
+    const size_t smem = sizeof(double) * (((size_t)n_theta + 1) & ~(size_t)1) + sizeof(double) * (2 * m.n_x * m.n_x + 2) + sizeof(int) * RW_MAXBLK +
+                        (mma ? sizeof(double) * (size_t)MMA_WARP_DOUBLES * (ST_NT_BIG / 32) : 0) + 32;
     const int per = small ? ST_PP_SMALL * ST_NT_SMALL : ST_PP_BIG * ST_NT_BIG;
     s.bpc = (s.a.N + per - 1) / per;
     const dim3 grid((unsigned)(s.nch * s.bpc));
-#define PGAS_ST_LAUNCH(NYv, INJv, NTv, PPv, Dv) do { \
-        PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, NYv, INJv, NTv, PPv, Dv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        csmc_state_kernel<2, NYv, INJv, NTv, PPv, Dv><<<grid, NTv, smem, st>>>(s); } while (0)
-#define PGAS_ST_GEOM(NYv, INJv, Dv) do { if (small) PGAS_ST_LAUNCH(NYv, INJv, ST_NT_SMALL, ST_PP_SMALL, Dv); else PGAS_ST_LAUNCH(NYv, INJv, ST_NT_BIG, ST_PP_BIG, Dv); } while (0)
+#define PGAS_ST_LAUNCH(NYv, INJv, NTv, PPv, Dv, MMAv) do { \
+        PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, NYv, INJv, NTv, PPv, Dv, MMAv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        csmc_state_kernel<2, NYv, INJv, NTv, PPv, Dv, MMAv><<<grid, NTv, smem, st>>>(s); } while (0)
+#define PGAS_ST_GEOM(NYv, INJv, Dv) do { if (small) PGAS_ST_LAUNCH(NYv, INJv, ST_NT_SMALL, ST_PP_SMALL, Dv, false); \
+        else if (mma && Dv == 2) PGAS_ST_LAUNCH(NYv, INJv, ST_NT_BIG, 2, 2, true); else PGAS_ST_LAUNCH(NYv, INJv, ST_NT_BIG, ST_PP_BIG, Dv, false); } while (0)
     if (m.D == 3) { if (inj) PGAS_ST_GEOM(1, true, 3); else PGAS_ST_GEOM(1, false, 3); }
     else if (m.n_y == 1) { if (inj) PGAS_ST_GEOM(1, true, 2); else PGAS_ST_GEOM(1, false, 2); }
     else { if (inj) PGAS_ST_GEOM(2, true, 2); else PGAS_ST_GEOM(2, false, 2); }

@@ -125,6 +125,20 @@ def test_sweep_parity_injected(built_lib, kind, N, T, cluster):
     assert r["rows_compared"] >= 1
 
 
+@pytest.mark.parametrize("kind,N,T,M", [("smo", 700, 40, 41), ("vehicle", 1536, 24, 36), ("smo", 512, 20, 256), ("plugin", 300, 30, 41)])
+def test_state_kernel_dmma_form_matches_oracle(built_lib, kind, N, T, M, monkeypatch):
+    """The contraction of the state kernel on DMMA tiles with the particles on the N dimension (csrc/basis_mma.cuh; opt-in,
+    PGAS_STATE_MMA=1): same oracle parity as the FMA row walk — ragged particle counts, both observation dimensions, a lattice with
+    five row blocks, the expression-program map."""
+    monkeypatch.setenv("PGAS_STATE_MMA", "1")
+    monkeypatch.setenv("PGAS_STATE_SMALL", "0")
+    p = helpers.make_problem(kind, T=T, N=N, M=M, seed=T + 1)
+    r = helpers.run_sweep_parity(p, cluster_size=0)
+    assert r["ok"], str(r)
+    r = helpers.run_sweep_parity(p, cluster_size=0, philox_seed=77)
+    assert r["ok"], str(r)
+
+
 def test_sweep_gather_mode(built_lib):
     p = helpers.make_problem("smo", T=30, N=384, seed=4, flags=1)
     for cluster in (1, 2):
