@@ -12,9 +12,10 @@
 //   * EXPONENTS AS INTEGERS: exp(lw) = p 2^n with n = rint(lw log2 e) kept as an integer; the softmax shift of a warp is the
 //     integer maximum of n (one redux.sync), and every later rescaling between warps / CTAs is a multiplication by an exact power
 //     of two — no second exponential anywhere, no rounding in the rescaling;
-//   * TWO-LEVEL FOLD WITH SEQUENTIAL OFFSETS: the 8 warp sums of a CTA, then the C CTA sums of the chain, are accumulated one
-//     after the other (8 dependent additions, every thread for itself) instead of with shuffle scans — fewer instructions, and
-//     the unit boundaries of the CDF are monotone by construction;
+//   * TWO-LEVEL FOLD IN FIXED POINT: the 8 warp sums of a CTA, then the C CTA sums of the chain, are rescaled to the largest
+//     exponent (exact) and converted to 64-bit fixed point (2^-48 of the largest unit); lane w of every warp handles record w
+//     and a three-level shuffle scan of INTEGERS gives the offsets — integer sums are associative, so every warp of the chain
+//     obtains bit-identical, monotone unit boundaries whatever the order of the additions (floating-point scans do not);
 //   * NO SEARCH: particle k computes the number of stratified points at or below its CDF value ARITHMETICALLY,
 //     c_k = #{j : U_j <= W_k} = floor(W_k N - u) + 1 (exactly-rounded fallback when W_k N - u is within 1e-9 of an integer),
 //     and writes its index over the points j in [c_{k-1}, c_k) — its offspring; the point's owner receives l_aux[k].  The counts
@@ -79,23 +80,14 @@ __device__ __forceinline__ int wl_points_guess(double W, double u, double dN, in
 // min(v, 1) for a non-negative, non-NaN v (the CDF values: sums of non-negative numerators times a positive reciprocal)
 __device__ __forceinline__ double wl_min1(double v) { return v > 1.0 ? 1.0 : v; }
 
-__device__ __forceinline__ double wl_scan_max_incl(double v, int lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double n = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v = fmax(v, n);
-    }
-    return v;
-}
-
-
 constexpr int WL_KNONE = -(1 << 29);    // exponent of an empty unit (all weights zero)
 constexpr int WL_KNAN = 1 << 29;        // exponent code of a unit that saw a NaN log-weight: wins every maximum, the step falls back to uniform weights
 constexpr int WL_QBITS2 = 48, WL_QBITS4 = 46;            // fixed-point fraction bits of the unit sums (values < 2^8 per warp of 128 particles, < 2^16 per chain of 16 CTAs x 16 warps: no overflow in 63 bits)
 
-// exp(x) = p * 2^n with |log p| <= ln2 / 2; x = -inf (or below -1e9) -> (0, WL_KNONE); NaN -> (0, WL_KNAN)
+// exp(x) = p * 2^n with |log p| <= ln2 / 2 for -1e9 < x < 1.4e9 (n fits an int); x = -inf or below -1e9 -> (0, WL_KNONE); NaN -> (0, WL_KNAN);
+// +inf or above 1.4e9: the conversion of n saturates above WL_KNAN, i.e. the step falls back to uniform weights like a NaN does
 __device__ __forceinline__ void wl_exp_parts(double x, double& p, int& n) {
-    const bool dead = !(x > -1e9);                                          // -inf, hugely negative — but not NaN
+    const bool dead = !(x > -1e9);                                          // -inf, hugely negative, or NaN (the comparison is false)
     const bool isnan_ = x != x;
     const double xs = (dead || isnan_) ? 0.0 : x;
     const double nd = rint(xs * 1.4426950408889634);
