@@ -73,18 +73,29 @@ __device__ __forceinline__ void rowwalk_slice(const double* __restrict__& th, co
     for (int b = 0; b < nblk; ++b) {
         double acc[PP][RW_RB][NX];
         double c[PP], pv[PP];
+        // the first position of a block has all RW_RB rows active (layout guarantee, model.cu): its products START the accumulators
+        // (no zeroing: ptxas had placed 2 x 16 CS2R per block, 5 % of the kernel's instructions)
+        th += RW_RB * NX;
+#pragma unroll
+        for (int i = 0; i < RW_RB; ++i) {
+#pragma unroll
+            for (int p = 0; p < PP; ++p)
+#pragma unroll
+                for (int k = 0; k < NX; ++k) acc[p][i][k] = w[i][k] * b_cur[p];
+            rw_load<NX>(th + i * NX, w[i]);
+        }
+        // the recurrence state of the block is produced HERE (opaque copy + one DFMA per particle): left to itself the compiler hoists
+        // the invariant second sine out of the block loop and then copies both values in on three paths (24 moves per block)
 #pragma unroll
         for (int p = 0; p < PP; ++p) {
-            c[p] = b_cur[p];
-            pv[p] = b_prev[p];
-#pragma unroll
-            for (int i = 0; i < RW_RB; ++i)
-#pragma unroll
-                for (int k = 0; k < NX; ++k) acc[p][i][k] = 0.0;
+            double s0 = b_cur[p];
+            asm volatile("" : "+d"(s0));
+            pv[p] = s0;
+            c[p] = fma(b_2c[p], s0, -b_prev[p]);
         }
         // positions with 4, 3, 2, 1 active rows (packed byte counts, common.cuh): only selected lattice entries are walked
         const int L = blen[b];
-        rw_segment<NX, PP, 4>(th, L & 255, acc, c, pv, b_2c, w);
+        rw_segment<NX, PP, 4>(th, (L & 255) - 1, acc, c, pv, b_2c, w);
         rw_segment<NX, PP, 3>(th, (L >> 8) & 255, acc, c, pv, b_2c, w);
         rw_segment<NX, PP, 2>(th, (L >> 16) & 255, acc, c, pv, b_2c, w);
         rw_segment<NX, PP, 1>(th, (L >> 24) & 255, acc, c, pv, b_2c, w);

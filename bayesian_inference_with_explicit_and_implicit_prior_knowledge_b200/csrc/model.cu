@@ -226,6 +226,8 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
             dm.rw_slice_nblk[sl] = used;
             for (int b = 0; b < used; ++b) {
                 if (nblk >= RW_MAXBLK) { fits = false; break; }
+                act[sl][b][0] = RW_RB;       // the first position of a block carries all RW_RB rows (zeros for rows the lattice lacks): the
+                                             // walk starts its accumulators with products there instead of zeroing them (rowwalk_slice)
                 int cnt[RW_RB + 1] = {0, 0, 0, 0, 0};
                 std::vector<int> jo(jtop + 1, 0);
                 for (int j = 0; j < jtop; ++j) {

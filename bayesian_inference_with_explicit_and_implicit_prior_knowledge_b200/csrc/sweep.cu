@@ -979,7 +979,7 @@ __global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_stat
         for (int p = 0; p < ST_PP; ++p) mapr.apply(x[p], cz, u, tzv[p]);
         double mu[ST_PP][NX];
         if constexpr (MMA) mma_mu<NX>(bd, m.mma_ks, m.mma_nblk, mma_w, tid & 31, f_start, f_step, tzv, mu);
-        else rowwalk_mu<NX, ST_PP, D>(bd, rwlen, m.rw_slice_nblk, m.rw_nslice, f_start, f_step, tzv, mu);
+        else rowwalk_mu<NX, ST_PP, D>(bd, m.rw_blen, m.rw_slice_nblk, m.rw_nslice, f_start, f_step, tzv, mu);
         const size_t prow = ((size_t)chain * s.rows + (size_t)(t - s.t0)) * N;
         // log-densities and the new state of all particles of the thread, branch-free; the stores follow
         double la[ST_PP], lr[ST_PP], ll[ST_PP];

@@ -109,6 +109,55 @@ __device__ __forceinline__ long long wl_scan3(long long v, int lane, int levels)
     return v;
 }
 
+// Offspring ranges of the PPT consecutive particles of one lane: particle g0 + u gets the stratified points [c_{u-1}, cend[u]) with
+// c_{-1} = the returned value.  W: the particles' CDF values; lo / hi: the CDF at the two boundaries of the lane's UNIT (the 32 PPT
+// particles of its warp), which the neighbouring units evaluate from the same integers, bit for bit.  Counts are made monotone inside
+// the unit and clamped between c(lo) and c(hi); the unit's last particle ends at c(hi): the ranges of a chain partition [0, N)
+// whatever the rounding of the prefix sums does (src/Filtering.py:28-35: idx_j = #{k : W_k < U_j}, clipped to N - 1).
+template <int PPT>
+__device__ __forceinline__ int wl_offspring_ranges(const double (&W)[PPT], double lo, double hi, bool first_unit, bool last_unit, bool empty_unit,
+                                                   int g0, int N, double u, double dN, double rN, int lane, int (&cend)[PPT]) {
+    bool n_lo, n_hi, n_w[PPT];
+    int c_lo = wl_points_guess(lo, u, dN, N, n_lo), c_hi = wl_points_guess(hi, u, dN, N, n_hi);
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) cend[q] = wl_points_guess(W[q], u, dN, N, n_w[q]);
+    bool any_near = n_lo || n_hi;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) any_near = any_near || n_w[q];
+    if (any_near) {                                                         // rare: a CDF value within 1e-9 / N of a stratified point
+        if (n_lo) c_lo = wl_points_exact(lo, u, N, dN, rN);
+        if (n_hi) c_hi = wl_points_exact(hi, u, N, dN, rN);
+#pragma unroll
+        for (int q = 0; q < PPT; ++q)
+            if (n_w[q]) cend[q] = wl_points_exact(W[q], u, N, dN, rN);
+    }
+    c_lo = first_unit ? 0 : c_lo;
+    c_hi = last_unit ? N : c_hi;                                            // the last particle takes what is left (Filtering.py:35)
+    if (empty_unit) c_lo = N;
+    c_hi = max(c_hi, c_lo);
+#pragma unroll
+    for (int q = 1; q < PPT; ++q) cend[q] = max(cend[q], cend[q - 1]);
+    // monotone inside the warp (running maximum over the lanes — only if some lane is out of order, which takes a rounding glitch
+    // of the scan), clamped between the unit's boundaries; the unit's last particle ends at the upper boundary
+    int rm = cend[PPT - 1];
+    int cp = __shfl_up_sync(0xffffffffu, rm, 1);
+    if (__any_sync(0xffffffffu, lane > 0 && cend[0] < cp)) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, rm, o);
+            if (lane >= o) rm = max(rm, v);
+        }
+        cp = __shfl_up_sync(0xffffffffu, rm, 1);
+    }
+    cp = lane ? min(max(cp, c_lo), c_hi) : c_lo;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        cend[q] = min(max(max(cend[q], cp), c_lo), c_hi);
+        if ((lane == 31 && q == PPT - 1) || g0 + q >= N - 1) cend[q] = c_hi;
+    }
+    return cp;
+}
+
 // CT: compile-time bound of the cluster size (1 | 2 | 4 | 8 | 16; records of CTAs c >= C stay empty), so that both folds unroll
 template <int NT, int PPT, int CT>
 __global__ void __launch_bounds__(NT) csmc_weights_lat_kernel(const __grid_constant__ SweepArgs a) {
@@ -314,45 +363,8 @@ __global__ void __launch_bounds__(NT) csmc_weights_lat_kernel(const __grid_const
                 W[u] = uni ? div_by_count((double)(g0 + u + 1), dN, rN) : wl_min1(__dmul_rn(__dadd_rn(of1, __dmul_rn(sc1, s1[u])), S1));
                 below[u] = (u < nvalid) && !nan2 && (__dmul_rn(__dadd_rn(of2, __dmul_rn(sc2, s2[u])), S2) < uanc);
             }
-            bool n_lo, n_hi, n_w[PPT];
-            int c_lo = wl_points_guess(lo1, ures, dN, N, n_lo), c_hi = wl_points_guess(hi1, ures, dN, N, n_hi);
             int cend[PPT];
-#pragma unroll
-            for (int u = 0; u < PPT; ++u) cend[u] = wl_points_guess(W[u], ures, dN, N, n_w[u]);
-            bool any_near = n_lo || n_hi;
-#pragma unroll
-            for (int u = 0; u < PPT; ++u) any_near = any_near || n_w[u];
-            if (any_near) {                                                 // rare: a CDF value within 1e-9 / N of a stratified point
-                if (n_lo) c_lo = wl_points_exact(lo1, ures, N, dN, rN);
-                if (n_hi) c_hi = wl_points_exact(hi1, ures, N, dN, rN);
-#pragma unroll
-                for (int u = 0; u < PPT; ++u)
-                    if (n_w[u]) cend[u] = wl_points_exact(W[u], ures, N, dN, rN);
-            }
-            c_lo = (mine == 0) ? 0 : c_lo;
-            c_hi = (end_of_unit >= N) ? N : c_hi;                           // the last particle takes what is left (Filtering.py:35)
-            if (first_of_unit >= N) c_lo = N;
-            c_hi = max(c_hi, c_lo);
-#pragma unroll
-            for (int u = 1; u < PPT; ++u) cend[u] = max(cend[u], cend[u - 1]);
-            // monotone inside the warp (running maximum over the lanes — only if some lane is out of order, which takes a rounding
-            // glitch of the scan), clamped between the warp's boundaries; the warp's last particle ends at the upper boundary
-            int rm = cend[PPT - 1];
-            int cp = __shfl_up_sync(0xffffffffu, rm, 1);
-            if (__any_sync(0xffffffffu, lane > 0 && cend[0] < cp)) {
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, rm, o);
-                    if (lane >= o) rm = max(rm, v);
-                }
-                cp = __shfl_up_sync(0xffffffffu, rm, 1);
-            }
-            cp = lane ? min(max(cp, c_lo), c_hi) : c_lo;
-#pragma unroll
-            for (int u = 0; u < PPT; ++u) {
-                cend[u] = min(max(max(cend[u], cp), c_lo), c_hi);
-                if ((lane == 31 && u == PPT - 1) || g0 + u >= N - 1) cend[u] = c_hi;
-            }
+            int cp = wl_offspring_ranges<PPT>(W, lo1, hi1, mine == 0, end_of_unit >= N, first_of_unit >= N, g0, N, ures, dN, rN, lane, cend);
             // reference ancestor (src/PGAS.py:118-124): the first particle whose second CDF value is not below u_anc
             bool bp = __shfl_up_sync(0xffffffffu, (int)below[PPT - 1], 1) != 0;
             bp = lane ? bp : (mine == 0 ? true : (!nan2 && lo2 < uanc));
