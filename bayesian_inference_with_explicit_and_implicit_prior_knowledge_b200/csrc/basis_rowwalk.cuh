@@ -33,27 +33,45 @@ __device__ __forceinline__ void rw_load(const double* __restrict__ p, double (&w
     }
 }
 
-// n last-dimension positions at which the first R rows of the block are active: R Theta' pairs per position.
-// The pairs travel through a register ring `w`: on entry w[i] holds the pair th[i] (i < R); a pair is re-loaded for the NEXT
-// position right after its DFMAs, i.e. (R-1) pairs = 4 (R-1) PP DFMAs ahead of its use, so that the ~25-cycle LDS latency is
-// covered inside ONE warp (ptxas left one pair of look-ahead: a warp walking alone reached a quarter of the pipe rate,
-// profiles/r02_state_kernel_summary.md).  On exit w[i] holds the pair at the new th[i] for i < R, which is what the next
-// segment (R - 1 rows) expects; the over-read past the last block touches the bytes that follow Theta' in shared memory.
-template <int NX, int PP, int R>
+// One walked position with the first R rows of the block active: R Theta' pairs, each feeding PP * NX DFMAs with the position's sine
+// `sn`.  The pairs travel through a register ring `w`: on entry w[i] holds the pair of THIS position; a pair is re-loaded for the
+// NEXT position (`nx`) right after its DFMAs, i.e. (R-1) pairs = 4 (R-1) PP DFMAs ahead of its use, so that the ~25-cycle LDS
+// latency is covered inside ONE warp (ptxas left one pair of look-ahead: a warp walking alone reached a quarter of the pipe rate,
+// profiles/r02_state_kernel_summary.md).  FIRST: the products start the accumulators (no zeroing).
+template <int NX, int PP, int R, bool FIRST = false>
+__device__ __forceinline__ void rw_position(const double* __restrict__ nx, double (&acc)[PP][RW_RB][NX], const double (&sn)[PP], double (&w)[RW_RB][NX]) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+#pragma unroll
+        for (int p = 0; p < PP; ++p)
+#pragma unroll
+            for (int k = 0; k < NX; ++k) acc[p][i][k] = FIRST ? w[i][k] * sn[p] : fma(w[i][k], sn[p], acc[p][i][k]);
+        rw_load<NX>(nx + i * NX, w[i]);
+    }
+}
+
+// n positions with R active rows.  Positions go in pairs with the sine recurrence in place (c, pv alternate as the current value:
+// no register rotation) and the loop bounded by the read pointer (one uniform add, one compare, one branch per pair); an odd
+// position at the end rotates.  On exit w[i] holds the pair at the new th[i] for i < R, which is what the next segment (R - 1
+// rows) expects; the over-read past the last block touches the bytes that follow Theta' in shared memory.
+template <int NX, int PP, int R, bool EVEN = false>
 __device__ __forceinline__ void rw_segment(const double* __restrict__& th, int n, double (&acc)[PP][RW_RB][NX], double (&c)[PP],
                                            double (&pv)[PP], const double (&b_2c)[PP], double (&w)[RW_RB][NX]) {
-    constexpr int RW_UNROLL = (R == RW_RB || !PGAS_RW_SHORT_ROLLED) ? PGAS_RW_UNROLL : 1;    // the staircase segments (R < 4) are 1-3 positions long
-#pragma unroll RW_UNROLL
-    for (int j = 0; j < n; ++j) {
-        th += R * NX;
+    const double* __restrict__ q = th;
+    const double* const e2 = q + (n >> 1) * (2 * R * NX);
+#pragma unroll 1
+    while (q != e2) {
+        rw_position<NX, PP, R>(q + R * NX, acc, c, w);
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
+        for (int p = 0; p < PP; ++p) pv[p] = fma(b_2c[p], c[p], -pv[p]);
+        rw_position<NX, PP, R>(q + 2 * R * NX, acc, pv, w);
 #pragma unroll
-            for (int p = 0; p < PP; ++p)
-#pragma unroll
-                for (int k = 0; k < NX; ++k) acc[p][i][k] = fma(w[i][k], c[p], acc[p][i][k]);
-            rw_load<NX>(th + i * NX, w[i]);
-        }
+        for (int p = 0; p < PP; ++p) c[p] = fma(b_2c[p], pv[p], -c[p]);
+        q += 2 * R * NX;
+    }
+    if (!EVEN && (n & 1)) {
+        q += R * NX;
+        rw_position<NX, PP, R>(q, acc, c, w);
 #pragma unroll
         for (int p = 0; p < PP; ++p) {
             const double n2 = fma(b_2c[p], c[p], -pv[p]);
@@ -61,10 +79,19 @@ __device__ __forceinline__ void rw_segment(const double* __restrict__& th, int n
             c[p] = n2;
         }
     }
+    th = q;
+}
+
+// the sine after `cur` as an instruction the compiler can neither hoist out of the block loop nor duplicate: left to itself it keeps
+// the (block-invariant) second sine in registers across the walk and copies the recurrence state in on three paths (24 moves per block)
+__device__ __forceinline__ double rw_next_sine(double two_c, double cur, double prev) {
+    double r;
+    asm volatile("{\n\t.reg .f64 t;\n\tneg.f64 t, %3;\n\tfma.rn.f64 %0, %1, %2, t;\n\t}" : "=d"(r) : "d"(two_c), "d"(cur), "d"(prev));
+    return r;
 }
 
 // One SLICE of the walk: nblk blocks of RW_RB rows x positions, mu += sum_i a_i (sum_j Theta'[.., i, j] b_j) with the row sines a
-// and the position sines b given by their recurrence seeds.  `w` is the Theta' register ring (rw_segment), `th` the read pointer.
+// and the position sines b given by their recurrence seeds.  `w` is the Theta' register ring (rw_position), `th` the read pointer.
 template <int NX, int PP>
 __device__ __forceinline__ void rowwalk_slice(const double* __restrict__& th, const int* __restrict__ blen, int nblk, double (&w)[RW_RB][NX],
                                               double (&a_cur)[PP], double (&a_prev)[PP], const double (&a_2c)[PP],
@@ -73,29 +100,31 @@ __device__ __forceinline__ void rowwalk_slice(const double* __restrict__& th, co
     for (int b = 0; b < nblk; ++b) {
         double acc[PP][RW_RB][NX];
         double c[PP], pv[PP];
-        // the first position of a block has all RW_RB rows active (layout guarantee, model.cu): its products START the accumulators
-        // (no zeroing: ptxas had placed 2 x 16 CS2R per block, 5 % of the kernel's instructions)
+        const int L = blen[b];
+        // The first position of a block has all RW_RB rows active (layout guarantee, model.cu): its products START the accumulators
+        // (ptxas had placed 2 x 16 CS2R per block, 5 % of the kernel's instructions).  The block opens with one position if its
+        // count of four-row positions is odd, with two if it is even: the four-row loop then runs whole pairs only, and the
+        // recurrence state it starts from comes out of DFMAs (two-position opening) or one copy (one-position opening).
         th += RW_RB * NX;
+        rw_position<NX, PP, RW_RB, true>(th, acc, b_cur, w);
+        if (L & 1) {
 #pragma unroll
-        for (int i = 0; i < RW_RB; ++i) {
+            for (int p = 0; p < PP; ++p) {
+                double s0 = b_cur[p];
+                asm volatile("" : "+d"(s0));
+                pv[p] = s0;
+                c[p] = rw_next_sine(b_2c[p], s0, b_prev[p]);
+            }
+        } else {
+            th += RW_RB * NX;
 #pragma unroll
-            for (int p = 0; p < PP; ++p)
+            for (int p = 0; p < PP; ++p) pv[p] = rw_next_sine(b_2c[p], b_cur[p], b_prev[p]);
+            rw_position<NX, PP, RW_RB>(th, acc, pv, w);
 #pragma unroll
-                for (int k = 0; k < NX; ++k) acc[p][i][k] = w[i][k] * b_cur[p];
-            rw_load<NX>(th + i * NX, w[i]);
-        }
-        // the recurrence state of the block is produced HERE (opaque copy + one DFMA per particle): left to itself the compiler hoists
-        // the invariant second sine out of the block loop and then copies both values in on three paths (24 moves per block)
-#pragma unroll
-        for (int p = 0; p < PP; ++p) {
-            double s0 = b_cur[p];
-            asm volatile("" : "+d"(s0));
-            pv[p] = s0;
-            c[p] = fma(b_2c[p], s0, -b_prev[p]);
+            for (int p = 0; p < PP; ++p) c[p] = fma(b_2c[p], pv[p], -b_cur[p]);
         }
         // positions with 4, 3, 2, 1 active rows (packed byte counts, common.cuh): only selected lattice entries are walked
-        const int L = blen[b];
-        rw_segment<NX, PP, 4>(th, (L & 255) - 1, acc, c, pv, b_2c, w);
+        rw_segment<NX, PP, 4, true>(th, ((L & 255) - 1) & ~1, acc, c, pv, b_2c, w);
         rw_segment<NX, PP, 3>(th, (L >> 8) & 255, acc, c, pv, b_2c, w);
         rw_segment<NX, PP, 2>(th, (L >> 16) & 255, acc, c, pv, b_2c, w);
         rw_segment<NX, PP, 1>(th, (L >> 24) & 255, acc, c, pv, b_2c, w);
