@@ -75,6 +75,7 @@ struct DevModel {
     const int* perm;        // [n_packed] fragment slot -> m * 4 + k of the Theta entry it holds, or -1 (zero)
     const int* row_pos;     // [8*NTN / n_x rounded up][MAX_LEAD] leading-dimension positions of each row (0 for padding rows)
     const int* freq;        // [M*D] integer frequencies, reference order
+    const int* lat_perm;    // [M] basis functions in lattice order (positions sorted lexicographically, last dimension fastest)
     const double* obs;      // (T,n_y)
     const double* inputs;   // (T,n_u)
 };

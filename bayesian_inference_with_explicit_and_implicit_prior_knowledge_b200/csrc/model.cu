@@ -291,7 +291,17 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
     const size_t b_obs = al(sizeof(double) * (size_t)p->T * p->n_y), b_in = al(sizeof(double) * (size_t)p->T * std::max(p->n_u, 1));
     const size_t b_rw = al(sizeof(int) * std::max<size_t>(rw_perm.size(), 1));
     const size_t b_mma = al(sizeof(int) * std::max<size_t>(mma_perm.size(), 1));
-    const size_t total = b_rows + b_perm + b_freq + b_obs + b_in + b_rw + b_mma;
+    // lattice order of the basis functions: the statistics kernel (suffstats.cu) walks its tiles in this order, so that the eight
+    // columns of a DMMA fragment share their leading positions (broadcast loads) and are neighbours in the last dimension
+    std::vector<int> lat_perm((size_t)M);
+    for (int i = 0; i < M; ++i) lat_perm[i] = i;
+    std::stable_sort(lat_perm.begin(), lat_perm.end(), [&](int a, int b) {
+        for (int d = 0; d < D; ++d)
+            if (pos[(size_t)a * D + d] != pos[(size_t)b * D + d]) return pos[(size_t)a * D + d] < pos[(size_t)b * D + d];
+        return false;
+    });
+    const size_t b_lat = al(sizeof(int) * (size_t)M);
+    const size_t total = b_rows + b_perm + b_freq + b_obs + b_in + b_rw + b_mma + b_lat;
     char* arena = nullptr;
     PGAS_CUDA(cudaMalloc((void**)&arena, total));
     size_t o = 0;
@@ -308,6 +318,7 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
     dm.inputs = (const double*)up(p->inputs, p->n_u ? sizeof(double) * (size_t)p->T * p->n_u : 0, b_in);
     dm.rw_perm = (const int*)up(rw_perm.data(), sizeof(int) * rw_perm.size(), b_rw);
     dm.mma_perm = (const int*)up(mma_perm.data(), sizeof(int) * mma_perm.size(), b_mma);
+    dm.lat_perm = (const int*)up(lat_perm.data(), sizeof(int) * (size_t)M, b_lat);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { cudaFree(arena); PGAS_FAIL((int)e, "model upload failed: %s", cudaGetErrorString(e)); }
 

@@ -6,16 +6,20 @@
 // trajectory (sine tables in shared memory) and never stored, and T1 is a SYRK over time on the
 // FP64 tensor pipe: lower-triangular 64x64 tiles, one CTA per (tile, chain).
 //
-// Warp-specialised (round 2): one PRODUCER warp builds the chunk's sine tables (one sincospi and a three-term recurrence per time
-// step and dimension) into a double-buffered stage; four CONSUMER warps own a 32x32 quadrant each = 4x4 accumulator fragments of
-// mma.sync.m8n8k4.f64 (SASS: DMMA.8x8x4) and form their fragments ON THE FLY from the table (D shared loads and D - 1 multiplies per
-// fragment element; the lattice positions of a thread's eight fragment columns are loop-invariant registers), one step of four time
-// rows ahead of the 16 DMMAs that use them: Phi itself is never staged.  Hand-over through named barriers (full / empty per stage,
-// bar.arrive on the giving side, bar.sync on the taking side).  Before, all four warps alternated between table, basis-value and
-// tensor phases behind __syncthreads: the scalar FP64 operations of the first two queued behind other CTAs' DMMAs on the one FP64
-// pipe and the tensor sub-pipe was 52 % busy (profiles/r02_tail_kernels_summary.md).  On diagonal tiles the upper quadrant is the
-// mirror of the lower one and is not computed.  Deterministic: every output element is accumulated by one warp in time order
-// (no atomics, no split over time).
+// Two kernels (round 2).  suff_table_kernel evaluates, once per chain and time step, the sines of every lattice position in every
+// dimension (one sincospi per dimension, then three interleaved three-term recurrences of stride 3) into a global table
+// [chain][D][time][position] that stays in L2.  suffstats_kernel is warp-specialised: one PRODUCER warp copies the chunk's slice of
+// that table into a double-buffered shared-memory stage with cp.async.bulk (the bulk-copy engine; completion on an mbarrier's
+// transaction count — no arithmetic, no registers), four CONSUMER warps own a 32x32 quadrant each = 4x4 accumulator fragments of
+// mma.sync.m8n8k4.f64 (SASS: DMMA.8x8x4) and form their fragments ON THE FLY from the stage (D shared loads and D - 1 multiplies per
+// fragment element; the stage offsets of a thread's eight fragment columns are loop-invariant registers): Phi itself is never
+// stored.  Tiles are walked in LATTICE order of the basis functions (DevModel::lat_perm), so that the eight columns of a fragment
+// share their leading positions (broadcast loads) and are neighbours in the last dimension; the write-back permutes to the
+// reference's order.  Why this shape: any scalar FP64 operation issued next to the DMMAs waits its turn behind whole batches of
+// them on the one FP64 pipe (one slot in four, 16 cycles each) — with the tables built inside the kernel, first by all warps
+// between __syncthreads, then by a producer warp, the tensor sub-pipe stayed 52-54 % busy and the consumers waited for the tables
+// (profiles/r02_tail_kernels_summary.md).  On diagonal tiles the upper quadrant is the mirror of the lower one and is not computed.
+// Deterministic: every output element is accumulated by one warp in time order (no atomics, no split over time).
 #include "basis_eval.cuh"
 #include "sweep_args.cuh"
 
@@ -24,11 +28,13 @@ constexpr int S_CONS = 128;    // consumer threads: 4 warps, a 32x32 quadrant ea
 constexpr int S_PROD = 32;     // producer threads (one warp: with 160 threads ptxas grants 128 registers at three CTAs per SM, with 192 only 96)
 constexpr int SNT = S_CONS + S_PROD;
 constexpr int MAXPOS = 48;     // lattice positions per dimension held in the shared sine table
-constexpr int BAR_FULL = 1, BAR_EMPTY = 3;      // named barriers: full[2], empty[2]
+constexpr int BAR_EMPTY = 3;   // named barriers empty[2] (consumers arrive, the producer waits); full[2] are mbarriers
 
 struct SuffArgs {
     DevModel m;
     int n_chains, ntile, npos, TK;   // TK = time steps per chunk (multiple of 4)
+    int TP;                          // time rows of the sine table: chunks * TK (rows past the trajectory are zero)
+    double* table;                   // (n_chains, D, TP, suff_row(npos))
     const double* traj;      // (n_chains, T, n_x), chain stride traj_stride elements
     long long traj_stride;
     double* T0;              // (n_chains, M, n_x)
@@ -44,6 +50,76 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 
 __host__ __device__ constexpr int suff_row(int npos) { return (npos + 1) | 1; }   // table row: >= npos + 1 (a zero slot), odd
 __host__ __device__ inline size_t suff_stage_doubles(int D, int npos, int TK) { return (size_t)D * suff_row(npos) * TK + (size_t)TK * PGAS_MAX_NX; }
+
+__device__ __forceinline__ uint32_t sf_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sf_mbar_init(uint32_t mbar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count)); }
+__device__ __forceinline__ void sf_mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sf_mbar_arrive(uint32_t mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); }
+__device__ __forceinline__ void sf_mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sf_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+// One thread per (chain, time row): the sines of all lattice positions in all D dimensions, three interleaved recurrences of stride 3
+// per dimension (s[p+3] = 2cos(3a) s[p] - s[p-3]); the normalisation rides on dimension 0 (the recurrence is linear); slot npos of
+// every row is zero (tile columns past M point there); rows past the trajectory are zero.
+template <int D>
+__global__ void __launch_bounds__(128) suff_table_kernel(const __grid_constant__ SuffArgs a) {
+    const DevModel& m = a.m;
+    const int t = blockIdx.x * 128 + threadIdx.x, chain = blockIdx.y;
+    if (t >= a.TP) return;
+    const int nx = m.n_x, npos = a.npos, nposp = suff_row(npos), nsteps = m.T - 1;
+    const bool live = t < nsteps;
+    const double* traj = a.traj + (size_t)chain * a.traj_stride;
+    double x[PGAS_MAX_NX], u[PGAS_MAX_NU], z[PGAS_MAX_D];
+#pragma unroll
+    for (int k = 0; k < PGAS_MAX_NX; ++k) x[k] = (live && k < nx) ? traj[(size_t)t * nx + k] : 0.0;
+#pragma unroll
+    for (int k = 0; k < PGAS_MAX_NU; ++k) u[k] = (live && k < m.n_u) ? m.inputs[(size_t)t * m.n_u + k] : 0.0;   // x_t pairs with u_t (src/PGAS.py:294-296)
+    if (m.map_kind == PGAS_MAP_AFFINE) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            double v = m.bz[d];
+#pragma unroll
+            for (int k = 0; k < PGAS_MAX_NX; ++k) v = (k < nx) ? fma(m.Az[d][k], x[k], v) : v;
+#pragma unroll
+            for (int k = 0; k < PGAS_MAX_NU; ++k) v = (k < m.n_u) ? fma(m.Az[d][nx + k], u[k], v) : v;
+            z[d] = v;
+        }
+    } else {
+        gp_map_any(m, x, u, z);                     // slip angles / expression program
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const double tn = (z[d] - m.center[d] + m.L[d]) * m.inv2L[d];
+        double s0, sm1, tc;
+        sine_seed(tn, m.f_start, m.f_step, s0, sm1, tc);
+        const double sc = (d == 0) ? m.norm : 1.0;
+        s0 = live ? s0 * sc : 0.0;                  // rows past the trajectory are zero (their map may not even be finite)
+        sm1 = live ? sm1 * sc : 0.0;
+        tc = live ? tc : 0.0;
+        const double s1 = fma(tc, s0, -sm1), sm2 = fma(tc, sm1, -s0);
+        const double s2 = fma(tc, s1, -s0), sm3 = fma(tc, sm2, -sm1);
+        const double c3 = tc * fma(tc, tc, -3.0);   // 2 cos(3a) from 2 cos(a)
+        double ca = s0, cb = s1, cc = s2, pa = sm3, pb = sm2, pc = sm1;
+        double* tb = a.table + (((size_t)chain * D + d) * a.TP + t) * nposp;
+        for (int p = 0; p < npos; p += 3) {
+            tb[p] = ca;
+            if (p + 1 < npos) tb[p + 1] = cb;
+            if (p + 2 < npos) tb[p + 2] = cc;
+            const double na = fma(c3, ca, -pa), nb = fma(c3, cb, -pb), nc = fma(c3, cc, -pc);
+            pa = ca; pb = cb; pc = cc;
+            ca = na; cb = nb; cc = nc;
+        }
+        tb[npos] = 0.0;
+    }
+}
 
 template <int D>
 __global__ void __launch_bounds__(SNT, 3) suffstats_kernel(const __grid_constant__ SuffArgs a) {
@@ -66,54 +142,39 @@ __global__ void __launch_bounds__(SNT, 3) suffstats_kernel(const __grid_constant
     const int nposp = suff_row(npos), dstride = TK * nposp;
     const size_t stage_sz = suff_stage_doubles(D, npos, TK);
 
+    __shared__ __align__(8) unsigned long long full_bar[2];
+    if (tid == 0) {
+        sf_mbar_init(sf_smem(&full_bar[0]), 32);
+        sf_mbar_init(sf_smem(&full_bar[1]), 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
     if (warp >= S_CONS / 32) {
-        // ------------------------------------------------------------------------------------------------ producers
+        // ------------------------------------------------------------------------------------------------ producer
+        // lane 0 starts the D bulk copies of the chunk's table slices (TK * nposp doubles each, 16-byte multiples at 16-byte aligned
+        // addresses since TK is even); every lane stores one Y row and arrives: the stage is full when 32 arrivals and the copies'
+        // bytes are in
         const int pt = tid - S_CONS;
+        const uint32_t slice_bytes = (uint32_t)(dstride * sizeof(double));
+        const double* gtab = a.table + (size_t)chain * D * a.TP * nposp;
         for (int c = 0; c < nchunks; ++c) {
-            const int t0 = c * TK;
+            const int t = c * TK + pt;
             double* tab = sm + (size_t)(c & 1) * stage_sz;
             double* ych = tab + (size_t)D * dstride;
+            const uint32_t mb = sf_smem(&full_bar[c & 1]);
+            double y[PGAS_MAX_NX];
+#pragma unroll
+            for (int k = 0; k < PGAS_MAX_NX; ++k) y[k] = (pt < TK && t < nsteps && k < nx) ? traj[(size_t)(t + 1) * nx + k] : 0.0;
             if (c >= 2) bar_sync(BAR_EMPTY + (c & 1), SNT);   // the consumers have released this stage (chunk c - 2)
-            // sine tables of the chunk: item (tt, d); the normalisation rides on dimension 0
-            for (int it = pt; it < TK * D; it += S_PROD) {
-                const int tt = it % TK, d = it / TK, t = t0 + tt;
-                double* tb = tab + ((size_t)d * TK + tt) * nposp;
-                if (t < nsteps) {
-                    double x[PGAS_MAX_NX], u[PGAS_MAX_NU], z = 0.0;
+            if (pt == 0) {
+                sf_mbar_expect_tx(mb, slice_bytes * D);
 #pragma unroll
-                    for (int k = 0; k < PGAS_MAX_NX; ++k) x[k] = (k < nx) ? traj[(size_t)t * nx + k] : 0.0;
-#pragma unroll
-                    for (int k = 0; k < PGAS_MAX_NU; ++k) u[k] = (k < m.n_u) ? m.inputs[(size_t)t * m.n_u + k] : 0.0;   // x_t pairs with u_t (src/PGAS.py:294-296)
-                    if (m.map_kind == PGAS_MAP_AFFINE) {
-                        z = m.bz[d];
-#pragma unroll
-                        for (int k = 0; k < PGAS_MAX_NX; ++k) z = (k < nx) ? fma(m.Az[d][k], x[k], z) : z;
-#pragma unroll
-                        for (int k = 0; k < PGAS_MAX_NU; ++k) z = (k < m.n_u) ? fma(m.Az[d][nx + k], u[k], z) : z;
-                    } else {                                   // slip angles / expression program: all components, this item keeps one
-                        double zz[PGAS_MAX_D];
-                        gp_map_any(m, x, u, zz);
-                        z = zz[d];
-                    }
-                    const double tn = (z - m.center[d] + m.L[d]) * m.inv2L[d];
-                    double cur, prev, twoc;
-                    sine_seed(tn, m.f_start, m.f_step, cur, prev, twoc);
-                    if (d == 0) { cur *= m.norm; prev *= m.norm; }                 // the recurrence is linear
-                    for (int p = 0; p < npos; ++p) {
-                        tb[p] = cur;
-                        const double n = fma(twoc, cur, -prev);
-                        prev = cur; cur = n;
-                    }
-                } else {
-                    for (int p = 0; p < npos; ++p) tb[p] = 0.0;
-                }
-                tb[npos] = 0.0;
+                for (int d = 0; d < D; ++d) sf_bulk_g2s(sf_smem(tab + (size_t)d * dstride), gtab + ((size_t)d * a.TP + (size_t)c * TK) * nposp, slice_bytes, mb);
             }
-            for (int tt = pt; tt < TK; tt += S_PROD) {    // Y rows of the chunk
-                const int t = t0 + tt;
-                for (int k = 0; k < nx; ++k) ych[tt * PGAS_MAX_NX + k] = (t < nsteps) ? traj[(size_t)(t + 1) * nx + k] : 0.0;
-            }
-            bar_arrive(BAR_FULL + (c & 1), SNT);
+            if (pt < TK)
+                for (int k = 0; k < nx; ++k) ych[pt * PGAS_MAX_NX + k] = y[k];
+            if (pt != 0) sf_mbar_arrive(mb);
         }
         return;
     }
@@ -128,18 +189,20 @@ __global__ void __launch_bounds__(SNT, 3) suffstats_kernel(const __grid_constant
         const int r = lane & 3, q = lane >> 2;
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
-            const int gi = I * ST + wi * 32 + 8 * f + q, gj = J * ST + wj * 32 + 8 * f + q;
+            const int ci = I * ST + wi * 32 + 8 * f + q, cj = J * ST + wj * 32 + 8 * f + q;     // tile columns, lattice order
+            const int gi = (ci < M) ? m.lat_perm[ci] : -1, gj = (cj < M) ? m.lat_perm[cj] : -1;
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                const int pi = (gi < M) ? (m.freq[(size_t)gi * D + d] - m.f_start) / m.f_step : (d == 0 ? npos : 0);
-                const int pj = (gj < M) ? (m.freq[(size_t)gj * D + d] - m.f_start) / m.f_step : (d == 0 ? npos : 0);
+                const int pi = (gi >= 0) ? (m.freq[(size_t)gi * D + d] - m.f_start) / m.f_step : (d == 0 ? npos : 0);
+                const int pj = (gj >= 0) ? (m.freq[(size_t)gj * D + d] - m.f_start) / m.f_step : (d == 0 ? npos : 0);
                 offA[f][d] = d * dstride + r * nposp + pi;
                 offB[f][d] = d * dstride + r * nposp + pj;
             }
         }
-        const int g0 = I * ST + (tid % ST);               // T0 column of this thread (diagonal tiles)
+        const int cc0 = I * ST + (tid % ST);              // T0 column of this thread (diagonal tiles)
+        const int g0 = (cc0 < M) ? m.lat_perm[cc0] : -1;
 #pragma unroll
-        for (int d = 0; d < D; ++d) off0[d] = d * dstride + ((g0 < M) ? (m.freq[(size_t)g0 * D + d] - m.f_start) / m.f_step : (d == 0 ? npos : 0));
+        for (int d = 0; d < D; ++d) off0[d] = d * dstride + ((g0 >= 0) ? (m.freq[(size_t)g0 * D + d] - m.f_start) / m.f_step : (d == 0 ? npos : 0));
     }
     double c0[4][4], c1[4][4];
 #pragma unroll
@@ -152,7 +215,7 @@ __global__ void __launch_bounds__(SNT, 3) suffstats_kernel(const __grid_constant
     for (int c = 0; c < nchunks; ++c) {
         const double* tab = sm + (size_t)(c & 1) * stage_sz;
         const double* ych = tab + (size_t)D * dstride;
-        bar_sync(BAR_FULL + (c & 1), SNT);
+        sf_mbar_wait(sf_smem(&full_bar[c & 1]), (uint32_t)((c >> 1) & 1));
         // rank-TK update on the tensor pipe: per 4 time steps 4 A + 4 B fragment elements feed 16 DMMAs; the elements of the next
         // four time steps are formed while the DMMAs of the current ones run
         if (work) {
@@ -201,29 +264,37 @@ __global__ void __launch_bounds__(SNT, 3) suffstats_kernel(const __grid_constant
         }
         if (c + 2 < nchunks) bar_arrive(BAR_EMPTY + (c & 1), SNT);
     }
-    // write back: lower tile and its mirror
+    // write back: lower tile and its mirror, from lattice order to the reference's order of the basis functions
     double* T1 = a.T1 + (size_t)chain * M * M;
     if (work) {
         const bool mirror = !diag || wi != wj;
+        int ri[4], rj[4][2];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const int ci = I * ST + wi * 32 + f * 8 + (lane >> 2), cj = J * ST + wj * 32 + f * 8 + 2 * (lane & 3);
+            ri[f] = (ci < M) ? m.lat_perm[ci] : -1;
+            rj[f][0] = (cj < M) ? m.lat_perm[cj] : -1;
+            rj[f][1] = (cj + 1 < M) ? m.lat_perm[cj + 1] : -1;
+        }
 #pragma unroll
         for (int fi = 0; fi < 4; ++fi)
 #pragma unroll
             for (int fj = 0; fj < 4; ++fj) {
-                const int gi = I * ST + wi * 32 + fi * 8 + (lane >> 2), gj = J * ST + wj * 32 + fj * 8 + 2 * (lane & 3);
-                if (gi < M && gj < M) {
-                    T1[(size_t)gi * M + gj] = c0[fi][fj];
-                    if (mirror) T1[(size_t)gj * M + gi] = c0[fi][fj];
+                const int gi = ri[fi];
+                if (gi >= 0 && rj[fj][0] >= 0) {
+                    T1[(size_t)gi * M + rj[fj][0]] = c0[fi][fj];
+                    if (mirror) T1[(size_t)rj[fj][0] * M + gi] = c0[fi][fj];
                 }
-                if (gi < M && gj + 1 < M) {
-                    T1[(size_t)gi * M + gj + 1] = c1[fi][fj];
-                    if (mirror) T1[(size_t)(gj + 1) * M + gi] = c1[fi][fj];
+                if (gi >= 0 && rj[fj][1] >= 0) {
+                    T1[(size_t)gi * M + rj[fj][1]] = c1[fi][fj];
+                    if (mirror) T1[(size_t)rj[fj][1] * M + gi] = c1[fi][fj];
                 }
             }
     }
     if (diag) {
         if (tid < ST * nx) {
-            const int mi = tid % ST, k = tid / ST, gi = I * ST + mi;
-            if (gi < M) a.T0[((size_t)chain * M + gi) * nx + k] = acc0;
+            const int k = tid / ST, cc0 = I * ST + (tid % ST);
+            if (cc0 < M) a.T0[((size_t)chain * M + m.lat_perm[cc0]) * nx + k] = acc0;
         }
         if (I == 0 && tid >= S_CONS - nx * nx) {
             const int e = tid - (S_CONS - nx * nx);
@@ -252,11 +323,37 @@ int pgas_launch_suffstats(const DevModel& m, const double* traj, long long traj_
     while (TK > 8 && suff_smem(m.D, npos, TK) > 74 * 1024) TK -= 4;
     a.TK = TK;
     const size_t smem = suff_smem(m.D, npos, TK);
+    a.TP = (m.T - 1 + TK - 1) / TK * TK;
+    if (a.TP <= 0) PGAS_FAIL(-2, "the statistics need at least two time steps");
+    // the sine table lives for the two launches only: stream-ordered allocation
+    const size_t tbytes = sizeof(double) * (size_t)n_chains * m.D * a.TP * suff_row(npos);
+    {   // keep the pool's memory across synchronisations (default: released to the OS at the next sync, ~0.3 ms per call to get it back)
+        static thread_local int pool_dev = -1;
+        int dev = 0;
+        PGAS_CUDA(cudaGetDevice(&dev));
+        if (pool_dev != dev) {
+            cudaMemPool_t pool;
+            PGAS_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+            unsigned long long keep = ~0ull;
+            PGAS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            pool_dev = dev;
+        }
+    }
+    PGAS_CUDA(cudaMallocAsync((void**)&a.table, tbytes, st));
+    {
+        dim3 g((unsigned)((a.TP + 127) / 128), (unsigned)n_chains, 1);
+        if (m.D == 1) suff_table_kernel<1><<<g, 128, 0, st>>>(a);
+        else if (m.D == 2) suff_table_kernel<2><<<g, 128, 0, st>>>(a);
+        else suff_table_kernel<3><<<g, 128, 0, st>>>(a);
+    }
     auto kern = (m.D == 1) ? suffstats_kernel<1> : (m.D == 2) ? suffstats_kernel<2> : suffstats_kernel<3>;
     PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(a.ntile * (a.ntile + 1) / 2), (unsigned)n_chains, 1);
     kern<<<grid, SNT, smem, st>>>(a);
-    PGAS_KERNEL_CHECK();
+    __atomic_add_fetch(&g_pgas_launches, 2, __ATOMIC_RELAXED);
+    const cudaError_t le = cudaGetLastError();
+    PGAS_CUDA(cudaFreeAsync(a.table, st));
+    if (le != cudaSuccess) PGAS_FAIL((int)le, "statistics kernels: %s", cudaGetErrorString(le));
     return 0;
 }
 
