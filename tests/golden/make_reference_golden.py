@@ -350,12 +350,35 @@ def gen_group_b():
     put("marg/kinds", np.array(list(MARG_CASES)))
 
 
+# ------------------------------------------------------------------------------------ PGAS.sample_params at configuration scale
+PARAMS_SCALE_CASES = {"smo256": dict(kind="smo", M=256, T=120, N=16, seed=77)}      # M of BASELINE.json configs[3]
+
+
+def gen_params_scale():
+    """the reference's own PGAS.sample_params (src/PGAS.py:288-343) at M = 256: statistics, the three M x M factorisations and the draw"""
+    for name, g in PARAMS_SCALE_CASES.items():
+        p = helpers.make_problem(g["kind"], T=g["T"], N=g["N"], M=g["M"], seed=g["seed"])
+        basis, lik, sd = reference_callables(p)
+        n_x, M = p["n_x"], p["M"]
+        pg = RP.PGAS(N_samples=g["N"], N_iterations=2, observations=jnp.array(p["obs"]), inputs=jnp.array(p["inputs"]),
+                     init_state_mean=jnp.array(p["m0"]), init_state_cov=jnp.array(p["P0"]), likelihood_fcn=lik,
+                     GP_prior=tuple(jnp.array(v) for v in p["prior"]), basis_fcn=basis)
+        jax.random.tape_reset()
+        A, S = pg.sample_params(jax.random.key(g["seed"] + 2), jnp.array(p["ref"]))
+        rd = Reader()
+        chi2, G, Nrm = read_param_variates(rd, n_x, M)
+        rd.done()
+        put(f"params_scale/{name}/chi2", chi2); put(f"params_scale/{name}/G", G); put(f"params_scale/{name}/Nrm", Nrm)
+        put(f"params_scale/{name}/A", A); put(f"params_scale/{name}/S", S)
+
+
 if __name__ == "__main__":
     gen_sisr()
     gen_basis()
     gen_mniw()
     gen_group_a()
     gen_group_b()
+    gen_params_scale()
     path = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(path, **OUT)
     print("wrote", path, len(OUT), "arrays,", os.path.getsize(path), "bytes")

@@ -55,6 +55,19 @@ def test_sample_params_reproduces_reference_source(kind):
     assert helpers.rel_err(_np(S[0]), s("S")) < REL
 
 
+@pytest.mark.parametrize("name", ["smo256"])
+def test_sample_params_reproduces_reference_source_at_config_scale(name):
+    """statistics kernels (sine table + DMMA SYRK) and the blocked-Cholesky draw against PGAS.sample_params of the reference's own
+    source at M = 256 (src/PGAS.py:288-343)"""
+    c = dict(kind="smo", M=256, T=120, N=16, seed=77)          # keep equal to tests/golden/make_reference_golden.py
+    p = helpers.make_problem(c["kind"], T=c["T"], N=c["N"], M=c["M"], seed=c["seed"])
+    pg = helpers.product_pgas(p, K=2)
+    s = lambda k: GOLD[f"params_scale/{name}/{k}"]  # noqa: E731
+    A, S = pg.sample_params(None, _dev(p["ref"][None]), variates=dict(chi2=_dev(s("chi2")[None]), G=_dev(s("G")[None]), Nrm=_dev(s("Nrm")[None])))
+    assert helpers.rel_err(_np(A[0]), s("A")) < REL
+    assert helpers.rel_err(_np(S[0]), s("S")) < REL
+
+
 def _marg_dev(prefix):
     V = dict(Z=GOLD[prefix + "V_Z"], ZXI0=GOLD[prefix + "V_ZXI0"], U=GOLD[prefix + "V_U"], TS=GOLD[prefix + "V_TS"])
     return HM.device_variates(V)

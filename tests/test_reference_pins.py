@@ -110,6 +110,20 @@ def test_sample_params_matches_reference_source(kind):
     assert rel_err(S, g("S")) < REL_TOL
 
 
+PARAMS_SCALE_CASES = {"smo256": dict(kind="smo", M=256, T=120, N=16, seed=77)}     # keep equal to tests/golden/make_reference_golden.py
+
+
+@pytest.mark.parametrize("name", list(PARAMS_SCALE_CASES))
+def test_sample_params_matches_reference_source_at_config_scale(name):
+    """PGAS.sample_params of the reference's own source (src/PGAS.py:288-343) at M = 256, the basis size of BASELINE.json configs[3]"""
+    c = PARAMS_SCALE_CASES[name]
+    p = helpers.make_problem(c["kind"], T=c["T"], N=c["N"], M=c["M"], seed=c["seed"])
+    g = lambda k: GOLD[f"params_scale/{name}/{k}"]  # noqa: E731
+    A, S, _ = OP.sample_params(p["omodel"], p["prior"], p["ref"], g("chi2"), g("G"), g("Nrm"))
+    assert rel_err(A, g("A")) < REL_TOL
+    assert rel_err(S, g("S")) < REL_TOL
+
+
 @pytest.mark.parametrize("kind", list(CSMC_CASES))
 def test_pgas_run_matches_reference_source(kind):
     c = CSMC_CASES[kind]
