@@ -192,3 +192,47 @@ __device__ __forceinline__ void rowwalk_mu(const double* __restrict__ bd, const 
         }
     }
 }
+
+
+// Three-dimensional bases, FEW particles (the EMPS PGAS baseline: N = 200, one chain — src/EMPS.py:100-123, :240-255): G lanes share a
+// particle, lane `sub` walks the slices sub, sub + G, ... (their own read pointer and register ring: loads are no longer warp-uniform)
+// and a butterfly sums the lanes' partial means — commutative additions, so all G lanes end with the same bits.  With one particle per
+// thread a 200-particle launch is 7 warps on 4 SMs and a step costs the latency of one thread walking all M entries (10.7 us at
+// M = 729, profiles/r02_state_kernel_summary.md).  slice_off / slice_blk: first Theta' slot and first block of every slice; blen in
+// shared memory (per-lane indices).
+template <int NX, int G>
+__device__ __forceinline__ void rowwalk_mu_lanes(const double* __restrict__ bd, const int* __restrict__ blen, const int* __restrict__ slice_nblk,
+                                                 const int* __restrict__ slice_off, const int* __restrict__ slice_blk, int nslice, int sub,
+                                                 int f_start, int f_step, const double (&tz)[1][3], double (&mu)[1][NX]) {
+    static_assert(G == 2 || G == 4 || G == 8 || G == 16, "lanes per particle: a power of two inside a warp");
+    double a_cur[1], a_prev[1], a_2c[1], b_cur[1], b_prev[1], b_2c[1], s_cur, s_prev, s_2c;
+    sine_seed(tz[0][1], f_start, f_step, a_cur[0], a_prev[0], a_2c[0]);
+    sine_seed(tz[0][2], f_start, f_step, b_cur[0], b_prev[0], b_2c[0]);
+    sine_seed(tz[0][0], f_start, f_step, s_cur, s_prev, s_2c);
+#pragma unroll
+    for (int k = 0; k < NX; ++k) mu[0][k] = 0.0;
+    for (int q = 0; q < sub; ++q) {                       // first-dimension sine at this lane's first slice
+        const double n = fma(s_2c, s_cur, -s_prev);
+        s_prev = s_cur; s_cur = n;
+    }
+    for (int sl = sub; sl < nslice; sl += G) {
+        const double* __restrict__ th = bd + slice_off[sl];
+        double w[RW_RB][NX], ac[1] = {a_cur[0]}, ap[1] = {a_prev[0]}, part[1][NX];
+#pragma unroll
+        for (int i = 0; i < RW_RB; ++i) rw_load<NX>(th + i * NX, w[i]);
+#pragma unroll
+        for (int k = 0; k < NX; ++k) part[0][k] = 0.0;
+        rowwalk_slice<NX, 1>(th, blen + slice_blk[sl], slice_nblk[sl], w, ac, ap, a_2c, b_cur, b_prev, b_2c, part);
+#pragma unroll
+        for (int k = 0; k < NX; ++k) mu[0][k] = fma(s_cur, part[0][k], mu[0][k]);
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            const double n = fma(s_2c, s_cur, -s_prev);
+            s_prev = s_cur; s_cur = n;
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1)
+#pragma unroll
+        for (int k = 0; k < NX; ++k) mu[0][k] += __shfl_xor_sync(0xffffffffu, mu[0][k], o);
+}

@@ -68,6 +68,7 @@ struct DevModel {
     int rw_ok, rw_nblk, rw_slots;                   // row-walk layout (D == 2): available, blocks, doubles
     int rw_blen[RW_MAXBLK];                         // positions with 4 | 3 | 2 | 1 active rows per block (one byte each)
     int rw_nslice, rw_slice_nblk[RW_MAXSLICE];      // D = 3: blocks per first-dimension position (D = 2: one slice holding all blocks)
+    int rw_slice_off[RW_MAXSLICE], rw_slice_blk[RW_MAXSLICE];   // first Theta' slot (doubles) and first block of every slice
     int mma_ok, mma_nblk, mma_slots;                // DMMA layout of a two-dimensional basis with n_x = 2 (basis_mma.cuh): available, blocks, doubles
     unsigned char mma_ks[RW_MAXBLK];                // k-steps (4 walked positions each) per block of RW_RB rows
     const int* rw_perm;     // [rw_slots] slot -> m * 4 + k of the Theta entry it holds, or -1 (zero)

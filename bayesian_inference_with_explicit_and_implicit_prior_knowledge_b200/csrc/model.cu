@@ -199,7 +199,7 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
     std::vector<int> rw_perm;
     dm.rw_ok = 0; dm.rw_nblk = 0; dm.rw_slots = 0; dm.rw_nslice = 0;
     for (int b = 0; b < RW_MAXBLK; ++b) dm.rw_blen[b] = 0;
-    for (int sl = 0; sl < RW_MAXSLICE; ++sl) dm.rw_slice_nblk[sl] = 0;
+    for (int sl = 0; sl < RW_MAXSLICE; ++sl) { dm.rw_slice_nblk[sl] = 0; dm.rw_slice_off[sl] = 0; dm.rw_slice_blk[sl] = 0; }
     if (D == 2 || D == 3) {
         const int dr = D - 2, dj = D - 1;                                    // row / walked dimension
         const int nslice = (D == 3) ? dm.npos_d[0] : 1;
@@ -224,6 +224,8 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
                 if (act[sl][b][0] > 0) used = b + 1;
             }
             dm.rw_slice_nblk[sl] = used;
+            dm.rw_slice_off[sl] = total;
+            dm.rw_slice_blk[sl] = nblk;
             for (int b = 0; b < used; ++b) {
                 if (nblk >= RW_MAXBLK) { fits = false; break; }
                 act[sl][b][0] = RW_RB;       // the first position of a block carries all RW_RB rows (zeros for rows the lattice lacks): the

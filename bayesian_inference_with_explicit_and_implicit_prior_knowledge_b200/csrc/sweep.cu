@@ -832,6 +832,7 @@ struct StateArgs {
 #endif
 constexpr int ST_NT_BIG = PGAS_ST_NT, ST_PP_BIG = PGAS_ST_PP;      // geometry of the state kernel when the launch fills the GPU
 constexpr int ST_NT_SMALL = 64, ST_PP_SMALL = 1;                   // ... and when it does not
+constexpr int ST_LANES = 8, ST_LANES_MAX_N = 1024;                 // lanes per particle / largest N of the lane-split form (three-dimensional bases)
 
 // INJ: injected variates (tests) instead of the in-kernel Philox stream — a template parameter so that the noise of a thread's
 // particles sits in ONE basic block (no run-time branch per draw) and ptxas interleaves their Philox / Box-Muller chains
@@ -840,9 +841,12 @@ constexpr int ST_NT_SMALL = 64, ST_PP_SMALL = 1;                   // ... and wh
 // four times as many, smaller CTAs spread over all SMs, and a step's dependent chain per thread is half as long).
 // D: dimension of the Hilbert basis (2, or 3: one more level of the row walk — the EMPS baseline of src/EMPS.py:101-123).
 // MMA: the contraction on DMMA tiles (basis_mma.cuh) instead of the FMA row walk; needs ST_PP == 2, D == 2, NX == 2.
-template <int NX, int NY, bool INJ, int ST_NT, int ST_PP, int D = 2, bool MMA = false>
+// G: lanes per particle (1, or 8 for a three-dimensional basis with few particles: rowwalk_mu_lanes, basis_rowwalk.cuh); all G lanes
+// carry the particle's state and variates (same Philox counters, same bits), lane 0 of the group stores.
+template <int NX, int NY, bool INJ, int ST_NT, int ST_PP, int D = 2, bool MMA = false, int G = 1>
 __global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_state_kernel(const __grid_constant__ StateArgs s) {
     static_assert(!MMA || (ST_PP == 2 && D == 2 && NX == 2), "DMMA form: two particles per thread, two-dimensional basis, n_x = 2");
+    static_assert(G == 1 || (ST_PP == 1 && D == 3 && !MMA), "lane-split form: one particle per lane group, three-dimensional basis");
     const SweepArgs& a = s.a;
     const DevModel& m = a.m;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -852,6 +856,7 @@ __global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_stat
     double* sw = chol + NX * NX;
     double* slogc = sw + NX * NX;
     int* rwlen = reinterpret_cast<int*>(slogc + 2);
+    __shared__ int rwslice[3 * RW_MAXSLICE];      // lane-split form: blocks, first slot, first block of every slice
     double* mma_w = reinterpret_cast<double*>(rwlen + RW_MAXBLK) + (size_t)(threadIdx.x >> 5) * MMA_WARP_DOUBLES;   // DMMA form: per-warp seeds + tile buffer
     const int tid = threadIdx.x, N = a.N;
     const int chain = s.chain0 + blockIdx.x / s.bpc, blk = blockIdx.x % s.bpc;
@@ -863,6 +868,11 @@ __global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_stat
             bd[e] = (q >= 0) ? m.norm * Th[(size_t)(q & 3) * m.M + (q >> 2)] : 0.0;
         }
         if (tid < RW_MAXBLK) rwlen[tid] = MMA ? (int)m.mma_ks[tid] : m.rw_blen[tid];
+        if (G > 1 && tid < RW_MAXSLICE) {
+            rwslice[tid] = m.rw_slice_nblk[tid];
+            rwslice[RW_MAXSLICE + tid] = m.rw_slice_off[tid];
+            rwslice[2 * RW_MAXSLICE + tid] = m.rw_slice_blk[tid];
+        }
         if (tid == 0) {
             const double* S = a.Sigma + (size_t)chain * NX * NX;
             double Lc[NX][NX], Li[NX][NX], logdet = 0.0;
@@ -898,12 +908,15 @@ __global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_stat
     mapr.init(m);
     const int f_start = m.f_start, f_step = m.f_step;
     int ip[ST_PP];
-    bool val[ST_PP];
+    bool val[ST_PP], own[ST_PP];                  // val: this thread stores the particle's rows; own: the particle exists
+    const int sub = (G > 1) ? (tid % G) : 0;
 #pragma unroll
     for (int p = 0; p < ST_PP; ++p) {
         // DMMA form: a warp owns 64 consecutive particles, lane l the particles l and 32 + l of them
-        ip[p] = MMA ? blk * ST_PP * ST_NT + (tid >> 5) * 64 + p * 32 + (tid & 31) : blk * ST_PP * ST_NT + p * ST_NT + tid;
-        val[p] = ip[p] < N;
+        ip[p] = (G > 1) ? blk * (ST_NT / G) + tid / G
+                        : MMA ? blk * ST_PP * ST_NT + (tid >> 5) * 64 + p * 32 + (tid & 31) : blk * ST_PP * ST_NT + p * ST_NT + tid;
+        own[p] = ip[p] < N;
+        val[p] = own[p] && sub == 0;
     }
     double x[ST_PP][NX];
     const double* refc = a.ref + (size_t)chain * a.ref_stride;
@@ -931,7 +944,7 @@ __global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_stat
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < NX; ++k) x[p][k] = val[p] ? s.x_carry[((size_t)chain * N + ip[p]) * NX + k] : 0.0;
+            for (int k = 0; k < NX; ++k) x[p][k] = own[p] ? s.x_carry[((size_t)chain * N + ip[p]) * NX + k] : 0.0;
         }
     }
     for (int t = s.t0; t < s.t1; ++t) {
@@ -979,6 +992,7 @@ __global__ void __launch_bounds__(ST_NT, ST_PP == 2 ? 512 / ST_NT : 8) csmc_stat
         for (int p = 0; p < ST_PP; ++p) mapr.apply(x[p], cz, u, tzv[p]);
         double mu[ST_PP][NX];
         if constexpr (MMA) mma_mu<NX>(bd, m.mma_ks, m.mma_nblk, mma_w, tid & 31, f_start, f_step, tzv, mu);
+        else if constexpr (G > 1) rowwalk_mu_lanes<NX, G>(bd, rwlen, rwslice, rwslice + RW_MAXSLICE, rwslice + 2 * RW_MAXSLICE, m.rw_nslice, sub, f_start, f_step, tzv, mu);
         else rowwalk_mu<NX, ST_PP, D>(bd, m.rw_blen, m.rw_slice_nblk, m.rw_nslice, f_start, f_step, tzv, mu);
         const size_t prow = ((size_t)chain * s.rows + (size_t)(t - s.t0)) * N;
         // log-densities and the new state of all particles of the thread, branch-free; the stores follow
@@ -1105,7 +1119,12 @@ static int launch_state(const StateArgs& s_in, cudaStream_t st) {
     const int n_theta = mma ? m.mma_slots : m.rw_slots;
     const size_t smem = sizeof(double) * (((size_t)n_theta + 1) & ~(size_t)1) + sizeof(double) * (2 * m.n_x * m.n_x + 2) + sizeof(int) * RW_MAXBLK +
                         (mma ? sizeof(double) * (size_t)MMA_WARP_DOUBLES * (ST_NT_BIG / 32) : 0) + 32;
-    const int per = small ? ST_PP_SMALL * ST_NT_SMALL : ST_PP_BIG * ST_NT_BIG;
+    // few particles on a three-dimensional basis: ST_LANES lanes share a particle (judged on N alone, so that a chain's bits do
+    // not depend on how many chains run next to it); PGAS_STATE_LANES=0|1 forces
+    bool lanes = m.D == 3 && s.a.N <= ST_LANES_MAX_N;
+    if (const char* e = getenv("PGAS_STATE_LANES")) lanes = atoi(e) != 0 && m.D == 3;
+    if (lanes) small = true;
+    const int per = lanes ? ST_NT_SMALL / ST_LANES : small ? ST_PP_SMALL * ST_NT_SMALL : ST_PP_BIG * ST_NT_BIG;
     s.bpc = (s.a.N + per - 1) / per;
     const dim3 grid((unsigned)(s.nch * s.bpc));
 #define PGAS_ST_LAUNCH(NYv, INJv, NTv, PPv, Dv, MMAv) do { \
@@ -1113,7 +1132,13 @@ static int launch_state(const StateArgs& s_in, cudaStream_t st) {
         csmc_state_kernel<2, NYv, INJv, NTv, PPv, Dv, MMAv><<<grid, NTv, smem, st>>>(s); } while (0)
 #define PGAS_ST_GEOM(NYv, INJv, Dv) do { if (small) PGAS_ST_LAUNCH(NYv, INJv, ST_NT_SMALL, ST_PP_SMALL, Dv, false); \
         else if (mma && Dv == 2) PGAS_ST_LAUNCH(NYv, INJv, ST_NT_BIG, 2, 2, true); else PGAS_ST_LAUNCH(NYv, INJv, ST_NT_BIG, ST_PP_BIG, Dv, false); } while (0)
-    if (m.D == 3) { if (inj) PGAS_ST_GEOM(1, true, 3); else PGAS_ST_GEOM(1, false, 3); }
+    if (m.D == 3 && lanes) {
+        if (inj) { PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, 1, true, ST_NT_SMALL, 1, 3, false, ST_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                   csmc_state_kernel<2, 1, true, ST_NT_SMALL, 1, 3, false, ST_LANES><<<grid, ST_NT_SMALL, smem, st>>>(s); }
+        else { PGAS_CUDA(cudaFuncSetAttribute(csmc_state_kernel<2, 1, false, ST_NT_SMALL, 1, 3, false, ST_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+               csmc_state_kernel<2, 1, false, ST_NT_SMALL, 1, 3, false, ST_LANES><<<grid, ST_NT_SMALL, smem, st>>>(s); }
+    }
+    else if (m.D == 3) { if (inj) PGAS_ST_GEOM(1, true, 3); else PGAS_ST_GEOM(1, false, 3); }
     else if (m.n_y == 1) { if (inj) PGAS_ST_GEOM(1, true, 2); else PGAS_ST_GEOM(1, false, 2); }
     else { if (inj) PGAS_ST_GEOM(2, true, 2); else PGAS_ST_GEOM(2, false, 2); }
 #undef PGAS_ST_GEOM
