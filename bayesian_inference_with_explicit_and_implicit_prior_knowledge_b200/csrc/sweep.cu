@@ -1224,8 +1224,9 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
         // force one or the other (developer override).
         const char* wk_env = getenv("PGAS_WEIGHTS_KERNEL");
         const int lc = getenv("PGAS_SPLIT_PRE_C") ? 0 : pgas_weights_lat_cluster(a.N);
-        // default only with portable cluster sizes (N <= 4096): clusters of 16 are co-resident 7 at a time on B200, and at
-        // configs[4] (16 chains of N = 16384, clusters of 16) the latency form measured 424 vs 342 ms per iteration
+        // default only with portable cluster sizes (N <= 16384: 2 | 4 | 8 particles per thread, weights_lat.cu): clusters of 16 are
+        // co-resident 7 at a time on B200 — at configs[4] (16 chains of N = 16384) they measured 424 ms per iteration, the general
+        // kernel 332-342, clusters of 8 with eight particles per thread 301
         const bool use_lat = lc > 0 && (wk_env ? atoi(wk_env) == 3 : (a.n_chains <= PGAS_LAT_MAX_CHAINS && lc <= 8));
         if (use_lat) {
             r.C = lc; r.P = (a.N + lc - 1) / lc;

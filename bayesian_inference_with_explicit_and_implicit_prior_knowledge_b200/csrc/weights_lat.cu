@@ -159,8 +159,11 @@ __device__ __forceinline__ int wl_offspring_ranges(const double (&W)[PPT], doubl
 }
 
 // CT: compile-time bound of the cluster size (1 | 2 | 4 | 8 | 16; records of CTAs c >= C stay empty), so that both folds unroll
+// eight particles per thread (N > 8192): capped at 128 registers (a few spills) so that a state CTA fits on the SM next to it — configs[4]:
+// 301 ms per iteration against 342 uncapped (251 registers: the cluster's SMs are lost to the state kernel while a chunk runs); two
+// particles per thread: uncapped (146 registers) measured 13.2 against 13.8 ms per iteration at 8 chains
 template <int NT, int PPT, int CT>
-__global__ void __launch_bounds__(NT) csmc_weights_lat_kernel(const __grid_constant__ SweepArgs a) {
+__global__ void __launch_bounds__(NT, PPT >= 8 ? 2 : 1) csmc_weights_lat_kernel(const __grid_constant__ SweepArgs a) {
     constexpr int NW = NT / 32, P = NT * PPT, WL_QBITS = (PPT * NT <= 512) ? WL_QBITS2 : WL_QBITS4 - (PPT * NT > 1024 ? 2 : 0);
     static_assert(PPT == 1 || PPT == 2 || PPT == 4 || PPT == 8, "1, 2, 4 or 8 consecutive particles per thread");
     const int C = a.C, N = a.N;
@@ -469,8 +472,16 @@ static size_t weights_lat_smem(int C, int ppt) {
     return (2 * NW * 4 + 2 * WL_MAXC * 4 + 2 * P + 2 * U * 2 + 4) * sizeof(double) + 4 * sizeof(unsigned long long) + 16;
 }
 
-// particles per thread: 2 while a cluster of <= 16 CTAs of 256 threads covers the chain (N <= 8192), else 4 (N <= 16384)
-static int weights_lat_ppt(int N) { return (N + WL_NT * WL_PPT - 1) / (WL_NT * WL_PPT) <= WL_MAXC ? WL_PPT : 2 * WL_PPT; }
+// particles per thread: the fewest of 2 | 4 | 8 with which a PORTABLE cluster (<= 8 CTAs of 256 threads) covers the chain — N <= 4096,
+// 8192, 16384; clusters of 16 are co-resident only 7 at a time on B200 (configs[4], 16 chains: they ran in three waves, 404 ms per
+// iteration) — beyond that 8 with up to 16 CTAs (N <= 32768).  PGAS_WL_PPT_MIN=2|4|8: developer override (tests: ragged tails, big units)
+static int weights_lat_ppt(int N) {
+    int lo = WL_PPT;
+    if (const char* e = getenv("PGAS_WL_PPT_MIN")) { const int v = atoi(e); if (v == 2 * WL_PPT || v == 4 * WL_PPT) lo = v; }
+    for (int ppt = lo; ppt < 4 * WL_PPT; ppt *= 2)
+        if ((N + WL_NT * ppt - 1) / (WL_NT * ppt) <= 8) return ppt;
+    return 4 * WL_PPT;
+}
 
 // cluster size of the latency form for N particles (0: not applicable)
 int pgas_weights_lat_cluster(int N) {
@@ -506,5 +517,7 @@ static int weights_lat_launch(const SweepArgs& a, cudaStream_t stream) {
 }
 
 int pgas_launch_weights_lat(const SweepArgs& a, cudaStream_t stream) {
-    return weights_lat_ppt(a.N) == WL_PPT ? weights_lat_launch<WL_PPT>(a, stream) : weights_lat_launch<2 * WL_PPT>(a, stream);
+    const int ppt = weights_lat_ppt(a.N);
+    return ppt == WL_PPT ? weights_lat_launch<WL_PPT>(a, stream) : ppt == 2 * WL_PPT ? weights_lat_launch<2 * WL_PPT>(a, stream)
+                                                                                   : weights_lat_launch<4 * WL_PPT>(a, stream);
 }

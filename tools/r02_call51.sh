@@ -1,0 +1,13 @@
+#!/bin/bash
+timeout 600 python bench.py --config 5 --steps 2 --warmup 2 --no-marginalised --no-cpu-baseline --no-strong 2>/dev/null | python -c "
+import json,sys
+for line in sys.stdin:
+    if line.startswith('{'):
+        d=json.loads(line); r=d['roofline']; print('[cfg5] ms_per_step %.2f state frac %.4f sweep_ms %.2f sweep_frac %.3f' % (d['ms_per_step'], r['frac'], r['sweep_ms'], r['sweep_frac']))"
+timeout 600 python bench.py --steps 3 --warmup 3 --no-marginalised --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+for line in sys.stdin:
+    if line.startswith('{'):
+        d=json.loads(line); r=d['roofline']; print('[cfg4] ms_per_step %.2f state frac %.4f sweep_ms %.2f' % (d['ms_per_step'], r['frac'], r['sweep_ms'])); print(d.get('split_8gpu_share'))"
+timeout 1500 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -n 3 | cut -c1-300
+PGAS_WL_PPT_MIN=8 PGAS_WEIGHTS_KERNEL=3 timeout 1500 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sweep or split or degenerate or full_size or run_chains or philox" 2>&1 | tail -n 3 | cut -c1-300
