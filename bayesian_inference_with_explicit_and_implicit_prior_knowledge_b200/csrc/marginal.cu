@@ -68,49 +68,96 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// The small model functions below run on every lane with the same operands.  Their loops are written over the compile-time
+// maxima with a guard on the run-time size, so that they unroll completely and the little vectors (x, xi, z, e) stay in
+// registers; with run-time trip counts they were indexed dynamically and lived in local memory (816 bytes of stack).
+
 // GP-input map z = p * link(a . x + b) + q   (pgas_b200.h, group B)
 __device__ __forceinline__ void gp_input(const MargDev& m, const MargGP& gp, int t, const double* x, double* z) {
-    for (int d = 0; d < gp.D; ++d) {
-        const double* c = gp.gp_in + ((size_t)t * gp.D + d) * (m.n_x + 1);
-        double s = c[m.n_x];
-        for (int k = 0; k < m.n_x; ++k) s = fma(c[k], x[k], s);
-        if (gp.link == PGAS_LINK_ATAN) s = atan(s);
-        const double* p = gp.gp_post + ((size_t)t * gp.D + d) * 2;
-        z[d] = fma(p[0], s, p[1]);
+    const int nx = m.n_x;
+#pragma unroll
+    for (int d = 0; d < MG_D; ++d) {
+        if (d < gp.D) {
+            const double* c = gp.gp_in + ((size_t)t * gp.D + d) * (nx + 1);
+            const double* p = gp.gp_post + ((size_t)t * gp.D + d) * 2;
+            const double p0 = p[0], p1 = p[1];
+            double s = c[nx];
+#pragma unroll
+            for (int k = 0; k < MG_NX; ++k) if (k < nx) s = fma(c[k], x[k], s);
+            if (gp.link == PGAS_LINK_ATAN) s = atan(s);
+            z[d] = fma(p0, s, p1);
+        }
     }
+}
+
+// sin(x), straight-line: Cody-Waite reduction r = x - n pi/2 with a three-part pi/2 (the first product is exact, so the reduced
+// argument carries half an ulp of ITS OWN size for |x| up to ~1e5), then the sine / cosine polynomials of fastmath.cuh on r / pi
+// (|r / pi| <= 1/4: that division's rounding is relative to r, not to x).  libm's sin() has the same fast path behind a slow-path
+// branch for huge arguments; the shipped vehicle configuration amplifies basis errors enough that a reduction of x / pi in one
+// rounding (error |x| 2^-53) fails the parity bar, so the reduction is done properly.
+__device__ __forceinline__ double sin_bf(double x) {
+    const double n = rint(x * 0.6366197723675814);
+    double r = fma(-n, 1.5707963267948966, x);
+    r = fma(-n, 6.123233995736766e-17, r);
+    r = fma(-n, -1.4973849048591698e-33, r);
+    const double rp = r * 0.3183098861837907;
+    const double t = rp * rp;
+    double ps = FM_SIN[0], pc = FM_COS[0];
+#pragma unroll
+    for (int i = 1; i < 10; ++i) {
+        ps = fma(ps, t, FM_SIN[i]);
+        pc = fma(pc, t, FM_COS[i]);
+    }
+    const double sn = rp * ps, cs = fma(pc, t, 1.0);
+    const int q = (int)__double2ll_rn(n) & 3;
+    const double v = (q & 1) ? cs : sn;
+    return (q & 2) ? -v : v;
 }
 
 // _eigen_fnc (src/BasisFunctions.py:77-80): phi_m = prod_d sqrt(1/L_d) sin(sqrt(eig_md) (z_d - c_d + L_d)),
 // lanes stride over m
 __device__ __forceinline__ void basis_eval(const MargGP& gp, const double* z, double* out, int lane) {
     double zz[MG_D];
-    for (int d = 0; d < gp.D; ++d) zz[d] = (z[d] - gp.center[d]) + gp.L[d];
+#pragma unroll
+    for (int d = 0; d < MG_D; ++d) zz[d] = (d < gp.D) ? (z[d] - gp.center[d]) + gp.L[d] : 0.0;
     for (int mI = lane; mI < gp.M; mI += 32) {
         double p = 1.0;
-        for (int d = 0; d < gp.D; ++d) p *= gp.sqrt_invL[d] * sin(gp.sqrt_eig[(size_t)mI * gp.D + d] * zz[d]);
+#pragma unroll
+        for (int d = 0; d < MG_D; ++d)
+            if (d < gp.D) p *= gp.sqrt_invL[d] * sin_bf(gp.sqrt_eig[(size_t)mI * gp.D + d] * zz[d]);
         out[mI] = p;
     }
 }
 
 __device__ __forceinline__ void transition(const MargDev& m, int t, const double* x, const double* xi, double* xn) {
-    const int W = m.n_x + m.G + 1;
-    for (int r = 0; r < m.n_x; ++r) {
-        const double* c = m.trans + ((size_t)t * m.n_x + r) * W;
-        double s = c[m.n_x + m.G];
-        for (int g = 0; g < m.G; ++g) s = fma(c[m.n_x + g], xi[g], s);
-        for (int k = 0; k < m.n_x; ++k) s = fma(c[k], x[k], s);
-        xn[r] = s;
+    const int nx = m.n_x, G = m.G, W = nx + G + 1;
+#pragma unroll
+    for (int r = 0; r < MG_NX; ++r) {
+        if (r < nx) {
+            const double* c = m.trans + ((size_t)t * nx + r) * W;
+            double s = c[nx + G];
+#pragma unroll
+            for (int g = 0; g < MG_GP; ++g) if (g < G) s = fma(c[nx + g], xi[g], s);
+#pragma unroll
+            for (int k = 0; k < MG_NX; ++k) if (k < nx) s = fma(c[k], x[k], s);
+            xn[r] = s;
+        }
     }
 }
 
 __device__ __forceinline__ void output_mdl(const MargDev& m, int t, const double* x, const double* xi, double* y) {
-    const int W = m.n_x + m.G + 1;
-    for (int r = 0; r < m.n_y; ++r) {
-        const double* c = m.outp + ((size_t)t * m.n_y + r) * W;
-        double s = c[m.n_x + m.G];
-        for (int g = 0; g < m.G; ++g) s = fma(c[m.n_x + g], xi[g], s);
-        for (int k = 0; k < m.n_x; ++k) s = fma(c[k], x[k], s);
-        y[r] = (m.out_link == PGAS_LINK_TANH) ? tanh(s) : s;
+    const int nx = m.n_x, G = m.G, W = nx + G + 1;
+#pragma unroll
+    for (int r = 0; r < MG_NY; ++r) {
+        if (r < m.n_y) {
+            const double* c = m.outp + ((size_t)t * m.n_y + r) * W;
+            double s = c[nx + G];
+#pragma unroll
+            for (int g = 0; g < MG_GP; ++g) if (g < G) s = fma(c[nx + g], xi[g], s);
+#pragma unroll
+            for (int k = 0; k < MG_NX; ++k) if (k < nx) s = fma(c[k], x[k], s);
+            y[r] = (m.out_link == PGAS_LINK_TANH) ? tanh(s) : s;
+        }
     }
 }
 
@@ -118,12 +165,17 @@ __device__ __forceinline__ void output_mdl(const MargDev& m, int t, const double
 __device__ __forceinline__ double log_likelihood(const MargDev& m, int t, const double* x, const double* xi) {
     double y[MG_NY], e[MG_NY];
     output_mdl(m, t, x, xi, y);
-    for (int r = 0; r < m.n_y; ++r) e[r] = m.obs[(size_t)t * m.n_y + r] - y[r];
+#pragma unroll
+    for (int r = 0; r < MG_NY; ++r) e[r] = (r < m.n_y) ? m.obs[(size_t)t * m.n_y + r] - y[r] : 0.0;
     double q = 0.0;
-    for (int r = 0; r < m.n_y; ++r) {
-        double w = 0.0;
-        for (int k = 0; k <= r; ++k) w = fma(m.Rw[r][k], e[k], w);
-        q = fma(w, w, q);
+#pragma unroll
+    for (int r = 0; r < MG_NY; ++r) {
+        if (r < m.n_y) {
+            double w = 0.0;
+#pragma unroll
+            for (int k = 0; k <= r; ++k) w = fma(m.Rw[r][k], e[k], w);
+            q = fma(w, w, q);
+        }
     }
     return -0.5 * q + m.R_logc;
 }
@@ -131,11 +183,16 @@ __device__ __forceinline__ double log_likelihood(const MargDev& m, int t, const 
 // log N(target; mean, Q)  (h_x, src/Algorithm3.py:107-114)
 __device__ __forceinline__ double log_trans_density(const MargDev& m, const double* target, const double* mean) {
     double e[MG_NX], q = 0.0;
-    for (int r = 0; r < m.n_x; ++r) e[r] = target[r] - mean[r];
-    for (int r = 0; r < m.n_x; ++r) {
-        double w = 0.0;
-        for (int k = 0; k <= r; ++k) w = fma(m.Qw[r][k], e[k], w);
-        q = fma(w, w, q);
+#pragma unroll
+    for (int r = 0; r < MG_NX; ++r) e[r] = (r < m.n_x) ? target[r] - mean[r] : 0.0;
+#pragma unroll
+    for (int r = 0; r < MG_NX; ++r) {
+        if (r < m.n_x) {
+            double w = 0.0;
+#pragma unroll
+            for (int k = 0; k <= r; ++k) w = fma(m.Qw[r][k], e[k], w);
+            q = fma(w, w, q);
+        }
     }
     return -0.5 * q + m.Q_logc;
 }
@@ -330,67 +387,50 @@ __device__ double warp_chol_packed(double* A, int M, int R, int lane, int& fail)
     return warp_sum(logdet);
 }
 
-// w = L^-1 b by columns: lane owns rows lane, lane + 32, ...; L packed with inverse diagonal
+// w = L^-1 b by columns: lane owns rows lane, lane + 32, ...; L packed with inverse diagonal.  The column loop is cut at the row
+// segments (see warp_fused_update).
 template <int ROWS>
 __device__ __forceinline__ void warp_fwd_solve(const double* Lpk, const double* b, int M, int lane, double (&w)[ROWS]) {
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) { const int idx = lane + 32 * r; w[r] = idx < M ? b[idx] : 0.0; }
-    for (int k = 0; k < M; ++k) {
-        double mine = w[0];
 #pragma unroll
-        for (int r = 1; r < ROWS; ++r) mine = ((k >> 5) == r) ? w[r] : mine;
-        const double wk = __shfl_sync(FULL, mine, k & 31) * Lpk[tri(k) + k];
+    for (int seg = 0; seg < ROWS; ++seg) {
+        const int kend = min(M, 32 * (seg + 1));
+        for (int k = 32 * seg; k < kend; ++k) {
+            const int src = k - 32 * seg;
+            const double wk = __shfl_sync(FULL, w[seg], src) * Lpk[tri(k) + k];
+            if (lane == src) w[seg] = wk;
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            const int idx = lane + 32 * r;
-            if (idx == k) w[r] = wk;
-            else if (idx > k && idx < M) w[r] = fma(-Lpk[tri(idx) + k], wk, w[r]);
-        }
-    }
-}
-
-// L L^T <- L L^T + sign x x^T for a packed lower factor with TRUE diagonal (n rows), by Givens (sign = +1) or
-// hyperbolic (sign = -1) rotations in the division-free form
-//   rho = L_kk^2 + sign x_k^2,  alpha = L_kk / sqrt(rho),  beta = x_k / sqrt(rho),
-//   L_ik <- alpha L_ik + sign beta x_i,   x_i <- alpha x_i - beta L_ik(old),   L_kk <- sqrt(rho).
-// Lanes own rows (lane + 32 q); x lives in registers.  A non-positive rho (lost definiteness) sets `bad`.
-template <int ROWS>
-__device__ __forceinline__ void warp_rank1(double* Lm, const double* xs, int n, double sign, int lane, int& bad) {
-    double xr[ROWS];
-#pragma unroll
-    for (int q = 0; q < ROWS; ++q) { const int idx = lane + 32 * q; xr[q] = idx < n ? xs[idx] : 0.0; }
-    for (int k = 0; k < n; ++k) {
-        double mine = xr[0];
-#pragma unroll
-        for (int q = 1; q < ROWS; ++q) mine = ((k >> 5) == q) ? xr[q] : mine;
-        const double xk = __shfl_sync(FULL, mine, k & 31);
-        const int dk = tri(k) + k;
-        const double Lkk = Lm[dk];
-        const double rho = fma(sign * xk, xk, Lkk * Lkk);
-        if (!(rho > 0.0)) bad = 1;
-        const double ri = rsqrt(rho);
-        const double alpha = Lkk * ri, beta = xk * ri;
-        __syncwarp();
-        if (lane == 0) Lm[dk] = rho * ri;
-#pragma unroll
-        for (int q = 0; q < ROWS; ++q) {
-            const int idx = lane + 32 * q;
-            if (idx > k && idx < n) {
-                double* p = Lm + tri(idx) + k;
-                const double Lik = *p;
-                *p = fma(sign * beta, xr[q], alpha * Lik);
-                xr[q] = fma(alpha, xr[q], -beta * Lik);
+            for (int r = seg; r < ROWS; ++r) {
+                const int idx = lane + 32 * r;
+                if ((r > seg || idx > k) && idx < M) w[r] = fma(-Lpk[tri(idx) + k], wk, w[r]);
             }
         }
     }
-    __syncwarp();
 }
 
-// One sweep over the columns that does, in lockstep (four independent dependency chains per column):
+// 1 / sqrt(a), a > 0: the bare MUFU.RSQ64H seed (2^-22) and two Newton steps in residual form — straight-line, ~2 ulp.  CUDA's
+// rsqrt() wraps the same seed in special-case handling (17 instructions and a branch per call; three calls per column made it
+// 12 % of the kernel's instruction stream, profiles/r02_marg_sweep_summary.md).  Non-positive arguments give NaN / inf, which the
+// callers detect on the argument itself.
+__device__ __forceinline__ double rsqrt_bf(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    y = fma(y, fma(-(h * y), y, 0.5), y);
+    y = fma(y, fma(-(h * y), y, 0.5), y);
+    return y;
+}
+
+// One sweep over the columns that does, in lockstep (three independent rotation chains and a substitution per column):
 //   A <- chol(A A^T + z z^T)                       (Givens)          statistics gain [phi; xi][phi; xi]^T
 //   B <- chol(B B^T + z z^T - r r^T)               (Givens, hyperbolic)  ... and the reference part loses [phi_ref; xi_ref](.)^T
 //   w <- (new A, leading M x M block)^-1 rhs       (column-oriented forward substitution; 1 / L'_kk is the rsqrt of the rotation)
 // A, B: packed augmented factors with true diagonal, n = M + 1 rows; z, r: n entries; rhs: M entries.
+// The column loop is cut at the lanes' row segments (rows lane + 32 q), so that the register holding column k's entry and the set of
+// rows still below the diagonal are compile-time facts: no selects, and rows of finished segments are not visited.  The squared
+// diagonal of B after the Givens step IS rho_b, so the hyperbolic pivot rho_b - c_k^2 does not wait for the first square root: the three
+// inverse square roots of a column are independent.
 template <int ROWS>
 __device__ __forceinline__ void warp_fused_update(double* A, double* B, const double* z, const double* r, const double* rhs, int M,
                                                   int lane, int& bad, double (&w)[ROWS]) {
@@ -403,64 +443,64 @@ __device__ __forceinline__ void warp_fused_update(double* A, double* B, const do
         xc[q] = idx < n ? r[idx] : 0.0;
         w[q] = idx < M ? rhs[idx] : 0.0;
     }
-    for (int k = 0; k < n; ++k) {
-        double ma = xa[0], mb = xb[0], mc = xc[0], mw = w[0];
 #pragma unroll
-        for (int q = 1; q < ROWS; ++q) {
-            const bool s = (k >> 5) == q;
-            ma = s ? xa[q] : ma; mb = s ? xb[q] : mb; mc = s ? xc[q] : mc; mw = s ? w[q] : mw;
-        }
-        const int src = k & 31, dk = tri(k) + k;
-        const double ak = __shfl_sync(FULL, ma, src), bk = __shfl_sync(FULL, mb, src), ck = __shfl_sync(FULL, mc, src);
-        const double Akk = A[dk], Bkk = B[dk];
-        const double rhoa = fma(ak, ak, Akk * Akk), rhob = fma(bk, bk, Bkk * Bkk);
-        const double ria = rsqrt(rhoa), rib = rsqrt(rhob);
-        const double Bk1 = rhob * rib;                                        // diagonal of B after the update
-        const double rhoc = fma(-ck, ck, Bk1 * Bk1);
-        if (!(rhoc > 0.0) || !(rhoa > 0.0)) bad = 1;
-        const double ric = rsqrt(rhoc);
-        const double aa = Akk * ria, ba = ak * ria, ab = Bkk * rib, bb = bk * rib, ac = Bk1 * ric, bc = ck * ric;
-        const double wk = __shfl_sync(FULL, mw, src) * ria;                   // forward substitution on the NEW factor
-        __syncwarp();
-        if (lane == 0) { A[dk] = rhoa * ria; B[dk] = rhoc * ric; }
+    for (int seg = 0; seg < ROWS; ++seg) {
+        const int kend = min(n, 32 * (seg + 1));
+        for (int k = 32 * seg; k < kend; ++k) {
+            const int src = k - 32 * seg, dk = tri(k) + k;
+            const double ak = __shfl_sync(FULL, xa[seg], src), bk = __shfl_sync(FULL, xb[seg], src), ck = __shfl_sync(FULL, xc[seg], src);
+            const double wk0 = __shfl_sync(FULL, w[seg], src);
+            const double Akk = A[dk], Bkk = B[dk];
+            const double rhoa = fma(ak, ak, Akk * Akk), rhob = fma(bk, bk, Bkk * Bkk);
+            const double rhoc = fma(-ck, ck, rhob);
+            if (!(rhoc > 0.0) || !(rhoa > 0.0)) bad = 1;
+            const double ria = rsqrt_bf(rhoa), rib = rsqrt_bf(rhob), ric = rsqrt_bf(rhoc);
+            const double Bk1 = rhob * rib;                                        // diagonal of B after the update
+            const double aa = Akk * ria, ba = ak * ria, ab = Bkk * rib, bb = bk * rib, ac = Bk1 * ric, bc = ck * ric;
+            const double wk = wk0 * ria;                                          // forward substitution on the NEW factor
+            __syncwarp();
+            if (lane == 0) { A[dk] = rhoa * ria; B[dk] = rhoc * ric; }
+            if (lane == src && k < M) w[seg] = wk;
 #pragma unroll
-        for (int q = 0; q < ROWS; ++q) {
-            const int idx = lane + 32 * q;
-            if (idx == k && k < M) w[q] = wk;
-            if (idx > k && idx < n) {
-                double* pa = A + tri(idx) + k;
-                double* pb = B + tri(idx) + k;
-                const double Aik = *pa, Bik = *pb;
-                const double An = fma(ba, xa[q], aa * Aik);
-                xa[q] = fma(aa, xa[q], -ba * Aik);
-                const double B1 = fma(bb, xb[q], ab * Bik);
-                xb[q] = fma(ab, xb[q], -bb * Bik);
-                const double B2 = fma(-bc, xc[q], ac * B1);
-                xc[q] = fma(ac, xc[q], -bc * B1);
-                *pa = An;
-                *pb = B2;
-                if (k < M && idx < M) w[q] = fma(-An, wk, w[q]);
+            for (int q = seg; q < ROWS; ++q) {
+                const int idx = lane + 32 * q;
+                if ((q > seg || idx > k) && idx < n) {
+                    double* pa = A + tri(idx) + k;
+                    double* pb = B + tri(idx) + k;
+                    const double Aik = *pa, Bik = *pb;
+                    const double An = fma(ba, xa[q], aa * Aik);
+                    xa[q] = fma(aa, xa[q], -ba * Aik);
+                    const double B1 = fma(bb, xb[q], ab * Bik);
+                    xb[q] = fma(ab, xb[q], -bb * Bik);
+                    const double B2 = fma(-bc, xc[q], ac * B1);
+                    xc[q] = fma(ac, xc[q], -bc * B1);
+                    *pa = An;
+                    *pb = B2;
+                    if (k < M && idx < M) w[q] = fma(-An, wk, w[q]);
+                }
             }
         }
     }
     __syncwarp();
 }
 
-// w = L^-1 b with the inverse diagonal given separately (inv[k] = 1 / L_kk)
+// w = L^-1 b with the inverse diagonal given separately (inv[k] = 1 / L_kk); column loop cut at the row segments as above
 template <int ROWS>
 __device__ __forceinline__ void warp_fwd_solve_inv(const double* Lpk, const double* inv, const double* b, int M, int lane, double (&w)[ROWS]) {
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) { const int idx = lane + 32 * r; w[r] = idx < M ? b[idx] : 0.0; }
-    for (int k = 0; k < M; ++k) {
-        double mine = w[0];
 #pragma unroll
-        for (int r = 1; r < ROWS; ++r) mine = ((k >> 5) == r) ? w[r] : mine;
-        const double wk = __shfl_sync(FULL, mine, k & 31) * inv[k];
+    for (int seg = 0; seg < ROWS; ++seg) {
+        const int kend = min(M, 32 * (seg + 1));
+        for (int k = 32 * seg; k < kend; ++k) {
+            const int src = k - 32 * seg;
+            const double wk = __shfl_sync(FULL, w[seg], src) * inv[k];
+            if (lane == src) w[seg] = wk;
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            const int idx = lane + 32 * r;
-            if (idx == k) w[r] = wk;
-            else if (idx > k && idx < M) w[r] = fma(-Lpk[tri(idx) + k], wk, w[r]);
+            for (int r = seg; r < ROWS; ++r) {
+                const int idx = lane + 32 * r;
+                if ((r > seg || idx > k) && idx < M) w[r] = fma(-Lpk[tri(idx) + k], wk, w[r]);
+            }
         }
     }
 }
@@ -573,11 +613,16 @@ struct WarpCtx {
     double* rv;
 };
 
-template <int MODE, int ROWS>
-__global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constant__ MargArgs a) {
+// WIDE: the launch has at most 128 threads per CTA and two CTAs per SM (the wide geometry of mg_geometry), so a thread may use 255
+// registers instead of 128.
+template <int MODE, int ROWS, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 128 : 512, WIDE ? 2 : 1) marg_sweep_kernel(const __grid_constant__ MargArgs a) {
     extern __shared__ double smem[];
     const MargDev& m = a.m;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+    // the thread index goes through a shuffle once: ptxas otherwise re-reads the special register wherever `lane` is used (100
+    // S2R per particle-step, 4 % of the stall samples of the round-1 kernel)
+    const int tid = __shfl_sync(FULL, (int)threadIdx.x, (int)(threadIdx.x & 31u));
+    const int lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
     const int CS = a.CS, NW = a.NW, N = a.N, T = m.T, G = m.G, nx = m.n_x;
     const int chain = blockIdx.x / CS, rank = blockIdx.x % CS;
     const int WT = CS * NW, wg = rank * NW + warp;
@@ -647,7 +692,9 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                 // the three per-GP gathers by ancestor (two augmented factors, packed T1: ~21 KB at M = 41) start now and
                 // land in shared memory while the new state, the basis and the variates are computed
                 __syncwarp();
-                for (int g = 0; g < G; ++g) {
+#pragma unroll
+                for (int g = 0; g < MG_GP; ++g) {
+                    if (g >= G) break;
                     const int Mg = m.gp[g].M, na = mg_naugp(Mg), np = mg_npkp(Mg);
                     const double* s0 = wq + L.Lp[g] + (size_t)ac * na;
                     const double* s1 = wq + L.LB[g] + (size_t)ac * na;
@@ -665,35 +712,55 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
         // ---- new state
         if (t == 0) {
             double zz[MG_NX];
-            for (int k = 0; k < nx; k += 2) {
-                double za, zb;
-                if (a.rng_mode == 1) { za = Zc[(size_t)i * nx + k]; zb = (k + 1 < nx) ? Zc[(size_t)i * nx + k + 1] : 0.0; }
-                else philox_normal2(a.seed, PURPOSE_STATE, pchain, a.iteration, (unsigned)(k >> 1) << 28, (unsigned)i, za, zb);
+#pragma unroll
+            for (int k = 0; k < MG_NX; k += 2) {
+                double za = 0.0, zb = 0.0;
+                if (k < nx) {
+                    if (a.rng_mode == 1) { za = Zc[(size_t)i * nx + k]; zb = (k + 1 < nx) ? Zc[(size_t)i * nx + k + 1] : 0.0; }
+                    else philox_normal2(a.seed, PURPOSE_STATE, pchain, a.iteration, (unsigned)(k >> 1) << 28, (unsigned)i, za, zb);
+                }
                 zz[k] = za;
-                if (k + 1 < nx) zz[k + 1] = zb;
+                if (k + 1 < MG_NX) zz[k + 1] = zb;
             }
-            for (int r = 0; r < nx; ++r) {
-                double s = m.m0[r];
-                for (int k = 0; k <= r; ++k) s = fma(m.P0c[r][k], zz[k], s);
+#pragma unroll
+            for (int r = 0; r < MG_NX; ++r) {
+                double s = 0.0;
+                if (r < nx) {
+                    s = m.m0[r];
+#pragma unroll
+                    for (int k = 0; k <= r; ++k) s = fma(m.P0c[r][k], zz[k], s);
+                }
                 x[r] = s;
             }
         } else {
             double zz[MG_NX];
             if (a.rng_mode != 1) sv = philox_step_variates(a.seed, pchain, a.iteration, (unsigned)t, (unsigned)i, G, nx, lane);
-            for (int k = 0; k < nx; ++k) {
+#pragma unroll
+            for (int k = 0; k < MG_NX; ++k) {
                 double za = 0.0;
-                if (!m.deterministic) za = (a.rng_mode == 1) ? Zc[((size_t)t * N + i) * nx + k] : sv.zs[k];
+                if (k < nx && !m.deterministic) za = (a.rng_mode == 1) ? Zc[((size_t)t * N + i) * nx + k] : sv.zs[k];
                 zz[k] = za;
             }
-            for (int r = 0; r < nx; ++r) {
-                double s = ldcg(wq + L.auxx + (size_t)ac * nx + r);     // f(x[a], u_{t-1}, xi[a]) = aux state of the ancestor
-                for (int k = 0; k <= r; ++k) s = fma(m.Qc[r][k], zz[k], s);
+#pragma unroll
+            for (int r = 0; r < MG_NX; ++r) {
+                double s = 0.0;
+                if (r < nx) {
+                    s = ldcg(wq + L.auxx + (size_t)ac * nx + r);        // f(x[a], u_{t-1}, xi[a]) = aux state of the ancestor
+#pragma unroll
+                    for (int k = 0; k <= r; ++k) s = fma(m.Qc[r][k], zz[k], s);
+                }
                 x[r] = s;
             }
         }
-        if (pinned) for (int r = 0; r < nx; ++r) x[r] = refx[(size_t)t * nx + r];
-        // ---- interface variables and statistics, GP by GP
-        for (int g = 0; g < G; ++g) {
+        if (pinned) {
+#pragma unroll
+            for (int r = 0; r < MG_NX; ++r) if (r < nx) x[r] = refx[(size_t)t * nx + r];
+        }
+        // ---- interface variables and statistics, GP by GP (unrolled over the compile-time maximum: everything indexed by g —
+        // buffers, workspace offsets, the per-GP scalars — is then a register, not a local-memory array)
+#pragma unroll
+        for (int g = 0; g < MG_GP; ++g) {
+            if (g >= G) break;
             const MargGP& gp = m.gp[g];
             const int M = gp.M, npk = gp.npk;
             gp_input(m, gp, t, x, z);
@@ -793,7 +860,9 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             // factors are rebuilt from the statistics.
             const bool more = t < T - 1;
             if (more) transition(m, t, x, xi, ax1);
-            for (int g = 0; g < G; ++g) {
+#pragma unroll
+            for (int g = 0; g < MG_GP; ++g) {
+                if (g >= G) break;
                 const MargGP& gp = m.gp[g];
                 const int M = gp.M, npk = gp.npk, rowM = tri(M), naug = npk + M + 1;
                 const size_t trow = (size_t)chain * T + t;
@@ -865,9 +934,15 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
                     const int idx = lane + 32 * r;
                     if (idx < M) yv = fma(Ag[rowM + idx], w[r], yv);
                 }
-                axi1[g] = warp_sum(yv);                                   // prior_mniw_mean . phi_aux of the next step
-                ldA[g] = factor_logdet(Ag, M, lane);
-                ldB[g] = factor_logdet(Bq, M, lane);
+                // one butterfly carries both sums: prior_mniw_mean . phi_aux of the next step, and log det A - log det B (g_t - g_T
+                // needs only the difference, src/Algorithm3.py:92-106)
+                double ld = 0.0;
+                for (int k = lane; k < M; k += 32) ld += log(Ag[tri(k) + k]) - log(Bq[tri(k) + k]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { yv += __shfl_xor_sync(FULL, yv, o); ld += __shfl_xor_sync(FULL, ld, o); }
+                axi1[g] = yv;
+                ldA[g] = 2.0 * ld;
+                ldB[g] = 0.0;
                 { const double sa = Ag[rowM + M], sb = Bq[rowM + M]; psA[g] = sa * sa; psB[g] = sb * sb; }
                 double* LBw = wp + L.LB[g] + (size_t)i * mg_naugp(M);
                 double* LAw = wp + L.Lp[g] + (size_t)i * mg_naugp(M);
@@ -883,17 +958,29 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             lwtrace[(size_t)t * N + i] = lw;
             if (t > 0) atrace[(size_t)(t - 1) * N + i] = anc;
         }
-        if (lane < nx) strace[((size_t)t * N + i) * nx + lane] = x[lane];
+        {
+            double xl = x[0];
+#pragma unroll
+            for (int r = 1; r < MG_NX; ++r) xl = (lane == r) ? x[r] : xl;
+            if (lane < nx) strace[((size_t)t * N + i) * nx + lane] = xl;
+        }
         if (t == T - 1) return;
 
         // ---- tail: auxiliary quantities of step t + 1
         double ax[MG_NX], axi[MG_GP], gdiff = 0.0;
-        transition(m, t, x, xi, ax);
-        for (int g = 0; g < G; ++g) {
+        if constexpr (MODE == 1) {
+#pragma unroll
+            for (int r = 0; r < MG_NX; ++r) ax[r] = ax1[r];               // computed before the factor updates
+        } else {
+            transition(m, t, x, xi, ax);
+        }
+#pragma unroll
+        for (int g = 0; g < MG_GP; ++g) {
+            if (g >= G) break;
             const MargGP& gp = m.gp[g];
             const int M = gp.M, npk = gp.npk, rowM = tri(M), rowV = tri(M + 1);
             double* Ag = wc.A[g];
-            gp_input(m, gp, t + 1, ax, z);
+            if constexpr (MODE == 0) gp_input(m, gp, t + 1, ax, z);
             if constexpr (MODE == 1) {
                 // Algorithm3: the factors, the auxiliary interface variable and the log-determinants were produced in the second
                 // GP pass above.  g_t - g_T (src/Algorithm3.py:92-106): only the particle-dependent terms of
@@ -934,7 +1021,12 @@ __global__ void __launch_bounds__(512, 1) marg_sweep_kernel(const __grid_constan
             wp[L.lwaux + i] = lwa;
             if (MODE == 1) wp[L.lwanc + i] = (lwa + gdiff) + log_trans_density(m, refx + (size_t)(t + 1) * nx, ax);
         }
-        if (lane < nx) wp[L.auxx + (size_t)i * nx + lane] = ax[lane];
+        {
+            double xl = ax[0];
+#pragma unroll
+            for (int r = 1; r < MG_NX; ++r) xl = (lane == r) ? ax[r] : xl;
+            if (lane < nx) wp[L.auxx + (size_t)i * nx + lane] = xl;
+        }
     };
 
     // weighted means of the per-particle statistics (src/Algorithm1.py:165-169, :445-457) for step tp
@@ -1441,9 +1533,9 @@ static int mg_fill_rng(MargArgs& a, const pgas_marg_rng* rng) {
     return 0;
 }
 
-template <int MODE, int ROWS>
+template <int MODE, int ROWS, bool WIDE>
 static int mg_launch_variant(const MargArgs& a, size_t smem, cudaStream_t st) {
-    auto kern = marg_sweep_kernel<MODE, ROWS>;
+    auto kern = marg_sweep_kernel<MODE, ROWS, WIDE>;
     PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (a.CS > 8) PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     if (a.sw_barrier) {
@@ -1524,8 +1616,18 @@ static int mg_launch_sweep(MargArgs& a, int requested_cs, cudaStream_t st) {
         size_t smem = 0;
         if (int rc = mg_geometry(a, requested_cs, &smem, attempt == 0)) return rc;
         int rc;
-        if (a.mode == 0) rc = small ? mg_launch_variant<0, 2>(a, smem, st) : mg_launch_variant<0, 4>(a, smem, st);
-        else rc = small ? mg_launch_variant<1, 2>(a, smem, st) : mg_launch_variant<1, 4>(a, smem, st);
+        // 255-register variant: at most 128 threads per CTA and every CTA of the launch resident at two CTAs per SM
+        int dev = 0, sms = 0;
+        PGAS_CUDA(cudaGetDevice(&dev));
+        PGAS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const bool wide = a.NW <= 4 && (!a.sw_barrier || (long long)a.n_chains * a.CS <= 2ll * sms) && !getenv("PGAS_MARG_NARROW");
+        if (a.mode == 0) {
+            if (wide) rc = small ? mg_launch_variant<0, 2, true>(a, smem, st) : mg_launch_variant<0, 4, true>(a, smem, st);
+            else rc = small ? mg_launch_variant<0, 2, false>(a, smem, st) : mg_launch_variant<0, 4, false>(a, smem, st);
+        } else {
+            if (wide) rc = small ? mg_launch_variant<1, 2, true>(a, smem, st) : mg_launch_variant<1, 4, true>(a, smem, st);
+            else rc = small ? mg_launch_variant<1, 2, false>(a, smem, st) : mg_launch_variant<1, 4, false>(a, smem, st);
+        }
         if (rc != -100) return rc;
     }
     PGAS_FAIL(-23, "marginalised filter: no launch geometry fits");
