@@ -39,17 +39,21 @@ namespace cg = cooperative_groups;
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
-// Barrier among the CTAs of one chain through a global counter (all CTAs are co-resident: cooperative launch).
-// Same shape as a cooperative-groups grid sync: CTA barrier, one thread publishes (fence + atomic) and spins.
-__device__ __forceinline__ void mg_sw_barrier(unsigned* ctr, unsigned target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
+// Barrier among the warps of one chain through a global counter (all CTAs are co-resident: cooperative launch).  Same shape as a
+// cooperative-groups grid sync — publish with fence + atomic, spin, fence — but with WARPS as participants: a warp arrives as soon
+// as its own particle is written and leaves as soon as the count is complete; no CTA barrier on either side, so a warp neither
+// waits for its three neighbours before publishing nor for thread 0's poll after the last arrival.  __syncwarp orders the lanes'
+// stores before lane 0's fence (cumulativity), the fence before the add.
+__device__ __forceinline__ void mg_warp_barrier(unsigned* ctr, unsigned target, int lane) {
+    __syncwarp();
+    if (lane == 0) {
         __threadfence();
         atomicAdd(ctr, 1u);
-        while (*((volatile unsigned*)ctr) < target) { }
+        unsigned v;
+        do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < target);
         __threadfence();
     }
-    __syncthreads();
+    __syncwarp();
 }
 
 __device__ __forceinline__ void mg_cluster_barrier(bool multi) {
@@ -448,9 +452,19 @@ __device__ __forceinline__ void warp_fused_update(double* A, double* B, const do
         const int kend = min(n, 32 * (seg + 1));
         for (int k = 32 * seg; k < kend; ++k) {
             const int src = k - 32 * seg, dk = tri(k) + k;
+            // the column's entries below the diagonal are read first: they do not depend on the rotation, and the __syncwarp that
+            // guards the diagonal would otherwise pin the loads behind the whole coefficient chain
+            double Aik[ROWS], Bik[ROWS];
+#pragma unroll
+            for (int q = seg; q < ROWS; ++q) {
+                const int idx = lane + 32 * q;
+                const bool act = (q > seg || idx > k) && idx < n;
+                Aik[q] = act ? A[tri(idx) + k] : 0.0;
+                Bik[q] = act ? B[tri(idx) + k] : 0.0;
+            }
+            const double Akk = A[dk], Bkk = B[dk];
             const double ak = __shfl_sync(FULL, xa[seg], src), bk = __shfl_sync(FULL, xb[seg], src), ck = __shfl_sync(FULL, xc[seg], src);
             const double wk0 = __shfl_sync(FULL, w[seg], src);
-            const double Akk = A[dk], Bkk = B[dk];
             const double rhoa = fma(ak, ak, Akk * Akk), rhob = fma(bk, bk, Bkk * Bkk);
             const double rhoc = fma(-ck, ck, rhob);
             if (!(rhoc > 0.0) || !(rhoa > 0.0)) bad = 1;
@@ -465,17 +479,14 @@ __device__ __forceinline__ void warp_fused_update(double* A, double* B, const do
             for (int q = seg; q < ROWS; ++q) {
                 const int idx = lane + 32 * q;
                 if ((q > seg || idx > k) && idx < n) {
-                    double* pa = A + tri(idx) + k;
-                    double* pb = B + tri(idx) + k;
-                    const double Aik = *pa, Bik = *pb;
-                    const double An = fma(ba, xa[q], aa * Aik);
-                    xa[q] = fma(aa, xa[q], -ba * Aik);
-                    const double B1 = fma(bb, xb[q], ab * Bik);
-                    xb[q] = fma(ab, xb[q], -bb * Bik);
+                    const double An = fma(ba, xa[q], aa * Aik[q]);
+                    xa[q] = fma(aa, xa[q], -ba * Aik[q]);
+                    const double B1 = fma(bb, xb[q], ab * Bik[q]);
+                    xb[q] = fma(ab, xb[q], -bb * Bik[q]);
                     const double B2 = fma(-bc, xc[q], ac * B1);
                     xc[q] = fma(ac, xc[q], -bc * B1);
-                    *pa = An;
-                    *pb = B2;
+                    A[tri(idx) + k] = An;
+                    B[tri(idx) + k] = B2;
                     if (k < M && idx < M) w[q] = fma(-An, wk, w[q]);
                 }
             }
@@ -589,6 +600,67 @@ __device__ void cta_softmax_cdf(const double* __restrict__ lw, int N, bool sisr,
     __syncthreads();
 }
 
+// The same table built by ONE WARP into its own buffer (every warp of the chain runs this on the same global log-weights with the
+// same code: identical bits everywhere, no CTA barrier, no idle warps).  Lane l owns the c = ceil(N / 32) consecutive entries
+// [l c, (l + 1) c): sums and the cumulative sum are thread-serial over the lane's entries plus one butterfly / one scan.  Quotients by
+// the two normalisers are Markstein-corrected products with the reciprocal.
+__device__ __forceinline__ double div_rcp(double x, double d, double rd) {
+    const double q = x * rd;
+    return fma(fma(-q, d, x), rd, q);
+}
+// own entries of a lane, eight at a time with the eight bodies unrolled side by side (independent chains interleave)
+#define MG_FOR_OWN(...)                                                        \
+    for (int j0_ = 0; j0_ < c; j0_ += 8) {                                     \
+        _Pragma("unroll") for (int j_ = 0; j_ < 8; ++j_) {                     \
+            const int i = lo + j0_ + j_;                                       \
+            if (j0_ + j_ < c && i < N) { __VA_ARGS__ }                         \
+        }                                                                      \
+    }
+__device__ void warp_softmax_cdf(const double* __restrict__ lw, int N, bool sisr, double* cdf, int lane) {
+    // global -> shared, eight loads in flight per lane before the first store (a load-store loop would pay one L2 round trip
+    // per entry)
+    for (int base = 0; base < N; base += 256) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int i = base + lane + 32 * j; v[j] = i < N ? ldcg(lw + i) : 0.0; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int i = base + lane + 32 * j; if (i < N) cdf[i] = v[j]; }
+    }
+    __syncwarp();
+    const int c = (N + 31) >> 5, lo = lane * c;
+    double mx = -INFINITY;
+    int isnan_ = 0;
+    MG_FOR_OWN(const double v = cdf[i]; isnan_ |= (v != v); mx = fmax(mx, v);)
+    mx = warp_max(mx);
+    if (__any_sync(FULL, isnan_)) mx = NAN;                 // jnp.max propagates NaN -> all weights NaN
+    double sm = 0.0;
+    MG_FOR_OWN(const double e = exp_neg_bf(cdf[i] - mx); cdf[i] = e; sm += e;)
+    const double tot = warp_sum(sm), rtot = 1.0 / tot;
+    bool ok = true;
+    double s2 = 1.0, rs2 = 1.0;
+    if (sisr) {
+        double s = 0.0;
+        MG_FOR_OWN(s += fmax(div_rcp(cdf[i], tot, rtot), 0.0);)
+        s2 = warp_sum(s);
+        rs2 = 1.0 / s2;
+        ok = (s2 > 0.0) && (tot == tot);
+    }
+    const double unif = 1.0 / (double)N;
+    double run = 0.0;
+    MG_FOR_OWN(double w = div_rcp(cdf[i], tot, rtot); if (sisr) w = ok ? div_rcp(fmax(w, 0.0), s2, rs2) : unif; run += w; cdf[i] = run;)
+    const double off = warp_scan_incl(run, lane) - run;
+    MG_FOR_OWN(const double v = off + cdf[i]; cdf[i] = sisr ? fmin(fmax(v, 0.0), 1.0) : v;)
+    __syncwarp();
+}
+#undef MG_FOR_OWN
+
+// #{j : cdf[j] < u} counted by the warp (the table is non-decreasing: this is searchsorted side = left)
+__device__ __forceinline__ int warp_count_below(const double* cdf, int N, double u, int lane) {
+    int n = 0;
+    for (int i = lane; i < N; i += 32) n += (cdf[i] < u) ? 1 : 0;
+    return __reduce_add_sync(FULL, n);
+}
+
 // #{j : cdf[j] < u}  (searchsorted side = left)
 __device__ __forceinline__ int count_below(const double* cdf, int N, double u) {
     int lo = 0, hi = N;
@@ -611,6 +683,7 @@ struct WarpCtx {
     double* inv;           // inverse diagonal of a factor (Algorithm3)
     double* zv;            // rank-1 vectors [phi; xi] and [phi_ref; xi_ref] (Algorithm3)
     double* rv;
+    double* cdf;           // the warp's copy of the resampling table (N entries)
 };
 
 // WIDE: the launch has at most 128 threads per CTA and two CTAs per SM (the wide geometry of mg_geometry), so a thread may use 255
@@ -630,36 +703,51 @@ __global__ void __launch_bounds__(WIDE ? 128 : 512, WIDE ? 2 : 1) marg_sweep_ker
     const double lam = a.lambda;
 
     // ---- shared memory carve-up: CTA part, then per-warp parts
-    double* cdf = smem;                                   // [N]
-    double* wsm = cdf + ((N + 3) & ~3);                   // [N]   (mode 0 statistics trace)
+    double* wsm = smem + ((N + 3) & ~3);                  // [N]   (mode 0 statistics trace)
     double* red = wsm + ((N + 3) & ~3);                   // [64]
+    // All loops of the carve-up run over the compile-time maximum with a guard: the buffer pointers are then plain values derived
+    // from `smem`, the compiler keeps their address space, and every access below is an LDS / STS.  (Filled in a run-time loop the
+    // pointer arrays lived in local memory and every access to the factors was a GENERIC load / store.)
     unsigned* ijt[MG_GP];
     {
         unsigned* q = (unsigned*)(red + 64);
+#pragma unroll
         for (int g = 0; g < MG_GP; ++g) { ijt[g] = q; q += (g < G) ? ((m.gp[g].npk + 1) & ~1) : 0; }
     }
-    __shared__ int s_refidx;
     WarpCtx wc;
     {
         double* q = smem + a.cta_doubles + (size_t)warp * a.warp_doubles;
         int mmax = 0;
-        for (int g = 0; g < G; ++g) { wc.A[g] = q; q += (tri(m.gp[g].M + 2) + 3) & ~3; mmax = max(mmax, m.gp[g].M); }
-        for (int g = G; g < MG_GP; ++g) wc.A[g] = nullptr;
+#pragma unroll
+        for (int g = 0; g < MG_GP; ++g) {
+            wc.A[g] = q;
+            if (g < G) { q += (tri(m.gp[g].M + 2) + 3) & ~3; mmax = max(mmax, m.gp[g].M); }
+        }
         wc.B = q; q += (MODE == 1) ? 0 : ((tri(mmax + 1) + 3) & ~3);       // Algorithm3 keeps per-GP buffers instead (Bg)
         wc.phi = q; q += (mmax + 3) & ~3;
         wc.inv = q; q += (mmax + 3) & ~3;
         wc.zv = q; q += (mmax + 4) & ~3;
         wc.rv = q; q += (mmax + 4) & ~3;
-        for (int g = 0; g < MG_GP; ++g) { wc.Bg[g] = wc.B; wc.T1s[g] = nullptr; }
-        if (MODE == 1)
-            for (int g = 0; g < G; ++g) {
-                wc.Bg[g] = q; q += (mg_naugp(m.gp[g].M) + 3) & ~3;
-                wc.T1s[g] = q; q += (mg_npkp(m.gp[g].M) + 3) & ~3;
+        wc.cdf = q; q += (N + 3) & ~3;
+#pragma unroll
+        for (int g = 0; g < MG_GP; ++g) {
+            wc.Bg[g] = wc.B;
+            wc.T1s[g] = q;
+            if (MODE == 1) {
+                wc.Bg[g] = q;
+                if (g < G) q += (mg_naugp(m.gp[g].M) + 3) & ~3;
+                wc.T1s[g] = q;
+                if (g < G) q += (mg_npkp(m.gp[g].M) + 3) & ~3;
             }
+        }
     }
-    for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int g = 0; g < MG_GP; ++g) {
+        if (g >= G) break;
         for (int i = tid; i < m.gp[g].M; i += nthr)
             for (int j = 0; j <= i; ++j) ijt[g][tri(i) + j] = (unsigned)i | ((unsigned)j << 16);
+        if (tid == 0) ijt[g][m.gp[g].npk] = 0u;                        // pad entry of the pair-wise loops (table length is even)
+    }
     __syncthreads();
 
     // ---- per-chain pointers
@@ -877,12 +965,15 @@ __global__ void __launch_bounds__(WIDE ? 128 : 512, WIDE ? 2 : 1) marg_sweep_ker
                 if (G > 1 || t == 0) { gp_input(m, gp, t, x, z); basis_eval(gp, z, wc.phi, lane); }     // G == 1: still in wc.phi
                 if (more) { gp_input(m, gp, t + 1, ax1, z); basis_eval(gp, z, wc.inv, lane); }           // phi(aux state) -> wc.inv
                 __syncwarp();
+                // two packed entries per lane and trip (16-byte loads / stores; the tables are padded to even length)
 #pragma unroll 4
-                for (int e = lane; e < npk; e += 32) {
-                    const unsigned ij = ijt[g][e];
-                    double v = wc.phi[ij & 0xffffu] * wc.phi[ij >> 16];
-                    if (t > 0) v += wc.T1s[g][e];
-                    T1w[e] = v;
+                for (int e = 2 * lane; e < npk; e += 64) {
+                    const uint2 ij = *reinterpret_cast<const uint2*>(ijt[g] + e);
+                    double2 v;
+                    v.x = wc.phi[ij.x & 0xffffu] * wc.phi[ij.x >> 16];
+                    v.y = wc.phi[ij.y & 0xffffu] * wc.phi[ij.y >> 16];
+                    if (t > 0) { const double2 o = *reinterpret_cast<const double2*>(wc.T1s[g] + e); v.x += o.x; v.y += o.y; }
+                    *reinterpret_cast<double2*>(T1w + e) = v;
                 }
                 for (int k = lane; k < M; k += 32) {
                     double v = wc.phi[k] * xiv;
@@ -946,8 +1037,11 @@ __global__ void __launch_bounds__(WIDE ? 128 : 512, WIDE ? 2 : 1) marg_sweep_ker
                 { const double sa = Ag[rowM + M], sb = Bq[rowM + M]; psA[g] = sa * sa; psB[g] = sb * sb; }
                 double* LBw = wp + L.LB[g] + (size_t)i * mg_naugp(M);
                 double* LAw = wp + L.Lp[g] + (size_t)i * mg_naugp(M);
-#pragma unroll 8
-                for (int e = lane; e < naug; e += 32) { LBw[e] = Bq[e]; LAw[e] = Ag[e]; }
+#pragma unroll 4
+                for (int e = 2 * lane; e < naug; e += 64) {
+                    *reinterpret_cast<double2*>(LBw + e) = *reinterpret_cast<const double2*>(Bq + e);
+                    *reinterpret_cast<double2*>(LAw + e) = *reinterpret_cast<const double2*>(Ag + e);
+                }
                 __syncwarp();
             }
         }
@@ -1063,37 +1157,40 @@ __global__ void __launch_bounds__(WIDE ? 128 : 512, WIDE ? 2 : 1) marg_sweep_ker
 
     // ------------------------------------------------------------------ t = 0 .. T-1
     const bool want_sst = (MODE == 0) && a.sst[0] != nullptr;
-    const int last_owner_rank = ((N - 1) % WT) / NW;
+    const int last_owner = (N - 1) % WT;                 // the warp that owns the conditioned particle N - 1
     int bar_gen = 0;
     const double dN = (double)N;
     for (int t = 0; t < T; ++t) {
         double u_res = 0.0, u_anc = 0.0;
+        int refidx = 0;
         if (t > 0) {
-            if (a.sw_barrier) mg_sw_barrier(a.bar_ctr + chain, (unsigned)CS * (unsigned)(++bar_gen));
+            // the step's only chain-wide dependency: every particle's auxiliary log-weight.  Warps are the participants of the
+            // software barrier, and every warp then builds the resampling table for itself (same data, same code, same bits).
+            if (a.sw_barrier) mg_warp_barrier(a.bar_ctr + chain, (unsigned)WT * (unsigned)(++bar_gen), lane);
             else mg_cluster_barrier(multi);
             const double* wq = wsc + (size_t)((t - 1) & 1) * L.parity_stride;
             if (want_sst) weighted_trace(t - 1);
             if (a.rng_mode == 1) { u_res = Uc[(size_t)t * 2]; u_anc = Uc[(size_t)t * 2 + 1]; }
             else philox_uniform2(a.seed, PURPOSE_STEP_U, pchain, a.iteration, (unsigned)t, 0u, u_res, u_anc);
-            if (MODE == 1 && rank == last_owner_rank) {
+            if (MODE == 1 && wg == last_owner) {
                 // ancestor of the conditioned path (src/Algorithm3.py:115-125); not clipped in the reference
-                cta_softmax_cdf(wq + L.lwanc, N, false, true, cdf, red, tid, nthr);
-                if (tid == 0) s_refidx = count_below(cdf, N, u_anc);
-                __syncthreads();
+                warp_softmax_cdf(wq + L.lwanc, N, false, wc.cdf, lane);
+                refidx = warp_count_below(wc.cdf, N, u_anc, lane);
+                __syncwarp();
             }
-            cta_softmax_cdf(wq + L.lwaux, N, true, true, cdf, red, tid, nthr);
+            warp_softmax_cdf(wq + L.lwaux, N, true, wc.cdf, lane);
         }
         for (int i = wg; i < N; i += WT) {
             int anc = 0;
             if (t > 0) {
-                anc = min(count_below(cdf, N, __ddiv_rn(__dadd_rn(u_res, (double)i), dN)), N - 1);   // src/Filtering.py:28-35
-                if (MODE == 1 && i == N - 1) anc = s_refidx;
+                anc = min(warp_count_below(wc.cdf, N, __ddiv_rn(__dadd_rn(u_res, (double)i), dN), lane), N - 1);   // src/Filtering.py:28-35
+                if (MODE == 1 && i == N - 1) anc = refidx;
             }
             particle_pass(t, i, anc);
         }
     }
     if (want_sst) {
-        if (a.sw_barrier) mg_sw_barrier(a.bar_ctr + chain, (unsigned)CS * (unsigned)(++bar_gen));
+        if (a.sw_barrier) mg_warp_barrier(a.bar_ctr + chain, (unsigned)WT * (unsigned)(++bar_gen), lane);
         else mg_cluster_barrier(multi);
         weighted_trace(T - 1);
     }
@@ -1508,8 +1605,8 @@ extern "C" size_t pgas_marg_workspace_bytes(const pgas_marg_model* model, int32_
     return mg_carve(model->dev, N, n_chains, nullptr).total;
 }
 
-static size_t mg_warp_doubles(const MargDev& m, int mode) {
-    size_t d = 0;
+static size_t mg_warp_doubles(const MargDev& m, int mode, int N) {
+    size_t d = (size_t)((N + 3) & ~3);
     int mmax = 0;
     for (int g = 0; g < m.G; ++g) { d += ((m.gp[g].M + 2) * (m.gp[g].M + 3) / 2 + 3) & ~3; mmax = std::max(mmax, m.gp[g].M); }
     if (mode != 1) d += ((mmax + 1) * (mmax + 2) / 2 + 3) & ~3;
@@ -1572,7 +1669,7 @@ static int mg_launch_variant(const MargArgs& a, size_t smem, cudaStream_t st) {
 // geometry: warps per CTA from the shared-memory budget, cluster size so that every particle has a warp
 static int mg_geometry(MargArgs& a, int requested_cs, size_t* smem_out, bool allow_wide = true) {
     const MargDev& m = a.m;
-    a.warp_doubles = mg_warp_doubles(m, a.mode);
+    a.warp_doubles = mg_warp_doubles(m, a.mode, a.N);
     a.cta_doubles = mg_cta_doubles(m, a.N);
     const size_t budget = 225 * 1024;
     const size_t cta_b = sizeof(double) * a.cta_doubles, warp_b = sizeof(double) * a.warp_doubles;
