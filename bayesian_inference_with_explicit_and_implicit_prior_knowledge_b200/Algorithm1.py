@@ -34,33 +34,70 @@ class MargDeviceModel:
         if not (1 <= self.G <= _lib.PGAS_MAX_GP):
             raise ValueError(f"{self.G} GPs; this build supports 1..{_lib.PGAS_MAX_GP}")
         n_xi = [np.atleast_1d(np.asarray(m)).shape[0] for m in xi_mean]
-        trans, outp, out_link = SSM.tables(inp, self.n_x, n_xi)
-        if outp.shape[1] != self.n_y:
-            raise ValueError(f"output_model returns {outp.shape[1]} values, observations have {self.n_y}")
+        p = _lib.MargParams()
+        dptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        keep = [obs]
+        self.programs = {}             # model plug-in: which callables run as interpreted expression programs
+
+        def set_program(q, name, prog):
+            ops, consts = np.asarray(prog[0], dtype=np.int32), np.asarray(prog[1], dtype=np.float64)
+            q.len, q.n_const = ops.shape[0], consts.shape[0]
+            q.ops, q.consts = ops.ctypes.data_as(C.POINTER(C.c_int32)), dptr(consts)
+            keep.extend([ops, consts])
+            self.programs[name] = prog
+
+        try:
+            trans, outp, out_link = SSM.tables(inp, self.n_x, n_xi)
+            n_out = outp.shape[1]
+            keep += [trans, outp]
+            p.trans, p.outp = dptr(trans), dptr(outp)
+        except TypeError:
+            # outside the coefficient-table families: expression programs (raises TypeError when outside those as well)
+            tprog, oprog, n_out = SSM.programs(inp, self.n_x, n_xi)
+            out_link = None
+            set_program(p.trans_prog, "transition_model", tprog)
+            set_program(p.outp_prog, "output_model", oprog)
+        if n_out != self.n_y:
+            raise ValueError(f"output_model returns {n_out} values, observations have {self.n_y}")
+        inp2 = np.ascontiguousarray(inp.reshape(T, -1))
+        p.n_u, p.inputs = inp2.shape[1], dptr(inp2)
+        keep.append(inp2)
         state, _ = _tr.variables(self.n_x, n_xi)
         self.hgp, self.M = [], []
-        keep = [obs, trans, outp]
-        p = _lib.MargParams()
         p.n_x, p.n_y, p.n_gp, p.T = self.n_x, self.n_y, self.G, T
-        dptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
         for g in range(self.G):
-            calls = []
-            for t in range(T):
-                c = basis_fcn[g](state, inp[t])
-                if not isinstance(c, _tr.BasisCall):
-                    raise TypeError("basis_fcn must return the value of a generate_Hilbert_BasisFunction basis applied to "
-                                    "an affine (optionally arctan-linked) map of the state")
-                calls.append(c)
-            hgp = calls[0].hgp
+            q = p.gp[g]
+            try:
+                calls = []
+                for t in range(T):
+                    c = basis_fcn[g](state, inp[t])
+                    if not isinstance(c, _tr.BasisCall):
+                        raise TypeError("basis_fcn must return the value of a generate_Hilbert_BasisFunction basis applied to "
+                                        "a map of the state")
+                    calls.append(c)
+                hgp = calls[0].hgp
+                link = calls[0].z.link
+                if link not in (None, "atan") or any(c.hgp is not hgp or c.z.link != link for c in calls):
+                    raise TypeError("basis_fcn: GP input must be affine or arctan-linked, with the same basis at every time step")
+                if any(np.any(c.z.A[:, self.n_x:] != 0) for c in calls):
+                    raise ValueError("basis_fcn must not depend on the interface variables")
+            except TypeError as first:
+                # GP-input map outside the affine / arctan family: one expression program over (state, inputs[t])
+                from . import StateSpaceModel as _ssm
+                from . import models as _md
+                s_sym, _, u_sym = _ssm.program_variables(self.n_x, 0, inp)
+                try:
+                    c = basis_fcn[g](s_sym, u_sym)
+                except TypeError as e:
+                    raise TypeError(f"basis_fcn[{g}] is outside the supported families ({first}; as an expression program: {e})") from e
+                if not isinstance(c, _md.ProgramBasis):
+                    raise TypeError("basis_fcn must return the value of a generate_Hilbert_BasisFunction basis applied to a map of the state")
+                hgp, link, calls = c.hgp, None, []
+                set_program(q.prog, f"basis_fcn[{g}]", (c.ops, c.consts))
             D, M = hgp.D, hgp.M
-            link = calls[0].z.link
-            if link not in (None, "atan") or any(c.hgp is not hgp or c.z.link != link for c in calls):
-                raise TypeError("basis_fcn: GP input must be affine or arctan-linked, with the same basis at every time step")
             gp_in = np.zeros((T, D, self.n_x + 1))
             gp_post = np.zeros((T, D, 2))
             for t, c in enumerate(calls):
-                if np.any(c.z.A[:, self.n_x:] != 0):
-                    raise TypeError("basis_fcn must not depend on the interface variables")
                 gp_in[t, :, :self.n_x] = c.z.A[:, :self.n_x]
                 gp_in[t, :, self.n_x] = c.z.b
                 gp_post[t, :, 0] = c.z.p
@@ -71,7 +108,6 @@ class MargDeviceModel:
                 raise NotImplementedError("interface variables must be scalar (n_xi = 1)")
             eta1 = np.ascontiguousarray(np.asarray(pr[1], dtype=np.float64).reshape(M, M))
             sqrt_eig = np.ascontiguousarray(np.sqrt(hgp.eigen_val))                # src/BasisFunctions.py:79
-            q = p.gp[g]
             q.M, q.D, q.link = M, D, _LINK[link]
             q.sqrt_eig, q.gp_in, q.gp_post, q.eta0, q.eta1 = dptr(sqrt_eig), dptr(gp_in), dptr(gp_post), dptr(eta0), dptr(eta1)
             for d in range(D):
@@ -83,7 +119,7 @@ class MargDeviceModel:
             keep += [sqrt_eig, gp_in, gp_post, eta0, eta1]
             self.hgp.append(hgp)
             self.M.append(M)
-        p.trans, p.outp, p.observations = dptr(trans), dptr(outp), dptr(obs)
+        p.observations = dptr(obs)
         p.out_link = _LINK[out_link]
         Q, R = SSM.process_noise, SSM.output_noise
         for i in range(self.n_x):
@@ -214,8 +250,13 @@ class Algorithm1:
 
     def _squeeze_obs(self, obs):
         # output_mdl returning a scalar (x[0]) gives (T, n); a vector gives (T, n, n_y)
-        probe = self.SSM.output_model(*_tr.variables(self.model.n_x, [1] * self.model.G)[:1], self.inputs[0],
-                                      *_tr.variables(self.model.n_x, [1] * self.model.G)[1])
+        if "output_model" in self.model.programs:                     # model plug-in: probe with the expression tracer
+            from . import StateSpaceModel as _ssm
+            s_sym, xi_sym, u_sym = _ssm.program_variables(self.model.n_x, self.model.G, self.inputs)
+            probe = self.SSM.output_model(s_sym, u_sym, *xi_sym)
+        else:
+            probe = self.SSM.output_model(*_tr.variables(self.model.n_x, [1] * self.model.G)[:1], self.inputs[0],
+                                          *_tr.variables(self.model.n_x, [1] * self.model.G)[1])
         return obs[..., 0] if getattr(probe, "scalar", False) else obs
 
     # ---- reference API

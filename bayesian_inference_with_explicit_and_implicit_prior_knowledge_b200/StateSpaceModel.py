@@ -6,7 +6,10 @@ Constructor and method names follow the reference.  `transition_model(state, inp
 filters never call them per particle — `tables()` traces them once per time step (tracing.py) and
 hands per-step coefficient tables to the CUDA kernels (csrc/marginal.cu).  A callable outside the
 compiled-in family (affine in state / interface variables given the input, optional tanh output
-link) raises at construction of the algorithm object; there is no host fallback.
+link) is traced once more by `programs()`, with the input symbolic as well, into a postfix expression
+program that the kernels interpret per particle (the model plug-in); what is
+outside that instruction set too raises at construction of the algorithm object; there is no host
+fallback.
 
 `draw_state` / `log_likelihood` / `transition_mdl` / `output_mdl` on CONCRETE numbers evaluate the
 user callable directly; the example modules use them once at import time to synthesise their
@@ -79,3 +82,39 @@ class StateSpaceModel:
             outp[t, :, :n_x + G] = g.A
             outp[t, :, n_x + G] = g.b
         return trans, outp, link
+
+    def programs(self, inputs, n_x, n_xi):
+        """Model plug-in (include/pgas_b200.h: pgas_marg_program): transition_model and output_model as postfix
+        expression programs over ([state; xi_1 .. xi_G], inputs[t]).  Returns ((ops, consts), (ops, consts), n_y);
+        raises TypeError when a callable uses something outside the instruction set."""
+        from . import models as _md
+        if any(k != 1 for k in n_xi):
+            raise NotImplementedError("interface variables must be scalar (n_xi = 1), as in every reference example")
+        state, xis, u = program_variables(n_x, len(n_xi), inputs)
+        out = []
+        for name, fn, n_out in (("transition_model", self.transition_model, n_x), ("output_model", self.output_model, None)):
+            try:
+                val = fn(state, u, *xis)
+                if isinstance(val, (list, tuple)):
+                    val = _md.hstack(list(val))
+                if not isinstance(val, _md.Sym):
+                    raise TypeError("the result does not depend on the state")
+                prog = _md.compile_program(val)
+            except TypeError as e:
+                raise TypeError(f"{name} is outside the supported model families (affine in state and interface variables with an "
+                                f"optional tanh output link, or an expression of numpy arithmetic / elementary functions): {e}") from e
+            if n_out is not None and len(val) != n_out:
+                raise TypeError(f"{name} returns {len(val)} values, expected {n_out}")
+            out.append((prog, len(val)))
+        return out[0][0], out[1][0], out[1][1]
+
+
+def program_variables(n_x, G, inputs):
+    """Symbolic (state, [xi_g], input) of the model plug-in: operand k of PUSH_X is state component k for k < n_x and interface
+    variable k - n_x otherwise; a one-dimensional `inputs` array hands the callables a scalar input, as inputs[t] would."""
+    from . import models as _md
+    inputs = np.asarray(inputs)
+    state = _md.Sym([("x", k) for k in range(n_x)])
+    xis = [_md.Sym([("x", n_x + g)]) for g in range(G)]
+    u = _md.Sym([("u", 0)], scalar=True) if inputs.ndim == 1 else _md.Sym([("u", k) for k in range(inputs.shape[1])])
+    return state, xis, u

@@ -116,6 +116,10 @@ class Rng(C.Structure):
     ]
 
 
+class MargProgram(C.Structure):
+    _fields_ = [("len", C.c_int32), ("n_const", C.c_int32), ("ops", C.POINTER(C.c_int32)), ("consts", C.POINTER(C.c_double))]
+
+
 class MargGP(C.Structure):
     _fields_ = [
         ("M", C.c_int32), ("D", C.c_int32),
@@ -126,6 +130,7 @@ class MargGP(C.Structure):
         ("eta0", C.POINTER(C.c_double)), ("eta1", C.POINTER(C.c_double)),
         ("eta2", C.c_double), ("eta3", C.c_double),
         ("xi_mean", C.c_double), ("xi_var", C.c_double),
+        ("prog", MargProgram),
     ]
 
 
@@ -140,6 +145,9 @@ class MargParams(C.Structure):
         ("R", (C.c_double * PGAS_MAX_NY) * PGAS_MAX_NY),
         ("m0", C.c_double * PGAS_MAX_NX),
         ("P0", (C.c_double * PGAS_MAX_NX) * PGAS_MAX_NX),
+        ("n_u", C.c_int32),
+        ("inputs", C.POINTER(C.c_double)),
+        ("trans_prog", MargProgram), ("outp_prog", MargProgram),
     ]
 
 

@@ -76,9 +76,78 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // maxima with a guard on the run-time size, so that they unroll completely and the little vectors (x, xi, z, e) stay in
 // registers; with run-time trip counts they were indexed dynamically and lived in local memory (816 bytes of stack).
 
+// Model plug-in (pgas_b200.h: pgas_marg_program): a user callable outside the coefficient-table families,
+// traced on the host into a postfix program (StateSpaceModel.programs, models.py: Sym) and interpreted here — by every lane with
+// the same operands, like the table forms.  v = [state; interface variables], u = inputs[t].  Out of line and only reachable from
+// the PROG instantiations of the sweep kernel: the table-driven instantiations do not change by a single instruction.
+static __device__ __noinline__ void mg_run_program(const int* __restrict__ ops, const double* __restrict__ consts, int len, int n_out,
+                                                   const double* v, const double* u, double* out) {
+    double st[PGAS_PROG_STACK];
+    int sp = 0;
+    for (int pc = 0; pc < len; ++pc) {
+        const int ins = __ldg(ops + pc), op = ins & 0xff, arg = ins >> 8;
+        if (op <= PGAS_OP_PUSH_C) {
+            st[sp & (PGAS_PROG_STACK - 1)] = (op == PGAS_OP_PUSH_X) ? v[arg] : (op == PGAS_OP_PUSH_U) ? u[arg] : __ldg(consts + arg);
+            ++sp;
+        } else if (op <= PGAS_OP_DIV || op >= PGAS_OP_POW) {
+            const double b = st[(--sp) & (PGAS_PROG_STACK - 1)], a = st[(sp - 1) & (PGAS_PROG_STACK - 1)];
+            double r;
+            switch (op) {
+                case PGAS_OP_ADD: r = a + b; break;
+                case PGAS_OP_SUB: r = a - b; break;
+                case PGAS_OP_MUL: r = a * b; break;
+                case PGAS_OP_DIV: r = a / b; break;
+                case PGAS_OP_POW: r = pow(a, b); break;
+                default: r = atan2(a, b); break;
+            }
+            st[(sp - 1) & (PGAS_PROG_STACK - 1)] = r;
+        } else {
+            const double a = st[(sp - 1) & (PGAS_PROG_STACK - 1)];
+            double r;
+            switch (op) {
+                case PGAS_OP_NEG: r = -a; break;
+                case PGAS_OP_SIN: r = sin(a); break;
+                case PGAS_OP_COS: r = cos(a); break;
+                case PGAS_OP_TAN: r = tan(a); break;
+                case PGAS_OP_TANH: r = tanh(a); break;
+                case PGAS_OP_ATAN: r = atan(a); break;
+                case PGAS_OP_EXP: r = exp(a); break;
+                case PGAS_OP_LOG: r = log(a); break;
+                case PGAS_OP_SQRT: r = sqrt(a); break;
+                default: r = fabs(a); break;
+            }
+            st[(sp - 1) & (PGAS_PROG_STACK - 1)] = r;
+        }
+    }
+    for (int d = 0; d < n_out; ++d) out[d] = st[d];
+}
+
+// operands of a transition / output program: [state; interface variables]
+__device__ __forceinline__ void mg_pack_operands(const MargDev& m, const double* x, const double* xi, double* v) {
+#pragma unroll
+    for (int k = 0; k < MG_NX + MG_GP; ++k) v[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < MG_NX; ++k) if (k < m.n_x) v[k] = x[k];
+    if (xi) {
+#pragma unroll
+        for (int g = 0; g < MG_GP; ++g) if (g < m.G) v[m.n_x + g] = xi[g];
+    }
+}
+
 // GP-input map z = p * link(a . x + b) + q   (pgas_b200.h, group B)
+template <bool PROG>
 __device__ __forceinline__ void gp_input(const MargDev& m, const MargGP& gp, int t, const double* x, double* z) {
     const int nx = m.n_x;
+    if constexpr (PROG) {
+        if (gp.prog.len) {
+            double v[MG_NX + MG_GP], o[PGAS_PROG_STACK];
+            mg_pack_operands(m, x, nullptr, v);
+            mg_run_program(gp.prog.ops, gp.prog.consts, gp.prog.len, gp.D, v, m.inputs + (size_t)t * m.n_u, o);
+#pragma unroll
+            for (int d = 0; d < MG_D; ++d) if (d < gp.D) z[d] = o[d];
+            return;
+        }
+    }
 #pragma unroll
     for (int d = 0; d < MG_D; ++d) {
         if (d < gp.D) {
@@ -133,8 +202,19 @@ __device__ __forceinline__ void basis_eval(const MargGP& gp, const double* z, do
     }
 }
 
+template <bool PROG>
 __device__ __forceinline__ void transition(const MargDev& m, int t, const double* x, const double* xi, double* xn) {
     const int nx = m.n_x, G = m.G, W = nx + G + 1;
+    if constexpr (PROG) {
+        if (m.tprog.len) {
+            double v[MG_NX + MG_GP], o[PGAS_PROG_STACK];
+            mg_pack_operands(m, x, xi, v);
+            mg_run_program(m.tprog.ops, m.tprog.consts, m.tprog.len, nx, v, m.inputs + (size_t)t * m.n_u, o);
+#pragma unroll
+            for (int r = 0; r < MG_NX; ++r) if (r < nx) xn[r] = o[r];
+            return;
+        }
+    }
 #pragma unroll
     for (int r = 0; r < MG_NX; ++r) {
         if (r < nx) {
@@ -149,8 +229,19 @@ __device__ __forceinline__ void transition(const MargDev& m, int t, const double
     }
 }
 
+template <bool PROG>
 __device__ __forceinline__ void output_mdl(const MargDev& m, int t, const double* x, const double* xi, double* y) {
     const int nx = m.n_x, G = m.G, W = nx + G + 1;
+    if constexpr (PROG) {
+        if (m.oprog.len) {
+            double v[MG_NX + MG_GP], o[PGAS_PROG_STACK];
+            mg_pack_operands(m, x, xi, v);
+            mg_run_program(m.oprog.ops, m.oprog.consts, m.oprog.len, m.n_y, v, m.inputs + (size_t)t * m.n_u, o);
+#pragma unroll
+            for (int r = 0; r < MG_NY; ++r) if (r < m.n_y) y[r] = o[r];
+            return;
+        }
+    }
 #pragma unroll
     for (int r = 0; r < MG_NY; ++r) {
         if (r < m.n_y) {
@@ -166,9 +257,10 @@ __device__ __forceinline__ void output_mdl(const MargDev& m, int t, const double
 }
 
 // StateSpaceModel.log_likelihood (src/StateSpaceModel.py:75-87)
+template <bool PROG>
 __device__ __forceinline__ double log_likelihood(const MargDev& m, int t, const double* x, const double* xi) {
     double y[MG_NY], e[MG_NY];
-    output_mdl(m, t, x, xi, y);
+    output_mdl<PROG>(m, t, x, xi, y);
 #pragma unroll
     for (int r = 0; r < MG_NY; ++r) e[r] = (r < m.n_y) ? m.obs[(size_t)t * m.n_y + r] - y[r] : 0.0;
     double q = 0.0;
@@ -688,7 +780,8 @@ struct WarpCtx {
 
 // WIDE: the launch has at most 128 threads per CTA and two CTAs per SM (the wide geometry of mg_geometry), so a thread may use 255
 // registers instead of 128.
-template <int MODE, int ROWS, bool WIDE>
+// PROG: the model carries at least one expression program (model plug-in); only this instantiation contains the interpreter.
+template <int MODE, int ROWS, bool WIDE, bool PROG = false>
 __global__ void __launch_bounds__(WIDE ? 128 : 512, WIDE ? 2 : 1) marg_sweep_kernel(const __grid_constant__ MargArgs a) {
     extern __shared__ double smem[];
     const MargDev& m = a.m;
@@ -851,7 +944,7 @@ __global__ void __launch_bounds__(WIDE ? 128 : 512, WIDE ? 2 : 1) marg_sweep_ker
             if (g >= G) break;
             const MargGP& gp = m.gp[g];
             const int M = gp.M, npk = gp.npk;
-            gp_input(m, gp, t, x, z);
+            gp_input<PROG>(m, gp, t, x, z);
             basis_eval(gp, z, wc.phi, lane);
             double xiv, T2a = 0.0, T3a = 0.0;
             if (t == 0) {
@@ -947,7 +1040,7 @@ __global__ void __launch_bounds__(WIDE ? 128 : 512, WIDE ? 2 : 1) marg_sweep_ker
             // auxiliary interface variable.  Every MG_REFRESH steps (and whenever a downdate loses definiteness) the
             // factors are rebuilt from the statistics.
             const bool more = t < T - 1;
-            if (more) transition(m, t, x, xi, ax1);
+            if (more) transition<PROG>(m, t, x, xi, ax1);
 #pragma unroll
             for (int g = 0; g < MG_GP; ++g) {
                 if (g >= G) break;
@@ -962,8 +1055,8 @@ __global__ void __launch_bounds__(WIDE ? 128 : 512, WIDE ? 2 : 1) marg_sweep_ker
                 const double T3n = (t > 0) ? T3av[g] + 1.0 : 1.0;
                 T2v[g] = T2n;
                 T3v[g] = T3n;
-                if (G > 1 || t == 0) { gp_input(m, gp, t, x, z); basis_eval(gp, z, wc.phi, lane); }     // G == 1: still in wc.phi
-                if (more) { gp_input(m, gp, t + 1, ax1, z); basis_eval(gp, z, wc.inv, lane); }           // phi(aux state) -> wc.inv
+                if (G > 1 || t == 0) { gp_input<PROG>(m, gp, t, x, z); basis_eval(gp, z, wc.phi, lane); }     // G == 1: still in wc.phi
+                if (more) { gp_input<PROG>(m, gp, t + 1, ax1, z); basis_eval(gp, z, wc.inv, lane); }           // phi(aux state) -> wc.inv
                 __syncwarp();
                 // two packed entries per lane and trip (16-byte loads / stores; the tables are padded to even length)
 #pragma unroll 4
@@ -1047,7 +1140,7 @@ __global__ void __launch_bounds__(WIDE ? 128 : 512, WIDE ? 2 : 1) marg_sweep_ker
         }
         // ---- weights and traces
         double lw = 0.0;
-        if (t > 0) lw = log_likelihood(m, t, x, xi) - ldcg(wq + L.ellaux + ac);
+        if (t > 0) lw = log_likelihood<PROG>(m, t, x, xi) - ldcg(wq + L.ellaux + ac);
         if (lane == 0) {
             lwtrace[(size_t)t * N + i] = lw;
             if (t > 0) atrace[(size_t)(t - 1) * N + i] = anc;
@@ -1066,7 +1159,7 @@ __global__ void __launch_bounds__(WIDE ? 128 : 512, WIDE ? 2 : 1) marg_sweep_ker
 #pragma unroll
             for (int r = 0; r < MG_NX; ++r) ax[r] = ax1[r];               // computed before the factor updates
         } else {
-            transition(m, t, x, xi, ax);
+            transition<PROG>(m, t, x, xi, ax);
         }
 #pragma unroll
         for (int g = 0; g < MG_GP; ++g) {
@@ -1074,7 +1167,7 @@ __global__ void __launch_bounds__(WIDE ? 128 : 512, WIDE ? 2 : 1) marg_sweep_ker
             const MargGP& gp = m.gp[g];
             const int M = gp.M, npk = gp.npk, rowM = tri(M), rowV = tri(M + 1);
             double* Ag = wc.A[g];
-            if constexpr (MODE == 0) gp_input(m, gp, t + 1, ax, z);
+            if constexpr (MODE == 0) gp_input<PROG>(m, gp, t + 1, ax, z);
             if constexpr (MODE == 1) {
                 // Algorithm3: the factors, the auxiliary interface variable and the log-determinants were produced in the second
                 // GP pass above.  g_t - g_T (src/Algorithm3.py:92-106): only the particle-dependent terms of
@@ -1108,7 +1201,7 @@ __global__ void __launch_bounds__(WIDE ? 128 : 512, WIDE ? 2 : 1) marg_sweep_ker
                 __syncwarp();
             }
         }
-        const double ell = log_likelihood(m, t + 1, ax, axi);
+        const double ell = log_likelihood<PROG>(m, t + 1, ax, axi);
         const double lwa = ell + lw;
         if (lane == 0) {
             wp[L.ellaux + i] = ell;
@@ -1258,7 +1351,7 @@ __global__ void __launch_bounds__(RS_THREADS) marg_refstats_kernel(const __grid_
             for (int s = warp; s < nt; s += RS_THREADS / 32) {
                 double x[MG_NX], z[MG_D];
                 for (int k = 0; k < m.n_x; ++k) x[k] = xt[(size_t)(t0 + s) * m.n_x + k];
-                gp_input(m, gp, t0 + s, x, z);
+                gp_input<true>(m, gp, t0 + s, x, z);
                 basis_eval(gp, z, phis + s * M, lane);
                 if (lane == 0) xis[s] = xit[t0 + s];
             }
@@ -1384,10 +1477,10 @@ __global__ void marg_outputs_kernel(const MargDev m, const double* __restrict__ 
         for (int k = 0; k < m.n_x; ++k) x[k] = states[q * m.n_x + k];
         for (int g = 0; g < m.G; ++g) xv[g] = xi[((size_t)g * m.T + t) * n + i];
         if (obs_out) {
-            output_mdl(m, t, x, xv, y);
+            output_mdl<true>(m, t, x, xv, y);
             for (int r = 0; r < m.n_y; ++r) obs_out[q * m.n_y + r] = y[r];
         }
-        if (ll_out) ll_out[q] = log_likelihood(m, t, x, xv);
+        if (ll_out) ll_out[q] = log_likelihood<true>(m, t, x, xv);
     }
 }
 
@@ -1477,13 +1570,37 @@ static void mg_tri_inv(const double* Lo, int n, double* W, double* logdet_half) 
     }
 }
 
+// a program of the model plug-in: known opcodes, operands in range, stack within bounds, exactly n_out results (len 0: no program)
+static int mg_check_program(const pgas_marg_program& q, int n_var, int n_u, int n_out, const char* what) {
+    if (q.len == 0) return 0;
+    if (q.len < 0 || q.len > PGAS_MAX_PROG || q.n_const < 0 || q.n_const > PGAS_MAX_PROG || !q.ops || (q.n_const > 0 && !q.consts))
+        PGAS_FAIL(-2, "%s: expression program of %d instructions / %d constants (limits %d)", what, q.len, q.n_const, PGAS_MAX_PROG);
+    int sp = 0;
+    for (int i = 0; i < q.len; ++i) {
+        const int op = q.ops[i] & 0xff, arg = q.ops[i] >> 8;
+        if (op == PGAS_OP_PUSH_X) { if (arg < 0 || arg >= n_var) PGAS_FAIL(-2, "%s: instruction %d reads variable %d of %d", what, i, arg, n_var); ++sp; }
+        else if (op == PGAS_OP_PUSH_U) { if (arg < 0 || arg >= n_u) PGAS_FAIL(-2, "%s: instruction %d reads input component %d of %d", what, i, arg, n_u); ++sp; }
+        else if (op == PGAS_OP_PUSH_C) { if (arg < 0 || arg >= q.n_const) PGAS_FAIL(-2, "%s: instruction %d reads constant %d of %d", what, i, arg, q.n_const); ++sp; }
+        else if ((op >= PGAS_OP_ADD && op <= PGAS_OP_DIV) || op == PGAS_OP_POW || op == PGAS_OP_ATAN2) { if (sp < 2) PGAS_FAIL(-2, "%s: instruction %d: stack underflow", what, i); --sp; }
+        else if (op >= PGAS_OP_NEG && op <= PGAS_OP_ABS) { if (sp < 1) PGAS_FAIL(-2, "%s: instruction %d: stack underflow", what, i); }
+        else PGAS_FAIL(-2, "%s: instruction %d: unknown opcode %d", what, i, op);
+        if (sp > PGAS_PROG_STACK) PGAS_FAIL(-2, "%s: instruction %d: more than %d operands on the stack", what, i, PGAS_PROG_STACK);
+    }
+    if (sp != n_out) PGAS_FAIL(-2, "%s: expression program leaves %d values, expected %d", what, sp, n_out);
+    return 0;
+}
+
 extern "C" int pgas_marg_model_create(const pgas_marg_params* p, pgas_marg_model** out) {
     if (!p || !out) PGAS_FAIL(-1, "pgas_marg_model_create: null argument");
     if (p->n_x < 1 || p->n_x > MG_NX) PGAS_FAIL(-2, "n_x=%d outside [1,%d]", p->n_x, MG_NX);
     if (p->n_y < 1 || p->n_y > MG_NY) PGAS_FAIL(-2, "n_y=%d outside [1,%d]", p->n_y, MG_NY);
     if (p->n_gp < 1 || p->n_gp > MG_GP) PGAS_FAIL(-2, "n_gp=%d outside [1,%d]", p->n_gp, MG_GP);
     if (p->T < 2) PGAS_FAIL(-2, "need T >= 2 (T=%d)", p->T);
-    if (!p->trans || !p->outp || !p->observations) PGAS_FAIL(-1, "trans / outp / observations must not be null");
+    if (!p->observations) PGAS_FAIL(-1, "observations must not be null");
+    if ((!p->trans && p->trans_prog.len <= 0) || (!p->outp && p->outp_prog.len <= 0)) PGAS_FAIL(-1, "trans / outp: neither a table nor a program");
+    if (p->n_u < 0 || p->n_u > 64 || (p->n_u > 0 && !p->inputs)) PGAS_FAIL(-2, "n_u=%d outside [0,64] or inputs null", p->n_u);
+    if (int rc = mg_check_program(p->trans_prog, p->n_x + p->n_gp, p->n_u, p->n_x, "transition_model")) return rc;
+    if (int rc = mg_check_program(p->outp_prog, p->n_x + p->n_gp, p->n_u, p->n_y, "output_model")) return rc;
     if (p->out_link != PGAS_LINK_IDENTITY && p->out_link != PGAS_LINK_TANH) PGAS_FAIL(-2, "unknown output link %d", p->out_link);
     MargDev dm;
     memset(&dm, 0, sizeof(dm));
@@ -1520,7 +1637,9 @@ extern "C" int pgas_marg_model_create(const pgas_marg_params* p, pgas_marg_model
         const pgas_marg_gp& q = p->gp[g];
         if (q.M < 1 || q.M > MG_MAX_M) PGAS_FAIL(-2, "GP %d: M=%d outside [1,%d]", g, q.M, MG_MAX_M);
         if (q.D < 1 || q.D > MG_D) PGAS_FAIL(-2, "GP %d: D=%d outside [1,%d]", g, q.D, MG_D);
-        if (!q.sqrt_eig || !q.gp_in || !q.gp_post || !q.eta0 || !q.eta1) PGAS_FAIL(-1, "GP %d: null table", g);
+        if (!q.sqrt_eig || !q.eta0 || !q.eta1) PGAS_FAIL(-1, "GP %d: null table", g);
+        if ((!q.gp_in || !q.gp_post) && q.prog.len <= 0) PGAS_FAIL(-1, "GP %d: neither input tables nor a program", g);
+        if (int rc = mg_check_program(q.prog, p->n_x, p->n_u, q.D, "basis_fcn")) return rc;
         if (q.link != PGAS_LINK_IDENTITY && q.link != PGAS_LINK_ATAN) PGAS_FAIL(-2, "GP %d: unknown input link %d", g, q.link);
         if (!(q.xi_var > 0.0)) PGAS_FAIL(-3, "GP %d: init_int_var_cov must be positive", g);
         MargGP& d = dm.gp[g];
@@ -1536,6 +1655,7 @@ extern "C" int pgas_marg_model_create(const pgas_marg_params* p, pgas_marg_model
         total += al(sizeof(double) * q.M * q.D) + al(sizeof(double) * (size_t)T * q.D * (nx + 1)) + al(sizeof(double) * (size_t)T * q.D * 2) +
                  al(sizeof(double) * q.M) + al(sizeof(double) * d.npk);
     }
+    total += al(sizeof(double) * (size_t)T * std::max(p->n_u, 1)) + (size_t)(2 + G) * (al(sizeof(int) * PGAS_MAX_PROG) + al(sizeof(double) * PGAS_MAX_PROG));
     char* arena = nullptr;
     PGAS_CUDA(cudaMalloc((void**)&arena, total));
     size_t o = 0;
@@ -1545,15 +1665,31 @@ extern "C" int pgas_marg_model_create(const pgas_marg_params* p, pgas_marg_model
         o += al(bytes);
         return d;
     };
-    dm.trans = up(p->trans, sizeof(double) * (size_t)T * nx * W);
-    dm.outp = up(p->outp, sizeof(double) * (size_t)T * ny * W);
+    auto up_prog = [&](const pgas_marg_program& q, int n_out) {
+        MargProg d;
+        d.ops = nullptr; d.consts = nullptr; d.len = 0; d.n_out = n_out;
+        if (q.len > 0) {
+            d.ops = (const int*)up(q.ops, sizeof(int) * q.len);
+            d.consts = q.n_const > 0 ? up(q.consts, sizeof(double) * q.n_const) : nullptr;
+            d.len = q.len;
+            dm.any_prog = 1;
+        }
+        return d;
+    };
+    dm.trans = p->trans ? up(p->trans, sizeof(double) * (size_t)T * nx * W) : nullptr;
+    dm.outp = p->outp ? up(p->outp, sizeof(double) * (size_t)T * ny * W) : nullptr;
     dm.obs = up(p->observations, sizeof(double) * (size_t)T * ny);
+    dm.n_u = p->n_u;
+    dm.inputs = p->n_u > 0 ? up(p->inputs, sizeof(double) * (size_t)T * p->n_u) : nullptr;
+    dm.tprog = up_prog(p->trans_prog, nx);
+    dm.oprog = up_prog(p->outp_prog, ny);
     for (int g = 0; g < G; ++g) {
         const pgas_marg_gp& q = p->gp[g];
         MargGP& d = dm.gp[g];
         d.sqrt_eig = up(q.sqrt_eig, sizeof(double) * q.M * q.D);
-        d.gp_in = up(q.gp_in, sizeof(double) * (size_t)T * q.D * (nx + 1));
-        d.gp_post = up(q.gp_post, sizeof(double) * (size_t)T * q.D * 2);
+        d.gp_in = q.gp_in ? up(q.gp_in, sizeof(double) * (size_t)T * q.D * (nx + 1)) : nullptr;
+        d.gp_post = q.gp_post ? up(q.gp_post, sizeof(double) * (size_t)T * q.D * 2) : nullptr;
+        d.prog = up_prog(q.prog, q.D);
         d.p0 = up(q.eta0, sizeof(double) * q.M);
         d.p1 = up(p1pk[g].data(), sizeof(double) * d.npk);
     }
@@ -1630,9 +1766,9 @@ static int mg_fill_rng(MargArgs& a, const pgas_marg_rng* rng) {
     return 0;
 }
 
-template <int MODE, int ROWS, bool WIDE>
+template <int MODE, int ROWS, bool WIDE, bool PROG = false>
 static int mg_launch_variant(const MargArgs& a, size_t smem, cudaStream_t st) {
-    auto kern = marg_sweep_kernel<MODE, ROWS, WIDE>;
+    auto kern = marg_sweep_kernel<MODE, ROWS, WIDE, PROG>;
     PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (a.CS > 8) PGAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     if (a.sw_barrier) {
@@ -1718,7 +1854,10 @@ static int mg_launch_sweep(MargArgs& a, int requested_cs, cudaStream_t st) {
         PGAS_CUDA(cudaGetDevice(&dev));
         PGAS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const bool wide = a.NW <= 4 && (!a.sw_barrier || (long long)a.n_chains * a.CS <= 2ll * sms) && !getenv("PGAS_MARG_NARROW");
-        if (a.mode == 0) {
+        if (a.m.any_prog) {
+            // model plug-in: one general instantiation per mode (four register rows cover every M, 128 registers every geometry)
+            rc = a.mode == 0 ? mg_launch_variant<0, 4, false, true>(a, smem, st) : mg_launch_variant<1, 4, false, true>(a, smem, st);
+        } else if (a.mode == 0) {
             if (wide) rc = small ? mg_launch_variant<0, 2, true>(a, smem, st) : mg_launch_variant<0, 4, true>(a, smem, st);
             else rc = small ? mg_launch_variant<0, 2, false>(a, smem, st) : mg_launch_variant<0, 4, false>(a, smem, st);
         } else {

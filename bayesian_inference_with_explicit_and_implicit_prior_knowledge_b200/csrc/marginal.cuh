@@ -12,6 +12,13 @@ constexpr int MG_MAX_M = 128;          // 4 register rows per lane in the triang
 
 enum { PURPOSE_XI0 = 5, PURPOSE_TVAR = 6 /* + GP index */ };
 
+// Model plug-in (pgas_b200.h: pgas_marg_program): a postfix expression program in the model's arena; len = 0: use the tables
+struct MargProg {
+    const int* ops;
+    const double* consts;
+    int len, n_out;
+};
+
 struct MargGP {
     int M, D, link, npk;               // npk = M (M + 1) / 2 packed lower-triangular entries
     double center[MG_D], L[MG_D], sqrt_invL[MG_D];
@@ -22,6 +29,7 @@ struct MargGP {
     const double* p1;                  // (npk)  prior eta1, packed lower triangle of its symmetric part
     double p2, p3;
     double xi_mean, xi_sd;
+    MargProg prog;                     // GP-input map as a program over (state, inputs[t])
 };
 
 struct MargDev {
@@ -35,6 +43,10 @@ struct MargDev {
     double Q_logc;                     // -n_x/2 log(2 pi) - sum log diag chol(Q)
     double Rw[MG_NY][MG_NY], R_logc;
     double m0[MG_NX], P0c[MG_NX][MG_NX];
+    // model plug-in: any_prog selects the interpreting instantiation of the sweep kernel
+    int n_u, any_prog;
+    const double* inputs;              // (T, n_u)
+    MargProg tprog, oprog;             // transition / output model over ([state; xi], inputs[t])
 };
 
 struct pgas_marg_model {

@@ -112,7 +112,7 @@ const char* pgas_last_error(void);
 int pgas_version(void);
 /* PGAS_ABI_VERSION of the header the library was compiled against: a binding compares it with its own copy of
  * the header before the first call (struct layouts and argument orders are only meaningful when they agree). */
-#define PGAS_ABI_VERSION 202
+#define PGAS_ABI_VERSION 203
 int pgas_abi_version(void);
 int pgas_device_count(void);
 /* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */
@@ -249,8 +249,21 @@ int pgas_philox_sweep_variates_f64(const pgas_rng* rng, int32_t n_chains, int32_
  * which covers every shipped example (RK4 of src/SingleMassOscillator.py:32-44 and src/EMPS.py:177-183
  * is affine in (x, xi); src/Vehicle.py:60-128 is affine in (x, xi) given u_t, with a tanh output and
  * the atan slip angles of :50-57).  Interface variables are scalar (n_xi = 1), as in every example.
+ *
+ * Model plug-in: a transition_model / output_model / GP-input map OUTSIDE those families is traced once,
+ * with the input symbolic as well, into a postfix expression program (same instruction set as PGAS_MAP_PROGRAM above) that the
+ * kernels interpret per particle.  Operands: PGAS_OP_PUSH_X k = state component k for k < n_x, interface variable k - n_x
+ * otherwise (GP-input programs read the state only); PGAS_OP_PUSH_U k = component k of inputs[t]; PGAS_OP_PUSH_C k = consts[k].
+ * After the last instruction the stack holds the n_x (transition), n_y (output) or D (GP input) results in order.  A program of
+ * length 0 means "use the table"; with a program the corresponding table pointer may be null.
  * ==================================================================================== */
 enum { PGAS_LINK_IDENTITY = 0, PGAS_LINK_ATAN = 1, PGAS_LINK_TANH = 2 };
+
+typedef struct pgas_marg_program {
+    int32_t len, n_const;          /* instructions (<= PGAS_MAX_PROG), constants (<= PGAS_MAX_PROG) */
+    const int32_t* ops;            /* (len) host: opcode | (argument << 8) */
+    const double* consts;          /* (n_const) host */
+} pgas_marg_program;
 
 typedef struct pgas_marg_gp {
     int32_t M, D;
@@ -264,6 +277,7 @@ typedef struct pgas_marg_gp {
     const double* eta1;            /* (M, M) host */
     double eta2, eta3;
     double xi_mean, xi_var;        /* init_int_var_mean / init_int_var_cov (src/Algorithm1.py:36-37) */
+    pgas_marg_program prog;        /* len > 0: z = program(state, inputs[t]) instead of gp_in / gp_post / link */
 } pgas_marg_gp;
 
 typedef struct pgas_marg_params {
@@ -277,6 +291,10 @@ typedef struct pgas_marg_params {
     double R[PGAS_MAX_NY][PGAS_MAX_NY];   /* output noise */
     double m0[PGAS_MAX_NX];
     double P0[PGAS_MAX_NX][PGAS_MAX_NX];
+    int32_t n_u;                   /* components of inputs[t] the programs may read (0: none) */
+    const double* inputs;          /* (T, n_u) host; may be null when n_u = 0 */
+    pgas_marg_program trans_prog;  /* len > 0: x' = program(state, xi, inputs[t]) instead of trans */
+    pgas_marg_program outp_prog;   /* len > 0: y  = program(state, xi, inputs[t]) instead of outp / out_link */
 } pgas_marg_params;
 
 typedef struct pgas_marg_model pgas_marg_model;

@@ -88,6 +88,34 @@ def make_marg_problem(kind, T=24, N=32, M=None, seed=0):
             Y[t] = S.f_y(x[t], inputs[t], mf, mr) + np.sqrt(np.diag(R)) * rng.normal(size=2)
             if t + 1 < T:
                 x[t + 1] = S.f_x(x[t], inputs[t], mf, mr, dt)
+    elif kind == "plugin":
+        # model plug-in: a driven pendulum with a GP friction torque — NOTHING of it is in the coefficient-table
+        # families: sin / cos / products of the state in the transition, a non-affine output without a tanh link, a GP input that
+        # is a sine of the state.  The product gets the per-particle callables below, the oracle their batched twins.
+        M = M or 10
+        dom = np.array([-6.0, 6.0])
+        hgp, sd = BF.generate_Hilbert_BasisFunction(M, dom, 12.0 / M, 10.0)
+        ohgp, osd = OB.generate_Hilbert_BasisFunction(M, dom, 12.0 / M, 10.0)
+        dt = 0.02
+        Q, R = np.diag([1e-6, 1e-5]), np.array([[1e-3]])
+        inputs = 3.0 * np.sin(np.arange(T) / 7.0 + 0.2)
+        ssm = SSMm.StateSpaceModel(Q, R, lambda s, u, *xi: plugin_f(s, u, xi[0], dt), lambda s, u, *xi: plugin_g(s, u))
+        ossm = OMg.SSM(Q, R, lambda x, u, *xi: np.stack([x[:, 0] + dt * x[:, 1], x[:, 1] + dt * (-9.81 * np.sin(x[:, 0]) - np.reshape(xi[0], -1)
+                                                                                                  + u * np.cos(x[:, 0]))], axis=1),
+                       lambda x, u, *xi: 1.5 * np.sin(x[:, 0]) + 0.05 * x[:, 1] * x[:, 1])
+        m0, P0 = np.array([0.3, 0.0]), np.diag([1e-4, 1e-4])
+        xi_mean, xi_cov = [np.zeros(1)], [np.diag([1e-6])]
+        priors = [BI.prior_mniw_2naturalPara(np.zeros((1, M)), np.diag(sd), np.eye(1), 3)]
+        opriors = [OM.prior_mniw_2naturalPara(np.zeros((1, M)), np.diag(osd), np.eye(1), 3)]
+        bases = [lambda s, u: hgp(plugin_z(s))]
+        obases = [lambda x, u: ohgp.batch(2.0 * np.sin(np.atleast_2d(x)[:, 0]) + np.atleast_2d(x)[:, 1])]
+        x = np.zeros((T, 2))
+        x[0] = m0
+        Y = np.zeros(T)
+        for t in range(T):
+            Y[t] = plugin_g(x[t], inputs[t]) + np.sqrt(R[0, 0]) * rng.normal()
+            if t + 1 < T:
+                x[t + 1] = plugin_f(x[t], inputs[t], np.array([0.4 * x[t, 1] + 0.2 * np.tanh(5.0 * x[t, 1])]), dt)
     else:
         raise ValueError(kind)
     p["prod_kwargs"] = dict(N_samples=N, observations=Y, inputs=inputs, SSM=ssm, init_state_mean=m0, init_state_cov=P0,
@@ -96,6 +124,18 @@ def make_marg_problem(kind, T=24, N=32, M=None, seed=0):
     p["G"], p["n_x"], p["M"] = len(bases), 2, M
     p["prior_df"] = [float(pr[3]) for pr in priors]
     return p
+
+
+def plugin_f(s, u, xi, dt):
+    return np.hstack([s[0] + dt * s[1], s[1] + dt * (-9.81 * np.sin(s[0]) - xi + u * np.cos(s[0]))])
+
+
+def plugin_g(s, u):
+    return 1.5 * np.sin(s[0]) + 0.05 * s[1] * s[1]
+
+
+def plugin_z(s):
+    return 2.0 * np.sin(s[0]) + s[1]
 
 
 def predictive_df(prob, lam):

@@ -31,6 +31,8 @@ def _tolerance(run_oracle, V, ref, fields):
 
 @pytest.mark.parametrize("kind,T,N,M,cs", [("smo", 24, 32, 12, 0), ("smo", 12, 200, 41, 0), ("emps", 30, 48, 9, 1),
                                            ("vehicle", 24, 40, 8, 0), ("smo", 16, 70, 12, 4),
+                                           # model plug-in: transition / output / GP-input map as interpreted expression programs
+                                           ("plugin", 24, 32, 10, 0), ("plugin", 40, 200, 20, 0), ("plugin", 20, 40, 10, 2),
                                            # the shipped sizes (BASELINE configs[0..2]: N = 200; M = 41 | 2 x 20 | 9), 60-100 steps
                                            ("smo", 100, 200, 41, 0), ("vehicle", 60, 200, 20, 0), ("emps", 100, 200, 9, 0)])
 def test_algorithm1_matches_oracle(kind, T, N, M, cs):
@@ -60,6 +62,7 @@ def test_algorithm1_matches_oracle(kind, T, N, M, cs):
 
 @pytest.mark.parametrize("kind,T,N,M,cs", [("smo", 24, 32, 12, 0), ("smo", 10, 200, 41, 0), ("emps", 30, 48, 9, 2),
                                            ("vehicle", 24, 40, 8, 0),
+                                           ("plugin", 24, 32, 10, 0), ("plugin", 40, 200, 20, 0), ("plugin", 20, 40, 10, 2),     # model plug-in
                                            # the shipped sizes, three refresh cycles of the rank-one updated factors
                                            ("smo", 100, 200, 41, 0), ("vehicle", 60, 200, 20, 0)])
 def test_algorithm3_matches_oracle(kind, T, N, M, cs):
@@ -102,7 +105,7 @@ def test_algorithm3_matches_oracle(kind, T, N, M, cs):
             assert HM.rel_err(_np(r["xi_traj"][0, g]), ref["xi_traj"][g][:, 0]) < REL
 
 
-@pytest.mark.parametrize("kind", ["smo", "vehicle"])
+@pytest.mark.parametrize("kind", ["smo", "vehicle", "plugin"])
 def test_algorithm2_matches_oracle(kind):
     import torch
     from oracle import marginal as OMg
@@ -263,3 +266,24 @@ def test_replicas_api_single_process():
     r1 = DI.run_replicas_distributed(A2, key, x0, [np.zeros(14)], 1)
     np.testing.assert_array_equal(_np(r3["x_trace"][0]), _np(r1["x_trace"][0]))
     assert not np.array_equal(_np(r3["x_trace"][1, 1:]), _np(r3["x_trace"][0, 1:]))
+
+
+def test_plugin_model_runs_as_expression_programs():
+    """model plug-in (src/StateSpaceModel.py:19-30): every callable of the pendulum model is outside the
+    coefficient-table families, so all three run as interpreted programs; the reference-API call returns the 8-tuple and its
+    observation / log-likelihood traces are the user's output model on the state trace"""
+    prob = HM.make_marg_problem("plugin", T=30, N=48, M=10, seed=2)
+    A1 = helpers.pkg("Algorithm1").Algorithm1(forgetting_factor=0.999, **prob["prod_kwargs"])
+    assert set(A1.model.programs) == {"transition_model", "output_model", "basis_fcn[0]"}
+    out = A1(helpers.pkg("random").key(5))
+    assert len(out) == 8
+    st, obs, ll = out[0], out[6], out[7]
+    assert st.shape == (30, 48, 2) and obs.shape == (30, 48) and np.isfinite(st).all()
+    want = 1.5 * np.sin(st[..., 0]) + 0.05 * st[..., 1] ** 2
+    assert np.allclose(obs, want, rtol=1e-12, atol=1e-14)
+    Y = prob["prod_kwargs"]["observations"]
+    want_ll = -0.5 * (Y[:, None] - want) ** 2 / 1e-3 - 0.5 * np.log(2 * np.pi * 1e-3)
+    assert np.allclose(ll, want_ll, rtol=1e-9, atol=1e-9)
+    # a shipped model keeps the table-driven kernels
+    smo = HM.make_marg_problem("smo", T=8, N=16, M=6)
+    assert helpers.pkg("Algorithm1").Algorithm1(forgetting_factor=0.999, **smo["prod_kwargs"]).model.programs == {}

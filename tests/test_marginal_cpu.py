@@ -154,6 +154,46 @@ def test_tracer_rejects_models_outside_the_families():
     assert c.z.link == "atan" and np.allclose(c.z.A, [[0, 3, 0]]) and np.allclose(c.z.b, [1]) and np.allclose(c.z.p, [-1]) and np.allclose(c.z.q, [2])
 
 
+def test_plugin_model_compiles_to_expression_programs():
+    """model plug-in (src/StateSpaceModel.py:19-30 'any callable'): a transition / output model / GP-input map
+    outside the coefficient-table families is rejected by the affine tracer and traced into postfix programs; the host mirror of
+    the device interpreter reproduces the callables and the oracle's batched twins"""
+    MD, SSMm, L = helpers.pkg("models"), helpers.pkg("StateSpaceModel"), helpers.pkg("_lib")
+    prob = HM.make_marg_problem("plugin", T=12, N=8, M=6)
+    ssm, inputs = prob["prod_kwargs"]["SSM"], prob["prod_kwargs"]["inputs"]
+    with pytest.raises(TypeError):
+        ssm.tables(inputs, 2, [1])
+    tprog, oprog, n_y = ssm.programs(inputs, 2, [1])
+    assert n_y == 1 and max(len(tprog[0]), len(oprog[0])) <= L.PGAS_MAX_PROG
+    s_sym, _, u_sym = SSMm.program_variables(2, 0, inputs)
+
+    class FakeBasis:                                   # stands in for HilbertBasis.__call__ without a device
+        D, M = 1, 6
+
+        def __call__(self, x):
+            return MD.ProgramBasis(self, x)
+    zprog = FakeBasis()(HM.plugin_z(s_sym))
+    rng = np.random.default_rng(1)
+    om = prob["oracle"]
+    for t in range(12):
+        x, xi = rng.normal(size=2), rng.normal(size=1)
+        v, u = np.concatenate([x, xi]), np.atleast_1d(inputs[t])
+        want_f = ssm.transition_model(x, inputs[t], xi)
+        assert np.allclose(MD.run_program(*tprog, v, u), want_f, rtol=1e-14, atol=1e-15)
+        assert np.allclose(om.ssm.transition(x[None], inputs[t], xi[None]), want_f[None], rtol=1e-14, atol=1e-15)
+        want_g = ssm.output_model(x, inputs[t], xi)
+        assert np.allclose(MD.run_program(*oprog, v, u), want_g, rtol=1e-14, atol=1e-15)
+        assert np.allclose(om.ssm.output(x[None], inputs[t], xi[None]), want_g, rtol=1e-14, atol=1e-15)
+        assert np.allclose(MD.run_program(zprog.ops, zprog.consts, x, u), HM.plugin_z(x), rtol=1e-14, atol=1e-15)
+    # outside the instruction set: raises, no host fallback
+    bad = SSMm.StateSpaceModel(np.eye(2), np.eye(1), lambda s, u, *xi: np.hstack([np.floor(s[0]), xi[0]]), lambda s, u, *xi: s[0])
+    with pytest.raises(TypeError):
+        bad.programs(inputs, 2, [1])
+    # the shipped models stay on the coefficient tables
+    S = helpers.pkg("SingleMassOscillator")
+    S.SMO_SSM.tables(S.F_ext[:3], 2, [1])
+
+
 # ------------------------------------------------------------------------------- ABI
 def test_marginal_struct_layouts_match_the_header(tmp_path):
     """compile a tiny C program against include/pgas_b200.h and compare sizeof / offsetof with the ctypes mirrors"""
@@ -161,14 +201,17 @@ def test_marginal_struct_layouts_match_the_header(tmp_path):
     L = helpers.pkg("_lib")
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pgas_b200.h"\nint main(void){\n'
-                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pgas_marg_gp), sizeof(pgas_marg_params), sizeof(pgas_marg_rng),'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pgas_marg_program), offsetof(pgas_marg_gp, prog),'
+                   'offsetof(pgas_marg_params, inputs), offsetof(pgas_marg_params, outp_prog),'
+                   'sizeof(pgas_marg_gp), sizeof(pgas_marg_params), sizeof(pgas_marg_rng),'
                    'offsetof(pgas_marg_gp, gp_in), offsetof(pgas_marg_gp, xi_var), offsetof(pgas_marg_params, trans),'
                    'offsetof(pgas_marg_params, Q), offsetof(pgas_marg_params, P0), offsetof(pgas_marg_rng, TS), sizeof(pgas_model_params));'
                    'return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    want = [C.sizeof(L.MargGP), C.sizeof(L.MargParams), C.sizeof(L.MargRng), L.MargGP.gp_in.offset, L.MargGP.xi_var.offset,
+    want = [C.sizeof(L.MargProgram), L.MargGP.prog.offset, L.MargParams.inputs.offset, L.MargParams.outp_prog.offset,
+            C.sizeof(L.MargGP), C.sizeof(L.MargParams), C.sizeof(L.MargRng), L.MargGP.gp_in.offset, L.MargGP.xi_var.offset,
             L.MargParams.trans.offset, L.MargParams.Q.offset, L.MargParams.P0.offset, L.MargRng.TS.offset, C.sizeof(L.ModelParams)]
     assert got == want
 
