@@ -13,6 +13,7 @@ import numpy as np
 
 from . import models as _models
 from . import random as _random
+from . import stats as _stats
 from ._examples import rk4_step
 from .Algorithm1 import Algorithm1
 from .Algorithm2 import Algorithm2
@@ -148,5 +149,7 @@ EMPS_Algorithm1 = Algorithm1(N_samples=N_particles, forgetting_factor=forget_fac
 EMPS_Algorithm2 = Algorithm2(N_samples=N_particles, N_iterations=N_PGAS_iter, **_common)
 
 EMPS_PGAS_baseline = PGAS(N_samples=N_particles, N_iterations=N_PGAS_iter * 3, observations=Y, inputs=ctrl_input,
-                          init_state_mean=x0, init_state_cov=P0, likelihood_fcn=_models.gaussian_likelihood(f_y, R),
+                          init_state_mean=x0, init_state_cov=P0,
+                          # the reference's own lambda (src/EMPS.py:250-252) with this package's stats module in place of jax.scipy.stats
+                          likelihood_fcn=lambda obs, state, input: np.squeeze(_stats.multivariate_normal.logpdf(obs, mean=f_y(state), cov=R)),
                           GP_prior=GP_prior_PGAS, basis_fcn=basis_fcn_f_PGAS)

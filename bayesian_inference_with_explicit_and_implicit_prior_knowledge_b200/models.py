@@ -392,14 +392,42 @@ class _LazyLikelihood:
         return self._build(n_x)
 
 
-def resolve_likelihood(lik, n_x):
+class ObservationMarker:
+    """stands for `obs` while a reference-style likelihood_fcn(obs, state, input) is traced"""
+
+
+class GaussianLogpdfTrace:
+    """value of stats.multivariate_normal.logpdf(obs, mean=<affine in the state>, cov=R) under tracing; np.squeeze passes it through"""
+
+    def __init__(self, mean, cov):
+        self.mean, self.cov = mean, np.atleast_2d(np.asarray(cov, dtype=np.float64))
+
+    def __array_function__(self, func, types, args, kwargs):
+        if func in (np.squeeze, np.asarray, np.atleast_1d, np.ravel):
+            return self
+        raise TypeError(f"numpy.{func.__name__} of a traced log-density is not supported")
+
+    def squeeze(self, *a, **k):
+        return self
+
+
+def resolve_likelihood(lik, n_x, n_u=0):
     if isinstance(lik, GaussianLikelihood):
         return lik
     if isinstance(lik, _LazyLikelihood):
         return lik.resolve(n_x)
-    raise TypeError("likelihood_fcn must be built with models.gaussian_likelihood(f_y, R) "
-                    "(Gaussian observation of an affine output map); arbitrary Python callables "
-                    "cannot run inside the persistent CUDA sweep")
+    if callable(lik):
+        # the reference's own form (src/EMPS.py:250-252): lambda obs, state, input: squeeze(multivariate_normal.logpdf(obs, mean=f_y(state), cov=R))
+        # written against this package's `stats` module; traced once with a symbolic state
+        s, u = _tracers(n_x, n_u)
+        out = lik(ObservationMarker(), s, u if n_u > 0 else np.zeros(0))
+        if isinstance(out, GaussianLogpdfTrace):
+            if np.any(out.mean.A[:, n_x:] != 0):
+                raise TypeError("likelihood_fcn: the output map must not depend on the input")
+            return GaussianLikelihood(out.mean.A[:, :n_x], out.mean.b, out.cov)
+    raise TypeError("likelihood_fcn must be a Gaussian observation of an affine output map: either models.gaussian_likelihood(f_y, R) "
+                    "or the reference's lambda written with this package's stats.multivariate_normal.logpdf(obs, mean=f_y(state), cov=R); "
+                    "other Python callables cannot run inside the CUDA sweep")
 
 
 # ----------------------------------------------------------------------------- device model
@@ -418,7 +446,7 @@ class DeviceModel:
         P0 = np.atleast_2d(np.asarray(P0, dtype=np.float64))
         self.n_x, self.n_y, self.n_u = m0.shape[0], obs.shape[1], inp.shape[1]
         self.basis = trace_basis(basis, self.n_x, self.n_u)
-        self.likelihood = resolve_likelihood(likelihood, self.n_x)
+        self.likelihood = resolve_likelihood(likelihood, self.n_x, self.n_u)
         hgp = self.basis.hgp
         self.M, self.D = hgp.M, hgp.D
         self.flags = int(flags)

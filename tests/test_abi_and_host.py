@@ -146,3 +146,28 @@ def test_expression_tracer_compiles_a_non_affine_basis_fcn():
     assert isinstance(a, MD.BasisExpr) and a.map_kind == L.MAP_AFFINE
     with pytest.raises(TypeError):
         MD.trace_basis(lambda s, u: hgp(np.floor(s)), 2, 1)       # not in the instruction set: raises, no host fallback
+
+
+def test_reference_style_likelihood_lambda_is_traced():
+    """the reference's likelihood_fcn form (src/EMPS.py:250-252, src/Toy_Example.py:142-144) with this package's stats module in place
+    of jax.scipy.stats reaches the same Gaussian observation model as models.gaussian_likelihood; on numbers it is SciPy's density"""
+    import helpers
+    import scipy.stats
+    MD, ST = helpers.pkg("models"), helpers.pkg("stats")
+    R = np.array([[1e-4]])
+    f_y = lambda x: x[0]                                                                          # noqa: E731  (src/EMPS.py:215-216)
+    lam = lambda obs, state, input: np.squeeze(ST.multivariate_normal.logpdf(obs, mean=f_y(state), cov=R))   # noqa: E731
+    a = MD.resolve_likelihood(lam, 2, 1)
+    b = MD.resolve_likelihood(MD.gaussian_likelihood(f_y, R), 2, 1)
+    assert np.array_equal(a.H, b.H) and np.array_equal(a.h0, b.h0) and np.array_equal(a.R, b.R) and a.H.tolist() == [[1.0, 0.0]]
+    R2 = np.array([[2.0, 0.3], [0.3, 1.0]])
+    lam2 = lambda obs, state, input: ST.multivariate_normal.logpdf(obs, mean=np.hstack([state[1] * 2.0 + 1.0, state[0] - state[2]]), cov=R2)  # noqa: E731
+    c = MD.resolve_likelihood(lam2, 3, 0)
+    assert np.allclose(c.H, [[0, 2, 0], [1, 0, -1]]) and np.allclose(c.h0, [1, 0]) and np.array_equal(c.R, R2)
+    x, y = np.array([0.3, -1.0, 2.0]), np.array([0.1, 0.2])
+    assert np.isclose(lam2(y, x, None), scipy.stats.multivariate_normal.logpdf(y, mean=[-1.0, -1.7], cov=R2), rtol=1e-13)
+    for bad in (lambda obs, state, input: ST.multivariate_normal.logpdf(obs, mean=np.sin(state[:1]), cov=R),          # not affine
+                lambda obs, state, input: ST.multivariate_normal.logpdf(obs, mean=state[:1] + input, cov=R),         # depends on the input
+                lambda obs, state, input: -0.5 * (obs - state[0]) ** 2):                                              # not a traced density
+        with pytest.raises(TypeError):
+            MD.resolve_likelihood(bad, 2, 1)
