@@ -235,7 +235,8 @@ def lib():
         if _stale():
             import warnings
             warnings.warn(f"{_SO} is older than csrc/ or include/pgas_b200.h: run __graft_entry__.build() to rebuild", RuntimeWarning)
-        L = C.CDLL(_SO)
+        # developer override (A/B measurements of compile-time variants): PGAS_LIB_PATH=<another build of this library>
+        L = C.CDLL(os.environ.get("PGAS_LIB_PATH") or _SO)
         want = _header_abi_version()
         try:
             L.pgas_abi_version.restype = C.c_int

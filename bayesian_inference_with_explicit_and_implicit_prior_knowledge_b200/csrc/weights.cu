@@ -294,8 +294,11 @@ __global__ void __launch_bounds__(NT, 2) csmc_weights_kernel(const __grid_consta
 // cluster form; what it buys is register space on H - 1 more SMs for the FP64-bound state kernel it shares the GPU with
 // (a resident resampling CTA takes half of an SM's register file: only one state CTA fits next to it instead of two).
 // Between the phases the per-particle prefixes wait in shared memory (registers: 64 per thread); three CTA barriers per step.
+#ifndef PGAS_WK1_MINB
+#define PGAS_WK1_MINB 2          // resident CTAs per SM the register allocation aims at (developer knob: 3 -> 40, 4 -> 32 registers)
+#endif
 template <int NT, int PPT, int H>
-__global__ void __launch_bounds__(NT, 2) csmc_weights1_kernel(const __grid_constant__ SweepArgs a) {
+__global__ void __launch_bounds__(NT, PGAS_WK1_MINB) csmc_weights1_kernel(const __grid_constant__ SweepArgs a) {
     constexpr int NW = NT / 32, U = H * NW;
     static_assert(U <= 32, "one fold pass");
     const int N = a.N, P = NT * PPT;                              // slice length (the last slice may be ragged or empty)
