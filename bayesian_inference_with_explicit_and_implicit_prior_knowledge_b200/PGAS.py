@@ -183,5 +183,8 @@ class PGAS:
                               want_params=False)
         st = res["state_trace"][0].permute(1, 0, 2).contiguous()            # (T,K,n_x)  (src/PGAS.py:380)
         obs = torch.as_tensor(m._obs).cuda()                                # (T,n_y)
-        ll = m.likelihood.logpdf_torch(obs[:, None, :], st)                 # (T,K)      (src/PGAS.py:383-392)
+        if isinstance(m.likelihood, _models.ProgramLikelihood):             # model plug-in: the program on whole trajectories
+            ll = m.likelihood.logpdf_torch(obs[:, None, :], st, torch.as_tensor(m._inp).cuda()[:, None, :])
+        else:
+            ll = m.likelihood.logpdf_torch(obs[:, None, :], st)             # (T,K)      (src/PGAS.py:383-392)
         return st.cpu().numpy(), ll.cpu().numpy()

@@ -23,7 +23,7 @@ LINK_IDENTITY, LINK_ATAN, LINK_TANH = 0, 1, 2
 MAP_AFFINE, MAP_VEHICLE_SLIP, MAP_PROGRAM = 0, 1, 2
 PGAS_MAX_PROG, PGAS_PROG_STACK = 64, 8
 OPS = dict(PUSH_X=1, PUSH_U=2, PUSH_C=3, ADD=4, SUB=5, MUL=6, DIV=7, NEG=8, SIN=9, COS=10, TAN=11, TANH=12, ATAN=13, EXP=14, LOG=15,
-           SQRT=16, ABS=17, POW=18, ATAN2=19)
+           SQRT=16, ABS=17, POW=18, ATAN2=19, PUSH_Y=20)
 FLAG_ANCESTOR_GATHER, FLAG_INPUT_PREV, FLAG_VCHOL_TRANSPOSE = 1, 2, 4
 
 
@@ -104,6 +104,7 @@ class ModelParams(C.Structure):
         ("m0", C.c_double * PGAS_MAX_NX),
         ("P0", (C.c_double * PGAS_MAX_NX) * PGAS_MAX_NX),
         ("flags", C.c_int32),
+        ("lik_prog_len", C.c_int32), ("lik_prog_op", C.c_int32 * PGAS_MAX_PROG), ("lik_prog_const", C.c_double * PGAS_MAX_PROG),
     ]
 
 

@@ -211,14 +211,15 @@ __device__ __forceinline__ void eval_mu_warp(const EvalCtx<D>& cx, const double*
 // (include/pgas_b200.h: PGAS_MAP_PROGRAM; models.py: Sym).  Interpreted per particle: the program is the same for every
 // thread (uniform control flow), the operand stack lives in local memory.  Kept out of line so that the compiled-in families
 // do not pay registers for it.
-static __device__ __noinline__ void pgas_map_program(const DevModel* m, const double* x, const double* u, double* z) {
+static __device__ __noinline__ void pgas_run_program(const DevModel* m, int pc0, int n, int coff, const double* x, const double* u,
+                                                     const double* y, double* out, int n_out) {
     double st[PGAS_PROG_STACK];
     int sp = 0;
-    const int n = m->prog_len;
-    for (int pc = 0; pc < n; ++pc) {
+    for (int pc = pc0; pc < pc0 + n; ++pc) {
         const int ins = m->prog_op[pc], op = ins & 0xff, arg = ins >> 8;
-        if (op <= PGAS_OP_PUSH_C) {
-            st[sp & (PGAS_PROG_STACK - 1)] = (op == PGAS_OP_PUSH_X) ? x[arg] : (op == PGAS_OP_PUSH_U) ? u[arg] : m->prog_const[arg];
+        if (op <= PGAS_OP_PUSH_C || op == PGAS_OP_PUSH_Y) {
+            st[sp & (PGAS_PROG_STACK - 1)] = (op == PGAS_OP_PUSH_X) ? x[arg] : (op == PGAS_OP_PUSH_U) ? u[arg] : (op == PGAS_OP_PUSH_Y) ? y[arg]
+                                                                                                                : m->prog_const[coff + arg];
             ++sp;
         } else if (op <= PGAS_OP_DIV || op >= PGAS_OP_POW) {
             const double b = st[(--sp) & (PGAS_PROG_STACK - 1)], a = st[(sp - 1) & (PGAS_PROG_STACK - 1)];
@@ -250,7 +251,18 @@ static __device__ __noinline__ void pgas_map_program(const DevModel* m, const do
             st[(sp - 1) & (PGAS_PROG_STACK - 1)] = r;
         }
     }
-    for (int d = 0; d < m->D; ++d) z[d] = st[d];
+    for (int d = 0; d < n_out; ++d) out[d] = st[d];
+}
+
+static __device__ __forceinline__ void pgas_map_program(const DevModel* m, const double* x, const double* u, double* z) {
+    pgas_run_program(m, 0, m->prog_len, 0, x, u, nullptr, z, m->D);
+}
+
+// likelihood_fcn as an expression program (model plug-in; pgas_b200.h: lik_prog_*): log-density of observation y given state x, input u
+static __device__ __forceinline__ double pgas_lik_program(const DevModel* m, const double* x, const double* u, const double* y) {
+    double r[1];
+    pgas_run_program(m, m->lik_off, m->lik_len, m->lik_coff, x, u, y, r, 1);
+    return r[0];
 }
 
 // GP-input map z = g(state, input) of any family on zero-padded arrays x[PGAS_MAX_NX], u[PGAS_MAX_NU] -> z[PGAS_MAX_D]

@@ -102,6 +102,31 @@ extern "C" int pgas_model_create(const pgas_model_params* p, pgas_model** out) {
     dm.slip_lf = p->slip_lf; dm.slip_lr = p->slip_lr;
     dm.prog_len = (p->map_kind == PGAS_MAP_PROGRAM) ? p->prog_len : 0;
     for (int i = 0; i < dm.prog_len; ++i) { dm.prog_op[i] = p->prog_op[i]; dm.prog_const[i] = p->prog_const[i]; }
+    if (p->lik_prog_len != 0) {
+        // likelihood program: validated like the map program (operands in range, stack within bounds, ONE result) and appended
+        // to the same instruction / constant arrays; its PUSH_C arguments are rebased onto the shared constant pool
+        if (p->lik_prog_len < 0 || dm.prog_len + p->lik_prog_len > PGAS_MAX_PROG)
+            PGAS_FAIL(-2, "likelihood program of %d instructions next to a map program of %d (limit %d together)", p->lik_prog_len, dm.prog_len, PGAS_MAX_PROG);
+        int ncst = 0, sp = 0;
+        for (int i = 0; i < dm.prog_len; ++i) if ((dm.prog_op[i] & 0xff) == PGAS_OP_PUSH_C) ncst = std::max(ncst, (dm.prog_op[i] >> 8) + 1);
+        int nlc = 0;
+        for (int i = 0; i < p->lik_prog_len; ++i) {
+            const int op = p->lik_prog_op[i] & 0xff, arg = p->lik_prog_op[i] >> 8;
+            if (op == PGAS_OP_PUSH_X) { if (arg < 0 || arg >= p->n_x) PGAS_FAIL(-2, "likelihood program instruction %d: state component %d", i, arg); ++sp; }
+            else if (op == PGAS_OP_PUSH_U) { if (arg < 0 || arg >= p->n_u) PGAS_FAIL(-2, "likelihood program instruction %d: input component %d", i, arg); ++sp; }
+            else if (op == PGAS_OP_PUSH_Y) { if (arg < 0 || arg >= p->n_y) PGAS_FAIL(-2, "likelihood program instruction %d: observation component %d", i, arg); ++sp; }
+            else if (op == PGAS_OP_PUSH_C) { if (arg < 0 || arg >= PGAS_MAX_PROG) PGAS_FAIL(-2, "likelihood program instruction %d: constant %d", i, arg); nlc = std::max(nlc, arg + 1); ++sp; }
+            else if ((op >= PGAS_OP_ADD && op <= PGAS_OP_DIV) || op == PGAS_OP_POW || op == PGAS_OP_ATAN2) { if (sp < 2) PGAS_FAIL(-2, "likelihood program instruction %d: stack underflow", i); --sp; }
+            else if (op >= PGAS_OP_NEG && op <= PGAS_OP_ABS) { if (sp < 1) PGAS_FAIL(-2, "likelihood program instruction %d: stack underflow", i); }
+            else PGAS_FAIL(-2, "likelihood program instruction %d: unknown opcode %d", i, op);
+            if (sp > PGAS_PROG_STACK) PGAS_FAIL(-2, "likelihood program instruction %d: more than %d operands on the stack", i, PGAS_PROG_STACK);
+        }
+        if (sp != 1) PGAS_FAIL(-2, "likelihood program leaves %d values, expected the log-density alone", sp);
+        if (ncst + nlc > PGAS_MAX_PROG) PGAS_FAIL(-2, "map and likelihood programs use %d constants together (limit %d)", ncst + nlc, PGAS_MAX_PROG);
+        dm.lik_off = dm.prog_len; dm.lik_len = p->lik_prog_len; dm.lik_coff = ncst;
+        for (int i = 0; i < p->lik_prog_len; ++i) dm.prog_op[dm.lik_off + i] = p->lik_prog_op[i];
+        for (int i = 0; i < nlc; ++i) dm.prog_const[ncst + i] = p->lik_prog_const[i];
+    }
     for (int r = 0; r < p->n_y; ++r) {
         dm.h0[r] = p->h0[r];
         for (int k = 0; k < p->n_x; ++k) dm.H[r][k] = p->H[r][k];

@@ -64,6 +64,15 @@ __device__ __forceinline__ double gauss_loglik(const DevModel& m, const double* 
     return m.R_logc - 0.5 * q;
 }
 
+// likelihood_fcn of any family (src/PGAS.py:93-100, :137-147: observations[time], state, inputs[time]): the Gaussian family above or
+// an expression program (model plug-in).  Fused kernel only — the split form's state kernel is specialised for the Gaussian family
+// and pgas_sweep_split_eligible sends models with a likelihood program here.
+template <int NX, int NY>
+__device__ __forceinline__ double loglik_any(const DevModel& m, int t, const double* y, const double x[NX]) {
+    if (m.lik_len) return pgas_lik_program(&m, x, m.inputs + (size_t)t * m.n_u, y);
+    return gauss_loglik<NX, NY>(m, y, x);
+}
+
 // log N(ref; mu, Sigma) with e = Sw (ref - mu)   (src/PGAS.py:109-116)
 template <int NX>
 __device__ __forceinline__ double gauss_logpdf_state(const double* __restrict__ Sw, double logc, const double* __restrict__ ref,
@@ -372,7 +381,7 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
                 auto weights = [&](int il, const double (&mu)[NX], double& lwa, double& lwr) {
 #pragma unroll
                     for (int k = 0; k < NX; ++k) mus[(size_t)k * P + il] = mu[k];
-                    const double la = gauss_loglik<NX, NY>(m, k_t.y, mu);
+                    const double la = loglik_any<NX, NY>(m, t, k_t.y, mu);
                     lwa = la + logw[il];
                     lwr = lwa + gauss_logpdf_state<NX>(sw, slogc[0], k_t.ref, mu);
                     laux[il] = la;
@@ -436,7 +445,7 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
                     double mu[NX];
 #pragma unroll
                     for (int k = 0; k < NX; ++k) mu[k] = mus[(size_t)k * P + il];
-                    const double la = gauss_loglik<NX, NY>(m, k_t.y, mu);
+                    const double la = loglik_any<NX, NY>(m, t, k_t.y, mu);
                     lwa = la + logw[il];
                     lwr = lwa + gauss_logpdf_state<NX>(sw, slogc[0], k_t.ref, mu);
                     laux[il] = la;
@@ -646,7 +655,7 @@ __global__ void __launch_bounds__(NT, PRE ? 1024 / NT : (NT == 256 ? 2 : 1)) csm
     #pragma unroll
                     for (int k = 0; k < NX; ++k) x[k] = k_t.ref[k];               // src/PGAS.py:134
                 }
-                const double lw = gauss_loglik<NX, NY>(m, k_t.y, x) - lauxg[il];   // :137-147
+                const double lw = loglik_any<NX, NY>(m, t, k_t.y, x) - lauxg[il];   // :137-147
                 logw[il] = lw;
     #pragma unroll
                 for (int k = 0; k < NX; ++k) { xs[(size_t)k * P + il] = x[k]; st_row[(size_t)i * NX + k] = x[k]; }
@@ -1054,6 +1063,7 @@ size_t pgas_sweep_split_workspace(const DevModel& m, int N, int n_chains) {
 bool pgas_sweep_split_eligible(const SweepArgs& a) {
     const DevModel& m = a.m;
     if (!((m.D == 2 || m.D == 3) && m.rw_ok) || (m.flags & PGAS_FLAG_ANCESTOR_GATHER)) return false;
+    if (m.lik_len) return false;                 // likelihood program (model plug-in): fused kernel
     if (!((m.n_x == 2 && m.n_y == 1) || (m.n_x == 2 && m.n_y == 2 && m.D == 2))) return false;
     if (a.init_state || a.init_logw || a.dbg || a.row_off != 0 || a.t_begin != 1 || a.t_end != m.T) return false;   // full sweeps only
     if (a.t_end - a.t_begin < 16 || !a.logw_last) return false;

@@ -117,8 +117,8 @@ _BINARY = {np.add: "ADD", np.subtract: "SUB", np.multiply: "MUL", np.divide: "DI
 
 
 class Sym:
-    """Symbolic vector of expression trees over (state, input).  A node is ("x", k) | ("u", k) | ("c", value) |
-    (opcode name, child[, child])."""
+    """Symbolic vector of expression trees over (state, input[, observation]).  A node is ("x", k) | ("u", k) | ("y", k) |
+    ("c", value) | (opcode name, child[, child])."""
     __array_priority__ = 1000
 
     def __init__(self, nodes, scalar=False):
@@ -213,7 +213,7 @@ def compile_program(sym):
     ops, consts = [], []
 
     def depth_of(node):
-        if node[0] in ("x", "u", "c"):
+        if node[0] in ("x", "u", "y", "c"):
             return 1
         ds = [depth_of(c) for c in node[1:]]
         return ds[0] if len(ds) == 1 else max(ds[0], ds[1] + 1)
@@ -224,6 +224,8 @@ def compile_program(sym):
             ops.append(_lib.OPS["PUSH_X"] | (node[1] << 8))
         elif kind == "u":
             ops.append(_lib.OPS["PUSH_U"] | (node[1] << 8))
+        elif kind == "y":
+            ops.append(_lib.OPS["PUSH_Y"] | (node[1] << 8))
         elif kind == "c":
             if node[1] not in consts:
                 consts.append(node[1])
@@ -241,8 +243,12 @@ def compile_program(sym):
     return ops, consts
 
 
-def run_program(ops, consts, x, u):
-    """Host mirror of the device interpreter (csrc/basis_eval.cuh: pgas_map_program), for tests and debugging."""
+def run_program(ops, consts, x, u, y=None):
+    """Host mirror of the device interpreter (csrc/basis_eval.cuh: pgas_run_program), for tests and debugging.  x, u, y may be
+    NumPy arrays or torch tensors with a trailing component axis: the operations broadcast (the final log-likelihood table of
+    PGAS.__call__ evaluates a likelihood program on whole trajectories this way)."""
+    if hasattr(x, "is_cuda") or hasattr(y, "is_cuda"):
+        return _run_program_torch(ops, consts, x, u, y)
     names = {v: k for k, v in _lib.OPS.items()}
     una = {"NEG": np.negative, "SIN": np.sin, "COS": np.cos, "TAN": np.tan, "TANH": np.tanh, "ATAN": np.arctan, "EXP": np.exp, "LOG": np.log,
            "SQRT": np.sqrt, "ABS": np.abs}
@@ -254,6 +260,8 @@ def run_program(ops, consts, x, u):
             st.append(float(x[arg]))
         elif name == "PUSH_U":
             st.append(float(u[arg]))
+        elif name == "PUSH_Y":
+            st.append(float(y[arg]))
         elif name == "PUSH_C":
             st.append(consts[arg])
         elif name in bina:
@@ -261,6 +269,31 @@ def run_program(ops, consts, x, u):
         else:
             st.append(float(una[name](st.pop())))
     return np.array(st)
+
+
+def _run_program_torch(ops, consts, x, u, y):
+    import torch
+    names = {v: k for k, v in _lib.OPS.items()}
+    una = {"NEG": torch.neg, "SIN": torch.sin, "COS": torch.cos, "TAN": torch.tan, "TANH": torch.tanh, "ATAN": torch.atan, "EXP": torch.exp,
+           "LOG": torch.log, "SQRT": torch.sqrt, "ABS": torch.abs}
+    bina = {"ADD": torch.add, "SUB": torch.sub, "MUL": torch.mul, "DIV": torch.div, "POW": torch.pow, "ATAN2": torch.atan2}
+    ref = x if hasattr(x, "is_cuda") else y
+    st = []
+    for ins in ops:
+        name, arg = names[ins & 0xFF], ins >> 8
+        if name == "PUSH_X":
+            st.append(x[..., arg])
+        elif name == "PUSH_U":
+            st.append(u[..., arg])
+        elif name == "PUSH_Y":
+            st.append(y[..., arg])
+        elif name == "PUSH_C":
+            st.append(torch.tensor(consts[arg], dtype=ref.dtype, device=ref.device))
+        elif name in bina:
+            b = st.pop(); a = st.pop(); st.append(bina[name](a, b))
+        else:
+            st.append(una[name](st.pop()))
+    return st
 
 
 def hstack(parts):
@@ -392,6 +425,23 @@ class _LazyLikelihood:
         return self._build(n_x)
 
 
+class ProgramLikelihood:
+    """likelihood_fcn(obs, state, input) as an expression program that leaves the log-density (model plug-in; pgas_b200.h:
+    lik_prog_*).  H / h0 / R are placeholders of the right shape for the Gaussian fields of pgas_model_params."""
+
+    def __init__(self, sym, n_x, n_y):
+        if len(sym.nodes) != 1:
+            raise TypeError(f"likelihood_fcn must return one log-density, got {len(sym.nodes)} values")
+        self.sym = sym
+        self.ops, self.consts = compile_program(sym)
+        self.H, self.h0, self.R = np.zeros((n_y, n_x)), np.zeros(n_y), np.eye(n_y)
+
+    def logpdf_torch(self, obs, states, inputs=None):
+        (out,) = run_program(self.ops, self.consts, states, inputs, obs)
+        import torch
+        return torch.broadcast_to(out, torch.broadcast_shapes(states.shape[:-1], obs.shape[:-1]))
+
+
 class ObservationMarker:
     """stands for `obs` while a reference-style likelihood_fcn(obs, state, input) is traced"""
 
@@ -411,8 +461,8 @@ class GaussianLogpdfTrace:
         return self
 
 
-def resolve_likelihood(lik, n_x, n_u=0):
-    if isinstance(lik, GaussianLikelihood):
+def resolve_likelihood(lik, n_x, n_u=0, n_y=None):
+    if isinstance(lik, (GaussianLikelihood, ProgramLikelihood)):
         return lik
     if isinstance(lik, _LazyLikelihood):
         return lik.resolve(n_x)
@@ -420,11 +470,25 @@ def resolve_likelihood(lik, n_x, n_u=0):
         # the reference's own form (src/EMPS.py:250-252): lambda obs, state, input: squeeze(multivariate_normal.logpdf(obs, mean=f_y(state), cov=R))
         # written against this package's `stats` module; traced once with a symbolic state
         s, u = _tracers(n_x, n_u)
-        out = lik(ObservationMarker(), s, u if n_u > 0 else np.zeros(0))
-        if isinstance(out, GaussianLogpdfTrace):
-            if np.any(out.mean.A[:, n_x:] != 0):
-                raise TypeError("likelihood_fcn: the output map must not depend on the input")
+        try:
+            out = lik(ObservationMarker(), s, u if n_u > 0 else np.zeros(0))
+        except TypeError:
+            out = None
+        if isinstance(out, GaussianLogpdfTrace) and not np.any(out.mean.A[:, n_x:] != 0):
             return GaussianLikelihood(out.mean.A[:, :n_x], out.mean.b, out.cov)
+        if n_y is not None:
+            # outside the Gaussian-of-an-affine-map family: the whole log-density as an expression program over
+            # (state, input, observation) — the model plug-in; such a model runs the fused sweep kernel
+            xs = Sym([("x", k) for k in range(n_x)])
+            us = Sym([("u", k) for k in range(n_u)]) if n_u > 0 else np.zeros(0)
+            ys = Sym([("y", k) for k in range(n_y)])
+            try:
+                out = lik(ys, xs, us)
+            except TypeError as e:
+                raise TypeError(f"likelihood_fcn is outside the supported families (Gaussian observation of an affine output map, or an "
+                                f"expression of numpy arithmetic / elementary functions of observation, state and input): {e}") from e
+            if isinstance(out, Sym):
+                return ProgramLikelihood(out, n_x, n_y)
     raise TypeError("likelihood_fcn must be a Gaussian observation of an affine output map: either models.gaussian_likelihood(f_y, R) "
                     "or the reference's lambda written with this package's stats.multivariate_normal.logpdf(obs, mean=f_y(state), cov=R); "
                     "other Python callables cannot run inside the CUDA sweep")
@@ -446,7 +510,7 @@ class DeviceModel:
         P0 = np.atleast_2d(np.asarray(P0, dtype=np.float64))
         self.n_x, self.n_y, self.n_u = m0.shape[0], obs.shape[1], inp.shape[1]
         self.basis = trace_basis(basis, self.n_x, self.n_u)
-        self.likelihood = resolve_likelihood(likelihood, self.n_x, self.n_u)
+        self.likelihood = resolve_likelihood(likelihood, self.n_x, self.n_u, self.n_y)
         hgp = self.basis.hgp
         self.M, self.D = hgp.M, hgp.D
         self.flags = int(flags)
@@ -471,6 +535,12 @@ class DeviceModel:
                 p.prog_op[i] = ins
             for i, c in enumerate(self.basis.consts):
                 p.prog_const[i] = c
+        if isinstance(self.likelihood, ProgramLikelihood):
+            p.lik_prog_len = len(self.likelihood.ops)
+            for i, ins in enumerate(self.likelihood.ops):
+                p.lik_prog_op[i] = ins
+            for i, c in enumerate(self.likelihood.consts):
+                p.lik_prog_const[i] = c
         for r in range(self.n_y):
             p.h0[r] = self.likelihood.h0[r]
             for k in range(self.n_x):

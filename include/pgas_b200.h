@@ -48,7 +48,8 @@ enum { PGAS_OP_PUSH_X = 1,   /* argument: state component          */
        PGAS_OP_PUSH_C = 3,   /* argument: index into prog_const    */
        PGAS_OP_ADD = 4, PGAS_OP_SUB = 5, PGAS_OP_MUL = 6, PGAS_OP_DIV = 7, PGAS_OP_NEG = 8,
        PGAS_OP_SIN = 9, PGAS_OP_COS = 10, PGAS_OP_TAN = 11, PGAS_OP_TANH = 12, PGAS_OP_ATAN = 13, PGAS_OP_EXP = 14,
-       PGAS_OP_LOG = 15, PGAS_OP_SQRT = 16, PGAS_OP_ABS = 17, PGAS_OP_POW = 18, PGAS_OP_ATAN2 = 19 };
+       PGAS_OP_LOG = 15, PGAS_OP_SQRT = 16, PGAS_OP_ABS = 17, PGAS_OP_POW = 18, PGAS_OP_ATAN2 = 19,
+       PGAS_OP_PUSH_Y = 20   /* argument: observation component (likelihood programs only) */ };
 
 /* reference quirks; the default 0 reproduces the reference bit for bit */
 enum { PGAS_FLAG_ANCESTOR_GATHER = 1, /* propagate x_t^i from x_{t-1}^{a_i} instead of x_{t-1}^i (src/PGAS.py:131-133) */
@@ -58,7 +59,8 @@ enum { PGAS_FLAG_ANCESTOR_GATHER = 1, /* propagate x_t^i from x_{t-1}^{a_i} inst
 /* Host-side description of one Theta-conditioned model: the data and the two user callables of
  * condSequentialMonteCarlo.__init__ (src/PGAS.py:24-43) restricted to the shipped families:
  * basis_fcn = Hilbert-space GP basis of a map of (state,input); likelihood_fcn = Gaussian
- * log-density of the observation around H state + h0.  All pointers are HOST pointers, copied. */
+ * log-density of the observation around H state + h0, or an expression program (lik_prog_*).
+ * All pointers are HOST pointers, copied. */
 typedef struct pgas_model_params {
     int32_t n_x, n_y, n_u, D, M, T;
     /* Hilbert basis (src/BasisFunctions.py:8-80): integer frequencies S (M x D), phi_m(z) =
@@ -86,6 +88,13 @@ typedef struct pgas_model_params {
     double m0[PGAS_MAX_NX];
     double P0[PGAS_MAX_NX][PGAS_MAX_NX];
     int32_t flags;                /* PGAS_FLAG_* */
+    /* Model plug-in for likelihood_fcn(obs, state, input) (src/PGAS.py:93-100, :137-147): lik_prog_len > 0 replaces the Gaussian
+     * family above by an expression program over (state, inputs[t], observations[t]) that leaves ONE value, the log-density.
+     * Together with the GP-input program at most PGAS_MAX_PROG instructions and constants.  Such a model runs the fused sweep
+     * kernel (the split form's state kernel is specialised for the Gaussian family). */
+    int32_t lik_prog_len;
+    int32_t lik_prog_op[PGAS_MAX_PROG];
+    double lik_prog_const[PGAS_MAX_PROG];
 } pgas_model_params;
 
 typedef struct pgas_model pgas_model;   /* opaque; owns device copies of the tables/data */
@@ -112,7 +121,7 @@ const char* pgas_last_error(void);
 int pgas_version(void);
 /* PGAS_ABI_VERSION of the header the library was compiled against: a binding compares it with its own copy of
  * the header before the first call (struct layouts and argument orders are only meaningful when they agree). */
-#define PGAS_ABI_VERSION 203
+#define PGAS_ABI_VERSION 204
 int pgas_abi_version(void);
 int pgas_device_count(void);
 /* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */

@@ -96,6 +96,19 @@ def make_problem(kind, T=30, N=64, M=None, seed=0, flags=0):
         inputs = 0.5 * rng.normal(size=(T, 1))
         ref = np.cumsum(0.05 * rng.normal(size=(T, 2)), axis=0)
         df = 3
+    elif kind == "pluginlik":
+        # a likelihood_fcn outside the Gaussian-of-an-affine-map family (model plug-in): Student-t log-density (4 degrees of freedom) of
+        # the observation around a non-affine output map that also reads the input; the basis is the single-mass oscillator's
+        M = M or 41
+        dom = np.array([[-7.5, 7.5], [-7.5, 7.5]])
+        args = (M, dom, 15.0 / M, 100.0)
+        n_x, n_u = 2, 1
+        A, b = np.array([[1.0, 0, 0], [0, 1.0, 0]]), np.zeros(2)
+        H, h0, R = np.array([[1.0, 0.0]]), np.zeros(1), np.array([[1e-2]])
+        m0, P0 = np.zeros(2), np.diag([1e-2, 1e-2])
+        inputs = 0.5 * rng.normal(size=(T, 1))
+        ref = np.cumsum(0.05 * rng.normal(size=(T, 2)), axis=0)
+        df = 3
     else:
         raise ValueError(kind)
     hgp, sd = OB.generate_Hilbert_BasisFunction(*args)
@@ -111,7 +124,12 @@ def make_problem(kind, T=30, N=64, M=None, seed=0, flags=0):
     else:
         obasis = OP.affine_hgp_basis(hgp, A, b)
     Sg = rng.normal(size=(n_x, n_x))
-    omodel = OP.ThetaModel(obs, inputs, m0, P0, obasis, OP.gaussian_loglik(H, h0, R))
+    ologlik = OP.gaussian_loglik(H, h0, R)
+    if kind == "pluginlik":
+        def ologlik(y, states, inp):             # the user callable evaluated directly with numpy, particle by column
+            st = np.atleast_2d(states)
+            return plugin_loglik(y, [st[:, 0], st[:, 1]], np.ravel(inp))
+    omodel = OP.ThetaModel(obs, inputs, m0, P0, obasis, ologlik)
     prior = OM.prior_mniw_2naturalPara(np.zeros((n_x, M)), np.diag(sd), np.eye(n_x), df)
     Theta = 0.3 * rng.normal(size=(n_x, M)) / np.sqrt(M)
     # Under reference quirk (i) every particle free-runs x_t = Theta phi(x_{t-1}) + noise for all T steps, so
@@ -137,6 +155,18 @@ def plugin_map(state, inp):
     return [z0, z1]
 
 
+def plugin_loglik(obs, state, inp):
+    """likelihood_fcn of the "pluginlik" problems, written the way a user writes it: plain numpy on observation / state / input"""
+    e = obs[0] - (state[0] + 0.2 * np.sin(state[1]) + 0.1 * inp[0])
+    return -2.5 * np.log(1.0 + e * e / (4.0 * 1e-2)) - 1.9
+
+
+def _product_likelihood(p, MD):
+    if p["kind"] == "pluginlik":
+        return plugin_loglik
+    return MD.GaussianLikelihood(p["H"], p["h0"], p["R"])
+
+
 def _product_basis(hgp, p, MD):
     if p["kind"] == "vehicle":
         return MD.VehicleSlipBasis(hgp, 1.16, 1.47)
@@ -150,7 +180,7 @@ def product_csmc(p, cluster_size=0):
     BF, MD, PG = pkg("BasisFunctions"), pkg("models"), pkg("PGAS")
     hgp, _ = BF.generate_Hilbert_BasisFunction(*p["hgp_args"])
     basis = _product_basis(hgp, p, MD)
-    lik = MD.GaussianLikelihood(p["H"], p["h0"], p["R"])
+    lik = _product_likelihood(p, MD)
     return PG.condSequentialMonteCarlo(N_samples=p["N"], observations=p["obs"], inputs=p["inputs"],
                                        init_state_mean=p["m0"], init_state_cov=p["P0"], likelihood_fcn=lik,
                                        basis_fcn=basis, flags=p["flags"], cluster_size=cluster_size)
@@ -176,7 +206,7 @@ def product_pgas(p, K, cluster_size=0):
     BF, MD, PG = pkg("BasisFunctions"), pkg("models"), pkg("PGAS")
     hgp, _ = BF.generate_Hilbert_BasisFunction(*p["hgp_args"])
     basis = _product_basis(hgp, p, MD)
-    lik = MD.GaussianLikelihood(p["H"], p["h0"], p["R"])
+    lik = _product_likelihood(p, MD)
     return PG.PGAS(N_samples=p["N"], N_iterations=K, observations=p["obs"], inputs=p["inputs"], init_state_mean=p["m0"],
                    init_state_cov=p["P0"], likelihood_fcn=lik, GP_prior=p["prior"], basis_fcn=basis, flags=p["flags"],
                    cluster_size=cluster_size)

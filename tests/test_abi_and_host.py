@@ -171,3 +171,35 @@ def test_reference_style_likelihood_lambda_is_traced():
                 lambda obs, state, input: -0.5 * (obs - state[0]) ** 2):                                              # not a traced density
         with pytest.raises(TypeError):
             MD.resolve_likelihood(bad, 2, 1)
+
+
+def test_likelihood_outside_the_gaussian_family_becomes_a_program():
+    """model plug-in (src/PGAS.py:24-43 hands ANY likelihood_fcn to the sampler): a Gaussian with a non-affine
+    mean, written with the stats stand-in, and a hand-written Student-t log-density both compile to expression programs over
+    (state, input, observation); the host mirror of the device interpreter reproduces the callables"""
+    import helpers
+    import scipy.stats
+    MD, ST, L = helpers.pkg("models"), helpers.pkg("stats"), helpers.pkg("_lib")
+    R2 = np.array([[2.0, 0.3], [0.3, 1.0]])
+    lam = lambda obs, state, input: np.squeeze(ST.multivariate_normal.logpdf(                     # noqa: E731
+        obs, mean=np.hstack([np.sin(state[0]) + input[0], state[1] * state[0]]), cov=R2))
+    a = MD.resolve_likelihood(lam, 2, 1, 2)
+    b = MD.resolve_likelihood(helpers.plugin_loglik, 2, 1, 1)
+    assert isinstance(a, MD.ProgramLikelihood) and isinstance(b, MD.ProgramLikelihood)
+    assert max(len(a.ops), len(b.ops)) <= L.PGAS_MAX_PROG and any((i & 0xFF) == L.OPS["PUSH_Y"] for i in b.ops)
+    rng = np.random.default_rng(3)
+    for _ in range(10):
+        x, u, y = rng.normal(size=2), rng.normal(size=1), rng.normal(size=2)
+        want = scipy.stats.multivariate_normal.logpdf(y, mean=[np.sin(x[0]) + u[0], x[1] * x[0]], cov=R2)
+        assert np.isclose(MD.run_program(a.ops, a.consts, x, u, y)[0], want, rtol=1e-13)
+        assert np.isclose(MD.run_program(b.ops, b.consts, x, u, y[:1])[0], helpers.plugin_loglik(y[:1], x, u), rtol=1e-14)
+    # the torch evaluation used for the final log-likelihood table of PGAS.__call__ (src/PGAS.py:383-392)
+    import torch
+    X, Y, U = torch.randn(5, 3, 2, dtype=torch.float64), torch.randn(5, 1, 1, dtype=torch.float64), torch.randn(5, 1, 1, dtype=torch.float64)
+    out = b.logpdf_torch(Y, X, U)
+    assert out.shape == (5, 3) and np.isclose(float(out[2, 1]), helpers.plugin_loglik(Y[2, 0].numpy(), X[2, 1].numpy(), U[2, 0].numpy()), rtol=1e-14)
+    # affine Gaussian stays in the compiled-in family even when the observation count is known
+    g = MD.resolve_likelihood(lambda obs, state, input: ST.multivariate_normal.logpdf(obs, mean=state[:1], cov=np.eye(1)), 2, 1, 1)
+    assert isinstance(g, MD.GaussianLikelihood)
+    with pytest.raises(TypeError):
+        MD.resolve_likelihood(lambda obs, state, input: np.floor(state[0]) - obs[0], 2, 1, 1)

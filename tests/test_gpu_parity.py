@@ -95,6 +95,7 @@ def test_basis_large_lattices(built_lib):
     ("smo", 200, 1), ("smo", 200, 2), ("smo", 1000, 1), ("smo", 1000, 4), ("smo", 777, 8), ("smo", 2048, 16),
     ("emps", 200, 1), ("emps", 512, 2), ("toy", 200, 1), ("toy", 300, 4), ("vehicle", 200, 1), ("vehicle", 640, 8),
     ("smo", 20, 16), ("smo", 2600, 1),
+    ("pluginlik", 200, 1), ("pluginlik", 1000, 4),     # model plug-in: likelihood_fcn as an expression program (Student-t, non-affine output map)
 ])
 def test_step_parity_teacher_forced(built_lib, kind, N, cluster):
     p = helpers.make_problem(kind, T=12, N=N, seed=N + cluster)
@@ -117,6 +118,8 @@ def test_step_parity_quirk_flags(built_lib, flags):
     ("smo", 4096, 12, 0), ("smo", 2501, 16, 0), ("vehicle", 6000, 8, 0),     # split form with the dedicated resampling kernel: clusters of 2 / 2 / 4
     # model plug-in: a GP-input map of sines / tanh / a rational term, traced into an expression program (split form; fused kernel)
     ("plugin", 512, 40, 0), ("plugin", 200, 30, 1), ("plugin", 4096, 12, 0),
+    # ... and a likelihood_fcn outside the Gaussian family as an expression program (fused kernel, with and without workspace / clusters)
+    ("pluginlik", 512, 40, 0), ("pluginlik", 200, 30, 1), ("pluginlik", 2048, 12, 4),
 ])
 def test_sweep_parity_injected(built_lib, kind, N, T, cluster):
     p = helpers.make_problem(kind, T=T, N=N, seed=T)
@@ -244,7 +247,7 @@ def test_draw_rejects_indefinite_eta1(built_lib):
 
 
 # ----------------------------------------------------------------------------- A14 full Gibbs loop
-@pytest.mark.parametrize("kind,cluster", [("smo", 1), ("smo", 2), ("toy", 1), ("plugin", 0)])
+@pytest.mark.parametrize("kind,cluster", [("smo", 1), ("smo", 2), ("toy", 1), ("plugin", 0), ("pluginlik", 0)])
 def test_run_chains_matches_oracle(built_lib, kind, cluster):
     from oracle import pgas as OP
     import torch
