@@ -497,7 +497,8 @@ def run_gpu_arm(args):
     # ncu captures of the same kernels at the same launch geometry (the state kernel's: one 16-step launch of one chain group of
     # configs[3]; the statistics': configs[3], 64 chains; the draw's: configs[4], 16 chains) — null for a configuration that was not captured
     tr_state = ncu_traffic(rf"csmc_state_kernel<2, {cfg['n_y']}, 0, 256, 2", "r02_state_kernel_raw.csv") if cnt * ((N + 511) // 512) >= 222 else None
-    tr_suff = ncu_traffic(r"suffstats_kernel", "r02_suffstats_kernel_raw.csv") if (args.config == 4 and cnt == 64) else None
+    tr_suff = (ncu_traffic(r"suffstats_kernel", "r02_suffstats_kernel_raw.csv") if (args.config == 4 and cnt == 64) else
+               ncu_traffic(r"suffstats_kernel", "r02_suffstats_kernel_cfg5_raw.csv") if (args.config == 5 and cnt == 16) else None)
     tr_draw = ncu_traffic(r"chol_update_kernel", "r02_tail_kernels_raw.csv") if args.config == 5 else None
 
     # ---- end-to-end leg: the public API with HOST buffers (pinned), H2D of the reference trajectories and D2H of the
