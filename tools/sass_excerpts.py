@@ -10,10 +10,10 @@ B = os.path.join(ROOT, "bayesian_inference_with_explicit_and_implicit_prior_know
 KERNELS = [("sweep.o", "csmc_state_kernelILi2ELi1ELb0ELi256ELi2", r"DFMA", "state kernel <n_x=2, n_y=1, Philox, 256 threads, 2 particles per thread>: the row walk"),
            ("weights_lat.o", "csmc_weights_lat_kernelILi256ELi2ELi8", r"SYNCS|STAS|ST\.ASYNC|UBLKCP", "latency form of the resampling kernel, cluster of 8: mbarrier waits and st.async hand-offs"),
            ("weights.o", "csmc_weights1_kernelILi512ELi4ELi2", r"BAR\.SYNC|DFMA", "one-CTA form of the resampling kernel"),
-           ("suffstats.o", "suffstats_kernel", r"DMMA", "sufficient statistics: SYRK over time on the FP64 tensor pipe"),
+           ("suffstats.o", "suffstats_kernelILi2", r"DMMA|UBLKCP|SYNCS", "sufficient statistics: SYRK over time on the FP64 tensor pipe"),
            ("mniw_draw.o", "chol_update", r"DMMA", "blocked Cholesky, trailing update on the FP64 tensor pipe"),
            ("mniw_draw.o", "mniw_draw_kernel", r"DFMA", "posterior draw"),
-           ("marginal.o", "marg_sweep_kernelILi1", r"DFMA", "marginalised conditional sweep (Algorithm3)")]
+           ("marginal.o", "marg_sweep_kernelILi1ELi2ELb1ELb0", r"DFMA", "marginalised conditional sweep (Algorithm3), 255-register instantiation of the wide geometry (the shipped single-mass oscillator runs this one)")]
 print("# r02 — SASS evidence (cuobjdump -sass of the in-tree objects built for sm_100a)\n")
 print("`tcgen05.mma` has no f64 kind: the Blackwell FP64 tensor instruction is `DMMA.8x8x4` (PTX `mma.sync.m8n8k4.f64`); it shares the FP64 pipe with `DFMA`")
 print("(profiles/r02_microbench.md), so kernels whose contraction is n_x = 2 columns wide use DFMA and the dense ones (statistics, trailing updates) DMMA.\n")
