@@ -8,4 +8,4 @@ CUDA device.  The top-level `src/` package re-exports these modules under the re
 """
 from . import _lib  # noqa: F401
 
-__all__ = ["_lib", "random", "models", "BasisFunctions", "Filtering", "BayesianInferrence", "PGAS", "distributed"]
+__all__ = ["_lib", "random", "models", "stats", "BasisFunctions", "Filtering", "BayesianInferrence", "PGAS", "distributed"]

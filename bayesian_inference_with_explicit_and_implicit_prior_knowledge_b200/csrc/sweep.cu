@@ -8,7 +8,7 @@
 // chain, many chains) or csmc_sweep_kernel<PRE> below (chains whose CDF does not fit one CTA).  About 290 launches per sweep at
 // T = 2000.
 //
-// FUSED FORM (csmc_sweep_kernel<PRE = false>; textbook ancestor gather, D != 2, single steps, no workspace): one CTA — or one
+// FUSED FORM (csmc_sweep_kernel<PRE = false>; textbook ancestor gather, D = 1, likelihood programs, single steps, no workspace): one CTA — or one
 // thread-block cluster of C CTAs — owns one chain for all T steps of a launch; the particle set (state, log-weight, auxiliary mean,
 // CDF) lives in shared memory / DSMEM and the only HBM traffic is the trace.  Each step, in one pass:
 //   A  mu_i = Theta phi(x_{t-1}^i, u_t)  (basis_eval.cuh), l_aux, h;  warp-local softmax shift + exp + scans
