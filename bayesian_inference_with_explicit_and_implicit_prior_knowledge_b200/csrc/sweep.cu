@@ -1113,16 +1113,22 @@ static int split_streams_init() {
     return 0;
 }
 
+// geometry of the state kernel: big CTAs (256 threads, 2 particles per thread) unless they would leave SMs idle (fewer than ~1.5 CTAs
+// per SM slot pair); judged on the whole sweep, not on one chain group; PGAS_STATE_SMALL=0|1 forces one (developer override)
+static bool state_geometry_small(int N, int n_chains) {
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int bpc_big = (N + ST_PP_BIG * ST_NT_BIG - 1) / (ST_PP_BIG * ST_NT_BIG);
+    bool small = n_chains * bpc_big < (3 * sms) / 2;
+    if (const char* e = getenv("PGAS_STATE_SMALL")) small = atoi(e) != 0;
+    return small;
+}
+
 static int launch_state(const StateArgs& s_in, cudaStream_t st) {
     StateArgs s = s_in;
     const DevModel& m = s.a.m;
     const bool inj = s.a.rng_mode == 1;
-    // geometry: big CTAs unless they would leave SMs idle (fewer than ~1.5 CTAs per SM slot pair); PGAS_STATE_SMALL=0|1 forces one
-    int sms = 148;
-    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    const int bpc_big = (s.a.N + ST_PP_BIG * ST_NT_BIG - 1) / (ST_PP_BIG * ST_NT_BIG);
-    bool small = s.a.n_chains * bpc_big < (3 * sms) / 2;                       // judged on the whole sweep, not on one chain group
-    if (const char* e = getenv("PGAS_STATE_SMALL")) small = atoi(e) != 0;     // developer override
+    bool small = state_geometry_small(s.a.N, s.a.n_chains);
     // contraction on DMMA tiles (basis_mma.cuh) in the big geometry of two-dimensional bases; PGAS_STATE_MMA=0|1 forces
     bool mma = !small && m.D == 2 && m.mma_ok && ST_PP_BIG == 2 && PGAS_STATE_MMA_DEFAULT;
     if (const char* e = getenv("PGAS_STATE_MMA")) mma = atoi(e) != 0 && !small && m.D == 2 && m.mma_ok && ST_PP_BIG == 2;
@@ -1233,11 +1239,17 @@ int pgas_launch_sweep(const SweepArgs& a, cudaStream_t stream) {
         // FP64 pipe does, and one CTA per chain (weights.cu) leaves the most room for the state kernel.  PGAS_WEIGHTS_KERNEL=3 / 1
         // force one or the other (developer override).
         const char* wk_env = getenv("PGAS_WEIGHTS_KERNEL");
+        if (wk_env && !*wk_env) wk_env = nullptr;                                  // set but empty: not an override
         const int lc = getenv("PGAS_SPLIT_PRE_C") ? 0 : pgas_weights_lat_cluster(a.N);
         // default only with portable cluster sizes (N <= 16384: 2 | 4 | 8 particles per thread, weights_lat.cu): clusters of 16 are
         // co-resident 7 at a time on B200 — at configs[4] (16 chains of N = 16384) they measured 424 ms per iteration, the general
         // kernel 332-342, clusters of 8 with eight particles per thread 301
-        const bool use_lat = lc > 0 && (wk_env ? atoi(wk_env) == 3 : (a.n_chains <= PGAS_LAT_MAX_CHAINS && lc <= 8));
+        // ... and only where its CTAs can share an SM with the state CTAs of this sweep: the two- / four-particle instantiations take
+        // 146+ registers, next to which a 256-thread state CTA (half of the register file) does not fit — 28 to 32 chains of
+        // N = 4096 measured 38.0 ms per iteration that way against 31.9 with one CTA per chain (2-GPU split of configs[3])
+        const bool lat_coresident = pgas_weights_lat_fits_beside_big_state(a.N) || state_geometry_small(a.N, a.n_chains) ||
+                                    (m.D == 3 && a.N <= ST_LANES_MAX_N);
+        const bool use_lat = lc > 0 && (wk_env ? atoi(wk_env) == 3 : (a.n_chains <= PGAS_LAT_MAX_CHAINS && lc <= 8 && lat_coresident));
         if (use_lat) {
             r.C = lc; r.P = (a.N + lc - 1) / lc;
             if (int rc = pgas_launch_weights_lat(r, stream)) return rc;

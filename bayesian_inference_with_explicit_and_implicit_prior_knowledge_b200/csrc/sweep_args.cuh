@@ -42,6 +42,7 @@ int pgas_launch_weights(const SweepArgs& a, cudaStream_t stream);         // ded
 int pgas_weights_cluster(int N);                                           // its cluster size for N particles; 0 = not applicable
 int pgas_launch_weights_lat(const SweepArgs& a, cudaStream_t stream);     // latency form: cluster per chain, st.async + mbarrier hand-offs (weights_lat.cu)
 int pgas_weights_lat_cluster(int N);                                       // its cluster size for N particles; 0 = not applicable
+bool pgas_weights_lat_fits_beside_big_state(int N);                        // its CTAs leave half of an SM's registers to a 256-thread state CTA
 bool pgas_sweep_split_eligible(const SweepArgs& a);
 size_t pgas_sweep_split_workspace(const DevModel& m, int N, int n_chains);
 int pgas_choose_cluster(const DevModel& m, int N, int n_chains, int requested);

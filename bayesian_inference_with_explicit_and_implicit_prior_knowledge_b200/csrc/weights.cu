@@ -530,7 +530,7 @@ static size_t weights_smem_bytes(int N) {
 // cluster size of the dedicated kernel for N particles (0: not applicable -> csmc_sweep_kernel<PRE>).  Chains of up to
 // 2 * NT * PPT particles run in ONE CTA (csmc_weights1_kernel, two slices), larger ones in a cluster (csmc_weights_kernel).
 int pgas_weights_cluster(int N) {
-    if (const char* e = getenv("PGAS_WEIGHTS_KERNEL")) { if (atoi(e) == 0) return 0; }      // developer override
+    if (const char* e = getenv("PGAS_WEIGHTS_KERNEL")) { if (*e && atoi(e) == 0) return 0; }      // developer override
     if (N < 64 || weights_smem_bytes(N) > 200 * 1024) return 0;
     const bool one_cta = !(getenv("PGAS_WEIGHTS_KERNEL") && atoi(getenv("PGAS_WEIGHTS_KERNEL")) == 2);   // 2: force the cluster form
     if (one_cta && N <= 2 * WK_NT * WK_PPT) return 1;

@@ -483,6 +483,11 @@ static int weights_lat_ppt(int N) {
     return 4 * WL_PPT;
 }
 
+// Does a CTA of the latency form leave room on its SM for a 256-thread state CTA (128 registers = half of the register file)?  Only the
+// eight-particle instantiation is capped at 128 registers; with two / four particles per thread the kernel takes 146+ registers
+// (39 K of the SM's 64 K: faster by itself, and right next to the 64-thread state CTAs of launches that do not fill the GPU).
+bool pgas_weights_lat_fits_beside_big_state(int N) { return weights_lat_ppt(N) >= 4 * WL_PPT; }
+
 // cluster size of the latency form for N particles (0: not applicable)
 int pgas_weights_lat_cluster(int N) {
     const int P = WL_NT * weights_lat_ppt(N);
