@@ -32,6 +32,34 @@ def test_struct_layout_matches_header():
     assert C.sizeof(L.Rng) == 64
 
 
+def test_header_constants_match_the_bindings(tmp_path):
+    """opcodes, limits, flags and the offsets of the plug-in fields as gcc sees them in include/pgas_b200.h vs the ctypes mirrors"""
+    import ctypes as C
+    import subprocess
+    L = helpers.pkg("_lib")
+    names = sorted(L.OPS)
+    src = tmp_path / "consts.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pgas_b200.h"\nint main(void){\n'
+                   + "".join(f'printf("%d\\n", (int)PGAS_OP_{n});\n' for n in names)
+                   + 'printf("%d %d %d %d %d %d %d\\n", PGAS_MAX_PROG, PGAS_PROG_STACK, PGAS_MAX_NX, PGAS_MAX_NY, PGAS_MAX_NU, PGAS_MAX_D, PGAS_MAX_GP);\n'
+                   + 'printf("%d %d %d %d %d %d\\n", PGAS_MAP_AFFINE, PGAS_MAP_VEHICLE_SLIP, PGAS_MAP_PROGRAM, PGAS_FLAG_ANCESTOR_GATHER, PGAS_FLAG_INPUT_PREV, PGAS_FLAG_VCHOL_TRANSPOSE);\n'
+                   + 'printf("%zu %zu %zu %zu %d\\n", offsetof(pgas_model_params, prog_len), offsetof(pgas_model_params, flags), offsetof(pgas_model_params, lik_prog_len),'
+                   + ' offsetof(pgas_model_params, lik_prog_const), PGAS_ABI_VERSION);\nreturn 0;}\n')
+    exe = tmp_path / "consts"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert [int(v) for v in out[:len(names)]] == [L.OPS[n] for n in names]
+    assert [int(v) for v in out[len(names)].split()] == [L.PGAS_MAX_PROG, L.PGAS_PROG_STACK, L.PGAS_MAX_NX, L.PGAS_MAX_NY, L.PGAS_MAX_NU,
+                                                         L.PGAS_MAX_D, L.PGAS_MAX_GP]
+    assert [int(v) for v in out[len(names) + 1].split()] == [L.MAP_AFFINE, L.MAP_VEHICLE_SLIP, L.MAP_PROGRAM, L.FLAG_ANCESTOR_GATHER,
+                                                             L.FLAG_INPUT_PREV, L.FLAG_VCHOL_TRANSPOSE]
+    offs = [int(v) for v in out[len(names) + 2].split()]
+    assert offs[:4] == [L.ModelParams.prog_len.offset, L.ModelParams.flags.offset, L.ModelParams.lik_prog_len.offset,
+                        L.ModelParams.lik_prog_const.offset]
+    assert offs[4] == 204
+
+
 def test_no_cpu_fallback_without_device(built_lib):
     import torch
     if torch.cuda.is_available():
