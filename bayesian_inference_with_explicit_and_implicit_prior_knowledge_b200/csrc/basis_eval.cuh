@@ -211,10 +211,56 @@ __device__ __forceinline__ void eval_mu_warp(const EvalCtx<D>& cx, const double*
 // (include/pgas_b200.h: PGAS_MAP_PROGRAM; models.py: Sym).  Interpreted per particle: the program is the same for every
 // thread (uniform control flow), the operand stack lives in local memory.  Kept out of line so that the compiled-in families
 // do not pay registers for it.
-static __device__ __noinline__ void pgas_run_program(const DevModel* m, int pc0, int n, int coff, const double* x, const double* u,
-                                                     const double* y, double* out, int n_out) {
+static __device__ __noinline__ void pgas_map_program(const DevModel* m, const double* x, const double* u, double* z) {
     double st[PGAS_PROG_STACK];
     int sp = 0;
+    const int n = m->prog_len;
+    for (int pc = 0; pc < n; ++pc) {
+        const int ins = m->prog_op[pc], op = ins & 0xff, arg = ins >> 8;
+        if (op <= PGAS_OP_PUSH_C) {
+            st[sp & (PGAS_PROG_STACK - 1)] = (op == PGAS_OP_PUSH_X) ? x[arg] : (op == PGAS_OP_PUSH_U) ? u[arg] : m->prog_const[arg];
+            ++sp;
+        } else if (op <= PGAS_OP_DIV || op >= PGAS_OP_POW) {
+            const double b = st[(--sp) & (PGAS_PROG_STACK - 1)], a = st[(sp - 1) & (PGAS_PROG_STACK - 1)];
+            double r;
+            switch (op) {
+                case PGAS_OP_ADD: r = a + b; break;
+                case PGAS_OP_SUB: r = a - b; break;
+                case PGAS_OP_MUL: r = a * b; break;
+                case PGAS_OP_DIV: r = a / b; break;
+                case PGAS_OP_POW: r = pow(a, b); break;
+                default: r = atan2(a, b); break;
+            }
+            st[(sp - 1) & (PGAS_PROG_STACK - 1)] = r;
+        } else {
+            const double a = st[(sp - 1) & (PGAS_PROG_STACK - 1)];
+            double r;
+            switch (op) {
+                case PGAS_OP_NEG: r = -a; break;
+                case PGAS_OP_SIN: r = sin(a); break;
+                case PGAS_OP_COS: r = cos(a); break;
+                case PGAS_OP_TAN: r = tan(a); break;
+                case PGAS_OP_TANH: r = tanh(a); break;
+                case PGAS_OP_ATAN: r = atan(a); break;
+                case PGAS_OP_EXP: r = exp(a); break;
+                case PGAS_OP_LOG: r = log(a); break;
+                case PGAS_OP_SQRT: r = sqrt(a); break;
+                default: r = fabs(a); break;
+            }
+            st[(sp - 1) & (PGAS_PROG_STACK - 1)] = r;
+        }
+    }
+    for (int d = 0; d < m->D; ++d) z[d] = st[d];
+}
+
+// likelihood_fcn as an expression program (model plug-in; pgas_b200.h: lik_prog_*): log-density of observation y given state x and
+// input u.  A SEPARATE interpreter on purpose: the GP-input interpreter above is reachable from the state kernel, whose register
+// allocation at the 128-register cap reacts to every change of that call site (a shared, more general interpreter cost the state
+// kernel 0.7 % at M = 256 and 3 % at M = 1024); this one is only reachable from the fused sweep kernel.
+static __device__ __noinline__ double pgas_lik_program(const DevModel* m, const double* x, const double* u, const double* y) {
+    double st[PGAS_PROG_STACK];
+    int sp = 0;
+    const int pc0 = m->lik_off, n = m->lik_len, coff = m->lik_coff;
     for (int pc = pc0; pc < pc0 + n; ++pc) {
         const int ins = m->prog_op[pc], op = ins & 0xff, arg = ins >> 8;
         if (op <= PGAS_OP_PUSH_C || op == PGAS_OP_PUSH_Y) {
@@ -251,18 +297,7 @@ static __device__ __noinline__ void pgas_run_program(const DevModel* m, int pc0,
             st[(sp - 1) & (PGAS_PROG_STACK - 1)] = r;
         }
     }
-    for (int d = 0; d < n_out; ++d) out[d] = st[d];
-}
-
-static __device__ __forceinline__ void pgas_map_program(const DevModel* m, const double* x, const double* u, double* z) {
-    pgas_run_program(m, 0, m->prog_len, 0, x, u, nullptr, z, m->D);
-}
-
-// likelihood_fcn as an expression program (model plug-in; pgas_b200.h: lik_prog_*): log-density of observation y given state x, input u
-static __device__ __forceinline__ double pgas_lik_program(const DevModel* m, const double* x, const double* u, const double* y) {
-    double r[1];
-    pgas_run_program(m, m->lik_off, m->lik_len, m->lik_coff, x, u, y, r, 1);
-    return r[0];
+    return st[0];
 }
 
 // GP-input map z = g(state, input) of any family on zero-padded arrays x[PGAS_MAX_NX], u[PGAS_MAX_NU] -> z[PGAS_MAX_D]

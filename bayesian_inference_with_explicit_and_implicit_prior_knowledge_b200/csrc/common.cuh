@@ -61,7 +61,6 @@ struct DevModel {
     double slip_lf, slip_lr;
     int prog_len, prog_op[PGAS_MAX_PROG];           // PGAS_MAP_PROGRAM: postfix expression program of the GP-input map (pgas_b200.h)
     double prog_const[PGAS_MAX_PROG];
-    int lik_off, lik_len, lik_coff;                 // likelihood program (model plug-in): instructions prog_op[lik_off ..], constants from lik_coff
     double H[PGAS_MAX_NY][PGAS_MAX_NX], h0[PGAS_MAX_NY];
     double Rw[PGAS_MAX_NY][PGAS_MAX_NY];            // inverse of chol(R) (lower): e = Rw (y - mean)
     double R_logc;                                  // -n_y/2 log(2 pi) - sum log diag chol(R)
@@ -80,6 +79,10 @@ struct DevModel {
     const int* lat_perm;    // [M] basis functions in lattice order (positions sorted lexicographically, last dimension fastest)
     const double* obs;      // (T,n_y)
     const double* inputs;   // (T,n_u)
+    // likelihood program (model plug-in): instructions prog_op[lik_off .. lik_off + lik_len), constants from prog_const[lik_coff].
+    // Kept at the END of the struct: the kernels address DevModel through the constant bank, and the state kernel's code should
+    // not move when a field is added.
+    int lik_off, lik_len, lik_coff;
 };
 
 struct pgas_model {
